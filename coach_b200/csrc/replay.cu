@@ -1,0 +1,698 @@
+// coach_b200/csrc/replay.cu -- HBM-resident prioritized / uniform replay: segment trees, sampling, column gather.
+//
+// Reference arithmetic being replaced (file:line under /root/reference/rl_coach/):
+//   memories/non_episodic/prioritized_experience_replay.py:43-156  SegmentTree
+//   memories/non_episodic/prioritized_experience_replay.py:188-283 PER._update_priority/update_priorities/sample/store
+//   memories/non_episodic/experience_replay.py:71-93,131-150        ExperienceReplay.sample/store
+//   core_types.py:488-623                                           Batch column extraction (AoS -> SoA)
+//
+// Exactness rules for everything that feeds an index: fp64, explicit round-to-nearest intrinsics (__dadd_rn ...)
+// so that nvcc can never contract a*b+c into an FMA (Python evaluates each operation separately), comparisons
+// written exactly as the reference writes them (`val <= tree[left]`).
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cb200 {
+
+// =====================================================================================================================
+// Segment-tree descent: one warp, all lanes carry the same `val`.
+// SegmentTree._retrieve (:76-92) walks one level per step; here each round fetches the next R<=5 levels below the
+// current node (2+4+...+2^R <= 62 nodes, contiguous per level in the heap array) with two loads per lane and
+// then replays the reference's comparisons out of registers with shuffles.  Same comparisons, same subtractions,
+// same order => same leaf, bit for bit.
+// =====================================================================================================================
+struct Descent {
+    int64_t leaf;
+    double priority;   // tree[leaf + size - 1]
+};
+
+__device__ __forceinline__ Descent warp_descent(const double* __restrict__ tree, int64_t size, int levels,
+                                                double val) {
+    const int lane = threadIdx.x & 31;
+    uint64_t j = 1;   // 1-based heap index of the current node
+    double p = 0.0;
+    if (levels == 0) p = __ldcg(tree);
+    int remaining = levels;
+    while (remaining > 0) {
+        const int r = remaining < 5 ? remaining : 5;
+        // element e of the sub-tree in level order without its root: e+2 = 2^k + off  ->  node = (j-1)*2^k + (e+2)
+        double v0 = 0.0, v1 = 0.0;
+        {
+            const int e2 = lane + 2;
+            const int k = 31 - __clz(e2);
+            if (k <= r) v0 = __ldcg(tree + (((j - 1) << k) + e2 - 1));
+        }
+        {
+            const int e2 = lane + 34;
+            const int k = 31 - __clz(e2);
+            if (k <= r) v1 = __ldcg(tree + (((j - 1) << k) + e2 - 1));
+        }
+        uint32_t rel = 1;
+        for (int s = 0; s < r; ++s) {
+            const int el = 2 * rel - 2, er = el + 1;
+            const double l0 = __shfl_sync(0xffffffffu, v0, el & 31), l1 = __shfl_sync(0xffffffffu, v1, el & 31);
+            const double r0 = __shfl_sync(0xffffffffu, v0, er & 31), r1 = __shfl_sync(0xffffffffu, v1, er & 31);
+            const double left = el < 32 ? l0 : l1;
+            const double right = er < 32 ? r0 : r1;
+            if (val <= left) {   // :89
+                rel = 2 * rel;
+                p = left;
+            } else {             // :92
+                val = __dsub_rn(val, left);
+                rel = 2 * rel + 1;
+                p = right;
+            }
+        }
+        j = (j << r) + (rel - (1u << r));
+        remaining -= r;
+    }
+    Descent d;
+    d.leaf = (int64_t)j - size;
+    d.priority = p;
+    return d;
+}
+
+struct SampleParams {
+    const double* sum_tree;
+    const double* min_tree;
+    int64_t size;
+    int levels;
+    const double* u;
+    int64_t n;
+    double nt;     // (double) num_transitions
+    double beta;
+    int64_t* idx_out;
+    double* w_out;
+    float* w32_out;
+};
+
+// PER.sample :232-248 for sample i (whole warp).  Returns the leaf; lane 0 stores idx / weights.
+__device__ __forceinline__ int64_t per_sample_one(const SampleParams& sp, int64_t i, bool write_outputs) {
+    const double total = __ldcg(sp.sum_tree);
+    const double segment = __ddiv_rn(total, (double)sp.n);                        // :232
+    const double a = __dmul_rn(segment, (double)i);                               // :240
+    const double b = __dmul_rn(segment, (double)(i + 1));                         // :241
+    const double val = __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), __ldg(sp.u + i)));  // random.uniform :244
+    const Descent d = warp_descent(sp.sum_tree, sp.size, sp.levels, val);
+    if (write_outputs && (threadIdx.x & 31) == 0) {
+        if (sp.idx_out) sp.idx_out[i] = d.leaf;
+        if (sp.w_out || sp.w32_out) {
+            const double min_probability = __ddiv_rn(__ldcg(sp.min_tree), total);       // :235
+            const double max_weight = pow(__dmul_rn(min_probability, sp.nt), -sp.beta);  // :236
+            const double prob = __ddiv_rn(d.priority, total);                           // :246
+            const double weight = pow(__dmul_rn(sp.nt, prob), -sp.beta);                // :247
+            const double w = __ddiv_rn(weight, max_weight);                             // :248
+            if (sp.w_out) sp.w_out[i] = w;
+            if (sp.w32_out) sp.w32_out[i] = (float)w;
+        }
+    }
+    return d.leaf;
+}
+
+__global__ void __launch_bounds__(128) per_sample_kernel(SampleParams sp) {
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= sp.n) return;
+    per_sample_one(sp, warp, true);
+}
+
+// =====================================================================================================================
+// Tree update: leaves (last writer wins) then ancestors level by level.
+// =====================================================================================================================
+struct UpdateParams {
+    double* sum_tree;
+    double* min_tree;
+    double* max_tree;
+    int32_t* winner;
+    int64_t size;
+    int levels;
+    const int64_t* idx;      // nullptr => ring mode: leaf = (cursor + i) % size, constant values
+    const double* p_alpha;
+    const double* p_raw;
+    int64_t cursor;
+    double c_alpha, c_raw;
+    int64_t n;
+    double* max_priority_out;
+};
+
+__device__ __forceinline__ int64_t upd_leaf(const UpdateParams& up, int64_t i) {
+    if (up.idx) return up.idx[i];
+    return (up.cursor + i) & (up.size - 1);
+}
+__device__ __forceinline__ double py_min(double a, double b) { return (b < a) ? b : a; }   // builtin min(a, b)
+__device__ __forceinline__ double py_max(double a, double b) { return (b > a) ? b : a; }   // builtin max(a, b)
+
+__device__ __forceinline__ void recompute_parent(const UpdateParams& up, int64_t parent) {
+    const int64_t l = 2 * parent + 1;                                                          // :71
+    // children sit at l (odd) and l+1: not 16-byte aligned as a pair, so two 8-byte loads per tree
+    const double sl = __ldcg(up.sum_tree + l), sr = __ldcg(up.sum_tree + l + 1);
+    const double ml = __ldcg(up.min_tree + l), mr = __ldcg(up.min_tree + l + 1);
+    const double xl = __ldcg(up.max_tree + l), xr = __ldcg(up.max_tree + l + 1);
+    __stcg(up.sum_tree + parent, __dadd_rn(sl, sr));
+    __stcg(up.min_tree + parent, py_min(ml, mr));
+    __stcg(up.max_tree + parent, py_max(xl, xr));
+}
+
+// n <= 1024: one CTA does everything, __syncthreads between levels.
+__global__ void __launch_bounds__(1024) per_update_cta_kernel(UpdateParams up) {
+    const int i = threadIdx.x;
+    int64_t leaf = -1;
+    bool active = false;
+    if (i < up.n) {
+        leaf = upd_leaf(up, i);
+        active = leaf >= 0 && leaf < up.size;
+    }
+    if (active) atomicMax(up.winner + leaf, i);
+    __syncthreads();
+    const bool win = active && (__ldcg(up.winner + leaf) == i);
+    __syncthreads();
+    int64_t node = leaf + up.size - 1;
+    if (win) {
+        const double pa = up.idx ? up.p_alpha[i] : up.c_alpha;
+        const double pr = up.idx ? up.p_raw[i] : up.c_raw;
+        __stcg(up.sum_tree + node, pa);
+        __stcg(up.min_tree + node, pa);
+        __stcg(up.max_tree + node, pr);
+        __stcg(up.winner + leaf, -1);
+    }
+    if (active) {
+        // pull every sibling on the path into L2 up front: the level loop below then only sees L2 latency
+        int64_t nd = node;
+        for (int l = 0; l < up.levels; ++l) {
+            const int64_t sib = ((nd - 1) ^ 1) + 1;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(up.sum_tree + sib));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(up.min_tree + sib));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(up.max_tree + sib));
+            nd = (nd - 1) >> 1;
+        }
+    }
+    __syncthreads();
+    for (int l = 0; l < up.levels; ++l) {
+        const int64_t parent = (node - 1) >> 1;   // :69
+        // threads sharing a parent all compute the same value; let the lowest-numbered writer per pair do it when
+        // cheap to know (sibling leaf within the same thread is not knowable) -- identical values, benign.
+        if (active) recompute_parent(up, parent);
+        node = parent;
+        __syncthreads();
+    }
+    if (i == 0 && up.max_priority_out) *up.max_priority_out = __ldcg(up.max_tree);   // :201
+}
+
+// large n: separate launches
+__global__ void per_update_claim_kernel(UpdateParams up) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= up.n) return;
+    const int64_t leaf = upd_leaf(up, i);
+    if (leaf < 0 || leaf >= up.size) return;
+    atomicMax(up.winner + leaf, (int32_t)(i & 0x7fffffff));
+}
+__global__ void per_update_leaf_kernel(UpdateParams up) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= up.n) return;
+    const int64_t leaf = upd_leaf(up, i);
+    if (leaf < 0 || leaf >= up.size) return;
+    if (__ldcg(up.winner + leaf) != (int32_t)(i & 0x7fffffff)) return;
+    const int64_t node = leaf + up.size - 1;
+    up.sum_tree[node] = up.idx ? up.p_alpha[i] : up.c_alpha;
+    up.min_tree[node] = up.idx ? up.p_alpha[i] : up.c_alpha;
+    up.max_tree[node] = up.idx ? up.p_raw[i] : up.c_raw;
+}
+__global__ void per_update_reset_kernel(UpdateParams up) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= up.n) return;
+    const int64_t leaf = upd_leaf(up, i);
+    if (leaf < 0 || leaf >= up.size) return;
+    up.winner[leaf] = -1;
+}
+__global__ void per_update_level_kernel(UpdateParams up, int shift) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= up.n) return;
+    const int64_t leaf = upd_leaf(up, i);
+    if (leaf < 0 || leaf >= up.size) return;
+    // 1-based ancestor `shift` levels above the leaf, then 0-based
+    const int64_t parent = ((leaf + up.size) >> shift) - 1;
+    recompute_parent(up, parent);
+}
+__global__ void per_write_max_kernel(const double* max_tree, double* out) { *out = max_tree[0]; }
+
+__global__ void per_init_kernel(double* sum_tree, double* min_tree, double* max_tree, int32_t* winner, int64_t size) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = 2 * size - 1;
+    if (i < n) {
+        sum_tree[i] = 0.0;                       // Operation.SUM initial_value :52
+        min_tree[i] = __longlong_as_double(0x7ff0000000000000LL);   // +inf :51
+        max_tree[i] = __longlong_as_double(0xfff0000000000000LL);   // -inf :50
+    }
+    if (i < size) winner[i] = -1;
+}
+
+__global__ void per_priorities_kernel(const double* err, int64_t n, double epsilon, double alpha, double* p_alpha,
+                                      double* p_raw, int32_t* neg_flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double e = err[i];
+    if (e < 0 && neg_flag) *neg_flag = 1;      // :195
+    const double p = __dadd_rn(e, epsilon);    // :197
+    p_raw[i] = p;
+    p_alpha[i] = pow(p, alpha);                // :198
+}
+
+// =====================================================================================================================
+// Column gather.
+// =====================================================================================================================
+constexpr int kStageBytes = 8192;       // smem stage capacity (one chunk of one row)
+constexpr int kMaxStages = 12;
+constexpr int kGatherThreads = 128;
+constexpr int kMaxCtaSamples = 16;      // descents a CTA may need for its contiguous item range (fused kernel)
+
+struct BigColumn {
+    const uint8_t* src;
+    uint8_t* dst;
+    int64_t row_bytes;
+    int32_t nchunk;
+    int32_t chunk_bytes;     // all chunks but the last
+    int32_t last_bytes;
+    int32_t first_item;      // prefix of nchunk over the preceding big columns
+};
+struct SmallColumn {
+    const uint8_t* src;
+    uint8_t* dst;
+    int64_t row_bytes;
+};
+struct GatherParams {
+    BigColumn big[CB200_MAX_COLUMNS];
+    SmallColumn small[CB200_MAX_COLUMNS];
+    int n_big, n_small;
+    int items_per_sample;
+    int64_t n;               // samples
+    int64_t total_items;
+    const int64_t* idx;      // plain gather: indices come from memory
+    int stages;
+};
+
+// copy `bytes` from src to dst with the widest access the three alignments allow; executed by one warp
+__device__ __forceinline__ void warp_copy_row(uint8_t* dst, const uint8_t* src, int64_t bytes, int lane) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes;
+    if ((a & 15) == 0) {
+        for (int64_t o = (int64_t)lane * 16; o < bytes; o += 32 * 16) st_stream16(dst + o, ld_stream16(src + o));
+    } else if ((a & 3) == 0) {
+        for (int64_t o = (int64_t)lane * 4; o < bytes; o += 32 * 4)
+            *reinterpret_cast<uint32_t*>(dst + o) = *reinterpret_cast<const uint32_t*>(src + o);
+    } else {
+        for (int64_t o = lane; o < bytes; o += 32) dst[o] = src[o];
+    }
+}
+
+// Bulk-copy pipeline executed by ONE thread of the CTA: items [lo, hi) of the flattened (sample, column, chunk) space
+// flow global -> smem stage -> global.  `leaf_of(sample)` yields the source row.
+template <typename LeafFn>
+__device__ __forceinline__ void bulk_pipeline(const GatherParams& gp, int64_t lo, int64_t hi, uint8_t* stage_mem,
+                                              uint64_t* full_bar, LeafFn leaf_of) {
+    const int S = gp.stages;
+    const int64_t cnt = hi - lo;
+    auto item_addr = [&](int64_t item, const uint8_t*& src, uint8_t*& dst, uint32_t& bytes) {
+        const int64_t sample = item / gp.items_per_sample;
+        const int r = (int)(item - sample * gp.items_per_sample);
+        int c = 0;
+#pragma unroll
+        for (int q = 1; q < CB200_MAX_COLUMNS; ++q)
+            if (q < gp.n_big && r >= gp.big[q].first_item) c = q;
+        const BigColumn& col = gp.big[c];
+        const int chunk = r - col.first_item;
+        const int64_t off = (int64_t)chunk * col.chunk_bytes;
+        bytes = (chunk == col.nchunk - 1) ? (uint32_t)col.last_bytes : (uint32_t)col.chunk_bytes;
+        src = col.src + leaf_of(sample) * col.row_bytes + off;
+        dst = col.dst + sample * col.row_bytes + off;
+    };
+    auto issue_load = [&](int64_t k) {
+        const int st = (int)(k % S);
+        const uint8_t* src;
+        uint8_t* dst;
+        uint32_t bytes;
+        item_addr(lo + k, src, dst, bytes);
+        mbar_expect_tx(full_bar + st, bytes);
+        bulk_g2s(stage_mem + (size_t)st * kStageBytes, src, bytes, full_bar + st);
+    };
+    const int64_t pre = cnt < S ? cnt : S;
+    for (int64_t k = 0; k < pre; ++k) issue_load(k);
+    for (int64_t k = 0; k < cnt; ++k) {
+        const int st = (int)(k % S);
+        mbar_wait(full_bar + st, (uint32_t)((k / S) & 1));
+        const uint8_t* src;
+        uint8_t* dst;
+        uint32_t bytes;
+        item_addr(lo + k, src, dst, bytes);
+        fence_proxy_async_smem();
+        bulk_s2g(dst, stage_mem + (size_t)st * kStageBytes, bytes);
+        bulk_commit();
+        // refill the stage whose store was issued one iteration ago (its smem read has had time to drain)
+        if (k >= 1 && (k - 1 + S) < cnt) {
+            bulk_wait_read<1>();
+            issue_load(k - 1 + S);
+        }
+    }
+    bulk_wait_all<0>();
+}
+
+__device__ __forceinline__ void cta_item_range(int64_t total, int64_t& lo, int64_t& hi) {
+    lo = total * blockIdx.x / gridDim.x;
+    hi = total * (blockIdx.x + 1) / gridDim.x;
+}
+
+__device__ __forceinline__ void init_barriers(uint64_t* full_bar, int stages) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(full_bar + s, 1);
+        fence_mbar_init();
+    }
+}
+
+// plain gather: indices in memory (uniform ExperienceReplay, or PER after cb200_per_sample)
+__global__ void __launch_bounds__(kGatherThreads) gather_bulk_kernel(GatherParams gp) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+    uint8_t* stage_mem = smem + 128;
+    init_barriers(full_bar, gp.stages);
+    __syncthreads();
+    int64_t lo, hi;
+    cta_item_range(gp.total_items, lo, hi);
+    if (threadIdx.x == 0 && hi > lo) {
+        const int64_t* idx = gp.idx;
+        bulk_pipeline(gp, lo, hi, stage_mem, full_bar, [idx](int64_t s) { return __ldg(idx + s); });
+    }
+}
+
+// small / unaligned columns: one warp per (sample, column)
+__global__ void __launch_bounds__(256) gather_small_kernel(GatherParams gp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t w = warp; w < gp.n * gp.n_small; w += nwarps) {
+        const int64_t sample = w / gp.n_small;
+        const SmallColumn& col = gp.small[w - sample * gp.n_small];
+        const int64_t leaf = __ldg(gp.idx + sample);
+        warp_copy_row(col.dst + sample * col.row_bytes, col.src + leaf * col.row_bytes, col.row_bytes, lane);
+    }
+}
+
+// fused PER sample + gather
+__global__ void __launch_bounds__(kGatherThreads) per_sample_gather_kernel(SampleParams sp, GatherParams gp) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+    int64_t* leaf_smem = reinterpret_cast<int64_t*>(smem + 128);           // kMaxCtaSamples entries
+    uint8_t* stage_mem = smem + 128 + kMaxCtaSamples * sizeof(int64_t);
+    init_barriers(full_bar, gp.stages);
+    int64_t lo, hi;
+    cta_item_range(gp.total_items, lo, hi);
+    if (hi <= lo) return;
+    const int ips = gp.items_per_sample;
+    const int64_t s_lo = lo / ips, s_hi = (hi - 1) / ips;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    // phase A: descents for the samples this CTA touches, one warp each, in parallel
+    for (int64_t s = s_lo + warp; s <= s_hi; s += nwarp) {
+        const bool owner = (s * ips >= lo);     // this CTA holds the sample's first item -> it publishes the outputs
+        const int64_t leaf = per_sample_one(sp, s, owner);
+        if (lane == 0) leaf_smem[(s - s_lo) % kMaxCtaSamples] = leaf;
+        if (owner) {
+            for (int c = 0; c < gp.n_small; ++c) {
+                const SmallColumn& col = gp.small[c];
+                warp_copy_row(col.dst + s * col.row_bytes, col.src + leaf * col.row_bytes, col.row_bytes, lane);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bulk_pipeline(gp, lo, hi, stage_mem, full_bar,
+                      [leaf_smem, s_lo](int64_t s) { return leaf_smem[(s - s_lo) % kMaxCtaSamples]; });
+    }
+}
+
+// generic row copy used by the ring append: dst row (cursor+i)%capacity <- src row i
+__global__ void __launch_bounds__(256) scatter_ring_kernel(uint8_t* ring, const uint8_t* staged, int64_t row_bytes,
+                                                           int64_t cursor, int64_t capacity, int64_t n,
+                                                           int64_t piece_bytes, int pieces) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t w = warp; w < n * pieces; w += nwarps) {
+        const int64_t i = w / pieces;
+        const int64_t off = (w - i * pieces) * piece_bytes;
+        const int64_t bytes = (off + piece_bytes <= row_bytes) ? piece_bytes : (row_bytes - off);
+        if (bytes <= 0) continue;
+        const int64_t slot = (cursor + i) % capacity;
+        warp_copy_row(ring + slot * row_bytes + off, staged + i * row_bytes + off, bytes, lane);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+#define g_tune_stages (cb200::tune_get("gather_stages", 6, 1, kMaxStages))
+#define g_tune_ctas_per_sm (cb200::tune_get("gather_ctas_per_sm", 2, 1, 16))
+
+static int ilog2_exact(int64_t size) {
+    int l = 0;
+    while (((int64_t)1 << l) < size) ++l;
+    return (((int64_t)1 << l) == size) ? l : -1;
+}
+
+static int build_gather_params(const cb200_column* cols, int n_columns, int64_t n, GatherParams& gp) {
+    gp.n_big = gp.n_small = 0;
+    gp.items_per_sample = 0;
+    gp.n = n;
+    gp.idx = nullptr;
+    gp.stages = g_tune_stages;
+    for (int c = 0; c < n_columns; ++c) {
+        const cb200_column& col = cols[c];
+        if (col.row_bytes <= 0 || !col.src || !col.dst) return -1;
+        const bool aligned = (col.row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(col.src) & 15) == 0) &&
+                             ((reinterpret_cast<uintptr_t>(col.dst) & 15) == 0);
+        if (aligned && col.row_bytes >= 2048) {
+            BigColumn& b = gp.big[gp.n_big++];
+            b.src = static_cast<const uint8_t*>(col.src);
+            b.dst = static_cast<uint8_t*>(col.dst);
+            b.row_bytes = col.row_bytes;
+            int64_t nchunk = (col.row_bytes + kStageBytes - 1) / kStageBytes;
+            int64_t cb = (((col.row_bytes + nchunk - 1) / nchunk) + 15) / 16 * 16;
+            while (cb > kStageBytes) {   // cannot happen, but keep the invariant explicit
+                ++nchunk;
+                cb = (((col.row_bytes + nchunk - 1) / nchunk) + 15) / 16 * 16;
+            }
+            nchunk = (col.row_bytes + cb - 1) / cb;
+            b.nchunk = (int32_t)nchunk;
+            b.chunk_bytes = (int32_t)cb;
+            b.last_bytes = (int32_t)(col.row_bytes - cb * (nchunk - 1));
+            b.first_item = gp.items_per_sample;
+            gp.items_per_sample += (int)nchunk;
+        } else {
+            SmallColumn& s = gp.small[gp.n_small++];
+            s.src = static_cast<const uint8_t*>(col.src);
+            s.dst = static_cast<uint8_t*>(col.dst);
+            s.row_bytes = col.row_bytes;
+        }
+    }
+    gp.total_items = (int64_t)gp.items_per_sample * n;
+    return 0;
+}
+
+static size_t gather_smem_bytes(const GatherParams& gp, bool fused) {
+    return 128 + (fused ? kMaxCtaSamples * sizeof(int64_t) : 0) + (size_t)gp.stages * kStageBytes;
+}
+
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_per_init(double* sum_tree, double* min_tree, double* max_tree, int32_t* winner, int64_t size, void* stream) {
+    CB200_CHECK_ARG(sum_tree && min_tree && max_tree && winner, "null pointer");
+    CB200_CHECK_ARG(ilog2_exact(size) >= 0, "size must be a positive power of 2");
+    const int64_t n = 2 * size - 1;
+    CB200_LAUNCH(per_init_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), sum_tree, min_tree, max_tree,
+                 winner, size);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+static int run_update(UpdateParams& up, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    if (up.n <= 0) return CB200_OK;
+    if (up.n <= 1024) {
+        int threads = (int)((up.n + 31) / 32 * 32);
+        CB200_LAUNCH(per_update_cta_kernel, 1, threads, 0, st, up);
+    } else {
+        CB200_CHECK_ARG(up.n < ((int64_t)1 << 31), "n too large");
+        const unsigned grid = (unsigned)((up.n + 255) / 256);
+        CB200_LAUNCH(per_update_claim_kernel, grid, 256, 0, st, up);
+        CB200_LAUNCH(per_update_leaf_kernel, grid, 256, 0, st, up);
+        CB200_LAUNCH(per_update_reset_kernel, grid, 256, 0, st, up);
+        for (int s = 1; s <= up.levels; ++s) CB200_LAUNCH(per_update_level_kernel, grid, 256, 0, st, up, s);
+        if (up.max_priority_out) CB200_LAUNCH(per_write_max_kernel, 1, 1, 0, st, up.max_tree, up.max_priority_out);
+    }
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_per_update(double* sum_tree, double* min_tree, double* max_tree, int32_t* winner, int64_t size,
+                     const int64_t* idx, const double* p_alpha, const double* p_raw, int64_t n,
+                     double* max_priority_out, void* stream) {
+    CB200_CHECK_ARG(sum_tree && min_tree && max_tree && winner, "null tree pointer");
+    CB200_CHECK_ARG(n >= 0, "negative n");
+    CB200_CHECK_ARG(n == 0 || (idx && p_alpha && p_raw), "null batch pointer");
+    const int levels = ilog2_exact(size);
+    CB200_CHECK_ARG(levels >= 0, "size must be a positive power of 2");
+    UpdateParams up{sum_tree, min_tree, max_tree, winner, size, levels, idx, p_alpha, p_raw, 0, 0.0, 0.0, n,
+                    max_priority_out};
+    return run_update(up, stream);
+}
+
+int cb200_per_store(double* sum_tree, double* min_tree, double* max_tree, int32_t* winner, int64_t size,
+                    int64_t cursor, int64_t n, double p_alpha, double p_raw, void* stream) {
+    CB200_CHECK_ARG(sum_tree && min_tree && max_tree && winner, "null tree pointer");
+    const int levels = ilog2_exact(size);
+    CB200_CHECK_ARG(levels >= 0, "size must be a positive power of 2");
+    CB200_CHECK_ARG(cursor >= 0 && cursor < size && n >= 0, "bad cursor / n");
+    CB200_CHECK_ARG(n <= size, "storing more than one full ring per call is not supported");
+    UpdateParams up{sum_tree, min_tree, max_tree, winner, size, levels, nullptr, nullptr, nullptr, cursor, p_alpha,
+                    p_raw, n, nullptr};
+    return run_update(up, stream);
+}
+
+int cb200_per_priorities_device(const double* err, int64_t n, double epsilon, double alpha, double* p_alpha,
+                                double* p_raw, int32_t* neg_flag, void* stream) {
+    CB200_CHECK_ARG(n >= 0 && (n == 0 || (err && p_alpha && p_raw)), "bad arguments");
+    if (n == 0) return CB200_OK;
+    CB200_LAUNCH(per_priorities_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), err, n, epsilon, alpha,
+                 p_alpha, p_raw, neg_flag);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_host_priorities(const double* h_err, int64_t n, double epsilon, double alpha, double* h_p_alpha,
+                          double* h_p_raw) {
+    CB200_CHECK_ARG(n >= 0 && (n == 0 || (h_err && h_p_alpha && h_p_raw)), "bad arguments");
+    for (int64_t i = 0; i < n; ++i)
+        if (h_err[i] < 0) {
+            set_error("cb200_host_priorities: The priorities must be non-negative values");
+            return CB200_ERR_INVALID_ARGUMENT;
+        }
+    for (int64_t i = 0; i < n; ++i) {
+        const double p = h_err[i] + epsilon;
+        h_p_raw[i] = p;
+        h_p_alpha[i] = pow(p, alpha);   // host libm == what Python's float ** float calls
+    }
+    return CB200_OK;
+}
+
+static int fill_sample_params(SampleParams& sp, const double* sum_tree, const double* min_tree, int64_t size,
+                              const double* u, int64_t n, int64_t nt, double beta, int64_t* idx_out, double* w_out,
+                              float* w32_out) {
+    const int levels = ilog2_exact(size);
+    if (levels < 0 || !sum_tree || !min_tree || !u || n <= 0) return -1;
+    sp = SampleParams{sum_tree, min_tree, size, levels, u, n, (double)nt, beta, idx_out, w_out, w32_out};
+    return 0;
+}
+
+int cb200_per_sample(const double* sum_tree, const double* min_tree, int64_t size, const double* u, int64_t n,
+                     int64_t nt, double beta, int64_t* idx_out, double* w_out, float* w32_out, void* stream) {
+    SampleParams sp;
+    CB200_CHECK_ARG(fill_sample_params(sp, sum_tree, min_tree, size, u, n, nt, beta, idx_out, w_out, w32_out) == 0,
+                    "bad arguments (size must be a power of 2, n > 0, non-null trees / uniforms)");
+    CB200_CHECK_ARG(idx_out != nullptr, "idx_out is required");
+    CB200_LAUNCH(per_sample_kernel, (unsigned)((n + 3) / 4), 128, 0, as_stream(stream), sp);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+static int launch_small_gather(const GatherParams& gp, cudaStream_t st) {
+    if (gp.n_small == 0) return CB200_OK;
+    const int64_t warps = gp.n * gp.n_small;
+    unsigned grid = (unsigned)((warps + 7) / 8);
+    const unsigned cap = (unsigned)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    CB200_LAUNCH(gather_small_kernel, grid, 256, 0, st, gp);
+    return CB200_OK;
+}
+
+static unsigned bulk_grid(const GatherParams& gp) {
+    int64_t g = (int64_t)sm_count() * g_tune_ctas_per_sm;
+    if (g > gp.total_items) g = gp.total_items;
+    return (unsigned)g;
+}
+
+int cb200_gather(const cb200_column* h_columns, int n_columns, const int64_t* idx, int64_t n, void* stream) {
+    CB200_CHECK_ARG(h_columns && n_columns > 0 && n_columns <= CB200_MAX_COLUMNS, "bad column table");
+    CB200_CHECK_ARG(idx && n > 0, "bad idx / n");
+    GatherParams gp;
+    CB200_CHECK_ARG(build_gather_params(h_columns, n_columns, n, gp) == 0, "bad column entry");
+    gp.idx = idx;
+    cudaStream_t st = as_stream(stream);
+    if (gp.n_big > 0) {
+        const size_t smem = gather_smem_bytes(gp, false);
+        static size_t configured = 0;
+        if (smem > configured) {
+            CB200_CUDA(cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        CB200_LAUNCH(gather_bulk_kernel, bulk_grid(gp), kGatherThreads, smem, st, gp);
+    }
+    launch_small_gather(gp, st);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_per_sample_gather(const double* sum_tree, const double* min_tree, int64_t size, const double* u, int64_t n,
+                            int64_t nt, double beta, int64_t* idx_out, double* w_out, float* w32_out,
+                            const cb200_column* h_columns, int n_columns, void* stream) {
+    SampleParams sp;
+    CB200_CHECK_ARG(fill_sample_params(sp, sum_tree, min_tree, size, u, n, nt, beta, idx_out, w_out, w32_out) == 0,
+                    "bad arguments (size must be a power of 2, n > 0, non-null trees / uniforms)");
+    CB200_CHECK_ARG(idx_out != nullptr, "idx_out is required");
+    CB200_CHECK_ARG(h_columns && n_columns > 0 && n_columns <= CB200_MAX_COLUMNS, "bad column table");
+    GatherParams gp;
+    CB200_CHECK_ARG(build_gather_params(h_columns, n_columns, n, gp) == 0, "bad column entry");
+    cudaStream_t st = as_stream(stream);
+    // a CTA's contiguous item range must not span more than kMaxCtaSamples samples
+    const unsigned grid = gp.n_big > 0 ? bulk_grid(gp) : 0;
+    const bool fusable = gp.n_big > 0 &&
+                         ((gp.total_items + grid - 1) / grid + gp.items_per_sample - 1) / gp.items_per_sample + 1 <=
+                             kMaxCtaSamples;
+    if (!fusable) {
+        CB200_LAUNCH(per_sample_kernel, (unsigned)((n + 3) / 4), 128, 0, st, sp);
+        CB200_CHECK_LAUNCH();
+        return cb200_gather(h_columns, n_columns, idx_out, n, stream);
+    }
+    const size_t smem = gather_smem_bytes(gp, true);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CB200_CUDA(cudaFuncSetAttribute(per_sample_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+        configured = smem;
+    }
+    CB200_LAUNCH(per_sample_gather_kernel, grid, kGatherThreads, smem, st, sp, gp);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_scatter_ring(const cb200_column* h_columns, int n_columns, int64_t cursor, int64_t capacity, int64_t n,
+                       void* stream) {
+    CB200_CHECK_ARG(h_columns && n_columns > 0 && n_columns <= CB200_MAX_COLUMNS, "bad column table");
+    CB200_CHECK_ARG(capacity > 0 && cursor >= 0 && cursor < capacity && n >= 0 && n <= capacity, "bad ring arguments");
+    if (n == 0) return CB200_OK;
+    cudaStream_t st = as_stream(stream);
+    for (int c = 0; c < n_columns; ++c) {
+        const cb200_column& col = h_columns[c];
+        CB200_CHECK_ARG(col.src && col.dst && col.row_bytes > 0, "bad column entry");
+        const int64_t piece = 4096;
+        const int pieces = (int)((col.row_bytes + piece - 1) / piece);
+        const int64_t warps = n * pieces;
+        unsigned grid = (unsigned)((warps + 7) / 8);
+        const unsigned cap = (unsigned)sm_count() * 16;
+        if (grid > cap) grid = cap;
+        CB200_LAUNCH(scatter_ring_kernel, grid, 256, 0, st, static_cast<uint8_t*>(const_cast<void*>(col.src)),
+                     static_cast<const uint8_t*>(col.dst), col.row_bytes, cursor, capacity, n, piece, pieces);
+    }
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+}  // extern "C"

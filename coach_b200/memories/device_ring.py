@@ -1,0 +1,205 @@
+"""HBM-resident struct-of-arrays transition ring.
+
+The reference keeps a Python ``list`` of ``Transition`` objects (memories/non_episodic/experience_replay.py:53,146)
+and converts AoS -> SoA on every sample (core_types.py:488-623).  Here every transition field is one row-major
+``[capacity, row_bytes]`` uint8 matrix in HBM ("column"); a sample is a row gather
+(``cb200_gather`` / ``cb200_per_sample_gather``), an append is a row scatter (``cb200_scatter_ring``).
+
+Layout for the Atari configuration (2^20 slots): state 28,224 B + next_state 28,224 B + action 8 B + reward 8 B +
+game_over 1 B per slot = 59.2 GB, sized for the 180 GB of a B200.
+
+Columns
+  ``state:<key>`` / ``next_state:<key>``  one per entry of the transition's state dict, dtype/shape as stored
+  ``action``     int64 scalar (discrete) or float vector (continuous), as given
+  ``reward``     float64 (the reference's rewards are Python floats, core_types.py:523)
+  ``game_over``  uint8
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from coach_b200 import _lib
+
+
+class ColumnSpec(object):
+    def __init__(self, name, shape, dtype):
+        self.name = name
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.row_bytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize if self.shape else \
+            self.dtype.itemsize
+
+    def torch_dtype(self):
+        return {np.dtype(np.uint8): torch.uint8, np.dtype(np.int8): torch.int8, np.dtype(np.int32): torch.int32,
+                np.dtype(np.int64): torch.int64, np.dtype(np.float32): torch.float32,
+                np.dtype(np.float64): torch.float64, np.dtype(np.bool_): torch.uint8,
+                np.dtype(np.float16): torch.float16, np.dtype(np.int16): torch.int16}[self.dtype]
+
+    def __repr__(self):
+        return "ColumnSpec(%s, %s, %s)" % (self.name, self.shape, self.dtype)
+
+
+def schema_from_transition(t):
+    """Column layout inferred from the first stored transition."""
+    specs = OrderedDict()
+    for prefix, d in (("state:", t.state), ("next_state:", t.next_state)):
+        for key in sorted(d.keys()):
+            a = np.asarray(d[key])
+            specs[prefix + key] = ColumnSpec(prefix + key, a.shape, a.dtype)
+    a = np.asarray(t.action)
+    if a.dtype.kind in "iub":
+        a = a.astype(np.int64)
+    specs["action"] = ColumnSpec("action", a.shape, a.dtype)
+    specs["reward"] = ColumnSpec("reward", (), np.float64)
+    specs["game_over"] = ColumnSpec("game_over", (), np.uint8)
+    return specs
+
+
+class DeviceTransitionRing(object):
+    """Owns the HBM columns plus a pinned host staging area so that single ``store(transition)`` calls are a memcpy
+    into pinned memory and reach the GPU in batches (one H2D copy + one scatter kernel per column per flush)."""
+
+    def __init__(self, capacity, device=None, stage_rows=256):
+        self.capacity = int(capacity)
+        self.device = torch.device(device if device is not None else "cuda")
+        self.lib = _lib.load()
+        self.specs = None
+        self.columns = None          # name -> uint8 [capacity, row_bytes] on device
+        self.stage_rows = int(stage_rows)
+        self._stage_host = None      # name -> pinned uint8 [stage_rows, row_bytes]
+        self._stage_dev = None
+        self._pending = 0
+        self._flush_event = None     # H2D of the pinned stage still in flight?
+        self.cursor = 0              # next slot to write
+        self.count = 0               # valid slots (<= capacity)
+
+    # -- schema ----------------------------------------------------------------------------------------------------
+    def set_schema(self, specs):
+        if self.specs is not None:
+            return
+        self.specs = specs
+        self.columns, self._stage_host, self._stage_dev = OrderedDict(), OrderedDict(), OrderedDict()
+        pin = self.device.type == "cuda"
+        for name, sp in specs.items():
+            self.columns[name] = torch.empty((self.capacity, sp.row_bytes), dtype=torch.uint8, device=self.device)
+            self._stage_host[name] = torch.empty((self.stage_rows, sp.row_bytes), dtype=torch.uint8, pin_memory=pin)
+            self._stage_dev[name] = torch.empty((self.stage_rows, sp.row_bytes), dtype=torch.uint8,
+                                                device=self.device)
+
+    def hbm_bytes(self):
+        return 0 if self.columns is None else sum(c.numel() for c in self.columns.values())
+
+    # -- append ----------------------------------------------------------------------------------------------------
+    def stage_transition(self, t):
+        """Copies one transition into the pinned staging rows; returns True when the stage is full."""
+        if self.specs is None:
+            self.set_schema(schema_from_transition(t))
+        r = self._pending
+        if r == 0 and self._flush_event is not None:
+            self._flush_event.synchronize()      # the previous flush's H2D must have drained the pinned rows
+            self._flush_event = None
+        for name, sp in self.specs.items():
+            if name.startswith("state:"):
+                v = t.state[name[6:]]
+            elif name.startswith("next_state:"):
+                v = t.next_state[name[11:]]
+            elif name == "action":
+                v = t.action
+            elif name == "reward":
+                v = t.reward
+            else:
+                v = t.game_over
+            a = np.ascontiguousarray(np.asarray(v), dtype=sp.dtype)
+            if a.shape != sp.shape:
+                raise ValueError("transition field %s has shape %s, the replay was created with %s"
+                                 % (name, a.shape, sp.shape))
+            self._stage_host[name][r].numpy()[:] = a.reshape(-1).view(np.uint8)
+        self._pending += 1
+        return self._pending >= min(self.stage_rows, self.capacity)
+
+    def flush(self):
+        """Moves the staged rows into the ring.  Returns (first_slot, n)."""
+        n = self._pending
+        if n == 0:
+            return self.cursor, 0
+        first = self.cursor
+        pairs = []
+        for name in self.specs:
+            self._stage_dev[name][:n].copy_(self._stage_host[name][:n], non_blocking=True)
+            pairs.append((self.columns[name].data_ptr(), self._stage_dev[name].data_ptr(),
+                          self.specs[name].row_bytes))
+        self._scatter(pairs, n)
+        self._pending = 0
+        if self.device.type == "cuda":
+            self._flush_event = torch.cuda.Event()
+            self._flush_event.record()
+        return first, n
+
+    def append_columns(self, cols):
+        """Bulk append of n transitions given as {column name: tensor/ndarray [n, ...]} (device tensors are used in
+        place, host arrays go through one H2D copy).  Returns (first_slot, n)."""
+        self.flush()
+        n = None
+        staged = {}
+        for name, v in cols.items():
+            tt = torch.as_tensor(v)
+            n = tt.shape[0] if n is None else n
+            if tt.shape[0] != n:
+                raise ValueError("all columns must have the same number of rows")
+            staged[name] = tt
+        if self.specs is None:
+            specs = OrderedDict()
+            for name, tt in staged.items():
+                dt = np.dtype(str(tt.dtype).replace("torch.", "")) if tt.dtype != torch.bool else np.dtype(np.uint8)
+                specs[name] = ColumnSpec(name, tuple(tt.shape[1:]), dt)
+            self.set_schema(specs)
+        if set(staged) != set(self.specs):
+            raise ValueError("append_columns needs exactly the columns %s" % list(self.specs))
+        if n > self.capacity:
+            raise ValueError("cannot append more rows than the ring holds in one call")
+        first = self.cursor
+        pairs, keep = [], []
+        for name, sp in self.specs.items():
+            tt = staged[name].to(self.device, non_blocking=True).contiguous()
+            tt = tt.view(torch.uint8).reshape(n, -1) if tt.dtype != torch.bool else tt.to(torch.uint8).reshape(n, -1)
+            if tt.shape[1] != sp.row_bytes:
+                raise ValueError("column %s: %d bytes per row, expected %d" % (name, tt.shape[1], sp.row_bytes))
+            keep.append(tt)
+            pairs.append((self.columns[name].data_ptr(), tt.data_ptr(), sp.row_bytes))
+        self._scatter(pairs, n)
+        return first, n
+
+    def _scatter(self, pairs, n):
+        for k in range(0, len(pairs), _lib.CB200_MAX_COLUMNS):
+            arr, cnt = _lib.make_columns(pairs[k:k + _lib.CB200_MAX_COLUMNS])
+            _lib.check(self.lib.cb200_scatter_ring(arr, cnt, self.cursor, self.capacity, n, _lib.current_stream()))
+        self.cursor = (self.cursor + n) % self.capacity
+        self.count = min(self.count + n, self.capacity)
+
+    def clear(self):
+        self.cursor = 0
+        self.count = 0
+        self._pending = 0
+
+    # -- gather ----------------------------------------------------------------------------------------------------
+    def alloc_batch(self, n):
+        """Output tensors for one minibatch: {column: typed tensor [n, *shape]}."""
+        out = OrderedDict()
+        for name, sp in self.specs.items():
+            out[name] = torch.empty((n,) + sp.shape, dtype=sp.torch_dtype(), device=self.device)
+        return out
+
+    def column_table(self, out):
+        pairs = [(self.columns[name].data_ptr(), out[name].data_ptr(), sp.row_bytes)
+                 for name, sp in self.specs.items()]
+        return _lib.make_columns(pairs)
+
+    def gather(self, idx, out=None):
+        """out[c][i] = column c of slot idx[i]; idx int64 CUDA tensor."""
+        n = idx.shape[0]
+        if out is None:
+            out = self.alloc_batch(n)
+        arr, cnt = self.column_table(out)
+        _lib.check(self.lib.cb200_gather(arr, cnt, idx.data_ptr(), n, _lib.current_stream()))
+        return out
