@@ -18,6 +18,17 @@ c_float = ctypes.c_float
 CB200_MAX_COLUMNS = 8
 
 
+class GemmDesc(ctypes.Structure):
+    """struct cb200_gemm_desc"""
+    _fields_ = [("a_src", c_void_p), ("a_lut", c_void_p), ("a_rowoff", c_void_p), ("a_coloff", c_void_p),
+                ("a_rowinfo", c_void_p), ("a_colinfo", c_void_p), ("a_oh", ctypes.c_int32), ("a_ow", ctypes.c_int32),
+                ("a_rows", ctypes.c_int32), ("a_cols", ctypes.c_int32), ("a_transposed", ctypes.c_int32),
+                ("b", c_void_p), ("ldb", ctypes.c_int32), ("n", ctypes.c_int32),
+                ("c", c_void_p), ("ldc", ctypes.c_int32), ("bias", c_void_p), ("act", ctypes.c_int32),
+                ("mask_y", c_void_p), ("mask_act", ctypes.c_int32), ("c_rowmap", c_void_p),
+                ("accumulate", ctypes.c_int32), ("workspace", c_void_p), ("splits", ctypes.c_int32)]
+
+
 class Column(ctypes.Structure):
     """struct cb200_column"""
     _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_bytes", c_i64)]
@@ -30,6 +41,7 @@ PROTOTYPES = {
     "cb200_launch_count": (c_i64, []),
     "cb200_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "cb200_tune": (c_int, [ctypes.c_char_p, c_int]),
+    "cb200_l2_persist": (c_int, [c_void_p, c_i64, c_void_p]),
     "cb200_per_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "cb200_per_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64,
                                  c_void_p, c_void_p]),
@@ -44,6 +56,22 @@ PROTOTYPES = {
     "cb200_per_sample_gather": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_double, c_void_p,
                                         c_void_p, c_void_p, ctypes.POINTER(Column), c_int, c_void_p]),
     "cb200_scatter_ring": (c_int, [ctypes.POINTER(Column), c_int, c_i64, c_i64, c_i64, c_void_p]),
+    "cb200_gemm": (c_int, [ctypes.POINTER(GemmDesc), c_void_p]),
+    "cb200_colsum": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p]),
+    "cb200_permute_f32": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "cb200_transpose": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p]),
+    "cb200_dqn_td_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_i64,
+                                     c_i64, c_void_p, c_void_p, c_void_p]),
+    "cb200_regression_head_loss_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int, c_float, c_void_p,
+                                                c_void_p, c_void_p]),
+    "cb200_dueling_combine_fwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p]),
+    "cb200_dueling_combine_bwd": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p]),
+    "cb200_sumsq": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
+    "cb200_clip_by_global_norm": (c_int, [c_void_p, c_i64, c_void_p, c_float, c_void_p]),
+    "cb200_scale": (c_int, [c_void_p, c_i64, c_float, c_void_p]),
+    "cb200_adam_tf": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float,
+                              c_float, c_float, c_void_p]),
+    "cb200_polyak": (c_int, [c_void_p, c_void_p, c_i64, c_double, c_void_p]),
 }
 
 _lib = None

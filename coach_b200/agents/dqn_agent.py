@@ -1,0 +1,285 @@
+"""DQN / DDQN / dueling-DDQN learn step on the GPU.  Drop-in for the replay -> learn_from_batch part of
+
+  rl_coach/agents/agent.py:701-784                 Agent.train            (driver, target-network cadence)
+  rl_coach/agents/dqn_agent.py:69-113              DQNAgent               (TD targets, PER update, train step)
+  rl_coach/agents/ddqn_agent.py:38-43              DDQNAgent.select_actions
+  rl_coach/agents/value_optimization_agent.py:74-80  priorities are updated with the PRE-update TD errors
+  rl_coach/architectures/network_wrapper.py:109-203 + tensorflow_components/architecture.py:312-521,598-607
+                                                   (accumulate_gradients / apply_gradients / set_weights)
+
+One learn step = fused PER sample+gather (memory) -> target & online forward -> TD-target kernel -> Huber/MSE head
+loss + its gradient -> backward -> global norm (+ clip) -> [NCCL all-reduce] -> TF-semantics Adam -> tree update.
+The online forward on ``s`` is computed once: the reference runs it twice (once for the TD targets, once inside the
+train op) with identical weights, hence identical values.
+
+``learn_from_batch`` keeps the reference contract ``-> (total_loss, losses, unclipped_grads)``; pass ``fetch=False`` to
+get device scalars instead of floats and avoid the host synchronisation.
+"""
+import numpy as np
+import torch
+
+from coach_b200 import _lib
+from coach_b200.architectures.layers import Workspace
+from coach_b200.architectures.q_network import QNetworkDef
+from coach_b200.base_parameters import (AgentParameters, AlgorithmParameters, EnvironmentSteps, NetworkParameters,
+                                        TrainingSteps)
+from coach_b200.memories.experience_replay import ExperienceReplayParameters
+from coach_b200.memories.prioritized_experience_replay import PrioritizedExperienceReplay
+from coach_b200.utils import dynamic_import_and_instantiate_module_from_params
+from coach_b200 import parallel
+
+
+class DQNAlgorithmParameters(AlgorithmParameters):
+    def __init__(self):
+        super().__init__()
+        self.num_steps_between_copying_online_weights_to_target = EnvironmentSteps(10000)
+        self.num_consecutive_playing_steps = EnvironmentSteps(4)
+        self.discount = 0.99
+
+
+class DQNNetworkParameters(NetworkParameters):
+    def __init__(self):
+        super().__init__()
+        self.heads_parameters = ["QHead"]              # or ["DuelingQHead"]
+        self.optimizer_type = 'Adam'
+        self.batch_size = 32
+        self.replace_mse_with_huber_loss = True
+        self.create_target_network = True
+
+
+class DQNAgentParameters(AgentParameters):
+    def __init__(self):
+        super().__init__(algorithm=DQNAlgorithmParameters(), memory=ExperienceReplayParameters(),
+                         networks={"main": DQNNetworkParameters()})
+
+    @property
+    def path(self):
+        return 'coach_b200.agents.dqn_agent:DQNAgent'
+
+
+class DDQNAgentParameters(DQNAgentParameters):
+    def __init__(self):
+        super().__init__()
+        self.algorithm.num_steps_between_copying_online_weights_to_target = EnvironmentSteps(30000)
+
+    @property
+    def path(self):
+        return 'coach_b200.agents.dqn_agent:DDQNAgent'
+
+
+class QNetworkWrapper(object):
+    """online + target parameter buffers over one QNetworkDef (network_wrapper.py:31-116), with the three forward
+    bindings a DQN step needs: online(s) [training], target(s'), online(s') [DDQN]."""
+
+    def __init__(self, lib, net_def, params: NetworkParameters, batch_size, batch_buffers, double_dqn, device):
+        self.lib, self.net, self.params, self.B = lib, net_def, params, batch_size
+        self.store = net_def.store
+        self.ws = Workspace(device)
+        self.theta = self.store.theta
+        self.theta_target = self.store.new_buffer() if params.create_target_network else None
+        s, s2 = batch_buffers["state:observation"], batch_buffers["next_state:observation"]
+        self.online_s = net_def.instantiate(lib, self.ws, batch_size, s, self.theta, self.store.grad, train=True)
+        self.target_s2 = net_def.instantiate(lib, self.ws, batch_size, s2, self.theta_target) \
+            if self.theta_target is not None else None
+        self.online_s2 = net_def.instantiate(lib, self.ws, batch_size, s2, self.theta) if double_dqn else None
+        # Adam state: fp32 running powers exactly like TF's non-slot beta1_power / beta2_power variables
+        self.beta1_power = np.float32(params.adam_optimizer_beta1)
+        self.beta2_power = np.float32(params.adam_optimizer_beta2)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=device)
+        self.has_target = self.theta_target is not None
+
+    def sync(self):
+        """online -> target hard copy (network_wrapper.py:94-107)."""
+        self.update_target_network(1.0)
+
+    def update_target_network(self, rate=1.0):
+        _lib.check(self.lib.cb200_polyak(self.theta_target.data_ptr(), self.theta.data_ptr(), self.store.size,
+                                         float(rate), _lib.current_stream()))
+
+    def apply_gradients(self, scaler=1.0):
+        """clip is applied by the caller (accumulate_gradients side in the reference); here: optional rescale,
+        then the optimizer (architecture.py:469-521)."""
+        st = _lib.current_stream()
+        n = self.store.size
+        if scaler != 1.0:
+            _lib.check(self.lib.cb200_scale(self.store.grad.data_ptr(), n, float(scaler), st))
+        p = self.params
+        if p.optimizer_type != 'Adam':
+            raise NotImplementedError("only the Adam optimizer of the DQN presets is implemented on device")
+        _lib.check(self.lib.cb200_adam_tf(self.theta.data_ptr(), self.store.m.data_ptr(), self.store.v.data_ptr(),
+                                          self.store.grad.data_ptr(), n, float(p.learning_rate),
+                                          float(p.adam_optimizer_beta1), float(p.adam_optimizer_beta2),
+                                          float(p.optimizer_epsilon), float(self.beta1_power),
+                                          float(self.beta2_power), st))
+        self.beta1_power = np.float32(self.beta1_power * np.float32(p.adam_optimizer_beta1))
+        self.beta2_power = np.float32(self.beta2_power * np.float32(p.adam_optimizer_beta2))
+
+
+class DQNAgent(object):
+    double_dqn = False
+
+    def __init__(self, agent_parameters, parent=None, observation_shape=None, num_actions=None, device=None,
+                 seed=None):
+        self.ap = agent_parameters
+        self.parent = parent
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        self.observation_shape = tuple(observation_shape if observation_shape is not None
+                                       else agent_parameters.observation_shape)
+        self.num_actions = int(num_actions if num_actions is not None else agent_parameters.num_actions)
+        net_params = self.ap.network_wrappers["main"]
+        self.batch_size = int(net_params.batch_size)
+        self.memory = dynamic_import_and_instantiate_module_from_params(self.ap.memory,
+                                                                        extra_kwargs={"device": self.device})
+        self.pre_network_filter = self.ap.pre_network_filter
+        B, A, dev = self.batch_size, self.num_actions, self.device
+        obs_dtype = torch.uint8 if len(self.observation_shape) == 3 else torch.float32
+        # persistent minibatch buffers: the replay's gather writes straight into the first conv's input
+        self.batch_buffers = {
+            "state:observation": torch.zeros((B,) + self.observation_shape, dtype=obs_dtype, device=dev),
+            "next_state:observation": torch.zeros((B,) + self.observation_shape, dtype=obs_dtype, device=dev),
+            "action": torch.zeros(B, dtype=torch.int64, device=dev),
+            "reward": torch.zeros(B, dtype=torch.float64, device=dev),
+            "game_over": torch.zeros(B, dtype=torch.uint8, device=dev),
+            "idx": torch.zeros(B, dtype=torch.int64, device=dev),
+            "weight": torch.ones(B, dtype=torch.float64, device=dev),
+            "weight32": torch.ones(B, dtype=torch.float32, device=dev),
+        }
+        dueling = "DuelingQHead" in getattr(net_params, "heads_parameters", ["QHead"])
+        gen = torch.Generator().manual_seed(int(seed)) if seed is not None else None
+        self.net_def = QNetworkDef(dev, self.observation_shape, A, dueling=dueling)
+        self.net_def.store.init_glorot(gen)
+        self.networks = {"main": QNetworkWrapper(self.lib, self.net_def, net_params, B, self.batch_buffers,
+                                                 self.double_dqn, dev)}
+        if self.networks["main"].has_target:
+            self.networks["main"].sync()
+        self.targets = torch.zeros((B, A), dtype=torch.float32, device=dev)
+        self.td_err = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        pin = dev.type == "cuda"
+        self._td_host = torch.zeros(B, dtype=torch.float64, pin_memory=pin)
+        self._pa_host = torch.zeros(B, dtype=torch.float64, pin_memory=pin)
+        self._pr_host = torch.zeros(B, dtype=torch.float64, pin_memory=pin)
+        self._pa_dev = torch.zeros(B, dtype=torch.float64, device=dev)
+        self._pr_dev = torch.zeros(B, dtype=torch.float64, device=dev)
+        # counters of agents/agent.py:112-135
+        self.training_iteration = 0
+        self.total_steps_counter = 0
+        self.last_target_network_update_step = 0
+        self.last_training_phase_step = 0
+
+    # ---- reference plumbing ------------------------------------------------------------------------------------------
+    @property
+    def is_on_policy(self) -> bool:
+        return False
+
+    def call_memory(self, func, args=()):
+        if not isinstance(args, tuple):
+            args = (args,)
+        return getattr(self.memory, func)(*args)
+
+    def _should_update_online_weights_to_target(self):
+        """agents/agent.py:640-660"""
+        step_method = self.ap.algorithm.num_steps_between_copying_online_weights_to_target
+        if step_method.__class__ == TrainingSteps:
+            should = (self.training_iteration - self.last_target_network_update_step) >= step_method.num_steps
+            if should:
+                self.last_target_network_update_step = self.training_iteration
+        elif step_method.__class__ == EnvironmentSteps:
+            should = (self.total_steps_counter - self.last_target_network_update_step) >= step_method.num_steps
+            if should:
+                self.last_target_network_update_step = self.total_steps_counter
+        else:
+            raise ValueError("The num_steps_between_copying_online_weights_to_target parameter should be either "
+                             "EnvironmentSteps or TrainingSteps. Instead it is {}".format(step_method.__class__))
+        return should
+
+    def _should_train(self):
+        """agents/agent.py:662-699 for EnvironmentSteps-paced agents"""
+        steps = self.ap.algorithm.num_consecutive_playing_steps
+        should = (self.total_steps_counter - self.last_training_phase_step) >= steps.num_steps
+        should = should and self.call_memory('num_transitions') > 0
+        if should:
+            self.last_training_phase_step = self.total_steps_counter
+        return should
+
+    # ---- the hot path ------------------------------------------------------------------------------------------------
+    def sample_batch(self):
+        """memory sample straight into the persistent minibatch buffers"""
+        return self.memory.sample_batch(self.batch_size, out=self.batch_buffers)
+
+    def learn_from_batch(self, batch, fetch=True):
+        lib, st = self.lib, _lib.current_stream()
+        net = self.networks["main"]
+        B, A = self.batch_size, self.num_actions
+        cols = batch.columns
+        for k in ("state:observation", "next_state:observation"):
+            if cols[k].data_ptr() != self.batch_buffers[k].data_ptr():
+                self.batch_buffers[k].copy_(cols[k])             # foreign batch: stage it (device -> device)
+        q_next = net.target_s2.forward()                          # dqn_agent.py:87-90
+        q_online = net.online_s.forward()
+        q_select = net.online_s2.forward() if self.double_dqn else q_next      # ddqn_agent.py:42-43
+        _lib.check(lib.cb200_dqn_td_targets(q_next.data_ptr(), q_select.data_ptr(), q_online.data_ptr(),
+                                            cols["action"].data_ptr(), cols["reward"].data_ptr(),
+                                            cols["game_over"].data_ptr(), float(self.ap.algorithm.discount), B, A,
+                                            self.targets.data_ptr(), self.td_err.data_ptr(), st))
+        # value_optimization_agent.py:74-80: priorities from the pre-update errors, weights from the batch
+        per = isinstance(self.memory, PrioritizedExperienceReplay)
+        weights, ev = None, None
+        if per:
+            weights = cols["weight32"] if "weight32" in cols else cols["weight"].to(torch.float32)
+            if self.memory.priority_mode == "libm":
+                self._td_host.copy_(self.td_err, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+        huber = 1 if net.params.replace_mse_with_huber_loss else 0
+        _lib.check(lib.cb200_regression_head_loss_grad(q_online.data_ptr(), self.targets.data_ptr(),
+                                                       weights.data_ptr() if weights is not None else None, B, A,
+                                                       huber, 1.0, net.online_s.dq.data_ptr(),
+                                                       self.loss_dev.data_ptr(), st))
+        net.online_s.backward()
+        n = net.store.size
+        _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(), st))
+        clip = net.params.clip_gradients
+        if clip is not None and clip != 0:
+            if net.params.gradients_clipping_method != "ClipByGlobalNorm":
+                raise NotImplementedError("only ClipByGlobalNorm is implemented on device")
+            _lib.check(lib.cb200_clip_by_global_norm(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), float(clip),
+                                                     st))
+        scaler = parallel.allreduce_gradients(
+            net.store.grad, net.params.scale_down_gradients_by_number_of_workers_for_sync_training)
+        net.apply_gradients(scaler)
+        if per:
+            if ev is not None:
+                ev.synchronize()                                  # GPU is busy with the backward pass meanwhile
+                pa, pr = self.memory.host_priorities(self._td_host.numpy())
+                self._pa_host.numpy()[:] = pa
+                self._pr_host.numpy()[:] = pr
+                self._pa_dev.copy_(self._pa_host, non_blocking=True)
+                self._pr_dev.copy_(self._pr_host, non_blocking=True)
+                self.memory.update_priorities_device(cols["idx"], self._pa_dev, self._pr_dev)
+            else:
+                self.memory.update_priorities(cols["idx"], self.td_err)
+        if fetch:
+            loss = float(self.loss_dev.item())
+            return loss, [loss], float(torch.sqrt(net.sumsq).item())
+        return self.loss_dev, [self.loss_dev], net.sumsq
+
+    def train(self, fetch=True):
+        """agents/agent.py:701-784 (single-agent, non batch-RL branch)."""
+        loss = 0
+        if not self._should_train():
+            return loss
+        for _ in range(self.ap.algorithm.num_consecutive_training_steps):
+            self.training_iteration += 1
+            batch = self.sample_batch()
+            total_loss, losses, unclipped_grads = self.learn_from_batch(batch, fetch=fetch)
+            loss = loss + total_loss if fetch else total_loss
+            net = self.networks["main"]
+            if net.has_target and self._should_update_online_weights_to_target():
+                net.update_target_network(self.ap.algorithm.rate_for_copying_weights_to_target)
+        return loss
+
+
+class DDQNAgent(DQNAgent):
+    double_dqn = True

@@ -1,0 +1,164 @@
+"""Flat-buffer networks for the learn step.
+
+``ParamStore`` keeps ALL trainable tensors of one network in a single fp32 buffer (plus same-shaped gradient and Adam
+slot buffers), in TensorFlow variable-creation order -- embedders (sorted by input name) -> middleware -> head ->
+``gradients_from_head_*_rescalers`` scalar (general_network.py:244-349) -- so that per-tensor
+comparisons with the reference line up, the optimizer / clipping / polyak / NCCL all-reduce are ONE launch each over
+the flat buffer, and a target network is just a second ``theta``.
+
+``Sequential`` wires a chain of layers (coach_b200/architectures/layers.py) to persistent activation / gradient
+buffers for one batch size; an "instance" binds the chain to one parameter buffer and one input tensor.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from coach_b200 import _lib
+from coach_b200.architectures.layers import ACT, Workspace
+
+
+class ParamStore(object):
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.entries = OrderedDict()      # name -> (offset, shape)
+        self.size = 0
+        self.theta = None
+
+    def add(self, name, shape):
+        if self.theta is not None:
+            raise RuntimeError("ParamStore is finalised")
+        n = int(np.prod(shape)) if len(shape) else 1
+        # keep every tensor 16-byte aligned inside the flat buffer (vector loads in the kernels)
+        self.size = (self.size + 3) // 4 * 4
+        self.entries[name] = (self.size, tuple(shape))
+        self.size += n
+        return name
+
+    def finalize(self):
+        self.size = (self.size + 3) // 4 * 4
+        z = lambda: torch.zeros(self.size, dtype=torch.float32, device=self.device)   # noqa: E731
+        self.theta, self.grad, self.m, self.v = z(), z(), z(), z()
+        return self
+
+    def view(self, buf, name):
+        off, shape = self.entries[name]
+        n = int(np.prod(shape)) if len(shape) else 1
+        return buf[off:off + n].view(shape if len(shape) else (1,))
+
+    def new_buffer(self):
+        return torch.zeros(self.size, dtype=torch.float32, device=self.device)
+
+    def num_params(self):
+        return sum(int(np.prod(s)) if len(s) else 1 for _, s in self.entries.values())
+
+    # -- initialisation (TF defaults: glorot-uniform kernels, zero biases; head.py:93 xavier) ------------------------
+    def init_glorot(self, generator=None):
+        for name, (off, shape) in self.entries.items():
+            v = self.view(self.theta, name)
+            if name.endswith("kernel"):
+                if len(shape) == 4:
+                    rf = shape[0] * shape[1]
+                    fan_in, fan_out = rf * shape[2], rf * shape[3]
+                else:
+                    fan_in, fan_out = shape[0], shape[1]
+                limit = float(np.sqrt(6.0 / (fan_in + fan_out)))
+                cpu = (torch.rand(shape, generator=generator, dtype=torch.float32) * 2 - 1) * limit
+                v.copy_(cpu)
+            elif name.endswith("rescalers"):
+                v.fill_(1.0)
+            else:
+                v.zero_()
+
+    def load_named(self, tensors: dict, buf=None):
+        buf = self.theta if buf is None else buf
+        for name, t in tensors.items():
+            self.view(buf, name).copy_(torch.as_tensor(t, dtype=torch.float32).reshape(self.entries[name][1] or (1,)))
+
+    def export_named(self, buf=None):
+        buf = self.theta if buf is None else buf
+        return OrderedDict((name, self.view(buf, name).detach().cpu().numpy().copy()) for name in self.entries)
+
+
+class Sequential(object):
+    """layers: list of layer objects; params registered as '<prefix>/<i>_<LayerType>/<kernel|bias>'."""
+
+    def __init__(self, layers, store, prefix):
+        self.layers = layers
+        self.store = store
+        self.names = []
+        for i, layer in enumerate(layers):
+            base = "%s/%s_%d" % (prefix, type(layer).__name__, i)
+            self.names.append([store.add(base + "/" + pname, shape) for pname, shape in layer.param_shapes])
+
+    def instantiate(self, lib, ws, B, x, theta, grad=None, x_is_u8=False, lut=None, need_input_grad=False,
+                    input_act=0, train=False, dx_in=None, dx_accumulate=False):
+        """need_input_grad: also produce the gradient wrt the (pre-activation of the) input, masked by
+        ``input_act``' evaluated on x; it is written (or, with dx_accumulate, added) to ``dx_in``."""
+        return SequentialInstance(self, lib, ws, B, x, theta, grad, x_is_u8, lut, need_input_grad, input_act, train,
+                                  dx_in, dx_accumulate)
+
+
+class SequentialInstance(object):
+    """Binds a Sequential to (batch size, input tensor, parameter buffer).  ``train=True`` also allocates the
+    pre-activation gradient buffers and prepares the backward ops (gradients land in ``grad``)."""
+
+    def __init__(self, seq, lib, ws, B, x, theta, grad, x_is_u8, lut, need_input_grad, input_act, train,
+                 dx_in=None, dx_accumulate=False):
+        import copy
+        self.seq, self.B = seq, B
+        dev = theta.device
+        store = seq.store
+        self.layers = [copy.copy(l) for l in seq.layers]
+        self.acts, self.dzs = [], []
+        self.x = x
+        self.dx_in = dx_in
+        prev, prev_act = x, input_act
+        if need_input_grad and dx_in is None:
+            self.dx_in = torch.empty((B, int(np.prod(self.layers[0].in_shape))), dtype=torch.float32, device=dev)
+        for i, layer in enumerate(self.layers):
+            y = torch.empty((B, layer.out_elems()), dtype=torch.float32, device=dev)
+            dz = torch.empty_like(y) if train else None
+            self.acts.append(y)
+            self.dzs.append(dz)
+        for i, layer in enumerate(self.layers):
+            wname, bname = seq.names[i]
+            w, b = store.view(theta, wname), store.view(theta, bname)
+            dw = store.view(grad, wname) if train else None
+            db = store.view(grad, bname) if train else None
+            first = i == 0
+            dx = (self.dx_in if first else self.dzs[i - 1]) if train else None
+            need_dx = train and (not first or need_input_grad)
+            if train:
+                layer.prepare(lib, ws, B, dev, prev, self.acts[i], w, b, dw, db, self.dzs[i], dx,
+                              x_is_u8=(x_is_u8 and first), lut=lut, need_dx=need_dx, prev_act=prev_act,
+                              dx_accumulate=(dx_accumulate and first))
+            else:
+                self._prepare_fwd_only(layer, lib, ws, B, dev, prev, self.acts[i], w, b, x_is_u8 and first, lut)
+            prev, prev_act = self.acts[i], layer.act
+        self.out = self.acts[-1]
+        self.d_out = self.dzs[-1]
+        self.train = train
+
+    @staticmethod
+    def _prepare_fwd_only(layer, lib, ws, B, dev, x, y, w, b, x_is_u8, lut):
+        # reuse prepare() with dummy gradient tensors but drop the backward ops: forward descriptors are identical
+        dummy = y
+        layer.prepare(lib, ws, B, dev, x, y, w, b, w, b, dummy, None, x_is_u8=x_is_u8, lut=lut, need_dx=False)
+        layer.bwd_w = None
+
+    def forward(self):
+        for layer in self.layers:
+            layer.forward()
+        return self.out
+
+    def backward(self):
+        for layer in reversed(self.layers):
+            layer.backward()
+
+
+def make_u8_lut(device, rescale=255.0, offset=0.0):
+    """lut[v] = float32(v) / rescale - offset, the embedder's input normalisation (embedder.py:103-104) evaluated in
+    fp32 exactly like TensorFlow would (true division, not a reciprocal multiply)."""
+    v = torch.arange(256, dtype=torch.float32)
+    return ((v / np.float32(rescale)) - np.float32(offset)).to(device)

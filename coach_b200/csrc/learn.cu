@@ -1,0 +1,262 @@
+// coach_b200/csrc/learn.cu -- element-wise and reduction kernels of learn_from_batch (TD targets, head losses,
+// global-norm clipping, TF-semantics Adam, polyak target update).  Reference lines are cited in include/coach_b200.h.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cb200 {
+
+// ---- DQN / DDQN TD targets ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dqn_td_targets_kernel(const float* __restrict__ q_next,
+                                                             const float* __restrict__ q_select,
+                                                             const float* __restrict__ q_online,
+                                                             const int64_t* __restrict__ actions,
+                                                             const double* __restrict__ rewards,
+                                                             const uint8_t* __restrict__ game_overs, double discount,
+                                                             int64_t B, int64_t A, float* __restrict__ targets,
+                                                             double* __restrict__ td_err) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    // np.argmax: first maximum
+    int64_t best = 0;
+    float bv = q_select[i * A];
+    for (int64_t a = 1; a < A; ++a) {
+        const float v = q_select[i * A + a];
+        if (v > bv) {
+            bv = v;
+            best = a;
+        }
+    }
+    const int64_t act = actions[i];
+    for (int64_t a = 0; a < A; ++a) targets[i * A + a] = q_online[i * A + a];
+    // new_target = r + (1.0 - done) * discount * q'[a*]     (dqn_agent.py:100-101; left-to-right, fp64)
+    const double not_done = __dsub_rn(1.0, game_overs[i] ? 1.0 : 0.0);
+    const double t1 = __dmul_rn(__dmul_rn(not_done, discount), (double)q_next[i * A + best]);
+    const double y = __dadd_rn(rewards[i], t1);
+    if (act >= 0 && act < A) {
+        td_err[i] = fabs(__dsub_rn(y, (double)q_online[i * A + act]));   // :102
+        targets[i * A + act] = (float)y;                                 // :103 (fp32 array element assignment)
+    } else {
+        td_err[i] = 0.0;
+    }
+}
+
+// ---- regression head loss (Huber / MSE) -----------------------------------------------------------------------------
+// one CTA; fixed-order reduction => run-to-run bit-stable loss
+__global__ void __launch_bounds__(1024) regression_head_kernel(const float* __restrict__ out,
+                                                               const float* __restrict__ target,
+                                                               const float* __restrict__ weights, int64_t B, int64_t W,
+                                                               int huber, float loss_weight, float* __restrict__ d_out,
+                                                               float* __restrict__ loss_out) {
+    __shared__ float red[1024];
+    float local = 0.f;
+    const float inv_b = 1.0f / (float)B;
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+        const float w = loss_weight * (weights ? weights[b] : 1.0f);
+        float row = 0.f;
+        for (int64_t a = 0; a < W; ++a) {
+            const float e = out[b * W + a] - target[b * W + a];     // predictions - labels
+            float l, g;
+            if (huber) {
+                const float ae = fabsf(e);
+                const float q = fminf(ae, 1.0f);                    // delta = 1
+                const float lin = ae - q;
+                l = 0.5f * q * q + lin;
+                g = (ae <= 1.0f) ? e : (e > 0.f ? 1.0f : -1.0f);
+            } else {
+                l = e * e;
+                g = 2.0f * e;
+            }
+            row += l;
+            d_out[b * W + a] = w * inv_b * g;
+        }
+        local += w * row;
+    }
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && loss_out) *loss_out = red[0] * inv_b;
+}
+
+__global__ void dueling_fwd_kernel(const float* __restrict__ v, const float* __restrict__ adv, int64_t B, int64_t A,
+                                   float* __restrict__ q) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    float s = 0.f;
+    for (int64_t a = 0; a < A; ++a) s += adv[i * A + a];
+    const float mean = s / (float)A;
+    for (int64_t a = 0; a < A; ++a) q[i * A + a] = v[i] + (adv[i * A + a] - mean);
+}
+__global__ void dueling_bwd_kernel(const float* __restrict__ dq, int64_t B, int64_t A, float* __restrict__ d_v,
+                                   float* __restrict__ d_adv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    float s = 0.f;
+    for (int64_t a = 0; a < A; ++a) s += dq[i * A + a];
+    d_v[i] = s;
+    const float mean = s / (float)A;
+    for (int64_t a = 0; a < A; ++a) d_adv[i * A + a] = dq[i * A + a] - mean;
+}
+
+// ---- flat-buffer reductions / updates -------------------------------------------------------------------------------
+constexpr int kRedBlocks = 1024;
+__global__ void __launch_bounds__(256) sumsq_stage1(const float* __restrict__ x, int64_t n, float* __restrict__ part) {
+    __shared__ float red[256];
+    // contiguous slab per block, strided inside the block: fixed association order for a given n
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
+    float s = 0.f;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s = fmaf(x[i], x[i], s);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(1024) sumsq_stage2(const float* __restrict__ part, int nparts,
+                                                     float* __restrict__ out) {
+    __shared__ float red[1024];
+    red[threadIdx.x] = (threadIdx.x < nparts) ? part[threadIdx.x] : 0.f;
+    __syncthreads();
+    for (int k = 512; k > 0; k >>= 1) {
+        if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+
+__global__ void __launch_bounds__(256) clip_kernel(float* __restrict__ g, int64_t n, const float* __restrict__ sumsq,
+                                                   float clip) {
+    const float norm = sqrtf(*sumsq);
+    const float scale = clip / fmaxf(norm, clip);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        g[i] *= scale;
+}
+__global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ g, int64_t n, float s) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        g[i] *= s;
+}
+
+__global__ void __launch_bounds__(256) adam_tf_kernel(float* __restrict__ theta, float* __restrict__ m,
+                                                      float* __restrict__ v, const float* __restrict__ g, int64_t n,
+                                                      float alpha, float one_minus_b1, float one_minus_b2, float eps) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = __fadd_rn(m[i], __fmul_rn(__fsub_rn(gi, m[i]), one_minus_b1));
+        const float vi = __fadd_rn(v[i], __fmul_rn(__fsub_rn(__fmul_rn(gi, gi), v[i]), one_minus_b2));
+        m[i] = mi;
+        v[i] = vi;
+        theta[i] = __fsub_rn(theta[i], __fdiv_rn(__fmul_rn(mi, alpha), __fadd_rn(__fsqrt_rn(vi), eps)));
+    }
+}
+
+__global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ target, const float* __restrict__ online,
+                                                     int64_t n, float rate, float one_minus_rate) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        target[i] = __fadd_rn(__fmul_rn(rate, online[i]), __fmul_rn(one_minus_rate, target[i]));
+}
+
+static unsigned flat_grid(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_dqn_td_targets(const float* q_next, const float* q_select, const float* q_online, const int64_t* actions,
+                         const double* rewards, const uint8_t* game_overs, double discount, int64_t batch,
+                         int64_t n_actions, float* targets_out, double* td_err_out, void* stream) {
+    CB200_CHECK_ARG(q_next && q_select && q_online && actions && rewards && game_overs && targets_out && td_err_out,
+                    "null pointer");
+    CB200_CHECK_ARG(batch > 0 && n_actions > 0, "bad shape");
+    CB200_LAUNCH(dqn_td_targets_kernel, (unsigned)((batch + 255) / 256), 256, 0, as_stream(stream), q_next, q_select,
+                 q_online, actions, rewards, game_overs, discount, batch, n_actions, targets_out, td_err_out);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_regression_head_loss_grad(const float* out, const float* target, const float* weights, int64_t batch,
+                                    int64_t width, int huber, float loss_weight, float* d_out, float* loss_out,
+                                    void* stream) {
+    CB200_CHECK_ARG(out && target && d_out && batch > 0 && width > 0, "bad arguments");
+    int threads = 32;
+    while (threads < batch && threads < 1024) threads *= 2;
+    CB200_LAUNCH(regression_head_kernel, 1, threads, 0, as_stream(stream), out, target, weights, batch, width, huber,
+                 loss_weight, d_out, loss_out);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_dueling_combine_fwd(const float* v, const float* adv, int64_t batch, int64_t n_actions, float* q,
+                              void* stream) {
+    CB200_CHECK_ARG(v && adv && q && batch > 0 && n_actions > 0, "bad arguments");
+    CB200_LAUNCH(dueling_fwd_kernel, (unsigned)((batch + 255) / 256), 256, 0, as_stream(stream), v, adv, batch,
+                 n_actions, q);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_dueling_combine_bwd(const float* dq, int64_t batch, int64_t n_actions, float* d_v, float* d_adv,
+                              void* stream) {
+    CB200_CHECK_ARG(dq && d_v && d_adv && batch > 0 && n_actions > 0, "bad arguments");
+    CB200_LAUNCH(dueling_bwd_kernel, (unsigned)((batch + 255) / 256), 256, 0, as_stream(stream), dq, batch, n_actions,
+                 d_v, d_adv);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_sumsq(const float* x, int64_t n, float* out, float* workspace, void* stream) {
+    CB200_CHECK_ARG(x && out && workspace && n > 0, "bad arguments");
+    int blocks = (int)((n + 4095) / 4096);
+    if (blocks > kRedBlocks) blocks = kRedBlocks;
+    CB200_LAUNCH(sumsq_stage1, blocks, 256, 0, as_stream(stream), x, n, workspace);
+    CB200_LAUNCH(sumsq_stage2, 1, 1024, 0, as_stream(stream), workspace, blocks, out);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_clip_by_global_norm(float* g, int64_t n, const float* sumsq, float clip, void* stream) {
+    CB200_CHECK_ARG(g && sumsq && n > 0 && clip > 0, "bad arguments");
+    CB200_LAUNCH(clip_kernel, flat_grid(n), 256, 0, as_stream(stream), g, n, sumsq, clip);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_scale(float* g, int64_t n, float s, void* stream) {
+    CB200_CHECK_ARG(g && n > 0, "bad arguments");
+    CB200_LAUNCH(scale_kernel, flat_grid(n), 256, 0, as_stream(stream), g, n, s);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_adam_tf(float* theta, float* m, float* v, const float* g, int64_t n, float lr, float beta1, float beta2,
+                  float epsilon, float beta1_power, float beta2_power, void* stream) {
+    CB200_CHECK_ARG(theta && m && v && g && n > 0, "bad arguments");
+    const float alpha = lr * sqrtf(1.0f - beta2_power) / (1.0f - beta1_power);
+    CB200_LAUNCH(adam_tf_kernel, flat_grid(n), 256, 0, as_stream(stream), theta, m, v, g, n, alpha, 1.0f - beta1,
+                 1.0f - beta2, epsilon);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_polyak(float* target, const float* online, int64_t n, double rate, void* stream) {
+    CB200_CHECK_ARG(target && online && n > 0, "bad arguments");
+    CB200_LAUNCH(polyak_kernel, flat_grid(n), 256, 0, as_stream(stream), target, online, n, (float)rate,
+                 (float)(1.0 - rate));
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+}  // extern "C"

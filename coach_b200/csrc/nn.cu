@@ -1,0 +1,150 @@
+// coach_b200/csrc/nn.cu -- C-ABI entry points of the dense contractions of the learn step (see nn_gemm.cuh).
+#include "nn_gemm.cuh"
+
+namespace cb200 {
+namespace gemm {
+
+using CfgN64 = Cfg<128, 64, 16, 8, 8>;   // 128 threads, 8x8 per thread
+using CfgN32 = Cfg<128, 32, 16, 8, 4>;   // 128 threads, 8x4 per thread
+using CfgSmall = Cfg<32, 32, 16, 4, 4>;  // 64 threads: small-batch MLPs
+
+template <class C, bool kT>
+static void launch(const cb200_gemm_desc& d, int M, int R, int splits, int r_per_split, cudaStream_t st) {
+    ALoader<C, kT> al;
+    al.a.src = d.a_src;
+    al.a.lut = d.a_lut;
+    al.a.rowoff = d.a_rowoff;
+    al.a.coloff = d.a_coloff;
+    al.a.rowinfo = d.a_rowinfo;
+    al.a.colinfo = d.a_colinfo;
+    al.a.oh = d.a_oh;
+    al.a.ow = d.a_ow;
+    al.a.rows = d.a_rows;
+    al.a.cols = d.a_cols;
+    BLoader<C> bl;
+    bl.b = d.b;
+    bl.N = d.n;
+    bl.ldb = d.ldb;
+    EpiParams ep{d.c, d.ldc, d.bias, d.act, d.mask_y, d.mask_act, d.c_rowmap, d.workspace, splits, d.accumulate};
+    dim3 grid((M + C::BM - 1) / C::BM, (d.n + C::BN - 1) / C::BN, splits);
+    gemm_kernel<C, kT><<<grid, C::T, 0, st>>>(al, bl, ep, M, d.n, R, r_per_split);
+    count_launch();
+    if (splits > 1) {
+        const int64_t total = (int64_t)M * d.n;
+        split_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ep, M, d.n);
+        count_launch();
+    }
+}
+
+// ---- small helpers -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ x, int64_t rows, int64_t cols,
+                                                     float* __restrict__ part, int nslab) {
+    // grid.x = column blocks (256 columns each... one thread per column), grid.y = row slabs
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    const int slab = blockIdx.y;
+    const int64_t per = (rows + nslab - 1) / nslab;
+    const int64_t lo = slab * per, hi = min(rows, lo + per);
+    float s = 0.f;
+    for (int64_t r = lo; r < hi; ++r) s += x[r * cols + col];
+    part[(int64_t)slab * cols + col] = s;
+}
+__global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ part, int64_t cols, int nslab,
+                                                     float* __restrict__ out) {
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    float s = 0.f;
+    for (int k = 0; k < nslab; ++k) s += part[(int64_t)k * cols + col];
+    out[col] = s;
+}
+
+__global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ src, const int32_t* __restrict__ table,
+                                                      int64_t n, float* __restrict__ dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __ldg(src + __ldg(table + i));
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, float* __restrict__ dst) {
+    __shared__ float tile[32][33];
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = src[r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+}  // namespace gemm
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_gemm(const cb200_gemm_desc* d, void* stream) {
+    CB200_CHECK_ARG(d != nullptr, "null descriptor");
+    CB200_CHECK_ARG(d->a_src && d->a_rowoff && d->a_coloff && d->b && d->c, "null operand pointer");
+    CB200_CHECK_ARG(d->a_rows > 0 && d->a_cols > 0 && d->n > 0 && d->ldb >= d->n && d->ldc >= d->n, "bad extents");
+    CB200_CHECK_ARG((d->a_rowinfo == nullptr) == (d->a_colinfo == nullptr), "rowinfo / colinfo must come together");
+    const bool tr = d->a_transposed != 0;
+    const int M = tr ? d->a_cols : d->a_rows;
+    const int R = tr ? d->a_rows : d->a_cols;
+    int splits = d->splits > 1 ? d->splits : 1;
+    CB200_CHECK_ARG(splits == 1 || d->workspace, "split reduction needs a workspace");
+    CB200_CHECK_ARG(splits == 1 || !d->accumulate || true, "");
+    int r_per_split = (R + splits - 1) / splits;
+    r_per_split = (r_per_split + 15) / 16 * 16;
+    splits = (R + r_per_split - 1) / r_per_split;
+    cudaStream_t st = as_stream(stream);
+    const bool small = (M <= 64);
+    if (small) {
+        if (tr) gemm::launch<gemm::CfgSmall, true>(*d, M, R, splits, r_per_split, st);
+        else gemm::launch<gemm::CfgSmall, false>(*d, M, R, splits, r_per_split, st);
+    } else if (d->n <= 32) {
+        if (tr) gemm::launch<gemm::CfgN32, true>(*d, M, R, splits, r_per_split, st);
+        else gemm::launch<gemm::CfgN32, false>(*d, M, R, splits, r_per_split, st);
+    } else {
+        if (tr) gemm::launch<gemm::CfgN64, true>(*d, M, R, splits, r_per_split, st);
+        else gemm::launch<gemm::CfgN64, false>(*d, M, R, splits, r_per_split, st);
+    }
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_colsum(const float* x, int64_t rows, int64_t cols, float* out, float* workspace, void* stream) {
+    CB200_CHECK_ARG(x && out && workspace && rows > 0 && cols > 0, "bad arguments");
+    int nslab = (int)((rows + 255) / 256);
+    if (nslab > 1024) nslab = 1024;
+    cudaStream_t st = as_stream(stream);
+    dim3 g1((unsigned)((cols + 255) / 256), nslab);
+    gemm::colsum_stage1<<<g1, 256, 0, st>>>(x, rows, cols, workspace, nslab);
+    gemm::colsum_stage2<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(workspace, cols, nslab, out);
+    count_launch(2);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_permute_f32(const float* src, const int32_t* table, int64_t n, float* dst, void* stream) {
+    CB200_CHECK_ARG(src && table && dst && n > 0, "bad arguments");
+    int64_t grid = (n + 255) / 256;
+    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+    gemm::permute_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(src, table, n, dst);
+    count_launch();
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_transpose(const float* src, int64_t rows, int64_t cols, float* dst, void* stream) {
+    CB200_CHECK_ARG(src && dst && rows > 0 && cols > 0, "bad arguments");
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    gemm::transpose_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, rows, cols, dst);
+    count_launch();
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+}  // extern "C"

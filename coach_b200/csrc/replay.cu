@@ -28,6 +28,21 @@ struct Descent {
     double priority;   // tree[leaf + size - 1]
 };
 
+// Levels fetched per memory round trip.  7 levels = 254 nodes = 8 independent loads per lane: a 2^20-leaf tree is
+// walked in 3 dependent round trips (7 + 7 + 6) instead of 20.
+constexpr int kRoundLevels = 7;
+constexpr int kRoundRegs = ((2 << kRoundLevels) - 2 + 31) / 32;   // 8
+
+// element `e` (warp-uniform) of the fetched sub-tree: register e / 32 of lane e % 32
+__device__ __forceinline__ double fetch_elem(const double (&v)[kRoundRegs], int e) {
+    const int q = e >> 5, src = e & 31;
+    double out = 0.0;
+#pragma unroll
+    for (int k = 0; k < kRoundRegs; ++k)
+        if (q == k) out = __shfl_sync(0xffffffffu, v[k], src);   // q is warp-uniform: exactly one shuffle executes
+    return out;
+}
+
 __device__ __forceinline__ Descent warp_descent(const double* __restrict__ tree, int64_t size, int levels,
                                                 double val) {
     const int lane = threadIdx.x & 31;
@@ -36,26 +51,21 @@ __device__ __forceinline__ Descent warp_descent(const double* __restrict__ tree,
     if (levels == 0) p = __ldcg(tree);
     int remaining = levels;
     while (remaining > 0) {
-        const int r = remaining < 5 ? remaining : 5;
-        // element e of the sub-tree in level order without its root: e+2 = 2^k + off  ->  node = (j-1)*2^k + (e+2)
-        double v0 = 0.0, v1 = 0.0;
-        {
-            const int e2 = lane + 2;
+        const int r = remaining < kRoundLevels ? remaining : kRoundLevels;
+        // element e of the sub-tree below j, in level order without the root: e + 2 = 2^k + off (k = level below j)
+        //   -> 1-based node (j << k) + off = ((j - 1) << k) + (e + 2)
+        double v[kRoundRegs];
+#pragma unroll
+        for (int q = 0; q < kRoundRegs; ++q) {
+            const int e2 = lane + 32 * q + 2;
             const int k = 31 - __clz(e2);
-            if (k <= r) v0 = __ldcg(tree + (((j - 1) << k) + e2 - 1));
-        }
-        {
-            const int e2 = lane + 34;
-            const int k = 31 - __clz(e2);
-            if (k <= r) v1 = __ldcg(tree + (((j - 1) << k) + e2 - 1));
+            v[q] = (k <= r) ? __ldcg(tree + (((j - 1) << k) + e2 - 1)) : 0.0;
         }
         uint32_t rel = 1;
         for (int s = 0; s < r; ++s) {
-            const int el = 2 * rel - 2, er = el + 1;
-            const double l0 = __shfl_sync(0xffffffffu, v0, el & 31), l1 = __shfl_sync(0xffffffffu, v1, el & 31);
-            const double r0 = __shfl_sync(0xffffffffu, v0, er & 31), r1 = __shfl_sync(0xffffffffu, v1, er & 31);
-            const double left = el < 32 ? l0 : l1;
-            const double right = er < 32 ? r0 : r1;
+            const int el = 2 * rel - 2;             // left child; the right child is element el + 1
+            const double left = fetch_elem(v, el);
+            const double right = fetch_elem(v, el + 1);
             if (val <= left) {   // :89
                 rel = 2 * rel;
                 p = left;
@@ -88,33 +98,36 @@ struct SampleParams {
     float* w32_out;
 };
 
-// PER.sample :232-248 for sample i (whole warp).  Returns the leaf; lane 0 stores idx / weights.
-__device__ __forceinline__ int64_t per_sample_one(const SampleParams& sp, int64_t i, bool write_outputs) {
+// PER.sample :232-245 for sample i (whole warp): the stratified draw and the tree descent.
+__device__ __forceinline__ Descent per_sample_descend(const SampleParams& sp, int64_t i) {
     const double total = __ldcg(sp.sum_tree);
     const double segment = __ddiv_rn(total, (double)sp.n);                        // :232
     const double a = __dmul_rn(segment, (double)i);                               // :240
     const double b = __dmul_rn(segment, (double)(i + 1));                         // :241
     const double val = __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), __ldg(sp.u + i)));  // random.uniform :244
-    const Descent d = warp_descent(sp.sum_tree, sp.size, sp.levels, val);
-    if (write_outputs && (threadIdx.x & 31) == 0) {
-        if (sp.idx_out) sp.idx_out[i] = d.leaf;
-        if (sp.w_out || sp.w32_out) {
-            const double min_probability = __ddiv_rn(__ldcg(sp.min_tree), total);       // :235
-            const double max_weight = pow(__dmul_rn(min_probability, sp.nt), -sp.beta);  // :236
-            const double prob = __ddiv_rn(d.priority, total);                           // :246
-            const double weight = pow(__dmul_rn(sp.nt, prob), -sp.beta);                // :247
-            const double w = __ddiv_rn(weight, max_weight);                             // :248
-            if (sp.w_out) sp.w_out[i] = w;
-            if (sp.w32_out) sp.w32_out[i] = (float)w;
-        }
+    return warp_descent(sp.sum_tree, sp.size, sp.levels, val);
+}
+
+// PER.sample :235-251: importance weight of one drawn leaf (one thread); off the gather's critical path
+__device__ __forceinline__ void per_sample_publish(const SampleParams& sp, int64_t i, int64_t leaf, double priority) {
+    if (sp.idx_out) sp.idx_out[i] = leaf;
+    if (sp.w_out || sp.w32_out) {
+        const double total = __ldcg(sp.sum_tree);
+        const double min_probability = __ddiv_rn(__ldcg(sp.min_tree), total);       // :235
+        const double max_weight = pow(__dmul_rn(min_probability, sp.nt), -sp.beta);  // :236
+        const double prob = __ddiv_rn(priority, total);                             // :246
+        const double weight = pow(__dmul_rn(sp.nt, prob), -sp.beta);                // :247
+        const double w = __ddiv_rn(weight, max_weight);                             // :248
+        if (sp.w_out) sp.w_out[i] = w;
+        if (sp.w32_out) sp.w32_out[i] = (float)w;
     }
-    return d.leaf;
 }
 
 __global__ void __launch_bounds__(128) per_sample_kernel(SampleParams sp) {
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (warp >= sp.n) return;
-    per_sample_one(sp, warp, true);
+    const Descent d = per_sample_descend(sp, warp);
+    if ((threadIdx.x & 31) == 0) per_sample_publish(sp, warp, d.leaf, d.priority);
 }
 
 // =====================================================================================================================
@@ -262,7 +275,8 @@ __global__ void per_priorities_kernel(const double* err, int64_t n, double epsil
 // Column gather.
 // =====================================================================================================================
 constexpr int kStageBytes = 8192;       // smem stage capacity (one chunk of one row)
-constexpr int kMaxStages = 12;
+constexpr int kMaxStages = 32;
+constexpr int kBarBytes = kMaxStages * 8;   // mbarrier array at the start of dynamic smem
 constexpr int kGatherThreads = 128;
 constexpr int kMaxCtaSamples = 16;      // descents a CTA may need for its contiguous item range (fused kernel)
 
@@ -289,6 +303,7 @@ struct GatherParams {
     int64_t total_items;
     const int64_t* idx;      // plain gather: indices come from memory
     int stages;
+    int stage_bytes;         // smem slot size (largest chunk, rounded up to 128 B)
 };
 
 // copy `bytes` from src to dst with the widest access the three alignments allow; executed by one warp
@@ -332,7 +347,7 @@ __device__ __forceinline__ void bulk_pipeline(const GatherParams& gp, int64_t lo
         uint32_t bytes;
         item_addr(lo + k, src, dst, bytes);
         mbar_expect_tx(full_bar + st, bytes);
-        bulk_g2s(stage_mem + (size_t)st * kStageBytes, src, bytes, full_bar + st);
+        bulk_g2s(stage_mem + (size_t)st * gp.stage_bytes, src, bytes, full_bar + st);
     };
     const int64_t pre = cnt < S ? cnt : S;
     for (int64_t k = 0; k < pre; ++k) issue_load(k);
@@ -344,7 +359,7 @@ __device__ __forceinline__ void bulk_pipeline(const GatherParams& gp, int64_t lo
         uint32_t bytes;
         item_addr(lo + k, src, dst, bytes);
         fence_proxy_async_smem();
-        bulk_s2g(dst, stage_mem + (size_t)st * kStageBytes, bytes);
+        bulk_s2g(dst, stage_mem + (size_t)st * gp.stage_bytes, bytes);
         bulk_commit();
         // refill the stage whose store was issued one iteration ago (its smem read has had time to drain)
         if (k >= 1 && (k - 1 + S) < cnt) {
@@ -371,7 +386,7 @@ __device__ __forceinline__ void init_barriers(uint64_t* full_bar, int stages) {
 __global__ void __launch_bounds__(kGatherThreads) gather_bulk_kernel(GatherParams gp) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
-    uint8_t* stage_mem = smem + 128;
+    uint8_t* stage_mem = smem + kBarBytes;
     init_barriers(full_bar, gp.stages);
     __syncthreads();
     int64_t lo, hi;
@@ -399,8 +414,9 @@ __global__ void __launch_bounds__(256) gather_small_kernel(GatherParams gp) {
 __global__ void __launch_bounds__(kGatherThreads) per_sample_gather_kernel(SampleParams sp, GatherParams gp) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
-    int64_t* leaf_smem = reinterpret_cast<int64_t*>(smem + 128);           // kMaxCtaSamples entries
-    uint8_t* stage_mem = smem + 128 + kMaxCtaSamples * sizeof(int64_t);
+    int64_t* leaf_smem = reinterpret_cast<int64_t*>(smem + kBarBytes);                       // kMaxCtaSamples entries
+    double* prio_smem = reinterpret_cast<double*>(smem + kBarBytes + kMaxCtaSamples * 8);    // kMaxCtaSamples entries
+    uint8_t* stage_mem = smem + kBarBytes + kMaxCtaSamples * 16;
     init_barriers(full_bar, gp.stages);
     int64_t lo, hi;
     cta_item_range(gp.total_items, lo, hi);
@@ -408,22 +424,32 @@ __global__ void __launch_bounds__(kGatherThreads) per_sample_gather_kernel(Sampl
     const int ips = gp.items_per_sample;
     const int64_t s_lo = lo / ips, s_hi = (hi - 1) / ips;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    // phase A: descents for the samples this CTA touches, one warp each, in parallel
+    // phase A: descents for the samples this CTA touches, one warp each, in parallel (3 memory round trips)
     for (int64_t s = s_lo + warp; s <= s_hi; s += nwarp) {
-        const bool owner = (s * ips >= lo);     // this CTA holds the sample's first item -> it publishes the outputs
-        const int64_t leaf = per_sample_one(sp, s, owner);
-        if (lane == 0) leaf_smem[(s - s_lo) % kMaxCtaSamples] = leaf;
-        if (owner) {
+        const Descent d = per_sample_descend(sp, s);
+        if (lane == 0) {
+            leaf_smem[(s - s_lo) % kMaxCtaSamples] = d.leaf;
+            prio_smem[(s - s_lo) % kMaxCtaSamples] = d.priority;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // phase B (one thread): every chunk of this CTA goes in flight at once when the stages allow it
+        bulk_pipeline(gp, lo, hi, stage_mem, full_bar,
+                      [leaf_smem, s_lo](int64_t s) { return leaf_smem[(s - s_lo) % kMaxCtaSamples]; });
+    } else if (warp >= 1 || nwarp == 1) {
+        // meanwhile the other warps publish indices / importance weights and move the small columns of the samples
+        // whose FIRST item belongs to this CTA (exactly one CTA per sample)
+        const int w0 = warp - 1, nw = nwarp - 1;
+        for (int64_t s = s_lo + w0; s <= s_hi; s += nw) {
+            if (s * ips < lo) continue;
+            const int64_t leaf = leaf_smem[(s - s_lo) % kMaxCtaSamples];
+            if (lane == 0) per_sample_publish(sp, s, leaf, prio_smem[(s - s_lo) % kMaxCtaSamples]);
             for (int c = 0; c < gp.n_small; ++c) {
                 const SmallColumn& col = gp.small[c];
                 warp_copy_row(col.dst + s * col.row_bytes, col.src + leaf * col.row_bytes, col.row_bytes, lane);
             }
         }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        bulk_pipeline(gp, lo, hi, stage_mem, full_bar,
-                      [leaf_smem, s_lo](int64_t s) { return leaf_smem[(s - s_lo) % kMaxCtaSamples]; });
     }
 }
 
@@ -445,8 +471,7 @@ __global__ void __launch_bounds__(256) scatter_ring_kernel(uint8_t* ring, const 
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
-#define g_tune_stages (cb200::tune_get("gather_stages", 6, 1, kMaxStages))
-#define g_tune_ctas_per_sm (cb200::tune_get("gather_ctas_per_sm", 2, 1, 16))
+#define g_tune_ctas_per_sm (cb200::tune_get("gather_ctas_per_sm", 4, 1, 16))
 
 static int ilog2_exact(int64_t size) {
     int l = 0;
@@ -459,7 +484,7 @@ static int build_gather_params(const cb200_column* cols, int n_columns, int64_t 
     gp.items_per_sample = 0;
     gp.n = n;
     gp.idx = nullptr;
-    gp.stages = g_tune_stages;
+    gp.stages = 1;
     for (int c = 0; c < n_columns; ++c) {
         const cb200_column& col = cols[c];
         if (col.row_bytes <= 0 || !col.src || !col.dst) return -1;
@@ -490,11 +515,32 @@ static int build_gather_params(const cb200_column* cols, int n_columns, int64_t 
         }
     }
     gp.total_items = (int64_t)gp.items_per_sample * n;
+    int max_chunk = 16;
+    for (int c = 0; c < gp.n_big; ++c) max_chunk = gp.big[c].chunk_bytes > max_chunk ? gp.big[c].chunk_bytes : max_chunk;
+    gp.stage_bytes = (max_chunk + 127) / 128 * 128;
     return 0;
 }
 
+// grid + stage count: `ctas_per_sm` persistent CTAs per SM share the ~200 KB of shared memory; when the slots suffice
+// every chunk of a CTA is loaded at once (the copy then costs one DRAM latency plus the drain).
+static unsigned plan_bulk(GatherParams& gp, bool fused) {
+    int64_t g = (int64_t)sm_count() * g_tune_ctas_per_sm;
+    if (g > gp.total_items) g = gp.total_items;
+    if (g < 1) g = 1;
+    const int64_t items_per_cta = (gp.total_items + g - 1) / g;
+    const int64_t budget = (int64_t)200 * 1024 / g_tune_ctas_per_sm - kBarBytes - (fused ? kMaxCtaSamples * 16 : 0);
+    int64_t st = budget / gp.stage_bytes;
+    if (st > items_per_cta) st = items_per_cta;
+    const int forced = cb200::tune_get("gather_stages", 0, 0, kMaxStages);
+    if (forced > 0 && forced < st) st = forced;
+    if (st > kMaxStages) st = kMaxStages;
+    if (st < 1) st = 1;
+    gp.stages = (int)st;
+    return (unsigned)g;
+}
+
 static size_t gather_smem_bytes(const GatherParams& gp, bool fused) {
-    return 128 + (fused ? kMaxCtaSamples * sizeof(int64_t) : 0) + (size_t)gp.stages * kStageBytes;
+    return kBarBytes + (fused ? kMaxCtaSamples * 16 : 0) + (size_t)gp.stages * gp.stage_bytes;
 }
 
 }  // namespace cb200
@@ -502,6 +548,32 @@ static size_t gather_smem_bytes(const GatherParams& gp, bool fused) {
 using namespace cb200;
 
 extern "C" {
+
+int cb200_l2_persist(const void* ptr, int64_t bytes, void* stream) {
+    int dev = 0, max_persist = 0, max_window = 0;
+    CB200_CUDA(cudaGetDevice(&dev));
+    CB200_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    CB200_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (ptr == nullptr || bytes <= 0) {
+        attr.accessPolicyWindow.num_bytes = 0;     // clear the window
+        CB200_CUDA(cudaStreamSetAttribute(as_stream(stream), cudaStreamAttributeAccessPolicyWindow, &attr));
+        return CB200_OK;
+    }
+    if (max_persist <= 0 || max_window <= 0) return CB200_ERR_UNSUPPORTED;
+    size_t want = (size_t)bytes;
+    if (want > (size_t)max_window) want = (size_t)max_window;
+    size_t carve = want < (size_t)max_persist ? want : (size_t)max_persist;
+    CB200_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+    attr.accessPolicyWindow.num_bytes = want;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CB200_CUDA(cudaStreamSetAttribute(as_stream(stream), cudaStreamAttributeAccessPolicyWindow, &attr));
+    return CB200_OK;
+}
 
 int cb200_per_init(double* sum_tree, double* min_tree, double* max_tree, int32_t* winner, int64_t size, void* stream) {
     CB200_CHECK_ARG(sum_tree && min_tree && max_tree && winner, "null pointer");
@@ -613,11 +685,6 @@ static int launch_small_gather(const GatherParams& gp, cudaStream_t st) {
     return CB200_OK;
 }
 
-static unsigned bulk_grid(const GatherParams& gp) {
-    int64_t g = (int64_t)sm_count() * g_tune_ctas_per_sm;
-    if (g > gp.total_items) g = gp.total_items;
-    return (unsigned)g;
-}
 
 int cb200_gather(const cb200_column* h_columns, int n_columns, const int64_t* idx, int64_t n, void* stream) {
     CB200_CHECK_ARG(h_columns && n_columns > 0 && n_columns <= CB200_MAX_COLUMNS, "bad column table");
@@ -627,13 +694,14 @@ int cb200_gather(const cb200_column* h_columns, int n_columns, const int64_t* id
     gp.idx = idx;
     cudaStream_t st = as_stream(stream);
     if (gp.n_big > 0) {
+        const unsigned grid = plan_bulk(gp, false);
         const size_t smem = gather_smem_bytes(gp, false);
         static size_t configured = 0;
         if (smem > configured) {
             CB200_CUDA(cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
-        CB200_LAUNCH(gather_bulk_kernel, bulk_grid(gp), kGatherThreads, smem, st, gp);
+        CB200_LAUNCH(gather_bulk_kernel, grid, kGatherThreads, smem, st, gp);
     }
     launch_small_gather(gp, st);
     CB200_CHECK_LAUNCH();
@@ -652,7 +720,7 @@ int cb200_per_sample_gather(const double* sum_tree, const double* min_tree, int6
     CB200_CHECK_ARG(build_gather_params(h_columns, n_columns, n, gp) == 0, "bad column entry");
     cudaStream_t st = as_stream(stream);
     // a CTA's contiguous item range must not span more than kMaxCtaSamples samples
-    const unsigned grid = gp.n_big > 0 ? bulk_grid(gp) : 0;
+    const unsigned grid = gp.n_big > 0 ? plan_bulk(gp, true) : 0;
     const bool fusable = gp.n_big > 0 &&
                          ((gp.total_items + grid - 1) / grid + gp.items_per_sample - 1) / gp.items_per_sample + 1 <=
                              kMaxCtaSamples;

@@ -110,7 +110,7 @@ class DeviceTransitionRing(object):
                 v = t.reward
             else:
                 v = t.game_over
-            a = np.ascontiguousarray(np.asarray(v), dtype=sp.dtype)
+            a = np.asarray(v, dtype=sp.dtype, order='C')
             if a.shape != sp.shape:
                 raise ValueError("transition field %s has shape %s, the replay was created with %s"
                                  % (name, a.shape, sp.shape))

@@ -46,6 +46,13 @@ int cb200_tune(const char* key, int value);
  * memories/non_episodic/prioritized_experience_replay.py:43-156 (SegmentTree).
  * ===================================================================================================================*/
 
+/* Marks [ptr, ptr+bytes) as L2-persisting for kernels subsequently launched on `stream` (stream access-policy window
+ * + persisting-L2 carve-out).  Used for the top levels of the sum tree (the first 2^k entries of the heap array are
+ * its top k levels), which every sample's descent re-reads while ~100 MB of minibatch traffic per step would
+ * otherwise evict them from the 126 MB L2.  ptr == NULL clears the window.  CB200_ERR_UNSUPPORTED if the device has
+ * no persisting-L2 support. */
+int cb200_l2_persist(const void* ptr, int64_t bytes, void* stream);
+
 /* SegmentTree.__init__ :54-61 -- sum tree <- 0, min tree <- +inf, max tree <- -inf. `winner` (int32[size]) is the
  * scratch array used by cb200_per_update for last-writer-wins duplicate resolution; it is set to -1. */
 int cb200_per_init(double* sum_tree, double* min_tree, double* max_tree, int32_t* winner, int64_t size, void* stream);
@@ -120,6 +127,117 @@ int cb200_per_sample_gather(const double* sum_tree, const double* min_tree, int6
  * `cb200_column.src` member is the ring (written), `.dst` the staged rows (read)). */
 int cb200_scatter_ring(const cb200_column* h_columns, int n_columns, int64_t cursor, int64_t capacity, int64_t n,
                        void* stream);
+
+
+/* =====================================================================================================================
+ * Learn step: dense contractions.  One primitive ("gather-GEMM") covers conv forward (implicit im2col over NHWC),
+ * conv weight / data gradients and dense forward / backward:
+ *
+ *      C[m, n] = epilogue( sum_r A(m, r) * B(r, n) ),      A(m, r) = a_src[ a_rowoff[m] + a_coloff[r] ]   (elements)
+ *
+ * Replaces the TensorFlow ops behind architectures/tensorflow_components/layers.py:108-183 (Conv2d / Dense),
+ * embedders/embedder.py:95-124 (x / 255 input rescale, via a_lut) and tf.gradients over them
+ * (architectures/tensorflow_components/architecture.py:193).  fp32 FFMA, deterministic (fixed reduction order).
+ * ===================================================================================================================*/
+#define CB200_ACT_NONE 0
+#define CB200_ACT_RELU 1
+#define CB200_ACT_TANH 2
+
+typedef struct cb200_gemm_desc {
+    /* A operand */
+    const void* a_src;          /* fp32 (a_lut == NULL) or uint8 (value = a_lut[byte]) element array                */
+    const float* a_lut;         /* 256-entry table, e.g. lut[v] = (float)v / 255.0f                                  */
+    const int32_t* a_rowoff;    /* [a_rows] element offset contributed by the row index                              */
+    const int32_t* a_coloff;    /* [a_cols] element offset contributed by the column (reduction) index               */
+    const int32_t* a_rowinfo;   /* optional (i << 16 | j) per row   } A(m, r) = 0 unless 0 <= i - a < a_oh and       */
+    const int32_t* a_colinfo;   /* optional (a << 16 | b) per col   }                    0 <= j - b < a_ow           */
+    int32_t a_oh, a_ow;
+    int32_t a_rows, a_cols;     /* logical extent of A                                                              */
+    int32_t a_transposed;       /* 0: C[a_rows, N] = A * B   (reduction over a_cols)                                */
+                                /* 1: C[a_cols, N] = A^T * B (reduction over a_rows; weight gradients)              */
+    /* B operand: row-major [R, N] */
+    const float* b;
+    int32_t ldb;
+    int32_t n;
+    /* output / epilogue */
+    float* c;                   /* [rows, ldc]                                                                       */
+    int32_t ldc;
+    const float* bias;          /* [n] or NULL                                                                       */
+    int32_t act;                /* CB200_ACT_* applied after the bias                                                */
+    const float* mask_y;        /* optional, indexed like c: c = value * act'(mask_y) with act' from the activation  */
+    int32_t mask_act;           /*   OUTPUT (relu: y > 0, tanh: 1 - y*y) -- fuses the activation backward            */
+    const int32_t* c_rowmap;    /* optional output row remap (transposed-conv stride classes)                        */
+    int32_t accumulate;         /* c += value instead of c = value                                                   */
+    /* split reduction */
+    float* workspace;           /* >= splits * rows * n floats when splits > 1                                       */
+    int32_t splits;             /* 0 / 1 = no split; k > 1 = k partial sums reduced in fixed order                   */
+} cb200_gemm_desc;
+
+int cb200_gemm(const cb200_gemm_desc* h_desc, void* stream);
+
+/* out[j] = sum_i x[i, j] for x [rows, cols] (bias gradients: tf.gradients wrt the bias of Dense / Conv2d), reduced in a
+ * fixed order (two deterministic stages; `workspace` >= 1024 * cols floats). */
+int cb200_colsum(const float* x, int64_t rows, int64_t cols, float* out, float* workspace, void* stream);
+
+/* dst[i] = src[table[i]], i < n  (fp32; static permutations of weight tensors for the data-gradient GEMMs, e.g. the
+ * per-stride-class [taps*N, Cin] matrices of the transposed convolution) */
+int cb200_permute_f32(const float* src, const int32_t* table, int64_t n, float* dst, void* stream);
+
+/* dst[c, r] = src[r, c]  (fp32; pre-transposition of weight matrices for the data-gradient GEMMs) */
+int cb200_transpose(const float* src, int64_t rows, int64_t cols, float* dst, void* stream);
+
+
+/* =====================================================================================================================
+ * Learn step: element-wise / reduction kernels.
+ * ===================================================================================================================*/
+
+/* DQNAgent.learn_from_batch, agents/dqn_agent.py:92-103 (+ ddqn_agent.py:42-43 action selection):
+ *   a*_i   = argmax_a q_select[i, a]                     (first maximum, np.argmax)
+ *   y_i    = r_i + (1.0 - done_i) * discount * q_next[i, a*_i]        evaluated in fp64 like the Python loop
+ *   err_i  = |y_i - q_online[i, act_i]|  (fp64)          -> td_err_out (the new priorities' input)
+ *   targets = copy of q_online with targets[i, act_i] = (float) y_i
+ * q_select = q_next for DQN, Q_online(s') for DDQN. */
+int cb200_dqn_td_targets(const float* q_next, const float* q_select, const float* q_online, const int64_t* actions,
+                         const double* rewards, const uint8_t* game_overs, double discount, int64_t batch,
+                         int64_t n_actions, float* targets_out, double* td_err_out, void* stream);
+
+/* Generic head loss of heads/head.py:165-177 for a Q / V style regression head:
+ *   loss = mean_b( loss_weight * w_b * sum_a l(target_ba, out_ba) ),  l = Huber(delta=1) (tf.losses.huber_loss,
+ *   q_head.py:44-45) or squared error (tf.losses.mean_squared_error);  w = importance weights (NULL => ones).
+ *   d_out[b, a] = loss_weight * w_b / batch * l'(out_ba - target_ba)
+ * loss_out: device float (fixed-order reduction). */
+int cb200_regression_head_loss_grad(const float* out, const float* target, const float* weights, int64_t batch,
+                                    int64_t width, int huber, float loss_weight, float* d_out, float* loss_out,
+                                    void* stream);
+
+/* DuelingQHead (heads/dueling_q_head.py:33-47): q = v + (adv - mean_a adv); backward: d_v = sum_a dq,
+ * d_adv = dq - mean_a dq. */
+int cb200_dueling_combine_fwd(const float* v, const float* adv, int64_t batch, int64_t n_actions, float* q,
+                              void* stream);
+int cb200_dueling_combine_bwd(const float* dq, int64_t batch, int64_t n_actions, float* d_v, float* d_adv,
+                              void* stream);
+
+/* sum of squares of a flat fp32 buffer in a fixed order -> *out (device float); tf.global_norm =
+ * sqrt(sum_t sum(t^2)) (architecture.py:194).  workspace >= 1024 floats. */
+int cb200_sumsq(const float* x, int64_t n, float* out, float* workspace, void* stream);
+
+/* tf.clip_by_global_norm (architecture.py:239-240): g *= clip / max(sqrt(*sumsq), clip)  -- in place. */
+int cb200_clip_by_global_norm(float* g, int64_t n, const float* sumsq, float clip, void* stream);
+
+/* g *= s (apply_gradients `scaler`, architecture.py:485-493: 1/num_workers for sync training) */
+int cb200_scale(float* g, int64_t n, float s, void* stream);
+
+/* tf.train.AdamOptimizer step with TF-1.x semantics (general_network.py:390-394; kernel form of
+ * tensorflow/core/kernels/training_ops.cc ApplyAdam):
+ *   alpha = lr * sqrt(1 - beta2_power) / (1 - beta1_power)       (fp32; the powers are the fp32 running products)
+ *   m += (g - m) * (1 - beta1);  v += (g*g - v) * (1 - beta2);  theta -= (m * alpha) / (sqrt(v) + epsilon)
+ * over the whole flat parameter buffer in one launch. */
+int cb200_adam_tf(float* theta, float* m, float* v, const float* g, int64_t n, float lr, float beta1, float beta2,
+                  float epsilon, float beta1_power, float beta2_power, void* stream);
+
+/* NetworkWrapper.update_target_network -> set_weights (architecture.py:598-607):
+ *   target = rate * online + (1 - rate) * target   in fp32, rate and (1 - rate) rounded to fp32 first (numpy). */
+int cb200_polyak(float* target, const float* online, int64_t n, double rate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,285 @@
+"""GPU parity tests of the learn step (pytest -m gpu): CUDA kernels vs the torch-CPU oracle (oracle/nets.py).
+
+Tolerance (north_star: "losses/gradients within 1e-5 rtol fp32"): every tensor is compared with
+``|got - want| <= 1e-5 * max|want| + 1e-5 * |want|`` -- 1e-5 relative to the tensor's scale plus 1e-5 element-wise --
+because two fp32 evaluations with different summation orders cannot agree to 1e-5 *element-wise* on entries that are
+the result of cancellation.  In addition the CUDA result must be at least as close to an fp64 evaluation of the same
+graph as the fp32 oracle is (factor 4 slack), which is the meaningful statement of "same result within fp32".
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import nets as on     # noqa: E402  (checker only)
+
+
+def close(got, want, rtol=1e-5, name=""):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = np.abs(want).max() if want.size else 0.0
+    err = np.abs(got - want)
+    tol = rtol * scale + rtol * np.abs(want)
+    assert np.all(err <= tol), "%s: max err %.3e (scale %.3e, allowed %.3e)" % (name, err.max(), scale, tol.min())
+
+
+def _lib():
+    from coach_b200 import _lib
+    return _lib, _lib.load()
+
+
+# ---- gather-GEMM primitive ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,K,N,act", [(512, 3136, 512, "relu"), (512, 512, 6, None), (32, 4, 256, "relu"),
+                                       (64, 17, 64, "tanh"), (100, 23, 400, "relu"), (1, 5, 3, None)])
+def test_dense_forward_backward(B, K, N, act):
+    from coach_b200.architectures.layers import Dense, Workspace
+    L, lib = _lib()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(B * 7 + K)
+    x = torch.randn(B, K, generator=g)
+    w = torch.randn(K, N, generator=g) / np.sqrt(K)
+    b = torch.randn(N, generator=g) * 0.1
+    dy = torch.randn(B, N, generator=g)
+    xd, wd, bd, dyd = x.to(dev), w.to(dev), b.to(dev), dy.to(dev)
+    y = torch.empty(B, N, device=dev)
+    dw, db, dx = torch.empty(K, N, device=dev), torch.empty(N, device=dev), torch.empty(B, K, device=dev)
+    ws = Workspace(dev)
+    layer = Dense(K, N, act)
+    layer.prepare(lib, ws, B, dev, xd, y, wd, bd, dw, db, dyd, dx, need_dx=True, prev_act=1)   # relu'(x) mask on dx
+    layer.forward()
+    layer.backward()
+    torch.cuda.synchronize()
+    x64, w64, b64, dy64 = x.double(), w.double(), b.double(), dy.double()
+    f = {"relu": torch.relu, "tanh": torch.tanh, None: lambda t: t}[act]
+    close(y.cpu(), f(x64 @ w64 + b64), name="y")
+    close(dw.cpu(), x64.t() @ dy64, name="dw")
+    close(db.cpu(), dy64.sum(0), name="db")
+    close(dx.cpu(), (dy64 @ w64.t()) * (x64 > 0), name="dx")
+
+
+@pytest.mark.parametrize("B,H,C,N,K,S,u8", [(8, 84, 4, 32, 8, 4, True), (8, 20, 32, 64, 4, 2, False),
+                                            (8, 9, 64, 64, 3, 1, False), (3, 11, 3, 5, 3, 2, False),
+                                            (2, 10, 2, 7, 4, 3, False)])
+def test_conv_forward_backward(B, H, C, N, K, S, u8):
+    from coach_b200.architectures.layers import Conv2d, Workspace
+    from coach_b200.architectures.network import make_u8_lut
+    import torch.nn.functional as F
+    L, lib = _lib()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(H * 31 + C)
+    layer = Conv2d((H, H), C, N, K, S, "relu")
+    OH = layer.OH
+    if u8:
+        x = torch.randint(0, 256, (B, H, H, C), generator=g, dtype=torch.uint8)
+        xf = x.double() / 255.0
+    else:
+        x = torch.relu(torch.randn(B, H, H, C, generator=g))
+        xf = x.double()
+    w = torch.randn(K, K, C, N, generator=g) / np.sqrt(K * K * C)
+    b = torch.randn(N, generator=g) * 0.1
+    dy = torch.randn(B, OH, OH, N, generator=g)
+    xd, wd, bd, dyd = x.to(dev), w.to(dev), b.to(dev), dy.to(dev)
+    y = torch.empty(B, OH * OH * N, device=dev)
+    dw, db = torch.empty(K, K, C, N, device=dev), torch.empty(N, device=dev)
+    dx = torch.empty(B, H * H * C, device=dev)
+    ws = Workspace(dev)
+    layer.prepare(lib, ws, B, dev, xd, y, wd, bd, dw, db, dyd, dx, x_is_u8=u8, lut=make_u8_lut(dev) if u8 else None,
+                  need_dx=not u8, prev_act=0 if u8 else 1)
+    layer.forward()
+    layer.backward()
+    torch.cuda.synchronize()
+    xt = xf.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wt = w.double().permute(3, 2, 0, 1).clone().requires_grad_(True)
+    bt = b.double().clone().requires_grad_(True)
+    z = F.conv2d(xt, wt, bt, stride=S)
+    close(y.cpu().view(B, OH, OH, N), torch.relu(z).permute(0, 2, 3, 1).detach(), name="y")
+    # gradient wrt the pre-activation z with upstream dy
+    z.backward(dy.double().permute(0, 3, 1, 2))
+    close(dw.cpu(), wt.grad.permute(2, 3, 1, 0), name="dw")
+    close(db.cpu(), bt.grad, name="db")
+    if not u8:
+        want_dx = xt.grad.permute(0, 2, 3, 1) * (xf > 0)
+        close(dx.cpu().view(B, H, H, C), want_dx, name="dx")
+
+
+# ---- element-wise kernels ------------------------------------------------------------------------------------------
+def test_adam_polyak_clip_match_numpy_fp32():
+    L, lib = _lib()
+    dev = torch.device("cuda")
+    n = 100003
+    rng = np.random.RandomState(0)
+    theta = rng.randn(n).astype(np.float32)
+    g = (rng.randn(n) * 0.01).astype(np.float32)
+    th, m, v = torch.from_numpy(theta).to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    gd = torch.from_numpy(g).to(dev)
+    opt = on.AdamTF([torch.from_numpy(theta)], 2.5e-4, 0.9, 0.99, 1e-4)
+    cur = [torch.from_numpy(theta)]
+    b1p, b2p = np.float32(0.9), np.float32(0.99)
+    for step in range(3):
+        L.check(lib.cb200_adam_tf(th.data_ptr(), m.data_ptr(), v.data_ptr(), gd.data_ptr(), n, 2.5e-4, 0.9, 0.99, 1e-4,
+                                  float(b1p), float(b2p), None))
+        b1p, b2p = np.float32(b1p * np.float32(0.9)), np.float32(b2p * np.float32(0.99))
+        cur = opt.step(cur, [torch.from_numpy(g)])
+        np.testing.assert_allclose(th.cpu().numpy(), cur[0].numpy(), rtol=2e-6, atol=1e-7)
+    # polyak: exact fp32 arithmetic
+    tgt = rng.randn(n).astype(np.float32)
+    td = torch.from_numpy(tgt).to(dev)
+    L.check(lib.cb200_polyak(td.data_ptr(), th.data_ptr(), n, 0.005, None))
+    want = np.float32(0.005) * th.cpu().numpy() + np.float32(1 - 0.005) * tgt
+    np.testing.assert_array_equal(td.cpu().numpy(), want)
+    L.check(lib.cb200_polyak(td.data_ptr(), th.data_ptr(), n, 1.0, None))
+    np.testing.assert_array_equal(td.cpu().numpy(), th.cpu().numpy())
+    # global norm + clip
+    ss = torch.zeros(1, device=dev)
+    wsb = torch.empty(2048, device=dev)
+    L.check(lib.cb200_sumsq(gd.data_ptr(), n, ss.data_ptr(), wsb.data_ptr(), None))
+    np.testing.assert_allclose(ss.item(), np.sum(g.astype(np.float64) ** 2), rtol=1e-6)
+    g2 = gd.clone()
+    L.check(lib.cb200_clip_by_global_norm(g2.data_ptr(), n, ss.data_ptr(), 0.5, None))
+    norm = np.sqrt(np.sum(g.astype(np.float64) ** 2))
+    np.testing.assert_allclose(g2.cpu().numpy(), g * (0.5 / max(norm, 0.5)), rtol=1e-6)
+
+
+def test_td_targets_match_python_loop():
+    L, lib = _lib()
+    dev = torch.device("cuda")
+    rng = np.random.RandomState(1)
+    B, A = 512, 6
+    qn = rng.randn(B, A).astype(np.float32)
+    qs = rng.randn(B, A).astype(np.float32)
+    qs[3, 2] = qs[3, 4] = qs[3].max() + 1          # tie: first maximum wins
+    qo = rng.randn(B, A).astype(np.float32)
+    act = rng.randint(0, A, B).astype(np.int64)
+    rew = rng.randint(-1, 2, B).astype(np.float64)
+    done = (rng.rand(B) < 0.2)
+    want_t, want_e = on.dqn_targets(qn, qs, qo, act, rew, done, 0.99)
+    out_t = torch.empty(B, A, device=dev)
+    out_e = torch.empty(B, dtype=torch.float64, device=dev)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)     # noqa: E731
+    L.check(lib.cb200_dqn_td_targets(d(qn).data_ptr(), d(qs).data_ptr(), d(qo).data_ptr(), d(act).data_ptr(),
+                                     d(rew).data_ptr(), d(done.astype(np.uint8)).data_ptr(), 0.99, B, A,
+                                     out_t.data_ptr(), out_e.data_ptr(), None))
+    np.testing.assert_array_equal(out_t.cpu().numpy(), want_t)       # bit-exact: same fp64 operations, one rounding
+    np.testing.assert_array_equal(out_e.cpu().numpy(), want_e)
+
+
+# ---- whole learn step ----------------------------------------------------------------------------------------------
+def _make_agent(obs_shape, A, B, dueling, double, per, clip=None, huber=True, seed=0):
+    from coach_b200.agents.dqn_agent import DQNAgent, DDQNAgent, DQNAgentParameters
+    from coach_b200.memories.memory import MemoryGranularity
+    from coach_b200.memories.prioritized_experience_replay import PrioritizedExperienceReplayParameters
+    from coach_b200.schedules import LinearSchedule
+    ap = DQNAgentParameters()
+    if per:
+        ap.memory = PrioritizedExperienceReplayParameters()
+        ap.memory.beta = LinearSchedule(0.4, 1, 1000)
+    ap.memory.max_size = (MemoryGranularity.Transitions, 1024)
+    net = ap.network_wrappers["main"]
+    net.batch_size = B
+    net.replace_mse_with_huber_loss = huber
+    net.clip_gradients = clip
+    if dueling:
+        net.heads_parameters = ["DuelingQHead"]
+    cls = DDQNAgent if double else DQNAgent
+    return cls(ap, observation_shape=obs_shape, num_actions=A, seed=seed)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(obs=(4,), A=2, B=32, dueling=False, double=False, per=False, huber=False, clip=None),       # CartPole_DQN
+    dict(obs=(84, 84, 4), A=6, B=16, dueling=False, double=False, per=True, huber=True, clip=None),  # Atari DQN + PER
+    dict(obs=(84, 84, 4), A=6, B=8, dueling=True, double=True, per=True, huber=True, clip=10.0),     # dueling DDQN + PER
+])
+def test_dqn_learn_step_matches_oracle(cfg):
+    import random
+    torch.manual_seed(0)
+    agent = _make_agent(cfg["obs"], cfg["A"], cfg["B"], cfg["dueling"], cfg["double"], cfg["per"], cfg["clip"],
+                        cfg["huber"])
+    B, A = cfg["B"], cfg["A"]
+    rng = np.random.RandomState(3)
+    n = 256
+    if len(cfg["obs"]) == 3:
+        s = rng.randint(0, 256, (n,) + cfg["obs"]).astype(np.uint8)
+        s2 = rng.randint(0, 256, (n,) + cfg["obs"]).astype(np.uint8)
+    else:
+        s = rng.uniform(-1, 1, (n,) + cfg["obs"]).astype(np.float32)
+        s2 = rng.uniform(-1, 1, (n,) + cfg["obs"]).astype(np.float32)
+    a = rng.randint(0, A, n).astype(np.int64)
+    r = rng.randint(-1, 2, n).astype(np.float64)
+    done = (rng.rand(n) < 0.1).astype(np.uint8)
+    agent.memory.store_columns({"state:observation": s, "next_state:observation": s2, "action": a, "reward": r,
+                                "game_over": done})
+    if cfg["per"]:
+        agent.memory.update_priorities(np.arange(n), np.abs(rng.randn(n)))
+    store = agent.net_def.store
+    # make target != online so that the test can tell them apart
+    net = agent.networks["main"]
+    net.theta_target.copy_(store.theta * 0.9 + 0.01)
+    oracle32 = on.QNetOracle(cfg["obs"], A, cfg["dueling"], torch.float32)
+    oracle64 = on.QNetOracle(cfg["obs"], A, cfg["dueling"], torch.float64)
+    results = {}
+    for step in range(2):
+        online_named = store.export_named()
+        target_named = store.export_named(net.theta_target)
+        random.seed(10 + step)
+        np.random.seed(10 + step)
+        batch = agent.sample_batch()
+        cols = {k: v.cpu().numpy() for k, v in batch.columns.items()}
+        if step == 0:
+            opt32 = on.AdamTF([torch.from_numpy(v) for v in online_named.values()], 2.5e-4, 0.9, 0.99, 1e-4)
+        loss, losses, gnorm = agent.learn_from_batch(batch)
+        torch.cuda.synchronize()
+        ob = dict(states=cols["state:observation"], next_states=cols["next_state:observation"],
+                  actions=cols["action"], rewards=cols["reward"], game_overs=cols["game_over"].astype(bool),
+                  weights=cols["weight32"] if cfg["per"] else None)
+        ref = on.dqn_learn_step(oracle32, oracle32.cast(online_named), oracle32.cast(target_named), opt32, ob, 0.99,
+                                cfg["huber"], cfg["double"], cfg["clip"])
+        opt64 = on.AdamTF([torch.from_numpy(v).double() for v in online_named.values()], 2.5e-4, 0.9, 0.99, 1e-4,
+                          dtype=torch.float64)
+        ref64 = on.dqn_learn_step(oracle64, oracle64.cast(online_named), oracle64.cast(target_named), opt64, ob, 0.99,
+                                  cfg["huber"], cfg["double"], cfg["clip"])
+        close(net.online_s.q.cpu().numpy(), ref["q_online"], name="q_online")
+        close(agent.targets.cpu().numpy(), ref["targets"], name="targets")
+        close(agent.td_err.cpu().numpy(), ref["td_errors"], name="td_errors")
+        close(loss, ref["loss"], name="loss")
+        close(gnorm, ref["grad_norm"], name="grad_norm")
+        got_grads = store.export_named(store.grad)
+        for name in ref["grads"]:
+            want = ref["grads"][name].numpy()
+            close(got_grads[name], want, name="grad " + name)
+            # closer to (or as close as) the fp32 oracle is to the fp64 evaluation, with slack 4
+            e_ours = np.abs(got_grads[name] - ref64["grads"][name].numpy()).max()
+            e_orc = np.abs(want - ref64["grads"][name].numpy()).max()
+            assert e_ours <= 4 * e_orc + 1e-7 * (np.abs(want).max() + 1e-30), (name, e_ours, e_orc)
+        got_params = store.export_named()
+        for name in ref["new_params"]:
+            close(got_params[name], ref["new_params"][name].numpy(), name="param " + name)
+        results[step] = loss
+    # PER priorities were updated with the pre-update TD errors of the last batch (value_optimization_agent.py:74-80)
+    if cfg["per"]:
+        from oracle import memory as om
+        idx = cols["idx"]
+        leaves = agent.memory.sum_tree.cpu().numpy()[agent.memory.power_of_2_size - 1:]
+        td = agent.td_err.cpu().numpy()
+        last = {int(i): k for k, i in enumerate(idx)}       # last writer wins
+        for i, k in last.items():
+            assert leaves[i] == (td[k] + 1e-6) ** 0.6
+
+
+def test_target_network_cadence_and_polyak():
+    from coach_b200.base_parameters import TrainingSteps
+    agent = _make_agent((4,), 2, 8, False, False, False)
+    agent.ap.algorithm.num_steps_between_copying_online_weights_to_target = TrainingSteps(3)
+    agent.ap.algorithm.num_consecutive_playing_steps.num_steps = 1
+    rng = np.random.RandomState(0)
+    n = 64
+    agent.memory.store_columns({"state:observation": rng.randn(n, 4).astype(np.float32),
+                                "next_state:observation": rng.randn(n, 4).astype(np.float32),
+                                "action": rng.randint(0, 2, n).astype(np.int64), "reward": rng.randn(n),
+                                "game_over": np.zeros(n, np.uint8)})
+    net = agent.networks["main"]
+    synced = []
+    for step in range(7):
+        agent.total_steps_counter += 1
+        agent.train()
+        synced.append(bool(torch.equal(net.theta, net.theta_target)))
+    assert synced == [False, False, True, False, False, True, False]

@@ -33,6 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--capacity", type=int, default=1 << 18)
     ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--quick", action="store_true", help="a few launches only (for ncu)")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda")
@@ -104,22 +105,83 @@ def main():
         o_s.copy_(state[:B])
         o_n.copy_(nstate[:B])
 
+    one = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def tiny():
+        _lib.check(lib.cb200_per_priorities_device(one.data_ptr(), 1, 1e-6, 0.6, one.data_ptr(), one.data_ptr(), None,
+                                                   None))
+
+    # burst timing: NB back-to-back launches on rotating inputs/outputs (outputs total > L2), one event pair
+    NB = 16
+    us_ = [torch.rand(B, dtype=torch.float64, device=dev) for _ in range(NB)]
+    outs = []
+    for _ in range(NB):
+        bs, bn = torch.empty_like(o_s), torch.empty_like(o_n)
+        outs.append((bs, bn, _lib.make_columns([(state.data_ptr(), bs.data_ptr(), row),
+                                                (nstate.data_ptr(), bn.data_ptr(), row),
+                                                (action.data_ptr(), o_a.data_ptr(), 8),
+                                                (reward.data_ptr(), o_r.data_ptr(), 8),
+                                                (done.data_ptr(), o_d.data_ptr(), 1)])))
+
+    def burst(kind):
+        def run():
+            for k in range(NB):
+                if kind == "fused":
+                    _lib.check(lib.cb200_per_sample_gather(trees[0].data_ptr(), trees[1].data_ptr(), size,
+                                                           us_[k].data_ptr(), B, 2 * cap, 0.4, idx.data_ptr(),
+                                                           w.data_ptr(), w32.data_ptr(), outs[k][2][0], outs[k][2][1],
+                                                           None))
+                elif kind == "sample":
+                    _lib.check(lib.cb200_per_sample(trees[0].data_ptr(), trees[1].data_ptr(), size,
+                                                    us_[k].data_ptr(), B, 2 * cap, 0.4, idx.data_ptr(), w.data_ptr(),
+                                                    w32.data_ptr(), None))
+                elif kind == "tiny":
+                    tiny()
+                elif kind == "update":
+                    update()
+                else:
+                    outs[k][0].copy_(state[k * B:(k + 1) * B])
+                    outs[k][1].copy_(nstate[k * B:(k + 1) * B])
+        return run
+
     sample_only()
-    for name, fn in (("per_sample", sample_only), ("gather", gather_only), ("per_update(+prio)", update),
+    if args.quick:
+        lib.cb200_tune(b"gather_stages", 0)
+        lib.cb200_tune(b"gather_ctas_per_sm", 4)
+        for _ in range(8):
+            flush.fill_(1)
+            fused()
+            update()
+        torch.cuda.synchronize()
+        return
+    for kind in ("tiny", "sample", "update", "torch_copy", "fused"):
+        med, mn, mean = timed(burst(kind), flush, iters=10, warmup=2)
+        print(json.dumps({"burst_of_16": kind, "us_per_call_median": round(med / NB, 2),
+                          "us_per_call_min": round(mn / NB, 2)}))
+    for name, fn in (("tiny_launch_baseline", tiny), ("per_sample", sample_only), ("gather", gather_only), ("per_update(+prio)", update),
                      ("torch_contiguous_copy_same_bytes", torch_copy)):
         med, mn, mean = timed(fn, flush)
         print(json.dumps({"kernel": name, "us_median": round(med, 2), "us_min": round(mn, 2)}))
-    for stages in (2, 4, 6, 8, 12):
-        for cps in (1, 2, 3, 4):
-            if stages * cps * 8192 > 220 * 1024:
-                continue
-            lib.cb200_tune(b"gather_stages", stages)
+    for persist in (0, 1):
+        if persist:
+            # top 17 levels of the sum tree (2^17 doubles = 1 MiB) + min-tree root stay L2 resident
+            rc = lib.cb200_l2_persist(trees[0].data_ptr(), (1 << 17) * 8, None)
+            print(json.dumps({"l2_persist_rc": rc}))
+        for cps in (1, 2, 3, 4, 6, 8):
+            lib.cb200_tune(b"gather_stages", 0)
             lib.cb200_tune(b"gather_ctas_per_sm", cps)
             med, mn, mean = timed(fused, flush)
-            print(json.dumps({"kernel": "per_sample_gather", "stages": stages, "ctas_per_sm": cps,
+            bmed, bmn, _ = timed(burst("fused"), flush, iters=8, warmup=2)
+            print(json.dumps({"kernel": "per_sample_gather", "l2_persist": persist, "ctas_per_sm": cps,
                               "us_median": round(med, 2), "us_min": round(mn, 2),
-                              "GBps_median": round(alg_bytes / med / 1e3, 1),
-                              "frac_of_measured_hbm": round(alg_bytes / med / 1e3 / hbm, 3)}))
+                              "burst_us_per_call": round(bmed / NB, 2),
+                              "GBps_burst": round(alg_bytes / (bmed / NB) / 1e3, 1),
+                              "frac_of_measured_hbm_burst": round(alg_bytes / (bmed / NB) / 1e3 / hbm, 3)}))
+        bmed, _, _ = timed(burst("sample"), flush, iters=8, warmup=2)
+        print(json.dumps({"burst_of_16": "sample", "l2_persist": persist, "us_per_call_median": round(bmed / NB, 2)}))
+        bmed, _, _ = timed(burst("update"), flush, iters=8, warmup=2)
+        print(json.dumps({"burst_of_16": "update", "l2_persist": persist, "us_per_call_median": round(bmed / NB, 2)}))
+    lib.cb200_l2_persist(None, 0, None)
 
 
 if __name__ == "__main__":
