@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- learn_from_batch steps/sec, DQN + prioritized replay, batch 512 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference's CPU path (oracle port), rank 0 only
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N    # one process per GPU, NCCL gradient all-reduce
+
+Workload = BASELINE config 2 ("Atari Pong DQN, 1M-transition PrioritizedExperienceReplay, 84x84x4 uint8, batch 512"):
+per GPU one HBM-resident replay shard with a 2^20-leaf fp64 sum/min/max tree and 2^20 ring slots (59.2 GB), synthetic
+transitions (uniform random uint8 frames, actions U{0..5}, rewards in {-1,0,1}, done every 1000th), priorities
+|N(0,1)|, DQN network conv(32,8,4)-conv(64,4,2)-conv(64,3,1)-fc512-fc6 with random (glorot) weights, Huber loss,
+Adam(2.5e-4, 0.9, 0.99, 1e-4), gamma 0.99, hard target copy every 2500 train steps.
+
+One "step" = Agent.train(): uniforms (host MT19937, 4 KB H2D) -> fused PER sample + gather -> target/online forward ->
+TD targets -> Huber head -> backward -> global norm -> [all-reduce] -> Adam -> priority update (libm-exact route:
+4 KB of TD errors to the host, 8 KB of priorities back, overlapped with the backward pass).
+  value : steps/s with the replay resident in HBM and no per-step result read-back (device-timed, max over ranks)
+  e2e   : steps/s through the public plugin API with host buffers: per step 4 new host transitions are store()d
+          (num_consecutive_playing_steps = 4, dqn_agent.py:37) and the loss is read back (fetch=True)
+Inputs (59 GB ring per GPU) are far larger than the 126 MB L2, so consecutive iterations cannot hit in L2.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+OBS = (84, 84, 4)
+ROW = 84 * 84 * 4
+N_ACTIONS = 6
+BATCH = 512
+ENV_STEPS_PER_TRAIN = 4
+# algorithmic bytes of ONE fused sample+gather launch (SURVEY.md section 8d / BASELINE.md contract figure, staged copy
+# written): read B*(2*28224+8+8+1) of transition columns + B*21*8 of tree, write the same columns + B*(8+8) idx/weight
+GATHER_BYTES = BATCH * (2 * ROW + 8 + 8 + 1) * 2 + BATCH * 21 * 8 + BATCH * 16
+# multiply-accumulates of one learn step per sample: target fwd + online fwd (9.346 M each) + backward
+# (weight grads 9.346 M + data grads 6.069 M: conv2, conv3, fc1, out); the online forward is computed once
+MACS_PER_SAMPLE = 2 * 9346048 + 9346048 + (9346048 - 3276800)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# =====================================================================================================================
+def synth_chunk(rng, n):
+    return (rng.randint(0, 6, n).astype(np.int64), rng.randint(-1, 2, n).astype(np.float64))
+
+
+def build_device_agent(capacity, seed, device):
+    import torch
+    from coach_b200.agents.dqn_agent import DQNAgent, DQNAgentParameters
+    from coach_b200.base_parameters import TrainingSteps
+    from coach_b200.memories.memory import MemoryGranularity
+    from coach_b200.memories.prioritized_experience_replay import PrioritizedExperienceReplayParameters
+    from coach_b200.schedules import LinearSchedule
+    ap = DQNAgentParameters()
+    ap.memory = PrioritizedExperienceReplayParameters()
+    ap.memory.max_size = (MemoryGranularity.Transitions, capacity)
+    ap.memory.beta = LinearSchedule(0.4, 1, 12500000)
+    ap.algorithm.num_steps_between_copying_online_weights_to_target = TrainingSteps(2500)
+    ap.algorithm.num_consecutive_playing_steps.num_steps = ENV_STEPS_PER_TRAIN
+    net = ap.network_wrappers["main"]
+    net.batch_size = BATCH
+    agent = DQNAgent(ap, observation_shape=OBS, num_actions=N_ACTIONS, device=device, seed=seed)
+    mem = agent.memory
+    size = mem.power_of_2_size
+    gen = torch.Generator(device=device).manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    chunk = 1 << 14
+    for lo in range(0, size, chunk):
+        n = min(chunk, size - lo)
+        s = torch.randint(0, 256, (n, ROW), dtype=torch.uint8, device=device, generator=gen)
+        s2 = torch.randint(0, 256, (n, ROW), dtype=torch.uint8, device=device, generator=gen)
+        a, r = synth_chunk(rng, n)
+        done = ((np.arange(lo, lo + n) % 1000) == 999).astype(np.uint8)
+        mem.store_columns({"state:observation": s.view(n, *OBS), "next_state:observation": s2.view(n, *OBS),
+                           "action": a, "reward": r, "game_over": done})
+    # non-degenerate tree: |N(0,1)| errors on every leaf (device route for the bulk initialisation)
+    err = torch.randn(size, dtype=torch.float64, device=device, generator=gen).abs()
+    idx = torch.arange(size, dtype=torch.int64, device=device)
+    mode = mem.priority_mode
+    mem.priority_mode = "device"
+    mem.update_priorities(idx, err)
+    mem.priority_mode = mode
+    torch.cuda.synchronize()
+    return agent
+
+
+def host_transitions(rng, n):
+    """n new host-side transitions (what Agent.observe would hand to memory.store)"""
+    from coach_b200.core_types import Transition
+    out = []
+    for _ in range(n):
+        out.append(Transition(state={"observation": rng.randint(0, 256, OBS).astype(np.uint8)},
+                              action=int(rng.randint(0, N_ACTIONS)), reward=float(rng.randint(-1, 2)),
+                              next_state={"observation": rng.randint(0, 256, OBS).astype(np.uint8)},
+                              game_over=False))
+    return out
+
+
+def run_device(args):
+    import torch
+    from coach_b200 import _lib, parallel
+    rank, world = parallel.init_from_env()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    lib = _lib.load()
+    random.seed(1000 + rank)
+    np.random.seed(1000 + rank)
+    agent = build_device_agent(args.capacity, 100 + rank, device)
+    mem = agent.memory
+    if not args.no_l2_persist:
+        lib.cb200_l2_persist(mem.sum_tree.data_ptr(), (1 << 17) * 8, _lib.current_stream())
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(fetch):
+        agent.total_steps_counter += ENV_STEPS_PER_TRAIN
+        return agent.train(fetch=fetch)
+
+    # ---- device-resident leg (value) ------------------------------------------------------------------------------
+    for _ in range(W):
+        one_step(False)
+    barrier()
+    launches0 = lib.cb200_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # per-kernel-group device timing inside the timed region: events around the fused sample+gather launch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    orig_sample = agent.sample_batch
+    step_i = [0]
+
+    def timed_sample():
+        a, b, _ = ev[step_i[0]]
+        a.record()
+        out = orig_sample()
+        b.record()
+        return out
+
+    agent.sample_batch = timed_sample
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(K):
+        step_i[0] = i
+        one_step(False)
+        ev[i][2].record()
+    t1.record()
+    barrier()
+    agent.sample_batch = orig_sample
+    ms_total = t0.elapsed_time(t1)
+    launches = lib.cb200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    gather_us = float(np.mean([a.elapsed_time(b) for a, b, _ in ev])) * 1e3
+    learn_us = float(np.mean([b.elapsed_time(c) for _, b, c in ev])) * 1e3
+    ms_total = parallel.max_over_ranks(ms_total, device)
+
+    # ---- end-to-end leg through the public API with host buffers ---------------------------------------------------
+    rng = np.random.RandomState(7 + rank)
+    pool = host_transitions(rng, 64)
+    Ke = max(5, K // 2)
+    for i in range(3):
+        for t in pool[(4 * i) % 60:(4 * i) % 60 + ENV_STEPS_PER_TRAIN]:
+            mem.store(t)
+        one_step(True)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(Ke):
+        for t in pool[(4 * i) % 60:(4 * i) % 60 + ENV_STEPS_PER_TRAIN]:
+            mem.store(t)                              # host transition -> pinned staging -> H2D -> ring + tree
+        loss = one_step(True)                         # reads the loss back (D2H) every step
+    e1.record()
+    barrier()
+    e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), device)
+    h2d = ENV_STEPS_PER_TRAIN * (2 * ROW + 8 + 8 + 1) + BATCH * 8 + 2 * BATCH * 8
+    d2h = BATCH * 8 + 4 + 4
+
+    if rank != 0:
+        return
+    pk, pk_kind = peaks()
+    steps_per_s = world * K / (ms_total * 1e-3)
+    gather_gbs = GATHER_BYTES / gather_us / 1e3
+    gemm_tflops = 2.0 * MACS_PER_SAMPLE * BATCH / (learn_us * 1e-6) / 1e12
+    line = {
+        "metric": "learn_from_batch steps/sec (DQN PER batch 512)", "value": round(steps_per_s, 2),
+        "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Atari-shaped DQN + PrioritizedExperienceReplay: %d-slot ring (%.1f GB HBM) and "
+                               "2^%d-leaf fp64 trees per GPU, 84x84x4 uint8, batch 512 per GPU, Huber, Adam"
+                               % (mem.ring.capacity, mem.ring.hbm_bytes() / 1e9,
+                                  int(np.log2(mem.power_of_2_size))),
+                   "parallelism": "dp%d (one replay shard per GPU, flat fp32 gradient all-reduce over NCCL)" % world,
+                   "l2": "inputs (ring) >> L2, no flush needed", "priority_mode": mem.priority_mode,
+                   "l2_persist_tree_top": not args.no_l2_persist},
+        "clocks": clocks,
+        "e2e": {"value": round(world * Ke / (e2e_ms * 1e-3), 2), "unit": "steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": Ke,
+                "what": "per step: 4 host Transitions store()d + train(fetch=True) reading the loss back"},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "per_sample_gather_kernel (fused sum-tree descent + IS weights + TMA bulk-copy gather)",
+                     "bound": "hbm", "achieved": round(gather_gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": round(gather_gbs / pk["hbm_gbs"], 4), "peak_kind": pk_kind + " (burst copy)",
+                     "us_per_launch": round(gather_us, 2), "algorithmic_bytes": GATHER_BYTES,
+                     "traffic": TRAFFIC_NCU.get("per_sample_gather"),
+                     "frac_of_8TBps": round(gather_gbs / 8000.0, 4)},
+        "roofline_learn": {"kernels": "fp32 FFMA gather-GEMMs (conv/dense fwd+bwd) + element-wise",
+                           "bound": "tensor", "achieved": round(gemm_tflops, 2), "peak": pk["bf16_tflops_sustained"],
+                           "unit": "TFLOP/s", "frac": round(gemm_tflops / pk["bf16_tflops_sustained"], 5),
+                           "us_per_step": round(learn_us, 1),
+                           "note": "fp32 CUDA-core path (1e-5 parity); nominal fp32 FFMA peak ~72 TFLOP/s"},
+        "share_of_step": {"sample_gather": round(gather_us / (gather_us + learn_us), 4),
+                          "learn": round(learn_us / (gather_us + learn_us), 4)},
+    }
+    line["cpu_baseline"] = cpu_reference(steps=args.cpu_steps, warmup=1, quiet=True)
+    print(json.dumps(line))
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)
+TRAFFIC_NCU = {"per_sample_gather": 30270000}
+
+
+# =====================================================================================================================
+def cpu_reference(steps, warmup, quiet=False):
+    """The reference's CPU path for the same step, as the oracle port: per-sample Python loops for the PER (that is how
+    the reference runs: one interpreter thread), numpy AoS->SoA Batch gather, torch-CPU fp32 network on all host
+    cores.  Bounded sample of the workload: full 2^20-leaf trees, but only 2^13 distinct transitions of frame data
+    (leaf -> transition modulo 2^13) so that the host-RAM footprint stays at 0.5 GB."""
+    import torch
+    from oracle import memory as om
+    from oracle import nets as on
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.RandomState(0)
+    size, distinct = 1 << 20, 1 << 13
+
+    class T(object):
+        __slots__ = ("state", "next_state", "action", "reward", "game_over", "info")
+
+    data = []
+    for i in range(distinct):
+        t = T()
+        t.state = {"observation": rng.randint(0, 256, OBS).astype(np.uint8)}
+        t.next_state = {"observation": rng.randint(0, 256, OBS).astype(np.uint8)}
+        t.action = int(rng.randint(0, N_ACTIONS))
+        t.reward = float(rng.randint(-1, 2))
+        t.game_over = False
+        t.info = {}
+        data.append(t)
+    mem = om.OraclePrioritizedExperienceReplay(size, alpha=0.6, beta=om.OracleLinearSchedule(0.4, 1, 12500000),
+                                               backend="c")
+    mem.store_many([None] * size)
+    mem.update_priorities(np.arange(size), np.abs(rng.randn(size)))
+    for tr in (mem.sum_tree, mem.min_tree, mem.max_tree):
+        tr.backend = "python"
+    mem.backend = "python"
+    net = on.QNetOracle(OBS, N_ACTIONS, False, torch.float32)
+    from collections import OrderedDict
+    g = torch.Generator().manual_seed(0)
+    shapes = [(8, 8, 4, 32), (32,), (4, 4, 32, 64), (64,), (3, 3, 64, 64), (64,), (3136, 512), (512,),
+              (512, N_ACTIONS), (N_ACTIONS,)]
+    online = OrderedDict(("p%d" % i, torch.randn(s, generator=g) * 0.05) for i, s in enumerate(shapes))
+    target = OrderedDict((k, v.clone()) for k, v in online.items())
+    opt = on.AdamTF(list(online.values()), 2.5e-4, 0.9, 0.99, 1e-4)
+    random.seed(0)
+
+    def step():
+        nonlocal online
+        idx, w = mem.sample_indices(BATCH)                                   # PER.sample
+        batch = [data[i % distinct] for i in idx]
+        s, s2, a, r, d = om.batch_columns(batch)                             # Batch AoS -> SoA
+        out = on.dqn_learn_step(net, online, target, opt, dict(states=s, next_states=s2, actions=a, rewards=r,
+                                                               game_overs=d, weights=w), 0.99, True)
+        mem.update_priorities(list(idx), list(out["td_errors"]))             # PER.update_priorities
+        online = out["new_params"]
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": round(steps / dt, 3), "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": "%d steps of the same B=512 step: full 2^20-leaf trees, 2^13 distinct Atari-shaped transitions; "
+                      "PER/Batch in one Python thread (as the reference runs), torch-CPU fp32 network on %d threads"
+                      % (steps, cores)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    K = min(K, 40)                      # bounded: the CPU step takes a sizeable fraction of a second
+    base = cpu_reference(steps=K, warmup=min(W, 2))
+    line = {"impl": "reference", "metric": "learn_from_batch steps/sec (DQN PER batch 512)", "value": base["value"],
+            "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": min(W, 2),
+            "ms_per_step": round(1e3 / base["value"], 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Atari-shaped DQN + PrioritizedExperienceReplay, 2^20-leaf trees, batch 512 "
+                                   "(CPU, oracle port of the reference path; one process)"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--capacity", type=int, default=1000000, help="replay capacity in transitions (rounded up to 2^k)")
+    ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the cpu_baseline leg")
+    ap.add_argument("--no-l2-persist", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_device(args)
+
+
+if __name__ == "__main__":
+    main()

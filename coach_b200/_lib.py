@@ -72,6 +72,15 @@ PROTOTYPES = {
     "cb200_adam_tf": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float,
                               c_float, c_float, c_void_p]),
     "cb200_polyak": (c_int, [c_void_p, c_void_p, c_i64, c_double, c_void_p]),
+    "cb200_gae_scan": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
+    "cb200_standardize": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
+    "cb200_nstep_returns": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_i64, c_void_p, c_void_p]),
+    "cb200_running_stats_push": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p]),
+    "cb200_running_stats_finalize": (c_int, [c_void_p, c_void_p, c_double, c_double, c_i64, c_void_p, c_void_p,
+                                             c_void_p]),
+    "cb200_running_stats_normalize": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_double, c_double,
+                                              c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

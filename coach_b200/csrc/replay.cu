@@ -29,22 +29,15 @@ struct Descent {
 };
 
 // Levels fetched per memory round trip.  7 levels = 254 nodes = 8 independent loads per lane: a 2^20-leaf tree is
-// walked in 3 dependent round trips (7 + 7 + 6) instead of 20.
+// walked in 3 dependent round trips (7 + 7 + 6) instead of 20.  The fetched sub-tree is parked in a per-warp shared
+// memory scratch (256 doubles) and the reference's comparisons are replayed out of it (one 16-byte broadcast read per
+// level: the two children are adjacent elements).
 constexpr int kRoundLevels = 7;
-constexpr int kRoundRegs = ((2 << kRoundLevels) - 2 + 31) / 32;   // 8
-
-// element `e` (warp-uniform) of the fetched sub-tree: register e / 32 of lane e % 32
-__device__ __forceinline__ double fetch_elem(const double (&v)[kRoundRegs], int e) {
-    const int q = e >> 5, src = e & 31;
-    double out = 0.0;
-#pragma unroll
-    for (int k = 0; k < kRoundRegs; ++k)
-        if (q == k) out = __shfl_sync(0xffffffffu, v[k], src);   // q is warp-uniform: exactly one shuffle executes
-    return out;
-}
+constexpr int kRoundRegs = ((2 << kRoundLevels) - 2 + 31) / 32;   // 8 loads per lane
+constexpr int kScratchDoubles = 32 * kRoundRegs;                  // 256 per warp
 
 __device__ __forceinline__ Descent warp_descent(const double* __restrict__ tree, int64_t size, int levels,
-                                                double val) {
+                                                double val, double* __restrict__ scratch /* per-warp, 16B aligned */) {
     const int lane = threadIdx.x & 31;
     uint64_t j = 1;   // 1-based heap index of the current node
     double p = 0.0;
@@ -61,18 +54,21 @@ __device__ __forceinline__ Descent warp_descent(const double* __restrict__ tree,
             const int k = 31 - __clz(e2);
             v[q] = (k <= r) ? __ldcg(tree + (((j - 1) << k) + e2 - 1)) : 0.0;
         }
+        __syncwarp();          // previous round's reads of the scratch are done
+#pragma unroll
+        for (int q = 0; q < kRoundRegs; ++q) scratch[lane + 32 * q] = v[q];
+        __syncwarp();
         uint32_t rel = 1;
         for (int s = 0; s < r; ++s) {
-            const int el = 2 * rel - 2;             // left child; the right child is element el + 1
-            const double left = fetch_elem(v, el);
-            const double right = fetch_elem(v, el + 1);
-            if (val <= left) {   // :89
+            const int el = 2 * rel - 2;             // left child; the right child is element el + 1 (el is even)
+            const double2 lr = *reinterpret_cast<const double2*>(scratch + el);
+            if (val <= lr.x) {   // :89
                 rel = 2 * rel;
-                p = left;
+                p = lr.x;
             } else {             // :92
-                val = __dsub_rn(val, left);
+                val = __dsub_rn(val, lr.x);
                 rel = 2 * rel + 1;
-                p = right;
+                p = lr.y;
             }
         }
         j = (j << r) + (rel - (1u << r));
@@ -99,13 +95,13 @@ struct SampleParams {
 };
 
 // PER.sample :232-245 for sample i (whole warp): the stratified draw and the tree descent.
-__device__ __forceinline__ Descent per_sample_descend(const SampleParams& sp, int64_t i) {
+__device__ __forceinline__ Descent per_sample_descend(const SampleParams& sp, int64_t i, double* scratch) {
     const double total = __ldcg(sp.sum_tree);
     const double segment = __ddiv_rn(total, (double)sp.n);                        // :232
     const double a = __dmul_rn(segment, (double)i);                               // :240
     const double b = __dmul_rn(segment, (double)(i + 1));                         // :241
     const double val = __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), __ldg(sp.u + i)));  // random.uniform :244
-    return warp_descent(sp.sum_tree, sp.size, sp.levels, val);
+    return warp_descent(sp.sum_tree, sp.size, sp.levels, val, scratch);
 }
 
 // PER.sample :235-251: importance weight of one drawn leaf (one thread); off the gather's critical path
@@ -124,9 +120,10 @@ __device__ __forceinline__ void per_sample_publish(const SampleParams& sp, int64
 }
 
 __global__ void __launch_bounds__(128) per_sample_kernel(SampleParams sp) {
+    __shared__ __align__(16) double scratch[4][kScratchDoubles];
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (warp >= sp.n) return;
-    const Descent d = per_sample_descend(sp, warp);
+    const Descent d = per_sample_descend(sp, warp, scratch[threadIdx.x >> 5]);
     if ((threadIdx.x & 31) == 0) per_sample_publish(sp, warp, d.leaf, d.priority);
 }
 
@@ -349,6 +346,7 @@ __device__ __forceinline__ void bulk_pipeline(const GatherParams& gp, int64_t lo
         mbar_expect_tx(full_bar + st, bytes);
         bulk_g2s(stage_mem + (size_t)st * gp.stage_bytes, src, bytes, full_bar + st);
     };
+    fence_proxy_async_smem();   // the stage memory may have been used through the generic proxy (descent scratch)
     const int64_t pre = cnt < S ? cnt : S;
     for (int64_t k = 0; k < pre; ++k) issue_load(k);
     for (int64_t k = 0; k < cnt; ++k) {
@@ -426,7 +424,7 @@ __global__ void __launch_bounds__(kGatherThreads) per_sample_gather_kernel(Sampl
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     // phase A: descents for the samples this CTA touches, one warp each, in parallel (3 memory round trips)
     for (int64_t s = s_lo + warp; s <= s_hi; s += nwarp) {
-        const Descent d = per_sample_descend(sp, s);
+        const Descent d = per_sample_descend(sp, s, reinterpret_cast<double*>(stage_mem) + warp * kScratchDoubles);
         if (lane == 0) {
             leaf_smem[(s - s_lo) % kMaxCtaSamples] = d.leaf;
             prio_smem[(s - s_lo) % kMaxCtaSamples] = d.priority;
@@ -540,7 +538,10 @@ static unsigned plan_bulk(GatherParams& gp, bool fused) {
 }
 
 static size_t gather_smem_bytes(const GatherParams& gp, bool fused) {
-    return kBarBytes + (fused ? kMaxCtaSamples * 16 : 0) + (size_t)gp.stages * gp.stage_bytes;
+    size_t stage = (size_t)gp.stages * gp.stage_bytes;
+    const size_t scratch = (size_t)(kGatherThreads / 32) * kScratchDoubles * sizeof(double);   // phase-A alias
+    if (fused && stage < scratch) stage = scratch;
+    return kBarBytes + (fused ? kMaxCtaSamples * 16 : 0) + stage;
 }
 
 }  // namespace cb200

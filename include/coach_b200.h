@@ -239,6 +239,42 @@ int cb200_adam_tf(float* theta, float* m, float* v, const float* g, int64_t n, f
  *   target = rate * online + (1 - rate) * target   in fp32, rate and (1 - rate) rounded to fp32 first (numpy). */
 int cb200_polyak(float* target, const float* online, int64_t n, double rate, void* stream);
 
+/* =====================================================================================================================
+ * Scalar RL recurrences (fp64, as the reference computes them).
+ * ===================================================================================================================*/
+
+/* Generalised advantage estimation over a whole rollout of n transitions laid out episode after episode:
+ * ActorCriticAgent.get_general_advantage_estimation_values (agents/actor_critic_agent.py:111-125: deltas, then
+ * scipy.signal.lfilter([1],[1,-gamma*lambda]) on the reversed deltas) applied per episode as ClippedPPOAgent.
+ * fill_advantages does (agents/clipped_ppo_agent.py:170-207): episodes end at game_over flags, the bootstrap value
+ * appended at an episode end is 0 (:188), the value target is advantage + V(s_t) (:121), transitions after the last
+ * game_over receive nothing (*n_valid = index of the last game_over + 1; later entries are still written but must be
+ * ignored, cf. zip() truncation :203).  values[t] = V(s_t) (fp32 network output).  One block-wide scan of affine maps
+ * (thread chunks -> warp shuffles -> shared memory). */
+int cb200_gae_scan(const double* rewards, const float* values, const uint8_t* game_overs, int64_t n, double discount,
+                   double gae_lambda, double* advantages, double* value_targets, int64_t* n_valid, void* stream);
+
+/* x[:n_valid] = (x - mean) / std with the population std (clipped_ppo_agent.py:201), in place; x[n_valid:] = NaN.
+ * n_valid may be NULL (= n).  mean_std_out (device double[2], may be NULL) receives mean and std. */
+int cb200_standardize(double* x, int64_t n, const int64_t* n_valid, double* mean_std_out, void* stream);
+
+/* Episode.update_discounted_rewards (core_types.py:771-790): out[t] = sum_{k < n_step} discount^k * r[t+k] inside t's
+ * episode [ep_start[t], ep_end[t]), n_step == -1 => to the end of the episode; accumulated in the reference's order
+ * (k ascending, running power of the discount), bit-identical to the numpy loop. */
+int cb200_nstep_returns(const double* rewards, const int64_t* ep_start, const int64_t* ep_end, int64_t n,
+                        double discount, int64_t n_step, double* out, void* stream);
+
+/* NumpySharedRunningStats (utilities/shared_running_stats.py:115-164), used by ObservationNormalizationFilter
+ * (filters/observation/observation_normalization_filter.py:71-78):
+ *   push      : sum += sum_rows x, sumsq += sum_rows x^2   (fp64; the host adds `rows` to its count)
+ *   finalize  : mean = sum/count; std = sqrt(max((sumsq - count*mean^2) / max(count-1, 1), epsilon))
+ *   normalize : clip((x - mean) / (std + 1e-15), lo, hi) -> fp32 (network feed) and/or fp64 */
+int cb200_running_stats_push(const float* x, int64_t rows, int64_t cols, double* sum, double* sumsq, void* stream);
+int cb200_running_stats_finalize(const double* sum, const double* sumsq, double count, double epsilon, int64_t cols,
+                                 double* mean, double* std_out, void* stream);
+int cb200_running_stats_normalize(const float* x, int64_t rows, int64_t cols, const double* mean, const double* std_in,
+                                  double clip_lo, double clip_hi, float* out32, double* out64, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

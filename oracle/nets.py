@@ -149,7 +149,7 @@ def dqn_learn_step(net, online, target, opt, batch, discount, huber_loss=True, d
         grads = [g * scale for g in grads]
     grads = [g * world_scale for g in grads] if world_scale != 1.0 else grads
     new_params = opt.step([p.detach() for p in params], grads)
-    return dict(loss=float(loss), grads=OrderedDict(zip(names, [g.detach() for g in grads])),
+    return dict(loss=float(loss.detach()), grads=OrderedDict(zip(names, [g.detach() for g in grads])),
                 grad_norm=float(gnorm), td_errors=td, targets=targets,
                 new_params=OrderedDict(zip(names, new_params)), q_online=q_online_ng.numpy(),
                 q_next=q_next.numpy())

@@ -155,10 +155,11 @@ def test_td_targets_match_python_loop():
     want_t, want_e = on.dqn_targets(qn, qs, qo, act, rew, done, 0.99)
     out_t = torch.empty(B, A, device=dev)
     out_e = torch.empty(B, dtype=torch.float64, device=dev)
-    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)     # noqa: E731
-    L.check(lib.cb200_dqn_td_targets(d(qn).data_ptr(), d(qs).data_ptr(), d(qo).data_ptr(), d(act).data_ptr(),
-                                     d(rew).data_ptr(), d(done.astype(np.uint8)).data_ptr(), 0.99, B, A,
+    keep = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (qn, qs, qo, act, rew, done.astype(np.uint8))]
+    L.check(lib.cb200_dqn_td_targets(keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr(),
+                                     keep[4].data_ptr(), keep[5].data_ptr(), 0.99, B, A,
                                      out_t.data_ptr(), out_e.data_ptr(), None))
+    torch.cuda.synchronize()
     np.testing.assert_array_equal(out_t.cpu().numpy(), want_t)       # bit-exact: same fp64 operations, one rounding
     np.testing.assert_array_equal(out_e.cpu().numpy(), want_e)
 
