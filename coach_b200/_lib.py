@@ -26,7 +26,8 @@ class GemmDesc(ctypes.Structure):
                 ("b", c_void_p), ("ldb", ctypes.c_int32), ("n", ctypes.c_int32),
                 ("c", c_void_p), ("ldc", ctypes.c_int32), ("bias", c_void_p), ("act", ctypes.c_int32),
                 ("mask_y", c_void_p), ("mask_act", ctypes.c_int32), ("c_rowmap", c_void_p),
-                ("accumulate", ctypes.c_int32), ("workspace", c_void_p), ("splits", ctypes.c_int32)]
+                ("accumulate", ctypes.c_int32), ("workspace", c_void_p), ("splits", ctypes.c_int32),
+                ("a_vec4", ctypes.c_int32), ("a_ones_col", ctypes.c_int32)]
 
 
 class Column(ctypes.Structure):
@@ -71,7 +72,14 @@ PROTOTYPES = {
     "cb200_scale": (c_int, [c_void_p, c_i64, c_float, c_void_p]),
     "cb200_adam_tf": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float,
                               c_float, c_float, c_void_p]),
+    "cb200_adam_tf_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float,
+                                  c_void_p, c_void_p]),
+    "cb200_add_i64": (c_int, [c_void_p, c_i64, c_void_p]),
     "cb200_polyak": (c_int, [c_void_p, c_void_p, c_i64, c_double, c_void_p]),
+    "cb200_ppo_continuous_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
+                                          ctypes.c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cb200_gather_at": (c_int, [ctypes.POINTER(Column), c_int, c_void_p, c_void_p, c_i64, c_void_p]),
+    "cb200_f64_to_f32": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
     "cb200_gae_scan": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
     "cb200_standardize": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),

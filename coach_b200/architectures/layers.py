@@ -7,8 +7,9 @@ conv kernels HWIO (= a row-major [KH*KW*Cin, N] matrix), dense kernels [in, out]
 
 Every contraction is ONE C-ABI call whose descriptor -- index tables included -- is built once per (layer, batch size)
 and reused every step: forward, weight gradient (A^T * dZ with a fixed-order split reduction over the batch*pixels
-axis), data gradient (dense: dZ * W^T; conv: transposed convolution in gather form, one call per stride-parity
-class, with the previous layer's activation derivative fused into the epilogue).
+axis; the bias gradient rides along as one extra output row when the bias gradient sits right behind the kernel
+gradient in the flat buffer), data gradient (dense: dZ * W^T; conv: transposed convolution in gather form, one call
+per stride-parity class, with the previous layer's activation derivative fused into the epilogue).
 """
 import ctypes
 
@@ -55,12 +56,10 @@ class GemmOp(object):
             setattr(self.desc, k, v)
         self.desc.splits = self.splits
         rows = self.desc.a_cols if self.desc.a_transposed else self.desc.a_rows
+        if self.desc.a_ones_col:
+            rows += 1
         if self.splits > 1:
             ws.require(self.splits * rows * self.desc.n)
-
-    def set_ptrs(self, **ptrs):
-        for k, v in ptrs.items():
-            setattr(self.desc, k, v.data_ptr() if torch.is_tensor(v) else v)
 
     def run(self):
         if self.splits > 1:
@@ -70,18 +69,32 @@ class GemmOp(object):
 
 def pick_splits(tiles, reduction, sm=148, min_chunk=128):
     """Split the reduction so that the grid has about two CTAs per SM, never below `min_chunk` per split."""
-    if tiles >= 2 * sm:
+    if tiles >= sm:          # one full wave already: the extra reduction pass would cost more than it saves
         return 1
     s = max(1, (2 * sm + tiles - 1) // tiles)
     s = min(s, max(1, reduction // min_chunk))
     return int(s)
 
 
-def _tiles(M, N):
+def _tiles(M, N, fast=True):
+    """CTA tiles of the kernel cb200_gemm will pick (csrc/nn.cu)."""
     if M <= 64:
         return ((M + 31) // 32) * ((N + 31) // 32)
+    if fast and N % 4 == 0:
+        if N <= 32:
+            return ((M + 255) // 256) * ((N + 31) // 32)
+        if N <= 64:
+            return ((M + 127) // 128) * ((N + 63) // 64)
+        return ((M + 127) // 128) * ((N + 127) // 128)
     bn = 32 if N <= 32 else 64
     return ((M + 127) // 128) * ((N + bn - 1) // bn)
+
+
+def _bias_rides_along(dw, db, K, N):
+    """True when the bias gradient is stored right behind the kernel gradient (flat ParamStore layout)."""
+    bm = 256 if N <= 32 else 128          # row tile of the kernel that will run; only use slack of the last tile
+    return (dw is not None and db is not None and N % 4 == 0 and K % 4 == 0 and K + 1 > 64 and K % bm != 0 and
+            db.data_ptr() == dw.data_ptr() + K * N * 4)
 
 
 # =====================================================================================================================
@@ -105,13 +118,20 @@ class Dense(object):
         K, N = self.K, self.N
         rowoff = _dev_i32(np.arange(B) * K, device)
         coloff = _dev_i32(np.arange(K), device)
-        common = dict(a_rowoff=rowoff, a_coloff=coloff, a_rows=B, a_cols=K)
-        self.fwd = GemmOp(lib, ws, a_src=x, a_lut=lut if x_is_u8 else None, a_transposed=0, b=w, ldb=N, n=N, c=y,
-                          ldc=N, bias=b, act=self.act, splits=pick_splits(_tiles(B, N), K), **common)
-        self.bwd_w = GemmOp(lib, ws, a_src=x, a_lut=lut if x_is_u8 else None, a_transposed=1, b=dy, ldb=N, n=N,
-                            c=dw, ldc=N, splits=pick_splits(_tiles(K, N), B), **common)
-        self.db_args = (dy, B, N, db)
-        ws.require(1024 * N)
+        vec = int(K % 4 == 0)
+        common = dict(a_rowoff=rowoff, a_coloff=coloff, a_rows=B, a_cols=K, a_vec4=vec, a_src=x,
+                      a_lut=lut if x_is_u8 else None)
+        self.fwd = GemmOp(lib, ws, a_transposed=0, b=w, ldb=N, n=N, c=y, ldc=N, bias=b, act=self.act,
+                          splits=pick_splits(_tiles(B, N, vec), K), **common)
+        self.bwd_w = None
+        self.db_args = None
+        if dw is not None and dy is not None:
+            ones = int(bool(vec) and _bias_rides_along(dw, db, K, N))
+            self.bwd_w = GemmOp(lib, ws, a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
+                                splits=pick_splits(_tiles(K + ones, N, vec), B), **common)
+            if not ones:
+                self.db_args = (dy, B, N, db)
+                ws.require(1024 * N)
         self.bwd_x = None
         if need_dx:
             self.wT = torch.empty((N, K), dtype=torch.float32, device=device)
@@ -119,9 +139,10 @@ class Dense(object):
             ro = _dev_i32(np.arange(B) * N, device)
             co = _dev_i32(np.arange(N), device)
             self.bwd_x = GemmOp(lib, ws, a_src=dy, a_rowoff=ro, a_coloff=co, a_rows=B, a_cols=N, a_transposed=0,
-                                b=self.wT, ldb=K, n=K, c=dx, ldc=K, mask_y=x if prev_act else None,
-                                mask_act=prev_act, accumulate=int(bool(dx_accumulate)),
-                                splits=pick_splits(_tiles(B, K), N))
+                                a_vec4=int(N % 4 == 0), b=self.wT, ldb=K, n=K, c=dx, ldc=K,
+                                mask_y=x if prev_act else None, mask_act=prev_act,
+                                accumulate=int(bool(dx_accumulate)),
+                                splits=pick_splits(_tiles(B, K, N % 4 == 0), N))
         self.lib, self.ws = lib, ws
 
     def forward(self):
@@ -130,8 +151,9 @@ class Dense(object):
     def backward(self):
         st = _lib.current_stream()
         self.bwd_w.run()
-        dy, B, N, db = self.db_args
-        _lib.check(self.lib.cb200_colsum(dy.data_ptr(), B, N, db.data_ptr(), self.ws.ptr(), st))
+        if self.db_args is not None:
+            dy, B, N, db = self.db_args
+            _lib.check(self.lib.cb200_colsum(dy.data_ptr(), B, N, db.data_ptr(), self.ws.ptr(), st))
         if self.bwd_x is not None:
             _lib.check(self.lib.cb200_transpose(self.w.data_ptr(), self.K, self.N, self.wT.data_ptr(), st))
             self.bwd_x.run()
@@ -168,14 +190,20 @@ class Conv2d(object):
         ky, kx, cc = np.meshgrid(np.arange(KH), np.arange(KW), np.arange(C), indexing="ij")
         coloff = ((ky * W + kx) * C + cc).reshape(-1)
         assert rowoff.max() + coloff.max() < 2 ** 31
+        vec = int(C % 4 == 0)          # (kx, c) runs are contiguous: groups of 4 channels never straddle a pixel
         common = dict(a_rowoff=_dev_i32(rowoff, device), a_coloff=_dev_i32(coloff, device), a_rows=M, a_cols=K,
-                      a_src=x, a_lut=lut if x_is_u8 else None)
+                      a_src=x, a_lut=lut if x_is_u8 else None, a_vec4=vec)
         self.fwd = GemmOp(lib, ws, a_transposed=0, b=w, ldb=N, n=N, c=y, ldc=N, bias=b, act=self.act,
-                          splits=pick_splits(_tiles(M, N), K), **common)
-        self.bwd_w = GemmOp(lib, ws, a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N,
-                            splits=pick_splits(_tiles(K, N), M, min_chunk=512), **common)
-        self.db_args = (dy, M, N, db)
-        ws.require(1024 * N)
+                          splits=pick_splits(_tiles(M, N, vec), K), **common)
+        self.bwd_w = None
+        self.db_args = None
+        if dw is not None and dy is not None:
+            ones = int(bool(vec) and _bias_rides_along(dw, db, K, N))
+            self.bwd_w = GemmOp(lib, ws, a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
+                                splits=pick_splits(_tiles(K + ones, N, vec), M, min_chunk=512), **common)
+            if not ones:
+                self.db_args = (dy, M, N, db)
+                ws.require(1024 * N)
         self.lib, self.ws = lib, ws
         self.w = w
         self.classes = []
@@ -204,13 +232,11 @@ class Conv2d(object):
                 wt = torch.empty((TA * TB * N, C), dtype=torch.float32, device=device)
                 op = GemmOp(lib, ws, a_src=dy, a_rowoff=_dev_i32(ro, device), a_coloff=_dev_i32(co, device),
                             a_rowinfo=_dev_i32(rinfo, device), a_colinfo=_dev_i32(cinfo, device), a_oh=OH, a_ow=OW,
-                            a_rows=B * IH * IW, a_cols=TA * TB * N, a_transposed=0, b=wt, ldb=C, n=C, c=dx, ldc=C,
+                            a_rows=B * IH * IW, a_cols=TA * TB * N, a_transposed=0, a_vec4=int(N % 4 == 0),
+                            b=wt, ldb=C, n=C, c=dx, ldc=C,
                             mask_y=x if prev_act else None, mask_act=prev_act, c_rowmap=_dev_i32(rowmap, device),
-                            splits=pick_splits(_tiles(B * IH * IW, C), TA * TB * N))
+                            splits=pick_splits(_tiles(B * IH * IW, C, N % 4 == 0), TA * TB * N))
                 self.classes.append((op, wt, _dev_i32(perm, device)))
-        # pixels no tap reaches (possible when S > KH) never occur for the Atari stack; dx is fully written
-        covered = all((H - py + S - 1) // S > 0 for py in range(S))
-        assert covered
 
     def forward(self):
         self.fwd.run()
@@ -218,8 +244,9 @@ class Conv2d(object):
     def backward(self):
         st = _lib.current_stream()
         self.bwd_w.run()
-        dy, M, N, db = self.db_args
-        _lib.check(self.lib.cb200_colsum(dy.data_ptr(), M, N, db.data_ptr(), self.ws.ptr(), st))
+        if self.db_args is not None:
+            dy, M, N, db = self.db_args
+            _lib.check(self.lib.cb200_colsum(dy.data_ptr(), M, N, db.data_ptr(), self.ws.ptr(), st))
         for op, wt, perm in self.classes:
             _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), perm.data_ptr(), perm.numel(), wt.data_ptr(), st))
             op.run()

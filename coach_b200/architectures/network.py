@@ -143,9 +143,7 @@ class SequentialInstance(object):
     @staticmethod
     def _prepare_fwd_only(layer, lib, ws, B, dev, x, y, w, b, x_is_u8, lut):
         # reuse prepare() with dummy gradient tensors but drop the backward ops: forward descriptors are identical
-        dummy = y
-        layer.prepare(lib, ws, B, dev, x, y, w, b, w, b, dummy, None, x_is_u8=x_is_u8, lut=lut, need_dx=False)
-        layer.bwd_w = None
+        layer.prepare(lib, ws, B, dev, x, y, w, b, None, None, None, None, x_is_u8=x_is_u8, lut=lut, need_dx=False)
 
     def forward(self):
         for layer in self.layers:

@@ -1,0 +1,202 @@
+// coach_b200/csrc/heads.cu -- policy / value head losses of the actor-critic agents (ClippedPPO, DDPG/TD3, SAC) and
+// the minibatch row gather used by the epoch loops.  Reference lines are cited in include/coach_b200.h.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cb200 {
+
+constexpr int kMaxActionDim = 32;
+constexpr float kLog2Pi = 1.8378770664093453f;
+constexpr float kTfEps = 1e-15f;          // `eps` of heads/ppo_head.py (std + eps)
+
+// fixed-order block reduction of one float per thread (blockDim.x a power of two <= 1024)
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    const float out = red[0];
+    __syncthreads();
+    return out;
+}
+
+// =====================================================================================================================
+// PPOHead, continuous actions (heads/ppo_head.py:52-144): diagonal Gaussian with state-independent log-std.
+//   sigma_j   = exp(logstd_j) + eps
+//   logp_i    = -0.5 * sum_j ((a_ij - mu_ij)/sigma_j)^2 - sum_j log sigma_j - 0.5*k*log(2 pi)
+//   ratio_i   = exp(logp_i - logp_old_i);  clipped_i = clip(ratio_i, 1 - e, 1 + e),  e = clip_eps * rescaler
+//   L         = -mean_i min(ratio_i * A_i, clipped_i * A_i)  -  beta * mean entropy
+// Outputs the gradients wrt mu and logstd and the scalars the reference logs (loss, KL(old||new), entropy, mean
+// ratio, mean clipped ratio).  One block; fixed reduction order.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) ppo_continuous_head_kernel(
+    const float* __restrict__ mu, const float* __restrict__ logstd, const float* __restrict__ actions,
+    const float* __restrict__ old_mu, const float* __restrict__ old_logstd, const float* __restrict__ advantages,
+    int64_t B, int A, float clip_eps, float beta_entropy, float* __restrict__ d_mu, float* __restrict__ d_logstd,
+    float* __restrict__ scalars /* [loss, kl, entropy, mean ratio, mean clipped ratio] */) {
+    __shared__ float red[256];
+    __shared__ float sig[kMaxActionDim], osig[kMaxActionDim], dls_part[kMaxActionDim];
+    if (threadIdx.x < A) {
+        sig[threadIdx.x] = expf(logstd[threadIdx.x]) + kTfEps;
+        osig[threadIdx.x] = expf(old_logstd[threadIdx.x]) + kTfEps;
+        dls_part[threadIdx.x] = 0.f;
+    }
+    __syncthreads();
+    float sum_log_sig = 0.f, sum_log_osig = 0.f;
+    for (int j = 0; j < A; ++j) {
+        sum_log_sig += logf(sig[j]);
+        sum_log_osig += logf(osig[j]);
+    }
+    const float inv_b = 1.0f / (float)B;
+    const float lo = 1.0f - clip_eps, hi = 1.0f + clip_eps;
+    float loss_acc = 0.f, kl_acc = 0.f, ratio_acc = 0.f, cratio_acc = 0.f;
+    float dls_local[kMaxActionDim];
+#pragma unroll
+    for (int j = 0; j < kMaxActionDim; ++j) dls_local[j] = 0.f;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+        float q = 0.f, qo = 0.f, kl = 0.f;
+        for (int j = 0; j < A; ++j) {
+            const float a = actions[i * A + j];
+            const float z = (a - mu[i * A + j]) / sig[j];
+            const float zo = (a - old_mu[i * A + j]) / osig[j];
+            q += z * z;
+            qo += zo * zo;
+            // KL(old || new) of diagonal Gaussians
+            const float dm = (mu[i * A + j] - old_mu[i * A + j]) / sig[j];
+            const float rs = osig[j] / sig[j];
+            kl += 0.5f * (rs * rs + dm * dm - 1.0f) - logf(rs);
+        }
+        const float logp = -0.5f * q - sum_log_sig - 0.5f * A * kLog2Pi;
+        const float logp_old = -0.5f * qo - sum_log_osig - 0.5f * A * kLog2Pi;
+        const float ratio = expf(logp - logp_old);
+        const float cl = fminf(fmaxf(ratio, lo), hi);
+        const float adv = advantages[i];
+        const float s1 = ratio * adv, s2 = cl * adv;
+        // tf.minimum passes the gradient to its first argument when s1 <= s2; clip_by_value passes it inside [lo, hi]
+        float ds_dratio;
+        if (s1 <= s2) ds_dratio = adv;
+        else ds_dratio = (ratio >= lo && ratio <= hi) ? adv : 0.f;
+        loss_acc += fminf(s1, s2);
+        kl_acc += kl;
+        ratio_acc += ratio;
+        cratio_acc += cl;
+        const float dlogp = -inv_b * ds_dratio * ratio;       // dL/dlogp_i
+        for (int j = 0; j < A; ++j) {
+            const float z = (actions[i * A + j] - mu[i * A + j]) / sig[j];
+            d_mu[i * A + j] = dlogp * z / sig[j];
+            // d logp / d logstd_j = (z^2 - 1) * exp(logstd_j) / sigma_j
+            dls_local[j] += dlogp * (z * z - 1.0f) * ((sig[j] - kTfEps) / sig[j]);
+        }
+    }
+    const float loss_sum = block_sum(loss_acc, red);
+    const float kl_sum = block_sum(kl_acc, red);
+    const float ratio_sum = block_sum(ratio_acc, red);
+    const float cratio_sum = block_sum(cratio_acc, red);
+    for (int j = 0; j < A; ++j) {
+        const float s = block_sum(dls_local[j], red);
+        if (threadIdx.x == 0) dls_part[j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float entropy = 0.5f * A * (1.0f + kLog2Pi) + sum_log_sig;     // state independent
+        for (int j = 0; j < A; ++j) {
+            // entropy regulariser -beta * H:  dH/dlogstd_j = exp(logstd_j) / sigma_j
+            d_logstd[j] = dls_part[j] - beta_entropy * ((sig[j] - kTfEps) / sig[j]);
+        }
+        if (scalars) {
+            scalars[0] = -loss_sum * inv_b - beta_entropy * entropy;
+            scalars[1] = kl_sum * inv_b;
+            scalars[2] = entropy;
+            scalars[3] = ratio_sum * inv_b;
+            scalars[4] = cratio_sum * inv_b;
+        }
+    }
+}
+
+// =====================================================================================================================
+// dst[c][i, :] = src[c][idx[*offset + i], :] -- minibatch extraction inside a (CUDA-graph captured) epoch loop: the
+// launch parameters stay constant, only the device scalar *offset changes between replays.
+// =====================================================================================================================
+struct AtColumns {
+    const uint8_t* src[CB200_MAX_COLUMNS];
+    uint8_t* dst[CB200_MAX_COLUMNS];
+    int64_t row_bytes[CB200_MAX_COLUMNS];
+    int n;
+};
+__global__ void __launch_bounds__(256) gather_at_kernel(AtColumns cols, const int64_t* __restrict__ idx,
+                                                        const int64_t* __restrict__ offset_ptr, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t off = offset_ptr ? *offset_ptr : 0;
+    for (int64_t w = warp; w < n * cols.n; w += nwarps) {
+        const int64_t i = w / cols.n;
+        const int c = (int)(w - i * cols.n);
+        const int64_t row = idx ? idx[off + i] : (off + i);
+        const uint8_t* s = cols.src[c] + row * cols.row_bytes[c];
+        uint8_t* d = cols.dst[c] + i * cols.row_bytes[c];
+        const int64_t bytes = cols.row_bytes[c];
+        const uintptr_t al = reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | (uintptr_t)bytes;
+        if ((al & 3) == 0) {
+            for (int64_t o = (int64_t)lane * 4; o < bytes; o += 128)
+                *reinterpret_cast<uint32_t*>(d + o) = *reinterpret_cast<const uint32_t*>(s + o);
+        } else {
+            for (int64_t o = lane; o < bytes; o += 32) d[o] = s[o];
+        }
+    }
+}
+
+// out[i] = (float) in[i]   (fp64 advantages / value targets -> fp32 network feeds)
+__global__ void __launch_bounds__(256) f64_to_f32_kernel(const double* __restrict__ in, int64_t n,
+                                                         float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_ppo_continuous_head(const float* mu, const float* logstd, const float* actions, const float* old_mu,
+                              const float* old_logstd, const float* advantages, int64_t batch, int32_t action_dim,
+                              float clip_eps, float beta_entropy, float* d_mu, float* d_logstd, float* scalars,
+                              void* stream) {
+    CB200_CHECK_ARG(mu && logstd && actions && old_mu && old_logstd && advantages && d_mu && d_logstd, "null pointer");
+    CB200_CHECK_ARG(batch > 0 && action_dim > 0 && action_dim <= kMaxActionDim, "bad shape (action_dim <= 32)");
+    CB200_LAUNCH(ppo_continuous_head_kernel, 1, 256, 0, as_stream(stream), mu, logstd, actions, old_mu, old_logstd,
+                 advantages, batch, action_dim, clip_eps, beta_entropy, d_mu, d_logstd, scalars);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_gather_at(const cb200_column* h_columns, int n_columns, const int64_t* idx, const int64_t* offset,
+                    int64_t n, void* stream) {
+    CB200_CHECK_ARG(h_columns && n_columns > 0 && n_columns <= CB200_MAX_COLUMNS && n > 0, "bad arguments");
+    AtColumns cols;
+    cols.n = n_columns;
+    for (int c = 0; c < n_columns; ++c) {
+        CB200_CHECK_ARG(h_columns[c].src && h_columns[c].dst && h_columns[c].row_bytes > 0, "bad column entry");
+        cols.src[c] = static_cast<const uint8_t*>(h_columns[c].src);
+        cols.dst[c] = static_cast<uint8_t*>(h_columns[c].dst);
+        cols.row_bytes[c] = h_columns[c].row_bytes;
+    }
+    int64_t grid = (n * n_columns + 7) / 8;
+    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+    CB200_LAUNCH(gather_at_kernel, (unsigned)grid, 256, 0, as_stream(stream), cols, idx, offset, n);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_f64_to_f32(const double* in, int64_t n, float* out, void* stream) {
+    CB200_CHECK_ARG(in && out && n > 0, "bad arguments");
+    CB200_LAUNCH(f64_to_f32_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), in, n, out);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+}  // extern "C"

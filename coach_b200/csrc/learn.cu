@@ -155,6 +155,28 @@ __global__ void __launch_bounds__(256) adam_tf_kernel(float* __restrict__ theta,
     }
 }
 
+// Adam with its step state on the device: state = {beta1_power, beta2_power}.  Launch-parameter-constant, so a whole
+// training step can be captured in a CUDA graph and replayed; adam_state_advance_kernel multiplies the powers.
+__global__ void __launch_bounds__(256) adam_tf_dev_kernel(float* __restrict__ theta, float* __restrict__ m,
+                                                          float* __restrict__ v, const float* __restrict__ g,
+                                                          int64_t n, float lr, float one_minus_b1, float one_minus_b2,
+                                                          float eps, const float* __restrict__ state) {
+    const float alpha = __fdiv_rn(__fmul_rn(lr, __fsqrt_rn(__fsub_rn(1.0f, state[1]))), __fsub_rn(1.0f, state[0]));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = __fadd_rn(m[i], __fmul_rn(__fsub_rn(gi, m[i]), one_minus_b1));
+        const float vi = __fadd_rn(v[i], __fmul_rn(__fsub_rn(__fmul_rn(gi, gi), v[i]), one_minus_b2));
+        m[i] = mi;
+        v[i] = vi;
+        theta[i] = __fsub_rn(theta[i], __fdiv_rn(__fmul_rn(mi, alpha), __fadd_rn(__fsqrt_rn(vi), eps)));
+    }
+}
+__global__ void adam_state_advance_kernel(float* state, float beta1, float beta2) {
+    state[0] = __fmul_rn(state[0], beta1);
+    state[1] = __fmul_rn(state[1], beta2);
+}
+__global__ void add_i64_kernel(int64_t* x, int64_t delta) { *x += delta; }
+
 __global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ target, const float* __restrict__ online,
                                                      int64_t n, float rate, float one_minus_rate) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -247,6 +269,23 @@ int cb200_adam_tf(float* theta, float* m, float* v, const float* g, int64_t n, f
     const float alpha = lr * sqrtf(1.0f - beta2_power) / (1.0f - beta1_power);
     CB200_LAUNCH(adam_tf_kernel, flat_grid(n), 256, 0, as_stream(stream), theta, m, v, g, n, alpha, 1.0f - beta1,
                  1.0f - beta2, epsilon);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_adam_tf_dev(float* theta, float* m, float* v, const float* g, int64_t n, float lr, float beta1, float beta2,
+                      float epsilon, float* state, void* stream) {
+    CB200_CHECK_ARG(theta && m && v && g && state && n > 0, "bad arguments");
+    CB200_LAUNCH(adam_tf_dev_kernel, flat_grid(n), 256, 0, as_stream(stream), theta, m, v, g, n, lr, 1.0f - beta1,
+                 1.0f - beta2, epsilon, state);
+    CB200_LAUNCH(adam_state_advance_kernel, 1, 1, 0, as_stream(stream), state, beta1, beta2);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_add_i64(int64_t* x, int64_t delta, void* stream) {
+    CB200_CHECK_ARG(x != nullptr, "null pointer");
+    CB200_LAUNCH(add_i64_kernel, 1, 1, 0, as_stream(stream), x, delta);
     CB200_CHECK_LAUNCH();
     return CB200_OK;
 }

@@ -1,5 +1,5 @@
 // coach_b200/csrc/nn.cu -- C-ABI entry points of the dense contractions of the learn step (see nn_gemm.cuh).
-#include "nn_gemm.cuh"
+#include "nn_gemm_fast.cuh"
 
 namespace cb200 {
 namespace gemm {
@@ -36,26 +36,72 @@ static void launch(const cb200_gemm_desc& d, int M, int R, int splits, int r_per
     }
 }
 
+template <class C, bool kT>
+static void launch_fast(const cb200_gemm_desc& d, int M, int R, int splits, int r_per_split, cudaStream_t st) {
+    FastA a;
+    a.src = d.a_src;
+    a.lut = d.a_lut;
+    a.rowoff = d.a_rowoff;
+    a.coloff = d.a_coloff;
+    a.rowinfo = d.a_rowinfo;
+    a.colinfo = d.a_colinfo;
+    a.oh = d.a_oh;
+    a.ow = d.a_ow;
+    a.rows = d.a_rows;
+    a.cols = d.a_cols;
+    a.ones_col = (kT && d.a_ones_col) ? d.a_cols : -1;
+    EpiParams ep{d.c, d.ldc, d.bias, d.act, d.mask_y, d.mask_act, d.c_rowmap, d.workspace, splits, d.accumulate};
+    dim3 grid((M + C::BM - 1) / C::BM, (d.n + C::BN - 1) / C::BN, splits);
+    gemm_fast_kernel<C, kT><<<grid, C::T, 0, st>>>(a, d.b, d.ldb, ep, M, d.n, R, r_per_split);
+    count_launch();
+    if (splits > 1) {
+        const int64_t total = (int64_t)M * d.n;
+        split_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ep, M, d.n);
+        count_launch();
+    }
+}
+
 // ---- small helpers -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ x, int64_t rows, int64_t cols,
                                                      float* __restrict__ part, int nslab) {
-    // grid.x = column blocks (256 columns each... one thread per column), grid.y = row slabs
-    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= cols) return;
+    // grid.x = column blocks of CW = min(cols, 256) columns, grid.y = row slabs.  The 256 threads of a block form
+    // RL = 256 / CW row lanes x CW columns (narrow matrices keep every thread busy and every load coalesced); the row
+    // lanes are folded in a fixed order through shared memory.
+    __shared__ float red[256];
+    const int cw = cols < 256 ? (int)cols : 256;
+    const int rl = 256 / cw;
+    const int c_local = threadIdx.x % cw, lane_r = threadIdx.x / cw;
+    const int64_t col = (int64_t)blockIdx.x * cw + c_local;
     const int slab = blockIdx.y;
     const int64_t per = (rows + nslab - 1) / nslab;
     const int64_t lo = slab * per, hi = min(rows, lo + per);
     float s = 0.f;
-    for (int64_t r = lo; r < hi; ++r) s += x[r * cols + col];
-    part[(int64_t)slab * cols + col] = s;
+    if (col < cols && lane_r < rl)
+        for (int64_t r = lo + lane_r; r < hi; r += rl) s += x[r * cols + col];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (lane_r == 0 && col < cols) {
+        for (int k = 1; k < rl; ++k) s += red[k * cw + c_local];
+        part[(int64_t)slab * cols + col] = s;
+    }
 }
 __global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ part, int64_t cols, int nslab,
                                                      float* __restrict__ out) {
-    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= cols) return;
+    // same thread shape as stage 1: RL row lanes x CW columns, lanes folded in a fixed order
+    __shared__ float red[256];
+    const int cw = cols < 256 ? (int)cols : 256;
+    const int rl = 256 / cw;
+    const int c_local = threadIdx.x % cw, lane_r = threadIdx.x / cw;
+    const int64_t col = (int64_t)blockIdx.x * cw + c_local;
     float s = 0.f;
-    for (int k = 0; k < nslab; ++k) s += part[(int64_t)k * cols + col];
-    out[col] = s;
+    if (col < cols && lane_r < rl)
+        for (int k = lane_r; k < nslab; k += rl) s += part[(int64_t)k * cols + col];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (lane_r == 0 && col < cols) {
+        for (int k = 1; k < rl; ++k) s += red[k * cw + c_local];
+        out[col] = s;
+    }
 }
 
 __global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ src, const int32_t* __restrict__ table,
@@ -91,7 +137,8 @@ int cb200_gemm(const cb200_gemm_desc* d, void* stream) {
     CB200_CHECK_ARG(d->a_rows > 0 && d->a_cols > 0 && d->n > 0 && d->ldb >= d->n && d->ldc >= d->n, "bad extents");
     CB200_CHECK_ARG((d->a_rowinfo == nullptr) == (d->a_colinfo == nullptr), "rowinfo / colinfo must come together");
     const bool tr = d->a_transposed != 0;
-    const int M = tr ? d->a_cols : d->a_rows;
+    const bool ones = tr && d->a_ones_col != 0;
+    const int M = (tr ? d->a_cols : d->a_rows) + (ones ? 1 : 0);
     const int R = tr ? d->a_rows : d->a_cols;
     int splits = d->splits > 1 ? d->splits : 1;
     CB200_CHECK_ARG(splits == 1 || d->workspace, "split reduction needs a workspace");
@@ -100,6 +147,23 @@ int cb200_gemm(const cb200_gemm_desc* d, void* stream) {
     r_per_split = (r_per_split + 15) / 16 * 16;
     splits = (R + r_per_split - 1) / r_per_split;
     cudaStream_t st = as_stream(stream);
+    const bool fast = d->a_vec4 && d->n % 4 == 0 && d->ldb % 4 == 0 && d->a_cols % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(d->b) & 15) == 0 && M > 64;
+    CB200_CHECK_ARG(!ones || fast, "a_ones_col needs the vectorised path (a_vec4, n % 4 == 0, more than 64 rows)");
+    if (fast) {
+        if (d->n <= 32) {
+            if (tr) gemm::launch_fast<gemm::FastCfg<256, 32>, true>(*d, M, R, splits, r_per_split, st);
+            else gemm::launch_fast<gemm::FastCfg<256, 32>, false>(*d, M, R, splits, r_per_split, st);
+        } else if (d->n <= 64) {
+            if (tr) gemm::launch_fast<gemm::FastCfg<128, 64>, true>(*d, M, R, splits, r_per_split, st);
+            else gemm::launch_fast<gemm::FastCfg<128, 64>, false>(*d, M, R, splits, r_per_split, st);
+        } else {
+            if (tr) gemm::launch_fast<gemm::FastCfg<128, 128>, true>(*d, M, R, splits, r_per_split, st);
+            else gemm::launch_fast<gemm::FastCfg<128, 128>, false>(*d, M, R, splits, r_per_split, st);
+        }
+        CB200_CHECK_LAUNCH();
+        return CB200_OK;
+    }
     const bool small = (M <= 64);
     if (small) {
         if (tr) gemm::launch<gemm::CfgSmall, true>(*d, M, R, splits, r_per_split, st);

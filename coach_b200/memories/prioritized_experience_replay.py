@@ -197,10 +197,15 @@ class PrioritizedExperienceReplay(ExperienceReplay):
             if k not in out:
                 out[k] = torch.empty(size, dtype=dt, device=self.device)
         arr, cnt = self.ring.column_table(out)
+        ke = getattr(self, "kernel_events", None)      # (start, end) CUDA events recorded right around the launch
+        if ke:
+            ke[0].record()
         _lib.check(self.lib.cb200_per_sample_gather(
             self.sum_tree.data_ptr(), self.min_tree.data_ptr(), self.power_of_2_size, u.data_ptr(), size,
             self.num_transitions(), float(self.beta.current_value), out["idx"].data_ptr(), out["weight"].data_ptr(),
             out["weight32"].data_ptr(), arr, cnt, _lib.current_stream()))
+        if ke:
+            ke[1].record()
         self.beta.step()                                                                 # :255
         return DeviceBatch(dict(out), size)
 

@@ -171,6 +171,11 @@ typedef struct cb200_gemm_desc {
     /* split reduction */
     float* workspace;           /* >= splits * rows * n floats when splits > 1                                       */
     int32_t splits;             /* 0 / 1 = no split; k > 1 = k partial sums reduced in fixed order                   */
+    /* fast-path hints (the tables are built by the caller, who knows their structure) */
+    int32_t a_vec4;             /* 1: every aligned group of 4 column indices is contiguous in memory, a_cols % 4 == 0 */
+                                /*    and every a_rowoff % 4 == 0  => 128-bit (fp32) / 32-bit (uint8) operand loads   */
+    int32_t a_ones_col;         /* a_transposed only: 1 = append an output row a_cols holding sum_m B[m, :] (the bias  */
+                                /*    gradient lands in c[a_cols, :], i.e. right behind the kernel gradient)          */
 } cb200_gemm_desc;
 
 int cb200_gemm(const cb200_gemm_desc* h_desc, void* stream);
@@ -235,9 +240,39 @@ int cb200_scale(float* g, int64_t n, float s, void* stream);
 int cb200_adam_tf(float* theta, float* m, float* v, const float* g, int64_t n, float lr, float beta1, float beta2,
                   float epsilon, float beta1_power, float beta2_power, void* stream);
 
+/* Same optimizer step with the running powers kept in DEVICE memory (state = {beta1_power, beta2_power}, initialised
+ * to {beta1, beta2}); the step multiplies them afterwards.  All launch parameters are constant from step to step, so
+ * a complete training step can be captured in a CUDA graph and replayed. */
+int cb200_adam_tf_dev(float* theta, float* m, float* v, const float* g, int64_t n, float lr, float beta1, float beta2,
+                      float epsilon, float* state, void* stream);
+
+/* *x += delta on the device (minibatch cursor of a captured epoch loop, see cb200_gather_at) */
+int cb200_add_i64(int64_t* x, int64_t delta, void* stream);
+
 /* NetworkWrapper.update_target_network -> set_weights (architecture.py:598-607):
  *   target = rate * online + (1 - rate) * target   in fp32, rate and (1 - rate) rounded to fp32 first (numpy). */
 int cb200_polyak(float* target, const float* online, int64_t n, double rate, void* stream);
+
+/* PPOHead for continuous actions (heads/ppo_head.py:52-98,118-144): diagonal Gaussian policy with a state-independent
+ * log-std variable, sigma = exp(logstd) + 1e-15; likelihood ratio exp(logp - logp_old) (:78), clipped to
+ * 1 +- clip_eps (clip_eps = clip_likelihood_ratio_using_epsilon * clipping_decay rescaler, :80-84), surrogate
+ * L = -mean(min(ratio*A, clip(ratio)*A)) (:85-90), entropy regulariser -beta*H (:93-95).  The old policy is given by
+ * its mean per sample and its log-std vector (the frozen target network, clipped_ppo_agent.py:240).
+ * Outputs d(L)/d(mu) [batch, action_dim], d(L)/d(logstd) [action_dim] and scalars[5] = {loss, KL(old||new), entropy,
+ * mean ratio, mean clipped ratio} (the signals clipped_ppo_agent.py:227-230 fetches).  action_dim <= 32. */
+int cb200_ppo_continuous_head(const float* mu, const float* logstd, const float* actions, const float* old_mu,
+                              const float* old_logstd, const float* advantages, int64_t batch, int32_t action_dim,
+                              float clip_eps, float beta_entropy, float* d_mu, float* d_logstd, float* scalars,
+                              void* stream);
+
+/* dst[c][i, :] = src[c][idx[*offset + i], :] for i < n (idx == NULL: rows *offset + i).  `offset` is a DEVICE scalar
+ * so that the launch is identical for every minibatch of an epoch (CUDA-graph replay; only *offset changes).
+ * Minibatch slicing of clipped_ppo_agent.py:232-265 after batch.shuffle(). */
+int cb200_gather_at(const cb200_column* h_columns, int n_columns, const int64_t* idx, const int64_t* offset,
+                    int64_t n, void* stream);
+
+/* out[i] = (float) in[i] */
+int cb200_f64_to_f32(const double* in, int64_t n, float* out, void* stream);
 
 /* =====================================================================================================================
  * Scalar RL recurrences (fp64, as the reference computes them).

@@ -250,7 +250,7 @@ def test_dqn_learn_step_matches_oracle(cfg):
             # closer to (or as close as) the fp32 oracle is to the fp64 evaluation, with slack 4
             e_ours = np.abs(got_grads[name] - ref64["grads"][name].numpy()).max()
             e_orc = np.abs(want - ref64["grads"][name].numpy()).max()
-            assert e_ours <= 4 * e_orc + 1e-7 * (np.abs(want).max() + 1e-30), (name, e_ours, e_orc)
+            assert e_ours <= 4 * e_orc + 2e-6 * (np.abs(want).max() + 1e-30), (name, e_ours, e_orc)
         got_params = store.export_named()
         for name in ref["new_params"]:
             close(got_params[name], ref["new_params"][name].numpy(), name="param " + name)
