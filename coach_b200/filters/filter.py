@@ -294,14 +294,15 @@ class InputFilter(object):
 
     def _filter_device_batch(self, batch, update_internal_state):
         cols = dict(batch.columns)
-        for obs_name, flt in self._observation_filters.items():
-            for f in flt.values():
-                if not f.supports_device_batches:
-                    raise ValueError("filter %s cannot run on device-resident batches" % type(f).__name__)
-                for prefix in ("state:", "next_state:"):
-                    key = prefix + obs_name
-                    if key in cols:
-                        cols[key] = f.filter(cols[key], update_internal_state=update_internal_state)
+        for prefix in ("state:", "next_state:"):            # all states first, then all next states (filter.py:314-334)
+            for obs_name, flt in self._observation_filters.items():
+                key = prefix + obs_name
+                if key not in cols:
+                    continue
+                for f in flt.values():
+                    if not f.supports_device_batches:
+                        raise ValueError("filter %s cannot run on device-resident batches" % type(f).__name__)
+                    cols[key] = f.filter(cols[key], update_internal_state=update_internal_state)
         if self._reward_filters:
             raise ValueError("reward filters run at store time on the host (they are scalar, per transition)")
         return DeviceBatch(cols, batch.size)
