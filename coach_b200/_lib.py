@@ -80,6 +80,14 @@ PROTOTYPES = {
                                           ctypes.c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb200_gather_at": (c_int, [ctypes.POINTER(Column), c_int, c_void_p, c_void_p, c_i64, c_void_p]),
     "cb200_f64_to_f32": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
+    "cb200_act_backward": (c_int, [c_void_p, ctypes.c_int32, c_void_p, ctypes.c_int32, c_i64, ctypes.c_int32,
+                                   ctypes.c_int32, c_void_p, ctypes.c_int32, c_void_p]),
+    "cb200_axpby_2d": (c_int, [c_void_p, ctypes.c_int32, c_i64, ctypes.c_int32, c_float, c_float, c_void_p,
+                               ctypes.c_int32, c_void_p]),
+    "cb200_ac_td_targets": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int32, c_i64, c_double, ctypes.c_int32,
+                                    ctypes.c_int32, c_double, c_double, c_void_p, c_void_p]),
+    "cb200_min2": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "cb200_td3_smooth_actions": (c_int, [c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_void_p]),
     "cb200_gae_scan": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
     "cb200_standardize": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),

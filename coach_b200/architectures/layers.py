@@ -148,12 +148,13 @@ class Dense(object):
     def forward(self):
         self.fwd.run()
 
-    def backward(self):
+    def backward(self, weights=True):
         st = _lib.current_stream()
-        self.bwd_w.run()
-        if self.db_args is not None:
-            dy, B, N, db = self.db_args
-            _lib.check(self.lib.cb200_colsum(dy.data_ptr(), B, N, db.data_ptr(), self.ws.ptr(), st))
+        if weights:
+            self.bwd_w.run()
+            if self.db_args is not None:
+                dy, B, N, db = self.db_args
+                _lib.check(self.lib.cb200_colsum(dy.data_ptr(), B, N, db.data_ptr(), self.ws.ptr(), st))
         if self.bwd_x is not None:
             _lib.check(self.lib.cb200_transpose(self.w.data_ptr(), self.K, self.N, self.wT.data_ptr(), st))
             self.bwd_x.run()
@@ -241,12 +242,13 @@ class Conv2d(object):
     def forward(self):
         self.fwd.run()
 
-    def backward(self):
+    def backward(self, weights=True):
         st = _lib.current_stream()
-        self.bwd_w.run()
-        if self.db_args is not None:
-            dy, M, N, db = self.db_args
-            _lib.check(self.lib.cb200_colsum(dy.data_ptr(), M, N, db.data_ptr(), self.ws.ptr(), st))
+        if weights:
+            self.bwd_w.run()
+            if self.db_args is not None:
+                dy, M, N, db = self.db_args
+                _lib.check(self.lib.cb200_colsum(dy.data_ptr(), M, N, db.data_ptr(), self.ws.ptr(), st))
         for op, wt, perm in self.classes:
             _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), perm.data_ptr(), perm.numel(), wt.data_ptr(), st))
             op.run()

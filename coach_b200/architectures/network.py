@@ -150,9 +150,10 @@ class SequentialInstance(object):
             layer.forward()
         return self.out
 
-    def backward(self):
+    def backward(self, weights=True):
+        """weights=False: data gradients only (d(out)/d(input), e.g. dQ/da through the critic)"""
         for layer in reversed(self.layers):
-            layer.backward()
+            layer.backward(weights)
 
 
 def make_u8_lut(device, rescale=255.0, offset=0.0):

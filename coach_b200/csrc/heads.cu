@@ -149,6 +149,66 @@ __global__ void __launch_bounds__(256) gather_at_kernel(AtColumns cols, const in
     }
 }
 
+
+// dz[r, c] = dy[r, c] * act'(y[r, c])  with independent leading dimensions (activation backward on a column block of a
+// wider buffer, e.g. the embedder part of a concatenated critic input)
+__global__ void __launch_bounds__(256) act_backward_kernel(const float* __restrict__ dy, int ld_dy,
+                                                           const float* __restrict__ y, int ld_y, int64_t rows,
+                                                           int cols, int act, float* __restrict__ dz, int ld_dz) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float yy = y[r * ld_y + c];
+    float g = 1.f;
+    if (act == CB200_ACT_RELU) g = yy > 0.f ? 1.f : 0.f;
+    else if (act == CB200_ACT_TANH) g = 1.f - yy * yy;
+    dz[r * ld_dz + c] = dy[r * ld_dy + c] * g;
+}
+
+// dst[r, c] = alpha * src[r, c] + beta * dst[r, c]   (strided 2-D; beta == 0 never reads dst)
+__global__ void __launch_bounds__(256) axpby_2d_kernel(const float* __restrict__ src, int ld_src, int64_t rows, int cols,
+                                                       float alpha, float beta, float* __restrict__ dst, int ld_dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float v = alpha * src[r * ld_src + c];
+    dst[r * ld_dst + c] = (beta == 0.f) ? v : (v + beta * dst[r * ld_dst + c]);
+}
+
+// DDPG / TD3 / SAC bootstrapped targets, evaluated like the numpy expression (fp64 rewards, fp32 network output):
+//   y = r + (1 - done) * discount * q_next      [done ignored when use_non_zero_discount_for_terminal_states]
+//   optional clip (ddpg_agent.py:163-164); written as fp32 (the TF placeholder dtype)
+__global__ void __launch_bounds__(256) ac_td_targets_kernel(const double* __restrict__ rewards,
+                                                            const uint8_t* __restrict__ dones,
+                                                            const float* __restrict__ q_next, int ld_q, int64_t B,
+                                                            double discount, int ignore_done, int use_clip,
+                                                            double clip_lo, double clip_hi, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const double nd = ignore_done ? 1.0 : __dsub_rn(1.0, dones[i] ? 1.0 : 0.0);
+    double y = __dadd_rn(rewards[i], __dmul_rn(__dmul_rn(nd, discount), (double)q_next[i * ld_q]));
+    if (use_clip) y = fmin(fmax(y, clip_lo), clip_hi);
+    out[i] = (float)y;
+}
+
+// out[i] = min(a[i], b[i])  (TD3 / SAC clipped double-Q)
+__global__ void __launch_bounds__(256) min2_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                   float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fminf(a[i], b[i]);
+}
+
+// TD3 target policy smoothing (td3_agent.py:162-164): a = clip(a + clip(noise, -c, c), lo, hi), in place
+__global__ void __launch_bounds__(256) td3_smooth_kernel(float* __restrict__ actions, const float* __restrict__ noise,
+                                                         int64_t n, float noise_clip, float lo, float hi) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float nz = fminf(fmaxf(noise[i], -noise_clip), noise_clip);
+    actions[i] = fminf(fmaxf(actions[i] + nz, lo), hi);
+}
+
 // out[i] = (float) in[i]   (fp64 advantages / value targets -> fp32 network feeds)
 __global__ void __launch_bounds__(256) f64_to_f32_kernel(const double* __restrict__ in, int64_t n,
                                                          float* __restrict__ out) {
@@ -188,6 +248,55 @@ int cb200_gather_at(const cb200_column* h_columns, int n_columns, const int64_t*
     int64_t grid = (n * n_columns + 7) / 8;
     if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
     CB200_LAUNCH(gather_at_kernel, (unsigned)grid, 256, 0, as_stream(stream), cols, idx, offset, n);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+
+int cb200_act_backward(const float* dy, int32_t ld_dy, const float* y, int32_t ld_y, int64_t rows, int32_t cols,
+                       int32_t act, float* dz, int32_t ld_dz, void* stream) {
+    CB200_CHECK_ARG(dy && y && dz && rows > 0 && cols > 0 && ld_dy >= cols && ld_y >= cols && ld_dz >= cols,
+                    "bad arguments");
+    const int64_t n = rows * cols;
+    CB200_LAUNCH(act_backward_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), dy, ld_dy, y, ld_y, rows,
+                 cols, act, dz, ld_dz);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_axpby_2d(const float* src, int32_t ld_src, int64_t rows, int32_t cols, float alpha, float beta, float* dst,
+                   int32_t ld_dst, void* stream) {
+    CB200_CHECK_ARG(src && dst && rows > 0 && cols > 0 && ld_src >= cols && ld_dst >= cols, "bad arguments");
+    const int64_t n = rows * cols;
+    CB200_LAUNCH(axpby_2d_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), src, ld_src, rows, cols,
+                 alpha, beta, dst, ld_dst);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_ac_td_targets(const double* rewards, const uint8_t* game_overs, const float* q_next, int32_t ld_q,
+                        int64_t batch, double discount, int32_t use_non_zero_discount_for_terminal_states,
+                        int32_t use_clip, double clip_lo, double clip_hi, float* targets_out, void* stream) {
+    CB200_CHECK_ARG(rewards && game_overs && q_next && targets_out && batch > 0 && ld_q >= 1, "bad arguments");
+    CB200_LAUNCH(ac_td_targets_kernel, (unsigned)((batch + 255) / 256), 256, 0, as_stream(stream), rewards, game_overs,
+                 q_next, ld_q, batch, discount, use_non_zero_discount_for_terminal_states, use_clip, clip_lo, clip_hi,
+                 targets_out);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_min2(const float* a, const float* b, int64_t n, float* out, void* stream) {
+    CB200_CHECK_ARG(a && b && out && n > 0, "bad arguments");
+    CB200_LAUNCH(min2_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), a, b, n, out);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_td3_smooth_actions(float* actions, const float* noise, int64_t n, float noise_clip, float lo, float hi,
+                             void* stream) {
+    CB200_CHECK_ARG(actions && noise && n > 0, "bad arguments");
+    CB200_LAUNCH(td3_smooth_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), actions, noise, n,
+                 noise_clip, lo, hi);
     CB200_CHECK_LAUNCH();
     return CB200_OK;
 }

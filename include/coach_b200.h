@@ -271,6 +271,31 @@ int cb200_ppo_continuous_head(const float* mu, const float* logstd, const float*
 int cb200_gather_at(const cb200_column* h_columns, int n_columns, const int64_t* idx, const int64_t* offset,
                     int64_t n, void* stream);
 
+/* dz[r, c] = dy[r, c] * act'(y[r, c]) with independent leading dimensions: activation backward on a column block of a
+ * wider buffer (the embedder part of a critic's concatenated [action, embedding] input, general_network.py:272-277). */
+int cb200_act_backward(const float* dy, int32_t ld_dy, const float* y, int32_t ld_y, int64_t rows, int32_t cols,
+                       int32_t act, float* dz, int32_t ld_dz, void* stream);
+
+/* dst[r, c] = alpha * src[r, c] + beta * dst[r, c] on strided 2-D fp32 blocks (beta == 0: dst is not read).  Used for
+ * the embedding merger concat, the actor's output scale and the -(1/B) * dQ/da seed of the actor update
+ * (ddpg_agent.py:171-186). */
+int cb200_axpby_2d(const float* src, int32_t ld_src, int64_t rows, int32_t cols, float alpha, float beta, float* dst,
+                   int32_t ld_dst, void* stream);
+
+/* Bootstrapped critic targets of DDPG / TD3 / SAC (ddpg_agent.py:156-164, td3_agent.py:172-181,
+ * soft_actor_critic_agent.py:265-266): y = r + (1 - done) * discount * q_next in fp64 (numpy), optional clip, stored
+ * as fp32.  q_next is read with stride ld_q. */
+int cb200_ac_td_targets(const double* rewards, const uint8_t* game_overs, const float* q_next, int32_t ld_q,
+                        int64_t batch, double discount, int32_t use_non_zero_discount_for_terminal_states,
+                        int32_t use_clip, double clip_lo, double clip_hi, float* targets_out, void* stream);
+
+/* out = min(a, b) element-wise (clipped double-Q: td3_v_head.py:61, sac_q_head.py:84-86) */
+int cb200_min2(const float* a, const float* b, int64_t n, float* out, void* stream);
+
+/* TD3 target policy smoothing (td3_agent.py:162-164): a = clip(a + clip(noise, -noise_clip, noise_clip), lo, hi) */
+int cb200_td3_smooth_actions(float* actions, const float* noise, int64_t n, float noise_clip, float lo, float hi,
+                             void* stream);
+
 /* out[i] = (float) in[i] */
 int cb200_f64_to_f32(const double* in, int64_t n, float* out, void* stream);
 

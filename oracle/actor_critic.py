@@ -83,3 +83,75 @@ def ppo_minibatch_step(named, old_named, opt, mb, clip_eps, beta_entropy, dtype=
 
 def make_adam(named, lr, beta1, beta2, eps, dtype=torch.float32):
     return AdamTF([torch.as_tensor(v).to(dtype) for v in named.values()], lr, beta1, beta2, eps, dtype=dtype)
+
+
+# ---- DDPG / TD3 ---------------------------------------------------------------------------------------------------------
+def actor_forward(p, s, scale):
+    """obs -> 400 relu -> 300 relu -> A tanh, * scale (ddpg_actor_head.py:46-63)"""
+    return torch.tanh(mlp(p[0:6], s, ["relu", "relu", None])) * scale
+
+
+def ddpg_critic_forward(p, s, a):
+    """concat[action, relu(Dense400(obs))] -> Dense300 relu -> Dense1 (general_network.py:252-279: action first)"""
+    e = torch.relu(s @ p[0] + p[1])
+    h = torch.relu(torch.cat([a, e], dim=1) @ p[2] + p[3])
+    return [h @ p[4] + p[5]]
+
+
+def td3_critic_forward(p, s, a):
+    """concat[action, obs] -> two streams (Dense400 relu, Dense300 relu) -> Dense1 each (td3_v_head.py:40-62)"""
+    x = torch.cat([a, s], dim=1)
+    outs = []
+    for k in range(2):
+        h = torch.relu(x @ p[4 * k] + p[4 * k + 1])
+        h = torch.relu(h @ p[4 * k + 2] + p[4 * k + 3])
+        outs.append(h @ p[8 + 2 * k] + p[9 + 2 * k])
+    return outs
+
+
+def ddpg_td3_step(actor, actor_t, critic, critic_t, opt_a, opt_c, batch, discount=0.99, scale=1.0, twin=False,
+                  noise=None, noise_clip=0.5, low=-1.0, high=1.0, update_actor=True, dtype=torch.float32):
+    """One learn_from_batch of DDPG (twin=False; ddpg_agent.py:137-195) or TD3 (twin=True; td3_agent.py:148-209).
+    actor / critic (+ *_t targets): OrderedDict name -> array in creation order.  Returns new params, grads, losses."""
+    t = lambda a: torch.as_tensor(np.asarray(a)).to(dtype)     # noqa: E731
+    an, cn = list(actor.keys()), list(critic.keys())
+    A = [t(actor[n]).clone().requires_grad_(True) for n in an]
+    C = [t(critic[n]).clone().requires_grad_(True) for n in cn]
+    At, Ct = [t(actor_t[n]) for n in an], [t(critic_t[n]) for n in cn]
+    cf = td3_critic_forward if twin else ddpg_critic_forward
+    s, s2, a = t(batch["states"]), t(batch["next_states"]), t(batch["actions"])
+    with torch.no_grad():
+        next_actions = actor_forward(At, s2, scale)
+        if twin:
+            nz = np.clip(np.asarray(noise, dtype=np.float64), -noise_clip, noise_clip)
+            next_actions = torch.clamp(next_actions + t(nz), low, high)
+        qn = cf(Ct, s2, next_actions)
+        q_next = torch.min(qn[0], qn[1]) if twin else qn[0]
+    r = np.asarray(batch["rewards"], dtype=np.float64).reshape(-1, 1)
+    d = np.asarray(batch["game_overs"]).reshape(-1, 1)
+    y = r + (1.0 - d) * discount * q_next.numpy().astype(np.float64 if dtype == torch.float64 else np.float32)
+    y = t(y.astype(np.float32) if dtype == torch.float32 else y)
+
+    def action_grad(Cp):
+        mu = actor_forward(A, s, scale)
+        q1 = cf(Cp, s, mu)[0]
+        return torch.autograd.grad(-q1.mean(), A, allow_unused=True)
+
+    actor_grads = None
+    if not twin:
+        actor_grads = action_grad([c.detach() for c in C])          # critic BEFORE its update
+    qs = cf(C, s, a)
+    loss = sum(((y - q) ** 2).mean() for q in qs)
+    cg = torch.autograd.grad(loss, C, allow_unused=True)
+    cg = [g if g is not None else torch.zeros_like(p) for g, p in zip(cg, C)]
+    newC = opt_c.step([p.detach() for p in C], cg)
+    if twin and update_actor:
+        actor_grads = action_grad(newC)                              # critic AFTER its update
+    newA = [p.detach() for p in A]
+    ag = None
+    if actor_grads is not None:
+        ag = [g if g is not None else torch.zeros_like(p) for g, p in zip(actor_grads, A)]
+        newA = opt_a.step([p.detach() for p in A], ag)
+    return dict(loss=float(loss.detach()), td_targets=y.numpy(), critic_grads=OrderedDict(zip(cn, cg)),
+                actor_grads=OrderedDict(zip(an, ag)) if ag is not None else None,
+                new_critic=OrderedDict(zip(cn, newC)), new_actor=OrderedDict(zip(an, newA)))
