@@ -170,6 +170,7 @@ def run_device(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     lib = _lib.load()
+    lib.cb200_tune(b"gemm_tc", 0 if args.no_tc else 1)
     random.seed(1000 + rank)
     np.random.seed(1000 + rank)
     agent = build_device_agent(args.capacity, 100 + rank, device)
@@ -276,11 +277,15 @@ def run_device(args):
                      "us_per_launch": round(gather_us, 2), "algorithmic_bytes": GATHER_BYTES,
                      "traffic": TRAFFIC_NCU.get("per_sample_gather"),
                      "frac_of_8TBps": round(gather_gbs / 8000.0, 4)},
-        "roofline_learn": {"kernels": "fp32 FFMA gather-GEMMs (conv/dense fwd+bwd) + element-wise",
+        "roofline_learn": {"kernels": ("fp32 FFMA gather-GEMMs" if args.no_tc else
+                                       "tcgen05 gather-GEMMs (3xBF16 split, 6 MMAs per product, fp32 TMEM accumulators)")
+                           + " (conv/dense fwd+bwd) + element-wise",
                            "bound": "tensor", "achieved": round(gemm_tflops, 2), "peak": pk["bf16_tflops_sustained"],
                            "unit": "TFLOP/s", "frac": round(gemm_tflops / pk["bf16_tflops_sustained"], 5),
                            "us_per_step": round(learn_us, 1),
-                           "note": "fp32 CUDA-core path (1e-5 parity); nominal fp32 FFMA peak ~72 TFLOP/s"},
+                           "note": "achieved = fp32-equivalent FLOPs of the step / time; the 3xBF16 split issues 6x "
+                                   "as many tensor-core MACs" if not args.no_tc else
+                                   "fp32 CUDA-core path; nominal fp32 FFMA peak ~72 TFLOP/s"},
         "share_of_step": {"sample_gather": round(gather_us / (gather_us + learn_us), 4),
                           "learn": round(learn_us / (gather_us + learn_us), 4)},
     }
@@ -402,6 +407,7 @@ def main():
     ap.add_argument("--capacity", type=int, default=1000000, help="replay capacity in transitions (rounded up to 2^k)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the cpu_baseline leg")
     ap.add_argument("--no-l2-persist", action="store_true")
+    ap.add_argument("--no-tc", action="store_true", help="fp32 FFMA GEMMs instead of the tcgen05 3xBF16 path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

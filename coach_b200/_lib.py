@@ -27,7 +27,7 @@ class GemmDesc(ctypes.Structure):
                 ("c", c_void_p), ("ldc", ctypes.c_int32), ("bias", c_void_p), ("act", ctypes.c_int32),
                 ("mask_y", c_void_p), ("mask_act", ctypes.c_int32), ("c_rowmap", c_void_p),
                 ("accumulate", ctypes.c_int32), ("workspace", c_void_p), ("splits", ctypes.c_int32),
-                ("a_vec4", ctypes.c_int32), ("a_ones_col", ctypes.c_int32)]
+                ("a_vec4", ctypes.c_int32), ("a_ones_col", ctypes.c_int32), ("a_u8_div", c_float)]
 
 
 class Column(ctypes.Structure):
@@ -80,6 +80,12 @@ PROTOTYPES = {
                                           ctypes.c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb200_gather_at": (c_int, [ctypes.POINTER(Column), c_int, c_void_p, c_void_p, c_i64, c_void_p]),
     "cb200_f64_to_f32": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
+    "cb200_sac_policy_sample": (c_int, [c_void_p, c_void_p, c_i64, ctypes.c_int32, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
+    "cb200_sac_policy_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_int32, c_void_p,
+                                      c_void_p]),
+    "cb200_sac_min_seed": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cb200_sub": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "cb200_act_backward": (c_int, [c_void_p, ctypes.c_int32, c_void_p, ctypes.c_int32, c_i64, ctypes.c_int32,
                                    ctypes.c_int32, c_void_p, ctypes.c_int32, c_void_p]),
     "cb200_axpby_2d": (c_int, [c_void_p, ctypes.c_int32, c_i64, ctypes.c_int32, c_float, c_float, c_void_p,

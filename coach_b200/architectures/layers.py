@@ -40,6 +40,10 @@ class Workspace(object):
         return self.buf.data_ptr()
 
 
+def _u8_div(lut, x_is_u8):
+    return float(getattr(lut, "u8_div", 0.0)) if (x_is_u8 and lut is not None) else 0.0
+
+
 class GemmOp(object):
     """A prepared cb200_gemm call.  Tensors referenced by the descriptor are kept alive here."""
 
@@ -69,11 +73,17 @@ class GemmOp(object):
 
 def pick_splits(tiles, reduction, sm=148, min_chunk=128):
     """Split the reduction so that the grid has about two CTAs per SM, never below `min_chunk` per split."""
+    # the tensor-core path accumulates in TMEM with truncation: never reduce more than TC_MAX_R terms in one launch,
+    # the partial sums are then added in fp32 round-to-nearest by the split-reduce kernel (csrc/nn_gemm_tc.cuh)
+    need = (reduction + TC_MAX_R - 1) // TC_MAX_R
     if tiles >= sm:          # one full wave already: the extra reduction pass would cost more than it saves
-        return 1
+        return int(max(1, need))
     s = max(1, (2 * sm + tiles - 1) // tiles)
     s = min(s, max(1, reduction // min_chunk))
-    return int(s)
+    return int(max(s, need))
+
+
+TC_MAX_R = 1024
 
 
 def _tiles(M, N, fast=True):
@@ -120,7 +130,7 @@ class Dense(object):
         coloff = _dev_i32(np.arange(K), device)
         vec = int(K % 4 == 0)
         common = dict(a_rowoff=rowoff, a_coloff=coloff, a_rows=B, a_cols=K, a_vec4=vec, a_src=x,
-                      a_lut=lut if x_is_u8 else None)
+                      a_lut=lut if x_is_u8 else None, a_u8_div=_u8_div(lut, x_is_u8))
         self.fwd = GemmOp(lib, ws, a_transposed=0, b=w, ldb=N, n=N, c=y, ldc=N, bias=b, act=self.act,
                           splits=pick_splits(_tiles(B, N, vec), K), **common)
         self.bwd_w = None
@@ -193,7 +203,7 @@ class Conv2d(object):
         assert rowoff.max() + coloff.max() < 2 ** 31
         vec = int(C % 4 == 0)          # (kx, c) runs are contiguous: groups of 4 channels never straddle a pixel
         common = dict(a_rowoff=_dev_i32(rowoff, device), a_coloff=_dev_i32(coloff, device), a_rows=M, a_cols=K,
-                      a_src=x, a_lut=lut if x_is_u8 else None, a_vec4=vec)
+                      a_src=x, a_lut=lut if x_is_u8 else None, a_vec4=vec, a_u8_div=_u8_div(lut, x_is_u8))
         self.fwd = GemmOp(lib, ws, a_transposed=0, b=w, ldb=N, n=N, c=y, ldc=N, bias=b, act=self.act,
                           splits=pick_splits(_tiles(M, N, vec), K), **common)
         self.bwd_w = None

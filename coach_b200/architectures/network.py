@@ -160,4 +160,8 @@ def make_u8_lut(device, rescale=255.0, offset=0.0):
     """lut[v] = float32(v) / rescale - offset, the embedder's input normalisation (embedder.py:103-104) evaluated in
     fp32 exactly like TensorFlow would (true division, not a reciprocal multiply)."""
     v = torch.arange(256, dtype=torch.float32)
-    return ((v / np.float32(rescale)) - np.float32(offset)).to(device)
+    lut = ((v / np.float32(rescale)) - np.float32(offset)).to(device)
+    # with no offset the table is exactly v / rescale: declared to the GEMM (cb200_gemm_desc.a_u8_div) so that the
+    # tensor-core path can contract the raw integers exactly and divide once
+    lut.u8_div = float(rescale) if offset == 0.0 else 0.0
+    return lut

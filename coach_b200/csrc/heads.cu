@@ -209,6 +209,87 @@ __global__ void __launch_bounds__(256) td3_smooth_kernel(float* __restrict__ act
     actions[i] = fminf(fmaxf(actions[i] + nz, lo), hi);
 }
 
+// =====================================================================================================================
+// SACPolicyHead (heads/sac_head.py:60-97): head output z = [mu | log_sigma_raw]  (2A columns),
+//   log_sigma = clip(log_sigma_raw, -20, 2);  u = mu + exp(log_sigma) * eps;  a = tanh(u);
+//   log pi(a|s) = sum_j [ -0.5 eps_j^2 - log_sigma_j - 0.5 log(2 pi) ] - sum_j log(1 - tanh(u_j)^2 + 1e-6)
+// (MultivariateNormalDiag.log_prob of the reparameterised sample, minus the squash correction :49-58).
+// =====================================================================================================================
+constexpr float kSacLogSigMin = -20.f, kSacLogSigMax = 2.f, kSacEps = 1e-6f;
+
+__global__ void __launch_bounds__(256) sac_policy_sample_kernel(const float* __restrict__ z, const float* __restrict__ eps,
+                                                                int64_t B, int A, float* __restrict__ raw,
+                                                                float* __restrict__ act, float* __restrict__ logp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    float lp = 0.f;
+    for (int j = 0; j < A; ++j) {
+        const float mu = z[i * 2 * A + j];
+        const float ls = fminf(fmaxf(z[i * 2 * A + A + j], kSacLogSigMin), kSacLogSigMax);
+        const float e = eps[i * A + j];
+        const float u = mu + expf(ls) * e;
+        const float t = tanhf(u);
+        if (raw) raw[i * A + j] = u;
+        if (act) act[i * A + j] = t;
+        lp += -0.5f * e * e - ls - 0.5f * kLog2Pi - logf(1.0f - t * t + kSacEps);
+    }
+    if (logp) logp[i] = lp;
+}
+
+// gradient of  mean_b log pi(a~|s)  (noise eps_lp)  minus  sum_b <dq_da_b, a~_b>  (noise eps_q)  wrt the head output z:
+// the two terms of policy_grads = dlogp_dphi - dq_dphi (soft_actor_critic_agent.py:213-232); each term was evaluated
+// by its own sess.run and therefore with its own noise sample.
+__global__ void __launch_bounds__(256) sac_policy_grad_kernel(const float* __restrict__ z, const float* __restrict__ eps_lp,
+                                                              const float* __restrict__ eps_q,
+                                                              const float* __restrict__ dq_da, int64_t B, int A,
+                                                              float* __restrict__ dz) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float inv_b = 1.0f / (float)B;
+    for (int j = 0; j < A; ++j) {
+        const float mu = z[i * 2 * A + j];
+        const float lsr = z[i * 2 * A + A + j];
+        const float ls = fminf(fmaxf(lsr, kSacLogSigMin), kSacLogSigMax);
+        const float in_range = (lsr >= kSacLogSigMin && lsr <= kSacLogSigMax) ? 1.f : 0.f;   // clip_by_value gradient
+        const float sig = expf(ls);
+        // --- d mean(log pi) ---
+        const float e2 = eps_lp[i * A + j];
+        const float u2 = mu + sig * e2, t2 = tanhf(u2);
+        const float gprime = (-2.0f * t2 * (1.0f - t2 * t2)) / (1.0f - t2 * t2 + kSacEps);   // d/du log(1 - t^2 + eps)
+        float d_mu = inv_b * (-gprime);
+        float d_ls = inv_b * (-1.0f - gprime * sig * e2) * in_range;
+        // --- minus sum <dq_da, tanh(mu + sig * eps3)> ---
+        const float e3 = eps_q[i * A + j];
+        const float u3 = mu + sig * e3, t3 = tanhf(u3);
+        const float w = dq_da[i * A + j] * (1.0f - t3 * t3);
+        d_mu -= w;
+        d_ls -= w * sig * e3 * in_range;
+        dz[i * 2 * A + j] = d_mu;
+        dz[i * 2 * A + A + j] = d_ls;
+    }
+}
+
+// seeds of d mean_b(min(q1, q2)) / dq_k (sac_q_head.py:84-86; tf.minimum sends the gradient to its first argument on
+// ties), optionally also out = min(q1, q2)
+__global__ void __launch_bounds__(256) sac_min_seed_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
+                                                           int64_t B, float* __restrict__ d1, float* __restrict__ d2,
+                                                           float* __restrict__ qmin) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const bool first = q1[i] <= q2[i];
+    const float s = 1.0f / (float)B;
+    if (d1) d1[i] = first ? s : 0.f;
+    if (d2) d2[i] = first ? 0.f : s;
+    if (qmin) qmin[i] = first ? q1[i] : q2[i];
+}
+
+// out[i] = a[i] - b[i]   (value targets = min Q - log pi, soft_actor_critic_agent.py:244)
+__global__ void __launch_bounds__(256) sub_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                  float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] - b[i];
+}
+
 // out[i] = (float) in[i]   (fp64 advantages / value targets -> fp32 network feeds)
 __global__ void __launch_bounds__(256) f64_to_f32_kernel(const double* __restrict__ in, int64_t n,
                                                          float* __restrict__ out) {
@@ -297,6 +378,42 @@ int cb200_td3_smooth_actions(float* actions, const float* noise, int64_t n, floa
     CB200_CHECK_ARG(actions && noise && n > 0, "bad arguments");
     CB200_LAUNCH(td3_smooth_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), actions, noise, n,
                  noise_clip, lo, hi);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+
+int cb200_sac_policy_sample(const float* head_out, const float* eps, int64_t batch, int32_t action_dim, float* raw_out,
+                            float* actions_out, float* logp_out, void* stream) {
+    CB200_CHECK_ARG(head_out && eps && batch > 0 && action_dim > 0, "bad arguments");
+    CB200_LAUNCH(sac_policy_sample_kernel, (unsigned)((batch + 255) / 256), 256, 0, as_stream(stream), head_out, eps,
+                 batch, action_dim, raw_out, actions_out, logp_out);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_sac_policy_grad(const float* head_out, const float* eps_logp, const float* eps_q, const float* dq_da,
+                          int64_t batch, int32_t action_dim, float* d_head_out, void* stream) {
+    CB200_CHECK_ARG(head_out && eps_logp && eps_q && dq_da && d_head_out && batch > 0 && action_dim > 0,
+                    "bad arguments");
+    CB200_LAUNCH(sac_policy_grad_kernel, (unsigned)((batch + 255) / 256), 256, 0, as_stream(stream), head_out, eps_logp,
+                 eps_q, dq_da, batch, action_dim, d_head_out);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_sac_min_seed(const float* q1, const float* q2, int64_t batch, float* d1, float* d2, float* qmin,
+                       void* stream) {
+    CB200_CHECK_ARG(q1 && q2 && batch > 0, "bad arguments");
+    CB200_LAUNCH(sac_min_seed_kernel, (unsigned)((batch + 255) / 256), 256, 0, as_stream(stream), q1, q2, batch, d1, d2,
+                 qmin);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_sub(const float* a, const float* b, int64_t n, float* out, void* stream) {
+    CB200_CHECK_ARG(a && b && out && n > 0, "bad arguments");
+    CB200_LAUNCH(sub_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), a, b, n, out);
     CB200_CHECK_LAUNCH();
     return CB200_OK;
 }

@@ -1,5 +1,5 @@
 // coach_b200/csrc/nn.cu -- C-ABI entry points of the dense contractions of the learn step (see nn_gemm.cuh).
-#include "nn_gemm_fast.cuh"
+#include "nn_gemm_tc.cuh"
 
 namespace cb200 {
 namespace gemm {
@@ -59,6 +59,40 @@ static void launch_fast(const cb200_gemm_desc& d, int M, int R, int splits, int 
         split_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ep, M, d.n);
         count_launch();
     }
+}
+
+template <int BN, bool kT, bool kU8>
+static int launch_tc(const cb200_gemm_desc& d, int M, int R, int splits, int r_per_split, cudaStream_t st) {
+    FastA a;
+    a.src = d.a_src;
+    a.lut = d.a_lut;
+    a.rowoff = d.a_rowoff;
+    a.coloff = d.a_coloff;
+    a.rowinfo = d.a_rowinfo;
+    a.colinfo = d.a_colinfo;
+    a.oh = d.a_oh;
+    a.ow = d.a_ow;
+    a.rows = d.a_rows;
+    a.cols = d.a_cols;
+    a.ones_col = (kT && d.a_ones_col) ? d.a_cols : -1;
+    EpiParams ep{d.c, d.ldc, d.bias, d.act, d.mask_y, d.mask_act, d.c_rowmap, d.workspace, splits, d.accumulate};
+    constexpr size_t smem = tc_smem_bytes<BN, kU8>();
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, kT, kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    dim3 grid((M + kTcBM - 1) / kTcBM, (d.n + BN - 1) / BN, splits);
+    gemm_tc_kernel<BN, kT, kU8><<<grid, 128, smem, st>>>(a, d.b, d.ldb, ep, M, d.n, R, r_per_split, d.a_u8_div);
+    count_launch();
+    if (splits > 1) {
+        const int64_t total = (int64_t)M * d.n;
+        split_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ep, M, d.n);
+        count_launch();
+    }
+    return 0;
 }
 
 // ---- small helpers -------------------------------------------------------------------------------------------------
@@ -150,6 +184,29 @@ int cb200_gemm(const cb200_gemm_desc* d, void* stream) {
     const bool fast = d->a_vec4 && d->n % 4 == 0 && d->ldb % 4 == 0 && d->a_cols % 4 == 0 &&
                       (reinterpret_cast<uintptr_t>(d->b) & 15) == 0 && M > 64;
     CB200_CHECK_ARG(!ones || fast, "a_ones_col needs the vectorised path (a_vec4, n % 4 == 0, more than 64 rows)");
+    // tensor-core path (tcgen05): operands split into 3 x bf16, fp32 accumulation in TMEM; the reduction length per
+    // launch is capped (split-R) because the TMEM accumulator truncates -- see nn_gemm_tc.cuh
+    const bool tc = fast && d->n % 16 == 0 && d->n >= 16 && tune_get("gemm_tc", 1, 0, 1) != 0 && d->ldc % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(d->c) | reinterpret_cast<uintptr_t>(d->mask_y) |
+                      reinterpret_cast<uintptr_t>(d->bias)) & 15) == 0 &&
+                    r_per_split <= gemm::kTcMaxSlice;
+    if (tc) {
+        // uint8 A with a declared divisor: the integers are contracted exactly from one bf16 plane
+        const bool u8 = d->a_lut != nullptr && d->a_u8_div > 0.f;
+        int rc;
+#define CB200_TC(BN_)                                                                                          \
+    (u8 ? (tr ? gemm::launch_tc<BN_, true, true>(*d, M, R, splits, r_per_split, st)                           \
+              : gemm::launch_tc<BN_, false, true>(*d, M, R, splits, r_per_split, st))                         \
+        : (tr ? gemm::launch_tc<BN_, true, false>(*d, M, R, splits, r_per_split, st)                          \
+              : gemm::launch_tc<BN_, false, false>(*d, M, R, splits, r_per_split, st)))
+        if (d->n <= 32) rc = CB200_TC(32);
+        else if (d->n <= 64) rc = CB200_TC(64);
+        else rc = CB200_TC(128);
+#undef CB200_TC
+        CB200_CHECK_ARG(rc == 0, "could not configure shared memory for the tcgen05 kernel");
+        CB200_CHECK_LAUNCH();
+        return CB200_OK;
+    }
     if (fast) {
         if (d->n <= 32) {
             if (tr) gemm::launch_fast<gemm::FastCfg<256, 32>, true>(*d, M, R, splits, r_per_split, st);

@@ -176,6 +176,9 @@ typedef struct cb200_gemm_desc {
                                 /*    and every a_rowoff % 4 == 0  => 128-bit (fp32) / 32-bit (uint8) operand loads   */
     int32_t a_ones_col;         /* a_transposed only: 1 = append an output row a_cols holding sum_m B[m, :] (the bias  */
                                 /*    gradient lands in c[a_cols, :], i.e. right behind the kernel gradient)          */
+    float a_u8_div;             /* uint8 A only, 0 = not declared: the caller states a_lut[v] == (float)v / a_u8_div.  */
+                                /*    The tensor-core path then contracts the raw integers (exact in bf16) and divides */
+                                /*    each accumulated sum by a_u8_div once; other paths read a_lut and ignore this.   */
 } cb200_gemm_desc;
 
 int cb200_gemm(const cb200_gemm_desc* h_desc, void* stream);
@@ -295,6 +298,25 @@ int cb200_min2(const float* a, const float* b, int64_t n, float* out, void* stre
 /* TD3 target policy smoothing (td3_agent.py:162-164): a = clip(a + clip(noise, -noise_clip, noise_clip), lo, hi) */
 int cb200_td3_smooth_actions(float* actions, const float* noise, int64_t n, float noise_clip, float lo, float hi,
                              void* stream);
+
+/* SACPolicyHead (heads/sac_head.py:60-97).  head_out [batch, 2*action_dim] = [mu | raw log-sigma]; log-sigma is clipped
+ * to [-20, 2]; u = mu + exp(log_sigma) * eps; a = tanh(u); logp = MVN-diag log-prob of u minus the tanh squash
+ * correction sum_j log(1 - a_j^2 + 1e-6).  Any output may be NULL. */
+int cb200_sac_policy_sample(const float* head_out, const float* eps, int64_t batch, int32_t action_dim, float* raw_out,
+                            float* actions_out, float* logp_out, void* stream);
+
+/* d/d(head_out) of  mean_b logp(eps_logp)  -  sum_b <dq_da_b, tanh(mu + sigma * eps_q)_b>  -- the combination
+ * policy_grads = dlogp_dphi - dq_dphi of soft_actor_critic_agent.py:213-232, each term with its own noise sample
+ * (the reference evaluates them in separate sess.run calls which re-sample, sac_head.py:80). */
+int cb200_sac_policy_grad(const float* head_out, const float* eps_logp, const float* eps_q, const float* dq_da,
+                          int64_t batch, int32_t action_dim, float* d_head_out, void* stream);
+
+/* qmin = min(q1, q2) and the seeds d mean_b(qmin) / dq1, dq2 (sac_q_head.py:84-86); outputs may be NULL. */
+int cb200_sac_min_seed(const float* q1, const float* q2, int64_t batch, float* d1, float* d2, float* qmin,
+                       void* stream);
+
+/* out = a - b  (fp32) */
+int cb200_sub(const float* a, const float* b, int64_t n, float* out, void* stream);
 
 /* out[i] = (float) in[i] */
 int cb200_f64_to_f32(const double* in, int64_t n, float* out, void* stream);

@@ -77,7 +77,7 @@ def ppo_minibatch_step(named, old_named, opt, mb, clip_eps, beta_entropy, dtype=
     new_params = opt.step([p.detach() for p in params], grads)
     return dict(total=float(total.detach()), value_loss=float(vl.detach()), policy_loss=float(pl.detach()),
                 grad_norm=float(gnorm), grads=OrderedDict(zip(names, [g.detach() for g in grads])),
-                new_params=OrderedDict(zip(names, new_params)), mean_ratio=float(ex["ratio"].mean()),
+                new_params=OrderedDict(zip(names, new_params)), mean_ratio=float(ex["ratio"].mean().detach()),
                 entropy=float(ex["entropy"].detach()), old_mu=old_mu.numpy(), v=ex["v"].detach().numpy())
 
 

@@ -62,14 +62,16 @@ def test_learn_from_batch_matches_oracle(twin):
             close(gc[n], ref["critic_grads"][n].numpy(), name="critic grad " + n)
         pc_new = ag.critic.store.export_named()
         for n in ref["new_critic"]:
-            close(pc_new[n], ref["new_critic"][n].numpy(), name="critic param " + n)
+            # Adam with eps = 1e-8 turns every gradient, however tiny, into a step of ~lr: entries whose gradient is
+            # at rounding-noise level legitimately differ by a small fraction of lr
+            close(pc_new[n], ref["new_critic"][n].numpy(), name="critic param " + n, atol=1e-2 * pc.learning_rate)
         if ref["actor_grads"] is not None:
             ga = ag.actor.store.export_named(ag.actor.store.grad)
             for n in ref["actor_grads"]:
                 close(ga[n], ref["actor_grads"][n].numpy(), name="actor grad " + n)
         pa_new = ag.actor.store.export_named()
         for n in ref["new_actor"]:
-            close(pa_new[n], ref["new_actor"][n].numpy(), name="actor param " + n)
+            close(pa_new[n], ref["new_actor"][n].numpy(), name="actor param " + n, atol=1e-2 * pa.learning_rate)
 
 
 def test_train_driver_with_episodic_replay_and_polyak():

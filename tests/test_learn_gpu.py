@@ -15,11 +15,11 @@ pytestmark = pytest.mark.gpu
 from oracle import nets as on     # noqa: E402  (checker only)
 
 
-def close(got, want, rtol=1e-5, name=""):
+def close(got, want, rtol=1e-5, name="", atol=0.0):
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     scale = np.abs(want).max() if want.size else 0.0
     err = np.abs(got - want)
-    tol = rtol * scale + rtol * np.abs(want)
+    tol = rtol * scale + rtol * np.abs(want) + atol
     assert np.all(err <= tol), "%s: max err %.3e (scale %.3e, allowed %.3e)" % (name, err.max(), scale, tol.min())
 
 
