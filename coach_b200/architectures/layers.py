@@ -40,6 +40,48 @@ class Workspace(object):
         return self.buf.data_ptr()
 
 
+class PlaneRegistry(object):
+    """fp32 device buffers that are shadowed by bf16 hi / mid / lo planes (cb200_gemm_desc.a_planes / b_planes /
+    c_planes).  A GemmOp whose operand lies inside a registered buffer picks the planes up automatically; whoever
+    writes a registered buffer outside a GEMM epilogue must refresh the planes (``refresh``)."""
+
+    def __init__(self):
+        self.entries = []            # (weakref to base tensor, base_ptr, nbytes, planes [3, stride] bf16)
+
+    def register(self, t):
+        import weakref
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        if t.numel() % 8 or t.data_ptr() % 16:
+            return None
+        self.entries = [e for e in self.entries if e[0]() is not None]
+        for ref, ptr, nbytes, planes in self.entries:
+            if ptr == t.data_ptr() and nbytes == t.numel() * 4:
+                return planes
+        stride = (t.numel() + 7) // 8 * 8
+        planes = torch.zeros((3, stride), dtype=torch.bfloat16, device=t.device)
+        self.entries.append((weakref.ref(t), t.data_ptr(), t.numel() * 4, planes))
+        return planes
+
+    def lookup(self, ptr):
+        """(pointer to the plane-0 element shadowing `ptr`, plane stride in elements) or (0, 0)"""
+        for ref, base, nbytes, planes in self.entries:
+            if ref() is not None and base <= ptr < base + nbytes:
+                e = (ptr - base) // 4
+                if e % 8 == 0 and planes.data_ptr() % 16 == 0:
+                    return planes.data_ptr() + 2 * e, planes.shape[1]
+        return 0, 0
+
+    def refresh(self, lib, t):
+        """re-derive the planes of a registered buffer from its fp32 content (one launch)"""
+        planes = self.register(t)
+        n = t.numel()
+        _lib.check(lib.cb200_split_planes(t.data_ptr(), n, planes.data_ptr(), planes.shape[1], _lib.current_stream()))
+        return planes
+
+
+PLANES = PlaneRegistry()
+
+
 def _u8_div(lut, x_is_u8):
     return float(getattr(lut, "u8_div", 0.0)) if (x_is_u8 and lut is not None) else 0.0
 
@@ -53,12 +95,22 @@ class GemmOp(object):
         self.keep = []
         self.desc = _lib.GemmDesc()
         self.splits = int(fields.pop("splits", 1))
+        use_planes = bool(fields.pop("use_planes", False))
         for k, v in fields.items():
             if torch.is_tensor(v):
                 self.keep.append(v)
                 v = v.data_ptr()
             setattr(self.desc, k, v)
         self.desc.splits = self.splits
+        # operands / outputs that live in plane-shadowed buffers (PlaneRegistry): hand the planes to the kernel
+        # (only for ops of an instance that keeps them current: use_planes)
+        d = self.desc
+        if use_planes and not d.a_lut and d.a_vec8:
+            d.a_planes, d.a_plane_stride = PLANES.lookup(d.a_src or 0)
+        if use_planes and d.n % 8 == 0 and d.ldb % 8 == 0:
+            d.b_planes, d.b_plane_stride = PLANES.lookup(d.b or 0)
+        if use_planes and d.ldc % 8 == 0:
+            d.c_planes, d.c_plane_stride = PLANES.lookup(d.c or 0)
         rows = self.desc.a_cols if self.desc.a_transposed else self.desc.a_rows
         if self.desc.a_ones_col:
             rows += 1
@@ -122,7 +174,7 @@ class Dense(object):
         return self.N
 
     def prepare(self, lib, ws, B, device, x, y, w, b, dw, db, dy, dx, x_is_u8=False, lut=None, need_dx=True,
-                prev_act=0, dx_accumulate=False):
+                prev_act=0, dx_accumulate=False, planes=False):
         """x [B,K], y [B,N], dy [B,N] (gradient wrt the PRE-activation of this layer), dx [B,K] (gradient wrt the
         pre-activation of the previous layer: masked with prev_act' evaluated on x)."""
         K, N = self.K, self.N
@@ -130,7 +182,8 @@ class Dense(object):
         coloff = _dev_i32(np.arange(K), device)
         vec = int(K % 4 == 0)
         common = dict(a_rowoff=rowoff, a_coloff=coloff, a_rows=B, a_cols=K, a_vec4=vec, a_src=x,
-                      a_lut=lut if x_is_u8 else None, a_u8_div=_u8_div(lut, x_is_u8))
+                      a_lut=lut if x_is_u8 else None, a_u8_div=_u8_div(lut, x_is_u8), a_vec8=int(K % 8 == 0),
+                      use_planes=planes)
         self.fwd = GemmOp(lib, ws, a_transposed=0, b=w, ldb=N, n=N, c=y, ldc=N, bias=b, act=self.act,
                           splits=pick_splits(_tiles(B, N, vec), K), **common)
         self.bwd_w = None
@@ -145,11 +198,13 @@ class Dense(object):
         self.bwd_x = None
         if need_dx:
             self.wT = torch.empty((N, K), dtype=torch.float32, device=device)
+            self.wT_planes = PLANES.register(self.wT) if planes else None
             self.w = w
             ro = _dev_i32(np.arange(B) * N, device)
             co = _dev_i32(np.arange(N), device)
             self.bwd_x = GemmOp(lib, ws, a_src=dy, a_rowoff=ro, a_coloff=co, a_rows=B, a_cols=N, a_transposed=0,
-                                a_vec4=int(N % 4 == 0), b=self.wT, ldb=K, n=K, c=dx, ldc=K,
+                                a_vec4=int(N % 4 == 0), a_vec8=int(N % 8 == 0), b=self.wT, ldb=K, n=K, c=dx, ldc=K,
+                                use_planes=planes,
                                 mask_y=x if prev_act else None, mask_act=prev_act,
                                 accumulate=int(bool(dx_accumulate)),
                                 splits=pick_splits(_tiles(B, K, N % 4 == 0), N))
@@ -166,7 +221,10 @@ class Dense(object):
                 dy, B, N, db = self.db_args
                 _lib.check(self.lib.cb200_colsum(dy.data_ptr(), B, N, db.data_ptr(), self.ws.ptr(), st))
         if self.bwd_x is not None:
-            _lib.check(self.lib.cb200_transpose(self.w.data_ptr(), self.K, self.N, self.wT.data_ptr(), st))
+            pl = self.wT_planes
+            _lib.check(self.lib.cb200_transpose(self.w.data_ptr(), self.K, self.N, self.wT.data_ptr(),
+                                                pl.data_ptr() if pl is not None else None,
+                                                pl.shape[1] if pl is not None else 0, st))
             self.bwd_x.run()
 
 
@@ -191,7 +249,7 @@ class Conv2d(object):
         return self.OH * self.OW * self.N
 
     def prepare(self, lib, ws, B, device, x, y, w, b, dw, db, dy, dx, x_is_u8=False, lut=None, need_dx=True,
-                prev_act=0, dx_accumulate=False):
+                prev_act=0, dx_accumulate=False, planes=False):
         assert not dx_accumulate, "accumulating data gradients is only wired for Dense layers"
         H, W, C, N, KH, KW, S, OH, OW, K = self.H, self.W, self.C, self.N, self.KH, self.KW, self.S, self.OH, \
             self.OW, self.K
@@ -203,7 +261,8 @@ class Conv2d(object):
         assert rowoff.max() + coloff.max() < 2 ** 31
         vec = int(C % 4 == 0)          # (kx, c) runs are contiguous: groups of 4 channels never straddle a pixel
         common = dict(a_rowoff=_dev_i32(rowoff, device), a_coloff=_dev_i32(coloff, device), a_rows=M, a_cols=K,
-                      a_src=x, a_lut=lut if x_is_u8 else None, a_vec4=vec, a_u8_div=_u8_div(lut, x_is_u8))
+                      a_src=x, a_lut=lut if x_is_u8 else None, a_vec4=vec, a_u8_div=_u8_div(lut, x_is_u8),
+                      a_vec8=int(C % 8 == 0), use_planes=planes)
         self.fwd = GemmOp(lib, ws, a_transposed=0, b=w, ldb=N, n=N, c=y, ldc=N, bias=b, act=self.act,
                           splits=pick_splits(_tiles(M, N, vec), K), **common)
         self.bwd_w = None
@@ -241,13 +300,15 @@ class Conv2d(object):
                 perm = w_index[S * a_ + py, S * t_ + px, :, n_]          # [TA, TB, N, C]
                 perm = perm.reshape(-1)
                 wt = torch.empty((TA * TB * N, C), dtype=torch.float32, device=device)
+                wt_planes = PLANES.register(wt) if planes else None
                 op = GemmOp(lib, ws, a_src=dy, a_rowoff=_dev_i32(ro, device), a_coloff=_dev_i32(co, device),
                             a_rowinfo=_dev_i32(rinfo, device), a_colinfo=_dev_i32(cinfo, device), a_oh=OH, a_ow=OW,
                             a_rows=B * IH * IW, a_cols=TA * TB * N, a_transposed=0, a_vec4=int(N % 4 == 0),
+                            a_vec8=int(N % 8 == 0), use_planes=planes,
                             b=wt, ldb=C, n=C, c=dx, ldc=C,
                             mask_y=x if prev_act else None, mask_act=prev_act, c_rowmap=_dev_i32(rowmap, device),
                             splits=pick_splits(_tiles(B * IH * IW, C, N % 4 == 0), TA * TB * N))
-                self.classes.append((op, wt, _dev_i32(perm, device)))
+                self.classes.append((op, wt, _dev_i32(perm, device), wt_planes))
 
     def forward(self):
         self.fwd.run()
@@ -259,6 +320,8 @@ class Conv2d(object):
             if self.db_args is not None:
                 dy, M, N, db = self.db_args
                 _lib.check(self.lib.cb200_colsum(dy.data_ptr(), M, N, db.data_ptr(), self.ws.ptr(), st))
-        for op, wt, perm in self.classes:
-            _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), perm.data_ptr(), perm.numel(), wt.data_ptr(), st))
+        for op, wt, perm, pl in self.classes:
+            _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), perm.data_ptr(), perm.numel(), wt.data_ptr(),
+                                                  pl.data_ptr() if pl is not None else None,
+                                                  pl.shape[1] if pl is not None else 0, st))
             op.run()

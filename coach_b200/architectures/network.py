@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from coach_b200 import _lib
-from coach_b200.architectures.layers import ACT, Workspace
+from coach_b200.architectures.layers import ACT, PLANES, Workspace
 
 
 class ParamStore(object):
@@ -29,14 +29,15 @@ class ParamStore(object):
         if self.theta is not None:
             raise RuntimeError("ParamStore is finalised")
         n = int(np.prod(shape)) if len(shape) else 1
-        # keep every tensor 16-byte aligned inside the flat buffer (vector loads in the kernels)
-        self.size = (self.size + 3) // 4 * 4
+        # keep every tensor 32-byte aligned inside the flat buffer (vector loads in the kernels; 16-byte aligned
+        # rows in the bf16 planes that shadow the buffer, layers.PlaneRegistry)
+        self.size = (self.size + 7) // 8 * 8
         self.entries[name] = (self.size, tuple(shape))
         self.size += n
         return name
 
     def finalize(self):
-        self.size = (self.size + 3) // 4 * 4
+        self.size = (self.size + 7) // 8 * 8
         z = lambda: torch.zeros(self.size, dtype=torch.float32, device=self.device)   # noqa: E731
         self.theta, self.grad, self.m, self.v = z(), z(), z(), z()
         return self
@@ -92,11 +93,11 @@ class Sequential(object):
             self.names.append([store.add(base + "/" + pname, shape) for pname, shape in layer.param_shapes])
 
     def instantiate(self, lib, ws, B, x, theta, grad=None, x_is_u8=False, lut=None, need_input_grad=False,
-                    input_act=0, train=False, dx_in=None, dx_accumulate=False):
+                    input_act=0, train=False, dx_in=None, dx_accumulate=False, planes=False):
         """need_input_grad: also produce the gradient wrt the (pre-activation of the) input, masked by
         ``input_act``' evaluated on x; it is written (or, with dx_accumulate, added) to ``dx_in``."""
         return SequentialInstance(self, lib, ws, B, x, theta, grad, x_is_u8, lut, need_input_grad, input_act, train,
-                                  dx_in, dx_accumulate)
+                                  dx_in, dx_accumulate, planes)
 
 
 class SequentialInstance(object):
@@ -104,7 +105,7 @@ class SequentialInstance(object):
     pre-activation gradient buffers and prepares the backward ops (gradients land in ``grad``)."""
 
     def __init__(self, seq, lib, ws, B, x, theta, grad, x_is_u8, lut, need_input_grad, input_act, train,
-                 dx_in=None, dx_accumulate=False):
+                 dx_in=None, dx_accumulate=False, planes=False):
         import copy
         self.seq, self.B = seq, B
         dev = theta.device
@@ -121,6 +122,13 @@ class SequentialInstance(object):
             dz = torch.empty_like(y) if train else None
             self.acts.append(y)
             self.dzs.append(dz)
+            # planes=True: the hidden activations / pre-activation gradients are produced by GEMM epilogues only and
+            # consumed by GEMMs, so they carry bf16 planes (the caller keeps the parameter planes current).  The
+            # last layer's output and gradient are touched by head kernels and stay plain fp32.
+            if planes and i + 1 < len(self.layers):
+                PLANES.register(y)
+                if dz is not None:
+                    PLANES.register(dz)
         for i, layer in enumerate(self.layers):
             wname, bname = seq.names[i]
             w, b = store.view(theta, wname), store.view(theta, bname)
@@ -132,18 +140,20 @@ class SequentialInstance(object):
             if train:
                 layer.prepare(lib, ws, B, dev, prev, self.acts[i], w, b, dw, db, self.dzs[i], dx,
                               x_is_u8=(x_is_u8 and first), lut=lut, need_dx=need_dx, prev_act=prev_act,
-                              dx_accumulate=(dx_accumulate and first))
+                              dx_accumulate=(dx_accumulate and first), planes=planes)
             else:
-                self._prepare_fwd_only(layer, lib, ws, B, dev, prev, self.acts[i], w, b, x_is_u8 and first, lut)
+                self._prepare_fwd_only(layer, lib, ws, B, dev, prev, self.acts[i], w, b, x_is_u8 and first, lut,
+                                       planes)
             prev, prev_act = self.acts[i], layer.act
         self.out = self.acts[-1]
         self.d_out = self.dzs[-1]
         self.train = train
 
     @staticmethod
-    def _prepare_fwd_only(layer, lib, ws, B, dev, x, y, w, b, x_is_u8, lut):
+    def _prepare_fwd_only(layer, lib, ws, B, dev, x, y, w, b, x_is_u8, lut, planes=False):
         # reuse prepare() with dummy gradient tensors but drop the backward ops: forward descriptors are identical
-        layer.prepare(lib, ws, B, dev, x, y, w, b, None, None, None, None, x_is_u8=x_is_u8, lut=lut, need_dx=False)
+        layer.prepare(lib, ws, B, dev, x, y, w, b, None, None, None, None, x_is_u8=x_is_u8, lut=lut, need_dx=False,
+                      planes=planes)
 
     def forward(self):
         for layer in self.layers:

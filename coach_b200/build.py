@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("CB200_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DCB200_TC_PROF (tools/tc_phase_probe.py)
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
         ["-shared", "-o", LIB_PATH + ".tmp"] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -8,6 +8,12 @@ using CfgN64 = Cfg<128, 64, 16, 8, 8>;   // 128 threads, 8x8 per thread
 using CfgN32 = Cfg<128, 32, 16, 8, 4>;   // 128 threads, 8x4 per thread
 using CfgSmall = Cfg<32, 32, 16, 4, 4>;  // 64 threads: small-batch MLPs
 
+static EpiParams make_epi(const cb200_gemm_desc& d, int splits) {
+    return EpiParams{d.c,        d.ldc,       d.bias, d.act,        d.mask_y,
+                     d.mask_act, d.c_rowmap,  d.workspace, splits,  d.accumulate,
+                     static_cast<uint16_t*>(d.c_planes), d.c_plane_stride};
+}
+
 template <class C, bool kT>
 static void launch(const cb200_gemm_desc& d, int M, int R, int splits, int r_per_split, cudaStream_t st) {
     ALoader<C, kT> al;
@@ -25,13 +31,12 @@ static void launch(const cb200_gemm_desc& d, int M, int R, int splits, int r_per
     bl.b = d.b;
     bl.N = d.n;
     bl.ldb = d.ldb;
-    EpiParams ep{d.c, d.ldc, d.bias, d.act, d.mask_y, d.mask_act, d.c_rowmap, d.workspace, splits, d.accumulate};
+    const EpiParams ep = make_epi(d, splits);
     dim3 grid((M + C::BM - 1) / C::BM, (d.n + C::BN - 1) / C::BN, splits);
     gemm_kernel<C, kT><<<grid, C::T, 0, st>>>(al, bl, ep, M, d.n, R, r_per_split);
     count_launch();
     if (splits > 1) {
-        const int64_t total = (int64_t)M * d.n;
-        split_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ep, M, d.n);
+        launch_split_reduce(ep, M, d.n, st);
         count_launch();
     }
 }
@@ -50,13 +55,12 @@ static void launch_fast(const cb200_gemm_desc& d, int M, int R, int splits, int 
     a.rows = d.a_rows;
     a.cols = d.a_cols;
     a.ones_col = (kT && d.a_ones_col) ? d.a_cols : -1;
-    EpiParams ep{d.c, d.ldc, d.bias, d.act, d.mask_y, d.mask_act, d.c_rowmap, d.workspace, splits, d.accumulate};
+    const EpiParams ep = make_epi(d, splits);
     dim3 grid((M + C::BM - 1) / C::BM, (d.n + C::BN - 1) / C::BN, splits);
     gemm_fast_kernel<C, kT><<<grid, C::T, 0, st>>>(a, d.b, d.ldb, ep, M, d.n, R, r_per_split);
     count_launch();
     if (splits > 1) {
-        const int64_t total = (int64_t)M * d.n;
-        split_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ep, M, d.n);
+        launch_split_reduce(ep, M, d.n, st);
         count_launch();
     }
 }
@@ -75,7 +79,7 @@ static int launch_tc(const cb200_gemm_desc& d, int M, int R, int splits, int r_p
     a.rows = d.a_rows;
     a.cols = d.a_cols;
     a.ones_col = (kT && d.a_ones_col) ? d.a_cols : -1;
-    EpiParams ep{d.c, d.ldc, d.bias, d.act, d.mask_y, d.mask_act, d.c_rowmap, d.workspace, splits, d.accumulate};
+    const EpiParams ep = make_epi(d, splits);
     constexpr size_t smem = tc_smem_bytes<BN, kU8>();
     static bool configured = false;
     if (!configured) {
@@ -85,14 +89,66 @@ static int launch_tc(const cb200_gemm_desc& d, int M, int R, int splits, int r_p
         configured = true;
     }
     dim3 grid((M + kTcBM - 1) / kTcBM, (d.n + BN - 1) / BN, splits);
-    gemm_tc_kernel<BN, kT, kU8><<<grid, 128, smem, st>>>(a, d.b, d.ldb, ep, M, d.n, R, r_per_split, d.a_u8_div);
+    const bool bp = d.b_planes != nullptr && d.n % 8 == 0 && d.ldb % 8 == 0;
+    gemm_tc_kernel<BN, kT, kU8><<<grid, 128, smem, st>>>(a, d.b, d.ldb, ep, M, d.n, R, r_per_split, d.a_u8_div,
+                                                         bp ? static_cast<const uint16_t*>(d.b_planes) : nullptr,
+                                                         d.b_plane_stride);
     count_launch();
     if (splits > 1) {
-        const int64_t total = (int64_t)M * d.n;
-        split_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ep, M, d.n);
+        launch_split_reduce(ep, M, d.n, st);
         count_launch();
     }
     return 0;
+}
+
+template <int BN, bool kT>
+static int launch_tc_planes(const cb200_gemm_desc& d, int M, int R, int splits, int r_per_split, cudaStream_t st) {
+    FastA a;
+    a.src = d.a_src;
+    a.lut = nullptr;
+    a.rowoff = d.a_rowoff;
+    a.coloff = d.a_coloff;
+    a.rowinfo = d.a_rowinfo;
+    a.colinfo = d.a_colinfo;
+    a.oh = d.a_oh;
+    a.ow = d.a_ow;
+    a.rows = d.a_rows;
+    a.cols = d.a_cols;
+    a.ones_col = (kT && d.a_ones_col) ? d.a_cols : -1;
+    const EpiParams ep = make_epi(d, splits);
+    PlaneOperands pl{static_cast<const uint16_t*>(d.a_planes), d.a_plane_stride,
+                     static_cast<const uint16_t*>(d.b_planes), d.b_plane_stride};
+    const int slice = kT ? r_per_split : (r_per_split + 7) / 8;
+    const size_t smem = tc_planes_smem_bytes<BN>(slice, d.a_rowinfo != nullptr);
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(gemm_tc_planes_kernel<BN, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return -1;
+        configured = smem;
+    }
+    dim3 grid((M + kTcBM - 1) / kTcBM, (d.n + BN - 1) / BN, splits);
+    gemm_tc_planes_kernel<BN, kT><<<grid, 128, smem, st>>>(a, pl, d.ldb, ep, M, d.n, R, r_per_split, slice);
+    count_launch();
+    if (splits > 1) {
+        launch_split_reduce(ep, M, d.n, st);
+        count_launch();
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int64_t n,
+                                                           uint16_t* __restrict__ planes, int64_t stride) {
+    // 8 elements per thread (n % 8 == 0, 16-byte aligned planes): two 128-bit loads, three 128-bit stores
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n;
+         i += (int64_t)gridDim.x * blockDim.x * 8) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + i));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+        const Split8 sp = split8(v0, v1);
+        *reinterpret_cast<uint4*>(planes + i) = sp.h;
+        *reinterpret_cast<uint4*>(planes + stride + i) = sp.m;
+        *reinterpret_cast<uint4*>(planes + 2 * stride + i) = sp.l;
+    }
 }
 
 // ---- small helpers -------------------------------------------------------------------------------------------------
@@ -139,12 +195,17 @@ __global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ p
 }
 
 __global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ src, const int32_t* __restrict__ table,
-                                                      int64_t n, float* __restrict__ dst) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        dst[i] = __ldg(src + __ldg(table + i));
+                                                      int64_t n, float* __restrict__ dst, uint16_t* __restrict__ planes,
+                                                      int64_t stride) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __ldg(src + __ldg(table + i));
+        dst[i] = v;
+        if (planes) split3(v, planes[i], planes[stride + i], planes[2 * stride + i]);
+    }
 }
 
-__global__ void transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, float* __restrict__ dst) {
+__global__ void transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, float* __restrict__ dst,
+                                 uint16_t* __restrict__ planes, int64_t stride) {
     __shared__ float tile[32][33];
     const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -154,7 +215,14 @@ __global__ void transpose_kernel(const float* __restrict__ src, int64_t rows, in
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int64_t c = c0 + i, r = r0 + threadIdx.x;
-        if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][i];
+        if (r < rows && c < cols) {
+            const float v = tile[threadIdx.x][i];
+            dst[c * rows + r] = v;
+            if (planes) {
+                const int64_t e = c * rows + r;
+                split3(v, planes[e], planes[stride + e], planes[2 * stride + e]);
+            }
+        }
     }
 }
 
@@ -190,6 +258,23 @@ int cb200_gemm(const cb200_gemm_desc* d, void* stream) {
                     ((reinterpret_cast<uintptr_t>(d->c) | reinterpret_cast<uintptr_t>(d->mask_y) |
                       reinterpret_cast<uintptr_t>(d->bias)) & 15) == 0 &&
                     r_per_split <= gemm::kTcMaxSlice;
+    const bool planes = tc && d->a_planes && d->b_planes && d->a_vec8 && !d->a_lut && d->a_cols % 8 == 0 &&
+                        d->n % 8 == 0 && d->ldb % 8 == 0 && tune_get("gemm_planes", 1, 0, 1) != 0 &&
+                        ((reinterpret_cast<uintptr_t>(d->a_planes) | reinterpret_cast<uintptr_t>(d->b_planes)) & 15) == 0 &&
+                        d->a_plane_stride % 8 == 0 && d->b_plane_stride % 8 == 0;
+    if (planes) {
+        int rc;
+#define CB200_TCP(BN_)                                                                 \
+    (tr ? gemm::launch_tc_planes<BN_, true>(*d, M, R, splits, r_per_split, st)        \
+        : gemm::launch_tc_planes<BN_, false>(*d, M, R, splits, r_per_split, st))
+        if (d->n <= 32) rc = CB200_TCP(32);
+        else if (d->n <= 64) rc = CB200_TCP(64);
+        else rc = CB200_TCP(128);
+#undef CB200_TCP
+        CB200_CHECK_ARG(rc == 0, "could not configure shared memory for the tcgen05 planes kernel");
+        CB200_CHECK_LAUNCH();
+        return CB200_OK;
+    }
     if (tc) {
         // uint8 A with a declared divisor: the integers are contracted exactly from one bf16 plane
         const bool u8 = d->a_lut != nullptr && d->a_u8_div > 0.f;
@@ -236,6 +321,32 @@ int cb200_gemm(const cb200_gemm_desc* d, void* stream) {
     return CB200_OK;
 }
 
+#ifdef CB200_TC_PROF
+int cb200_tc_prof_read(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, gemm::g_tc_prof, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(gemm::g_tc_prof, z, sizeof(z));
+    }
+    return CB200_OK;
+}
+#endif
+
+int cb200_split_planes(const float* src, int64_t n, void* planes, int64_t plane_stride, void* stream) {
+    CB200_CHECK_ARG(src && planes && n > 0 && n % 8 == 0 && plane_stride >= n && plane_stride % 8 == 0,
+                    "bad arguments (n and plane_stride must be multiples of 8)");
+    CB200_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(planes)) & 15) == 0,
+                    "src and planes must be 16-byte aligned");
+    int64_t grid = (n / 8 + 255) / 256;
+    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+    gemm::split_planes_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(src, n, static_cast<uint16_t*>(planes),
+                                                                             plane_stride);
+    count_launch();
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
 int cb200_colsum(const float* x, int64_t rows, int64_t cols, float* out, float* workspace, void* stream) {
     CB200_CHECK_ARG(x && out && workspace && rows > 0 && cols > 0, "bad arguments");
     int nslab = (int)((rows + 255) / 256);
@@ -249,20 +360,24 @@ int cb200_colsum(const float* x, int64_t rows, int64_t cols, float* out, float* 
     return CB200_OK;
 }
 
-int cb200_permute_f32(const float* src, const int32_t* table, int64_t n, float* dst, void* stream) {
+int cb200_permute_f32(const float* src, const int32_t* table, int64_t n, float* dst, void* dst_planes,
+                      int64_t plane_stride, void* stream) {
     CB200_CHECK_ARG(src && table && dst && n > 0, "bad arguments");
     int64_t grid = (n + 255) / 256;
     if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
-    gemm::permute_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(src, table, n, dst);
+    gemm::permute_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(src, table, n, dst,
+                                                                        static_cast<uint16_t*>(dst_planes), plane_stride);
     count_launch();
     CB200_CHECK_LAUNCH();
     return CB200_OK;
 }
 
-int cb200_transpose(const float* src, int64_t rows, int64_t cols, float* dst, void* stream) {
+int cb200_transpose(const float* src, int64_t rows, int64_t cols, float* dst, void* dst_planes, int64_t plane_stride,
+                    void* stream) {
     CB200_CHECK_ARG(src && dst && rows > 0 && cols > 0, "bad arguments");
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
-    gemm::transpose_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, rows, cols, dst);
+    gemm::transpose_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, rows, cols, dst,
+                                                                        static_cast<uint16_t*>(dst_planes), plane_stride);
     count_launch();
     CB200_CHECK_LAUNCH();
     return CB200_OK;

@@ -174,7 +174,22 @@ struct EpiParams {
     float* partial;            // splits > 1: raw partial sums [splits][M][N]
     int splits;
     int accumulate;            // c += v instead of c = v (after bias/act/mask); used by multi-class data gradients
+    uint16_t* c_planes;        // optional bf16 hi / mid / lo planes of c (same element indexing), see split3()
+    int64_t c_plane_stride;    // elements between planes
 };
+
+// Exact 3-way bf16 split of an fp32 value (truncation): x == hi + mid + lo, each the upper half-word of an fp32.
+// The tensor-core GEMM (nn_gemm_tc.cuh) consumes operands in this form; producers that know their output feeds another
+// GEMM write the planes next to the fp32 result so that consumers need no conversion work.
+__device__ __forceinline__ void split3(float x, uint16_t& h, uint16_t& m, uint16_t& l) {
+    const uint32_t hb = __float_as_uint(x) & 0xffff0000u;
+    const float r1 = x - __uint_as_float(hb);
+    const uint32_t mb = __float_as_uint(r1) & 0xffff0000u;
+    const uint32_t lb = __float_as_uint(r1 - __uint_as_float(mb));
+    h = (uint16_t)(hb >> 16);
+    m = (uint16_t)(mb >> 16);
+    l = (uint16_t)(lb >> 16);
+}
 
 __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int m, int n, float v) {
     const size_t row = ep.c_rowmap ? (size_t)__ldg(ep.c_rowmap + m) : (size_t)m;
@@ -182,7 +197,12 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int m, int n
     v = apply_act(v, ep.act);
     if (ep.mask_y) v *= act_grad_from_output(ep.mask_y[row * ep.ldc + n], ep.mask_act);
     float* dst = ep.c + row * ep.ldc + n;
-    *dst = ep.accumulate ? (*dst + v) : v;
+    if (ep.accumulate) v += *dst;
+    *dst = v;
+    if (ep.c_planes) {
+        uint16_t* p = ep.c_planes + row * ep.ldc + n;
+        split3(v, p[0], p[ep.c_plane_stride], p[2 * ep.c_plane_stride]);
+    }
 }
 
 template <class C, bool kTransposedA>
@@ -239,13 +259,57 @@ __global__ void __launch_bounds__(C::T) gemm_kernel(ALoader<C, kTransposedA> al,
     }
 }
 
-// deterministic split reduction: fixed order over the split index, then the normal epilogue
+// deterministic split reduction: fixed order over the split index, then the normal epilogue.
+// kVec (M * N % 4 == 0, N % 4 == 0): four consecutive outputs per thread through 128-bit loads of the partials.
+template <bool kVec>
 __global__ void __launch_bounds__(256) split_reduce_kernel(EpiParams ep, int M, int N) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)M * N) return;
+    const int64_t total = (int64_t)M * N;
+    if (kVec) {
+        const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (i >= total) return;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < ep.splits; ++s) {
+            const float4 p = *reinterpret_cast<const float4*>(ep.partial + (size_t)s * total + i);
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+        const int m = (int)(i / N), n = (int)(i % N);
+        epilogue_store(ep, m, n, v.x);
+        epilogue_store(ep, m, n + 1, v.y);
+        epilogue_store(ep, m, n + 2, v.z);
+        epilogue_store(ep, m, n + 3, v.w);
+    } else {
+        const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= total) return;
+        float v = 0.f;
+        for (int s = 0; s < ep.splits; ++s) v += ep.partial[(size_t)s * total + i];
+        epilogue_store(ep, (int)(i / N), (int)(i % N), v);
+    }
+}
+// many splits, few outputs (conv1 weight gradient: 291 partial tiles of 257 x 32): one warp per 4 outputs would still
+// walk 291 partials serially, so the splits are strided over the lanes of a warp and folded in a fixed order
+// (lane-strided partial sums, then a fixed shuffle tree) -- deterministic, but a different association than the
+// serial kernels, selected only by the split count.
+__global__ void __launch_bounds__(256) split_reduce_wide_kernel(EpiParams ep, int M, int N) {
+    const int64_t total = (int64_t)M * N;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= total) return;
     float v = 0.f;
-    for (int s = 0; s < ep.splits; ++s) v += ep.partial[(size_t)s * M * N + i];
-    epilogue_store(ep, (int)(i / N), (int)(i % N), v);
+    for (int s = lane; s < ep.splits; s += 32) v += ep.partial[(size_t)s * total + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) epilogue_store(ep, (int)(i / N), (int)(i % N), v);
+}
+
+inline void launch_split_reduce(const EpiParams& ep, int M, int N, cudaStream_t st) {
+    const int64_t total = (int64_t)M * N;
+    if (ep.splits >= 64 && total <= (1 << 16)) {
+        split_reduce_wide_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(ep, M, N);
+    } else if (N % 4 == 0 && total % 4 == 0 && (reinterpret_cast<uintptr_t>(ep.partial) & 15) == 0) {
+        split_reduce_kernel<true><<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(ep, M, N);
+    } else {
+        split_reduce_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ep, M, N);
+    }
 }
 
 }  // namespace gemm

@@ -26,6 +26,13 @@
 // registers right after chunk c has been converted (their latency overlaps the barrier, the MMA issue and the wait
 // for the stage).
 //
+// PLANES.  A producer that knows its output feeds another GEMM writes the bf16 hi / mid / lo planes next to the fp32
+// result (EpiParams::c_planes; weights are split once per step by cb200_split_planes).  When both operands come with
+// planes (a_planes, b_planes, a_vec8) the loader does no arithmetic at all: gemm_tc_planes_kernel moves 16-byte core
+// matrix rows global -> shared with cp.async through a 3-stage ring, invalid taps zero-filled by the copy itself.
+// The register-staged kernel below remains for uint8 sources (exact path), LUT sources and plane-less fp32 operands;
+// it accepts B planes too (conv1: weights / dY), which removes the B-side split.
+//
 // CTA = 128 threads = one 128 x BN output tile.  Two shared-memory stages: while the tensor core works on chunk c
 // (asynchronously, tracked by tcgen05.commit -> mbarrier), all threads convert chunk c+1.  Thread t owns output row t
 // in the epilogue (TMEM lane t): tcgen05.ld -> bias / activation / activation-derivative mask -> global.
@@ -118,9 +125,108 @@ __device__ __forceinline__ uint4 u8x8_to_bf16(uint32_t w0, uint32_t w1) {
                       __byte_perm(f[6], f[7], 0x7632));
 }
 
+__device__ __forceinline__ float4 as_float4(const uint4& q) {
+    return make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+}
 __device__ __forceinline__ bool tap_ok(int ri, int ci, int oh, int ow) {
     const int y = (ri >> 16) - (ci >> 16), x = (ri & 0xffff) - (ci & 0xffff);
     return y >= 0 && y < oh && x >= 0 && x < ow;
+}
+
+// thread = output row (TMEM lane): tcgen05.ld -> (1 / a_u8_div) -> bias / activation / activation-derivative mask ->
+// fp32 result (+ bf16 planes) or split-R partial
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_main, uint32_t tmem_corr, bool have_acc,
+                                            int m0, int n0, int M, int N, int split, bool u8, float a_u8_div,
+                                            int unscaled_row) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m = m0 + tid;
+    const bool scale_row = u8 && m != unscaled_row;
+#pragma unroll 1
+    for (int col = 0; col < BN; col += 8) {
+        uint32_t vm[8], vc[8];
+        if (have_acc) {
+            const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(vm[0]), "=r"(vm[1]), "=r"(vm[2]), "=r"(vm[3]), "=r"(vm[4]), "=r"(vm[5]), "=r"(vm[6]),
+                           "=r"(vm[7])
+                         : "r"(tmem_main + lane_base + (uint32_t)col));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(vc[0]), "=r"(vc[1]), "=r"(vc[2]), "=r"(vc[3]), "=r"(vc[4]), "=r"(vc[5]), "=r"(vc[6]),
+                           "=r"(vc[7])
+                         : "r"(tmem_corr + lane_base + (uint32_t)col));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vm[j] = vc[j] = 0u;
+        }
+        if (m < M) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+                if (scale_row) v[j] = __fdiv_rn(v[j], a_u8_div);
+            }
+            const int nb = n0 + col;
+            if (nb + 8 <= N && !ep.accumulate) {
+                // 2 x 128-bit stores per 8 columns (rows of C / the partial buffer are 16-byte aligned: N % 16 == 0)
+                float* dst;
+                size_t elem = 0;
+                if (ep.splits > 1) {
+                    dst = ep.partial + ((size_t)split * M + m) * N + nb;
+                } else {
+                    const size_t row = ep.c_rowmap ? (size_t)__ldg(ep.c_rowmap + m) : (size_t)m;
+                    elem = row * ep.ldc + nb;
+                    dst = ep.c + elem;
+                    if (ep.bias) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + 4));
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
+                    if (ep.mask_y) {
+                        const float4 y0 = *reinterpret_cast<const float4*>(ep.mask_y + elem);
+                        const float4 y1 = *reinterpret_cast<const float4*>(ep.mask_y + elem + 4);
+                        const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_output(yy[j], ep.mask_act);
+                    }
+                }
+                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = v[j];
+                }
+                if (ep.c_planes && ep.splits <= 1) {
+                    uint16_t* p = ep.c_planes + elem;
+                    if ((elem & 7) == 0) {
+                        const Split8 sp = split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+                        *reinterpret_cast<uint4*>(p) = sp.h;
+                        *reinterpret_cast<uint4*>(p + ep.c_plane_stride) = sp.m;
+                        *reinterpret_cast<uint4*>(p + 2 * ep.c_plane_stride) = sp.l;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            split3(v[j], p[j], p[ep.c_plane_stride + j], p[2 * ep.c_plane_stride + j]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = nb + j;
+                    if (n >= N) continue;
+                    if (ep.splits > 1)
+                        ep.partial[((size_t)split * M + m) * N + n] = v[j];
+                    else
+                        epilogue_store(ep, m, n, v[j]);
+                }
+            }
+        }
+    }
 }
 
 template <int BN, bool kU8>
@@ -132,7 +238,8 @@ constexpr size_t tc_smem_bytes() {
 // kU8: A is uint8 and contracted exactly (see the header); otherwise A is fp32, or uint8 through the LUT (general).
 template <int BN, bool kTransA, bool kU8>
 __global__ void __launch_bounds__(128) gemm_tc_kernel(FastA a, const float* __restrict__ b, int ldb, EpiParams ep,
-                                                      int M, int N, int R, int r_per_split, float a_u8_div) {
+                                                      int M, int N, int R, int r_per_split, float a_u8_div,
+                                                      const uint16_t* __restrict__ b_planes, int64_t b_plane_stride) {
     constexpr int NA = kU8 ? 1 : 3;                       // bf16 planes of the A operand
     constexpr int A_SPLIT = kTcBM * kTcBK * 2;            // bytes of one bf16 plane of the A chunk (8 KB)
     constexpr int B_SPLIT = BN * kTcBK * 2;
@@ -226,7 +333,7 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(FastA a, const float* __re
 
     float4 va[kU8 ? 1 : 4][2];
     uint2 wa[kU8 ? 4 : 1];
-    float4 vb[NB_IT][2];
+    uint4 vb[NB_IT][3];                                      // two float4 (fp32 B) or the three plane rows (B planes)
     const uint8_t* src8 = static_cast<const uint8_t*>(a.src);
     const float* src32 = static_cast<const float*>(a.src);
     auto load_group = [&](int off, float4& v, uint32_t& w) {       // one gather group of 4 elements
@@ -302,14 +409,23 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(FastA a, const float* __re
             const int it = tid + i * 128;
             const int kk = (it & 7) + 8 * (it / (8 * NG)), g = (it >> 3) % NG;
             const int r = r0 + kk, n = n0 + 8 * g;
-            float4 v0 = z4, v1 = z4;
-            if (r < r_hi) {
-                const float* p = b + (size_t)r * ldb + n;
-                if (n < N) v0 = __ldg(reinterpret_cast<const float4*>(p));
-                if (n + 4 < N) v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+            const uint4 zq = make_uint4(0u, 0u, 0u, 0u);
+            uint4 q0 = zq, q1 = zq, q2 = zq;
+            if (r < r_hi && n < N) {
+                if (b_planes) {                                   // N % 8 == 0: the 8 columns are all inside
+                    const uint16_t* p = b_planes + (size_t)r * ldb + n;
+                    q0 = __ldg(reinterpret_cast<const uint4*>(p));
+                    q1 = __ldg(reinterpret_cast<const uint4*>(p + b_plane_stride));
+                    q2 = __ldg(reinterpret_cast<const uint4*>(p + 2 * b_plane_stride));
+                } else {
+                    const float* p = b + (size_t)r * ldb + n;
+                    q0 = __ldg(reinterpret_cast<const uint4*>(p));
+                    if (n + 4 < N) q1 = __ldg(reinterpret_cast<const uint4*>(p + 4));
+                }
             }
-            vb[i][0] = v0;
-            vb[i][1] = v1;
+            vb[i][0] = q0;
+            vb[i][1] = q1;
+            vb[i][2] = q2;
         }
     };
     auto convert_store = [&](uint8_t* sA, uint8_t* sB) {
@@ -336,7 +452,14 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(FastA a, const float* __re
             const int it = tid + i * 128;
             const int kk = (it & 7) + 8 * (it / (8 * NG)), g = (it >> 3) % NG;
             const int off = (kk >> 3) * NG * 128 + g * 128 + (kk & 7) * 16;
-            const Split8 sp = split8(vb[i][0], vb[i][1]);
+            Split8 sp;
+            if (b_planes) {
+                sp.h = vb[i][0];
+                sp.m = vb[i][1];
+                sp.l = vb[i][2];
+            } else {
+                sp = split8(as_float4(vb[i][0]), as_float4(vb[i][1]));
+            }
             *reinterpret_cast<uint4*>(sB + 0 * B_SPLIT + off) = sp.h;
             *reinterpret_cast<uint4*>(sB + 1 * B_SPLIT + off) = sp.m;
             *reinterpret_cast<uint4*>(sB + 2 * B_SPLIT + off) = sp.l;
@@ -380,79 +503,264 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(FastA a, const float* __re
         mbar_wait(done_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    // ---------------- epilogue: thread = output row (TMEM lane) ----------------
-    const int m = m0 + tid;
-    const bool scale_row = kU8 && !(kTransA && m == a.ones_col);
-#pragma unroll 1
-    for (int col = 0; col < BN; col += 8) {
-        uint32_t vm[8], vc[8];
-        if (nchunks > 0) {
-            const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(vm[0]), "=r"(vm[1]), "=r"(vm[2]), "=r"(vm[3]), "=r"(vm[4]), "=r"(vm[5]), "=r"(vm[6]),
-                           "=r"(vm[7])
-                         : "r"(tmem_main + lane_base + (uint32_t)col));
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(vc[0]), "=r"(vc[1]), "=r"(vc[2]), "=r"(vc[3]), "=r"(vc[4]), "=r"(vc[5]), "=r"(vc[6]),
-                           "=r"(vc[7])
-                         : "r"(tmem_corr + lane_base + (uint32_t)col));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) vm[j] = vc[j] = 0u;
+    tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, N, split, kU8, a_u8_div,
+                    (kU8 && kTransA) ? a.ones_col : -1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_main), "r"(TMEM_COLS));
+    }
+}
+
+// =====================================================================================================================
+// Both operands pre-split (bf16 hi / mid / lo planes with the fp32 tensors' element indexing): pure data movement.
+// =====================================================================================================================
+constexpr int kPlStages = 3;
+
+#ifdef CB200_TC_PROF
+// build-time instrumentation (python -m coach_b200.build with CB200_EXTRA_NVCC_FLAGS=-DCB200_TC_PROF): cycles thread 0
+// of CTA (0,0,0) spends in each phase of the chunk loop, read back with cb200_tc_prof_read (tools/tc_phase_probe.py)
+__device__ unsigned long long g_tc_prof[16];
+#define TC_PROF_T(var) const long long var = clock64()
+#define TC_PROF_ADD(i, a, b) \
+    if (prof_on) g_tc_prof[i] += (unsigned long long)((b) - (a))
+#else
+#define TC_PROF_T(var)
+#define TC_PROF_ADD(i, a, b)
+#endif
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
+    // 16-byte global -> shared copy; src-size 0 zero-fills the destination without reading (invalid taps, tails)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 16 : 0)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct PlaneOperands {
+    const uint16_t* a;         // planes of the A source
+    int64_t a_stride;
+    const uint16_t* b;         // planes of B [R, ldb]
+    int64_t b_stride;
+};
+
+template <int BN>
+constexpr size_t tc_planes_stage_bytes() {
+    return (size_t)3 * kTcBM * kTcBK * 2 + 3 * BN * kTcBK * 2;
+}
+// dynamic shared memory: stages | barriers (64 B) | tab_off [slice] | tab_info [slice] (only with validity tables)
+template <int BN>
+inline size_t tc_planes_smem_bytes(int slice_entries, bool has_info) {
+    return kPlStages * tc_planes_stage_bytes<BN>() + 64 + (has_info ? 2 : 1) * sizeof(int32_t) * (size_t)slice_entries;
+}
+
+template <int BN, bool kTransA>
+__global__ void __launch_bounds__(128) gemm_tc_planes_kernel(FastA a, PlaneOperands pl, int ldb, EpiParams ep, int M,
+                                                             int N, int R, int r_per_split, int slice_entries) {
+    constexpr int A_SPLIT = kTcBM * kTcBK * 2;
+    constexpr int B_SPLIT = BN * kTcBK * 2;
+    constexpr int STAGE = 3 * A_SPLIT + 3 * B_SPLIT;
+    constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + kPlStages * STAGE);      // [kPlStages]
+    uint64_t* done_bar = empty_bar + kPlStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+    int32_t* tab_off = reinterpret_cast<int32_t*>(smem + kPlStages * STAGE + 64);
+    int32_t* tab_info = tab_off + slice_entries;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * BN;
+    const int split = blockIdx.z;
+    const int r_lo = split * r_per_split;
+    const int r_hi = min(R, r_lo + r_per_split);
+    const bool has_info = a.rowinfo != nullptr;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kPlStages; ++s) mbar_init(empty_bar + s, 1);
+        mbar_init(done_bar, 1);
+        fence_mbar_init();
+    }
+    // K-major: one table entry per group of 8 reduction indices; MN-major: one per reduction row
+    if (!kTransA) {
+        for (int j = tid; 8 * j < r_hi - r_lo; j += 128) {
+            tab_off[j] = __ldg(a.coloff + r_lo + 8 * j);
+            if (has_info) tab_info[j] = __ldg(a.colinfo + r_lo + 8 * j);
         }
-        if (m < M) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                v[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
-                if (scale_row) v[j] = __fdiv_rn(v[j], a_u8_div);
-            }
-            const int nb = n0 + col;
-            if (nb + 8 <= N && !ep.accumulate) {
-                // 2 x 128-bit stores per 8 columns (rows of C / the partial buffer are 16-byte aligned: N % 16 == 0)
-                float* dst;
-                if (ep.splits > 1) {
-                    dst = ep.partial + ((size_t)split * M + m) * N + nb;
-                } else {
-                    const size_t row = ep.c_rowmap ? (size_t)__ldg(ep.c_rowmap + m) : (size_t)m;
-                    dst = ep.c + row * ep.ldc + nb;
-                    if (ep.bias) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + 4));
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
-                    if (ep.mask_y) {
-                        const float4 y0 = *reinterpret_cast<const float4*>(ep.mask_y + row * ep.ldc + nb);
-                        const float4 y1 = *reinterpret_cast<const float4*>(ep.mask_y + row * ep.ldc + nb + 4);
-                        const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_output(yy[j], ep.mask_act);
-                    }
-                }
-                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = v[j];
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int n = nb + j;
-                    if (n >= N) continue;
-                    if (ep.splits > 1)
-                        ep.partial[((size_t)split * M + m) * N + n] = v[j];
-                    else
-                        epilogue_store(ep, m, n, v[j]);
-                }
-            }
+    } else {
+        for (int j = tid; j < r_hi - r_lo; j += 128) {
+            tab_off[j] = __ldg(a.rowoff + r_lo + j);
+            if (has_info) tab_info[j] = __ldg(a.rowinfo + r_lo + j);
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_main = *tmem_slot;
+    const uint32_t tmem_corr = tmem_main + BN;
+    const uint32_t idesc = umma_instr_desc_bf16(BN, kTransA ? 1 : 0, 1);
+
+    // item -> thread mapping as in gemm_tc_kernel (a quarter-warp fills one 128-byte core matrix)
+    const int kgrp = lane >> 3;
+    int fix_off[4] = {-1, -1, -1, -1};     // K-major: rowoff[m_i];  MN-major: [0] = coloff[k] (or -2: the ones row)
+    int fix_info[4] = {0, 0, 0, 0};
+    if (!kTransA) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + 8 * warp + (lane & 7) + 32 * i;
+            if (m < a.rows) {
+                fix_off[i] = __ldg(a.rowoff + m);
+                if (has_info) fix_info[i] = __ldg(a.rowinfo + m);
+            }
+        }
+    } else {
+        const int k = m0 + 8 * (tid >> 3);
+        if (k < a.cols) {
+            fix_off[0] = __ldg(a.coloff + k);
+            if (has_info) fix_info[0] = __ldg(a.colinfo + k);
+        } else if (k == a.ones_col) {
+            fix_off[0] = -2;
+        }
+    }
+    constexpr int NG = BN / 8;
+    constexpr int NB_IT = kTcBK * NG / 128;
+    static_assert(kTcBK * NG % 128 == 0, "B loader shape");
+    const uint32_t smem_base = smem_u32(smem);
+
+    auto issue = [&](int c, int s) {
+        const int r0 = r_lo + c * kTcBK;
+        const uint32_t sA = smem_base + s * STAGE, sB = sA + 3 * A_SPLIT;
+        if (!kTransA) {
+            const int ra = r0 + kgrp * 8;
+            const int ja = (ra - r_lo) >> 3;
+            const bool in = ra < r_hi;
+            const int ca = in ? tab_off[ja] : 0;
+            const int ia = (in && has_info) ? tab_info[ja] : 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rr = 8 * warp + (lane & 7) + 32 * i;
+                const uint32_t off = kgrp * (kTcBM / 8) * 128 + (rr >> 3) * 128 + (rr & 7) * 16;
+                const bool ok = in && fix_off[i] >= 0 && (!has_info || tap_ok(fix_info[i], ia, a.oh, a.ow));
+                const uint16_t* src = pl.a + (ok ? (int64_t)(fix_off[i] + ca) : 0);
+                cp_async16(sA + off, src, ok);
+                cp_async16(sA + A_SPLIT + off, src + pl.a_stride, ok);
+                cp_async16(sA + 2 * A_SPLIT + off, src + 2 * pl.a_stride, ok);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int mrow = r0 + 8 * i + (tid & 7);
+                const uint32_t off = i * (kTcBM / 8) * 128 + (tid >> 3) * 128 + (tid & 7) * 16;
+                const bool in = mrow < r_hi;
+                if (fix_off[0] == -2) {
+                    // bias-gradient row: A^T element 1.0 in the group's first column (bf16 0x3F80 in the hi plane)
+                    uint8_t* g = smem + s * STAGE + off;
+                    *reinterpret_cast<uint4*>(g) = make_uint4(in ? 0x3F80u : 0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(g + A_SPLIT) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(g + 2 * A_SPLIT) = make_uint4(0u, 0u, 0u, 0u);
+                    continue;
+                }
+                bool ok = in && fix_off[0] >= 0;
+                int64_t e = 0;
+                if (ok) {
+                    if (has_info && !tap_ok(tab_info[mrow - r_lo], fix_info[0], a.oh, a.ow)) ok = false;
+                    else e = (int64_t)tab_off[mrow - r_lo] + fix_off[0];
+                }
+                const uint16_t* src = pl.a + e;
+                cp_async16(sA + off, src, ok);
+                cp_async16(sA + A_SPLIT + off, src + pl.a_stride, ok);
+                cp_async16(sA + 2 * A_SPLIT + off, src + 2 * pl.a_stride, ok);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB_IT; ++i) {
+            const int it = tid + i * 128;
+            const int kk = (it & 7) + 8 * (it / (8 * NG)), g = (it >> 3) % NG;
+            const int r = r0 + kk, n = n0 + 8 * g;
+            const uint32_t off = (kk >> 3) * NG * 128 + g * 128 + (kk & 7) * 16;
+            const bool ok = r < r_hi && n < N;
+            const uint16_t* src = pl.b + (ok ? ((int64_t)r * ldb + n) : 0);
+            cp_async16(sB + off, src, ok);
+            cp_async16(sB + B_SPLIT + off, src + pl.b_stride, ok);
+            cp_async16(sB + 2 * B_SPLIT + off, src + 2 * pl.b_stride, ok);
+        }
+    };
+
+    const int nchunks = (r_hi - r_lo + kTcBK - 1) / kTcBK;
+#ifdef CB200_TC_PROF
+    const bool prof_on = tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#endif
+    TC_PROF_T(tp0);
+#pragma unroll
+    for (int p = 0; p < kPlStages - 1; ++p) {
+        if (p < nchunks) issue(p, p);
+        cp_async_commit();
+    }
+    TC_PROF_T(tp1);
+    TC_PROF_ADD(0, tp0, tp1);
+    for (int c = 0; c < nchunks; ++c) {
+        const int s = c % kPlStages;
+        TC_PROF_T(t0);
+        cp_async_wait<kPlStages - 2>();       // this thread's copies of chunk c have landed
+        TC_PROF_T(t1);
+        fence_proxy_async_smem();             // ... and are visible to the tensor core (async proxy)
+        __syncthreads();                      // ... as are everybody else's
+        TC_PROF_T(t2);
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            constexpr uint32_t A_LBO = (kTcBM / 8) * 128, B_LBO = (BN / 8) * 128, SBO = 128;
+            const uint32_t a_base = smem_base + s * STAGE, b_base = a_base + 3 * A_SPLIT;
+#pragma unroll
+            for (int ks = 0; ks < kTcBK / 16; ++ks) {
+                const uint32_t ao = ks * 2 * A_LBO, bo = ks * 2 * B_LBO;
+                auto desc_a = [&](int sp) { return umma_smem_desc(a_base + sp * A_SPLIT + ao, A_LBO, SBO); };
+                auto desc_b = [&](int sp) { return umma_smem_desc(b_base + sp * B_SPLIT + bo, B_LBO, SBO); };
+                const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
+                umma_bf16(tmem_main, desc_a(0), desc_b(0), idesc, first);          // a1 b1
+                umma_bf16(tmem_corr, desc_a(0), desc_b(2), idesc, first);          // a1 b3
+                umma_bf16(tmem_corr, desc_a(2), desc_b(0), idesc, 1u);             // a3 b1
+                umma_bf16(tmem_corr, desc_a(1), desc_b(1), idesc, 1u);             // a2 b2
+                umma_bf16(tmem_corr, desc_a(0), desc_b(1), idesc, 1u);             // a1 b2
+                umma_bf16(tmem_corr, desc_a(1), desc_b(0), idesc, 1u);             // a2 b1
+            }
+            umma_commit(empty_bar + s);
+            if (c == nchunks - 1) umma_commit(done_bar);
+        }
+        TC_PROF_T(t3);
+        // refill the stage chunk c-1 used (its MMAs were issued one iteration ago) with chunk c + kPlStages - 1
+        const int nc = c + kPlStages - 1;
+        if (nc < nchunks) {
+            if (c >= 1) mbar_wait(empty_bar + (c - 1) % kPlStages, (uint32_t)(((c - 1) / kPlStages) & 1));
+        }
+        TC_PROF_T(t4);
+        if (nc < nchunks) issue(nc, nc % kPlStages);
+        cp_async_commit();
+        TC_PROF_T(t5);
+        TC_PROF_ADD(1, t0, t1);
+        TC_PROF_ADD(2, t1, t2);
+        TC_PROF_ADD(3, t2, t3);
+        TC_PROF_ADD(4, t3, t4);
+        TC_PROF_ADD(5, t4, t5);
+        TC_PROF_ADD(6, t0 - 1, t0);      // chunk count
+    }
+    TC_PROF_T(tq0);
+    if (nchunks > 0) {
+        mbar_wait(done_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    TC_PROF_T(tq1);
+    tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, N, split, false, 1.f, -1);
+    TC_PROF_T(tq2);
+    TC_PROF_ADD(7, tq0, tq1);
+    TC_PROF_ADD(8, tq1, tq2);
+    TC_PROF_ADD(9, tp0, tq2);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {

@@ -179,9 +179,26 @@ typedef struct cb200_gemm_desc {
     float a_u8_div;             /* uint8 A only, 0 = not declared: the caller states a_lut[v] == (float)v / a_u8_div.  */
                                 /*    The tensor-core path then contracts the raw integers (exact in bf16) and divides */
                                 /*    each accumulated sum by a_u8_div once; other paths read a_lut and ignore this.   */
+    /* pre-split operands ("planes"): three bf16 arrays (hi, mid, lo; x == hi + mid + lo exactly, truncation split) */
+    /* indexed like the fp32 array they shadow, plane p at planes + p * plane_stride elements.  Optional; when A and  */
+    /* B both have them the tensor-core path moves operands with cp.async and does no conversion work.  The caller   */
+    /* guarantees they are current (cb200_split_planes, or produced by a GEMM through c_planes).                      */
+    const void* a_planes;       /* planes of a_src (fp32 sources only)                                              */
+    int64_t a_plane_stride;
+    const void* b_planes;       /* planes of b                                                                      */
+    int64_t b_plane_stride;
+    void* c_planes;             /* if set, the epilogue also writes the planes of the final c values                */
+    int64_t c_plane_stride;
+    int32_t a_vec8;             /* like a_vec4 for groups of 8: aligned groups of 8 column indices are contiguous,   */
+                                /*    a_cols % 8 == 0, every a_rowoff / a_coloff group start % 8 == 0                */
 } cb200_gemm_desc;
 
 int cb200_gemm(const cb200_gemm_desc* h_desc, void* stream);
+
+/* planes[p * plane_stride + i] = p-th bf16 piece of src[i] (p = 0 hi, 1 mid, 2 lo); n, plane_stride % 8 == 0, both
+ * pointers 16-byte aligned.  Used for the parameter buffers once per step (the activations get their planes from the
+ * producing GEMM's epilogue). */
+int cb200_split_planes(const float* src, int64_t n, void* planes, int64_t plane_stride, void* stream);
 
 /* out[j] = sum_i x[i, j] for x [rows, cols] (bias gradients: tf.gradients wrt the bias of Dense / Conv2d), reduced in a
  * fixed order (two deterministic stages; `workspace` >= 1024 * cols floats). */
@@ -189,10 +206,12 @@ int cb200_colsum(const float* x, int64_t rows, int64_t cols, float* out, float* 
 
 /* dst[i] = src[table[i]], i < n  (fp32; static permutations of weight tensors for the data-gradient GEMMs, e.g. the
  * per-stride-class [taps*N, Cin] matrices of the transposed convolution) */
-int cb200_permute_f32(const float* src, const int32_t* table, int64_t n, float* dst, void* stream);
+int cb200_permute_f32(const float* src, const int32_t* table, int64_t n, float* dst, void* dst_planes,
+                      int64_t plane_stride, void* stream);   /* dst_planes optional (NULL): also write dst's planes */
 
 /* dst[c, r] = src[r, c]  (fp32; pre-transposition of weight matrices for the data-gradient GEMMs) */
-int cb200_transpose(const float* src, int64_t rows, int64_t cols, float* dst, void* stream);
+int cb200_transpose(const float* src, int64_t rows, int64_t cols, float* dst, void* dst_planes, int64_t plane_stride,
+                    void* stream);
 
 
 /* =====================================================================================================================

@@ -28,11 +28,23 @@ def _lib():
     return _lib, _lib.load()
 
 
+def _check_planes(registry, t, ld):
+    """the planes a GEMM epilogue wrote next to `t` (row length ld) reconstruct it exactly: hi + mid + lo == t"""
+    ptr, stride = registry.lookup(t.data_ptr())
+    if not ptr or ld % 8:
+        return
+    planes = [e[3] for e in registry.entries if e[1] == t.data_ptr()][0]
+    n = t.numel()
+    h, m, l = (planes[i, :n].float() for i in range(3))
+    assert torch.equal((h + m) + l, t.reshape(-1)), "planes do not reconstruct the fp32 output"
+
+
 # ---- gather-GEMM primitive ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,K,N,act", [(512, 3136, 512, "relu"), (512, 512, 6, None), (32, 4, 256, "relu"),
                                        (64, 17, 64, "tanh"), (100, 23, 400, "relu"), (1, 5, 3, None)])
-def test_dense_forward_backward(B, K, N, act):
-    from coach_b200.architectures.layers import Dense, Workspace
+@pytest.mark.parametrize("planes", [False, True])
+def test_dense_forward_backward(B, K, N, act, planes):
+    from coach_b200.architectures.layers import PLANES, Dense, Workspace
     L, lib = _lib()
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(B * 7 + K)
@@ -45,10 +57,18 @@ def test_dense_forward_backward(B, K, N, act):
     dw, db, dx = torch.empty(K, N, device=dev), torch.empty(N, device=dev), torch.empty(B, K, device=dev)
     ws = Workspace(dev)
     layer = Dense(K, N, act)
-    layer.prepare(lib, ws, B, dev, xd, y, wd, bd, dw, db, dyd, dx, need_dx=True, prev_act=1)   # relu'(x) mask on dx
+    if planes:          # pre-split operands (bf16 planes next to every fp32 buffer): the cp.async tensor-core path
+        for t in (xd, wd, dyd):
+            if PLANES.register(t) is not None:
+                PLANES.refresh(lib, t)
+        PLANES.register(y), PLANES.register(dx)
+    layer.prepare(lib, ws, B, dev, xd, y, wd, bd, dw, db, dyd, dx, need_dx=True, prev_act=1,   # relu'(x) mask on dx
+                  planes=planes)
     layer.forward()
     layer.backward()
     torch.cuda.synchronize()
+    if planes:
+        _check_planes(PLANES, y, N), _check_planes(PLANES, dx, K)
     x64, w64, b64, dy64 = x.double(), w.double(), b.double(), dy.double()
     f = {"relu": torch.relu, "tanh": torch.tanh, None: lambda t: t}[act]
     close(y.cpu(), f(x64 @ w64 + b64), name="y")
@@ -60,8 +80,9 @@ def test_dense_forward_backward(B, K, N, act):
 @pytest.mark.parametrize("B,H,C,N,K,S,u8", [(8, 84, 4, 32, 8, 4, True), (8, 20, 32, 64, 4, 2, False),
                                             (8, 9, 64, 64, 3, 1, False), (3, 11, 3, 5, 3, 2, False),
                                             (2, 10, 2, 7, 4, 3, False)])
-def test_conv_forward_backward(B, H, C, N, K, S, u8):
-    from coach_b200.architectures.layers import Conv2d, Workspace
+@pytest.mark.parametrize("planes", [False, True])
+def test_conv_forward_backward(B, H, C, N, K, S, u8, planes):
+    from coach_b200.architectures.layers import PLANES, Conv2d, Workspace
     from coach_b200.architectures.network import make_u8_lut
     import torch.nn.functional as F
     L, lib = _lib()
@@ -83,11 +104,20 @@ def test_conv_forward_backward(B, H, C, N, K, S, u8):
     dw, db = torch.empty(K, K, C, N, device=dev), torch.empty(N, device=dev)
     dx = torch.empty(B, H * H * C, device=dev)
     ws = Workspace(dev)
+    if planes:
+        for t in (wd, dyd) + (() if u8 else (xd,)):
+            if PLANES.register(t) is not None:
+                PLANES.refresh(lib, t)
+        PLANES.register(y), PLANES.register(dx)
     layer.prepare(lib, ws, B, dev, xd, y, wd, bd, dw, db, dyd, dx, x_is_u8=u8, lut=make_u8_lut(dev) if u8 else None,
-                  need_dx=not u8, prev_act=0 if u8 else 1)
+                  need_dx=not u8, prev_act=0 if u8 else 1, planes=planes)
     layer.forward()
     layer.backward()
     torch.cuda.synchronize()
+    if planes:
+        _check_planes(PLANES, y, N)
+        if not u8:
+            _check_planes(PLANES, dx, C)
     xt = xf.permute(0, 3, 1, 2).clone().requires_grad_(True)
     wt = w.double().permute(3, 2, 0, 1).clone().requires_grad_(True)
     bt = b.double().clone().requires_grad_(True)
@@ -189,6 +219,7 @@ def _make_agent(obs_shape, A, B, dueling, double, per, clip=None, huber=True, se
     dict(obs=(4,), A=2, B=32, dueling=False, double=False, per=False, huber=False, clip=None),       # CartPole_DQN
     dict(obs=(84, 84, 4), A=6, B=16, dueling=False, double=False, per=True, huber=True, clip=None),  # Atari DQN + PER
     dict(obs=(84, 84, 4), A=6, B=8, dueling=True, double=True, per=True, huber=True, clip=10.0),     # dueling DDQN + PER
+    dict(obs=(84, 84, 4), A=6, B=128, dueling=False, double=True, per=True, huber=True, clip=None),  # bf16-plane path
 ])
 def test_dqn_learn_step_matches_oracle(cfg):
     import random
@@ -246,10 +277,18 @@ def test_dqn_learn_step_matches_oracle(cfg):
         got_grads = store.export_named(store.grad)
         for name in ref["grads"]:
             want = ref["grads"][name].numpy()
-            close(got_grads[name], want, name="grad " + name)
-            # closer to (or as close as) the fp32 oracle is to the fp64 evaluation, with slack 4
+            # distance to the fp64 evaluation of the same graph: ours, and the fp32 oracle's own
             e_ours = np.abs(got_grads[name] - ref64["grads"][name].numpy()).max()
             e_orc = np.abs(want - ref64["grads"][name].numpy()).max()
+            try:
+                close(got_grads[name], want, name="grad " + name)
+            except AssertionError as exc:
+                # A weight gradient is a sum over batch x pixels of terms of either sign (51200 for conv1 at B = 128):
+                # two fp32 evaluations differ by the rounding noise of that ill-conditioned sum, which can exceed
+                # 1e-5 of the result.  The 1e-5 rule is then replaced by: at least as close to the fp64 value as
+                # the fp32 oracle itself is.
+                assert e_ours <= e_orc, "%s; vs fp64: ours %.3e, fp32 oracle %.3e" % (exc, e_ours, e_orc)
+            # always: closer to (or as close as) the fp32 oracle is to the fp64 evaluation, with slack 4
             assert e_ours <= 4 * e_orc + 2e-6 * (np.abs(want).max() + 1e-30), (name, e_ours, e_orc)
         got_params = store.export_named()
         for name in ref["new_params"]:
