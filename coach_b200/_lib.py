@@ -28,8 +28,20 @@ class GemmDesc(ctypes.Structure):
                 ("mask_y", c_void_p), ("mask_act", ctypes.c_int32), ("c_rowmap", c_void_p),
                 ("accumulate", ctypes.c_int32), ("workspace", c_void_p), ("splits", ctypes.c_int32),
                 ("a_vec4", ctypes.c_int32), ("a_ones_col", ctypes.c_int32), ("a_u8_div", c_float),
-                ("a_planes", c_void_p), ("a_plane_stride", c_i64), ("b_planes", c_void_p), ("b_plane_stride", c_i64),
-                ("c_planes", c_void_p), ("c_plane_stride", c_i64), ("a_vec8", ctypes.c_int32)]
+                ("b_planes", c_void_p), ("b_plane_stride", c_i64), ("b_prow_npix", ctypes.c_int32),
+                ("b_prow_batch", ctypes.c_int32), ("c_planes", c_void_p), ("c_plane_stride", c_i64),
+                ("c_plane_cols", ctypes.c_int32), ("c_prow_npix", ctypes.c_int32), ("c_prow_batch", ctypes.c_int32)]
+
+
+class TGemmDesc(ctypes.Structure):
+    """struct cb200_tgemm_desc"""
+    _fields_ = [("mode", ctypes.c_int32), ("batch", ctypes.c_int32), ("a_planes", c_void_p), ("a_plane_stride", c_i64),
+                ("a_cols", ctypes.c_int32), ("b_planes", c_void_p), ("b_plane_stride", c_i64), ("n", ctypes.c_int32),
+                ("list_ptr", c_void_p), ("list", c_void_p), ("max_list_len", ctypes.c_int32), ("a_pix", c_void_p),
+                ("num_q", ctypes.c_int32), ("taps", ctypes.c_int32), ("c", c_void_p), ("ldc", ctypes.c_int32),
+                ("bias", c_void_p), ("act", ctypes.c_int32), ("mask_y", c_void_p), ("mask_act", ctypes.c_int32),
+                ("c_rowmap", c_void_p), ("workspace", c_void_p), ("splits", ctypes.c_int32), ("c_planes", c_void_p),
+                ("c_plane_stride", c_i64), ("c_plane_cols", ctypes.c_int32)]
 
 
 class Column(ctypes.Structure):
@@ -61,9 +73,10 @@ PROTOTYPES = {
     "cb200_scatter_ring": (c_int, [ctypes.POINTER(Column), c_int, c_i64, c_i64, c_i64, c_void_p]),
     "cb200_gemm": (c_int, [ctypes.POINTER(GemmDesc), c_void_p]),
     "cb200_colsum": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p]),
-    "cb200_permute_f32": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_void_p]),
+    "cb200_permute_f32": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "cb200_gemm_tiled": (c_int, [c_void_p, c_void_p]),
     "cb200_transpose": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_void_p]),
-    "cb200_split_planes": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
+    "cb200_split_planes": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_int, c_i64, c_void_p]),
     "cb200_dqn_td_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_i64,
                                      c_i64, c_void_p, c_void_p, c_void_p]),
     "cb200_regression_head_loss_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int, c_float, c_void_p,

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from coach_b200 import _lib
+from coach_b200.architectures import tiled as tl
 
 ACT = {None: 0, "none": 0, "relu": 1, "tanh": 2}
 
@@ -40,48 +41,6 @@ class Workspace(object):
         return self.buf.data_ptr()
 
 
-class PlaneRegistry(object):
-    """fp32 device buffers that are shadowed by bf16 hi / mid / lo planes (cb200_gemm_desc.a_planes / b_planes /
-    c_planes).  A GemmOp whose operand lies inside a registered buffer picks the planes up automatically; whoever
-    writes a registered buffer outside a GEMM epilogue must refresh the planes (``refresh``)."""
-
-    def __init__(self):
-        self.entries = []            # (weakref to base tensor, base_ptr, nbytes, planes [3, stride] bf16)
-
-    def register(self, t):
-        import weakref
-        assert t.dtype == torch.float32 and t.is_contiguous()
-        if t.numel() % 8 or t.data_ptr() % 16:
-            return None
-        self.entries = [e for e in self.entries if e[0]() is not None]
-        for ref, ptr, nbytes, planes in self.entries:
-            if ptr == t.data_ptr() and nbytes == t.numel() * 4:
-                return planes
-        stride = (t.numel() + 7) // 8 * 8
-        planes = torch.zeros((3, stride), dtype=torch.bfloat16, device=t.device)
-        self.entries.append((weakref.ref(t), t.data_ptr(), t.numel() * 4, planes))
-        return planes
-
-    def lookup(self, ptr):
-        """(pointer to the plane-0 element shadowing `ptr`, plane stride in elements) or (0, 0)"""
-        for ref, base, nbytes, planes in self.entries:
-            if ref() is not None and base <= ptr < base + nbytes:
-                e = (ptr - base) // 4
-                if e % 8 == 0 and planes.data_ptr() % 16 == 0:
-                    return planes.data_ptr() + 2 * e, planes.shape[1]
-        return 0, 0
-
-    def refresh(self, lib, t):
-        """re-derive the planes of a registered buffer from its fp32 content (one launch)"""
-        planes = self.register(t)
-        n = t.numel()
-        _lib.check(lib.cb200_split_planes(t.data_ptr(), n, planes.data_ptr(), planes.shape[1], _lib.current_stream()))
-        return planes
-
-
-PLANES = PlaneRegistry()
-
-
 def _u8_div(lut, x_is_u8):
     return float(getattr(lut, "u8_div", 0.0)) if (x_is_u8 and lut is not None) else 0.0
 
@@ -95,22 +54,12 @@ class GemmOp(object):
         self.keep = []
         self.desc = _lib.GemmDesc()
         self.splits = int(fields.pop("splits", 1))
-        use_planes = bool(fields.pop("use_planes", False))
         for k, v in fields.items():
             if torch.is_tensor(v):
                 self.keep.append(v)
                 v = v.data_ptr()
             setattr(self.desc, k, v)
         self.desc.splits = self.splits
-        # operands / outputs that live in plane-shadowed buffers (PlaneRegistry): hand the planes to the kernel
-        # (only for ops of an instance that keeps them current: use_planes)
-        d = self.desc
-        if use_planes and not d.a_lut and d.a_vec8:
-            d.a_planes, d.a_plane_stride = PLANES.lookup(d.a_src or 0)
-        if use_planes and d.n % 8 == 0 and d.ldb % 8 == 0:
-            d.b_planes, d.b_plane_stride = PLANES.lookup(d.b or 0)
-        if use_planes and d.ldc % 8 == 0:
-            d.c_planes, d.c_plane_stride = PLANES.lookup(d.c or 0)
         rows = self.desc.a_cols if self.desc.a_transposed else self.desc.a_rows
         if self.desc.a_ones_col:
             rows += 1
@@ -173,21 +122,36 @@ class Dense(object):
     def out_elems(self):
         return self.N
 
+    def out_pixels(self):
+        return 1
+
     def prepare(self, lib, ws, B, device, x, y, w, b, dw, db, dy, dx, x_is_u8=False, lut=None, need_dx=True,
-                prev_act=0, dx_accumulate=False, planes=False):
+                prev_act=0, dx_accumulate=False, planes=None):
         """x [B,K], y [B,N], dy [B,N] (gradient wrt the PRE-activation of this layer), dx [B,K] (gradient wrt the
-        pre-activation of the previous layer: masked with prev_act' evaluated on x)."""
+        pre-activation of the previous layer: masked with prev_act' evaluated on x).  planes: tiled.PlaneCtx or None."""
         K, N = self.K, self.N
+        self.lib, self.ws, self.w = lib, ws, w
+        self.tiled_x = False
+        self.db_args = None
+        pl = planes
+        if (pl is not None and pl.x is not None and not x_is_u8 and not dx_accumulate and B % 32 == 0 and pl.w_ptr and
+                tl.width_ok(N) and tl.channels_ok(pl.x.cols) and pl.x.npix * pl.x.cols == K):
+            self._prepare_tiled(lib, ws, B, device, x, y, w, b, dw, db, dy, dx, need_dx, prev_act, pl)
+            return
+        # operands without planes (uint8 / small / odd shapes): the register-staged paths of cb200_gemm; results
+        # that feed plane consumers still get their planes written by the epilogue
+        yp = dict(c_planes=pl.y.ptr, c_plane_stride=pl.y.stride, c_plane_cols=N) \
+            if (pl is not None and pl.y is not None) else {}
+        dxp = dict(c_planes=pl.dx.ptr, c_plane_stride=pl.dx.stride, c_plane_cols=K) \
+            if (pl is not None and pl.dx is not None and pl.dx.npix == 1) else {}
         rowoff = _dev_i32(np.arange(B) * K, device)
         coloff = _dev_i32(np.arange(K), device)
         vec = int(K % 4 == 0)
         common = dict(a_rowoff=rowoff, a_coloff=coloff, a_rows=B, a_cols=K, a_vec4=vec, a_src=x,
-                      a_lut=lut if x_is_u8 else None, a_u8_div=_u8_div(lut, x_is_u8), a_vec8=int(K % 8 == 0),
-                      use_planes=planes)
+                      a_lut=lut if x_is_u8 else None, a_u8_div=_u8_div(lut, x_is_u8))
         self.fwd = GemmOp(lib, ws, a_transposed=0, b=w, ldb=N, n=N, c=y, ldc=N, bias=b, act=self.act,
-                          splits=pick_splits(_tiles(B, N, vec), K), **common)
+                          splits=pick_splits(_tiles(B, N, vec), K), **common, **yp)
         self.bwd_w = None
-        self.db_args = None
         if dw is not None and dy is not None:
             ones = int(bool(vec) and _bias_rides_along(dw, db, K, N))
             self.bwd_w = GemmOp(lib, ws, a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
@@ -198,17 +162,55 @@ class Dense(object):
         self.bwd_x = None
         if need_dx:
             self.wT = torch.empty((N, K), dtype=torch.float32, device=device)
-            self.wT_planes = PLANES.register(self.wT) if planes else None
             self.w = w
             ro = _dev_i32(np.arange(B) * N, device)
             co = _dev_i32(np.arange(N), device)
             self.bwd_x = GemmOp(lib, ws, a_src=dy, a_rowoff=ro, a_coloff=co, a_rows=B, a_cols=N, a_transposed=0,
-                                a_vec4=int(N % 4 == 0), a_vec8=int(N % 8 == 0), b=self.wT, ldb=K, n=K, c=dx, ldc=K,
-                                use_planes=planes,
+                                a_vec4=int(N % 4 == 0), b=self.wT, ldb=K, n=K, c=dx, ldc=K,
                                 mask_y=x if prev_act else None, mask_act=prev_act,
                                 accumulate=int(bool(dx_accumulate)),
-                                splits=pick_splits(_tiles(B, K, N % 4 == 0), N))
-        self.lib, self.ws = lib, ws
+                                splits=pick_splits(_tiles(B, K, N % 4 == 0), N), **dxp)
+
+    def _prepare_tiled(self, lib, ws, B, device, x, y, w, b, dw, db, dy, dx, need_dx, prev_act, pl):
+        """input available as planes [npix * B, Ca] (npix > 1: a flattened conv map, one tap per pixel)"""
+        K, N = self.K, self.N
+        xp = pl.x
+        npix, Ca = xp.npix, xp.cols
+        self.tiled_x = True
+        self.fwd = tl.forward_op(lib, ws, B, device, xp, Ca, pl.w_ptr, pl.w_stride, N,
+                                 [[(p, p) for p in range(npix)]], 1, y, N, b, self.act, None, pl.y)
+        self.bwd_w = None
+        if dw is not None and dy is not None:
+            if pl.dy is not None:
+                self.bwd_w = tl.wgrad_op(lib, ws, B, device, xp, Ca, pl.dy, N, np.arange(npix), npix, 1, dw)
+                self.db_args = (dy, B, N, db)
+                ws.require(1024 * N)
+            else:       # the gradient of this layer's output has no planes (written by a head kernel)
+                vec = int(K % 4 == 0)
+                ones = int(bool(vec) and _bias_rides_along(dw, db, K, N))
+                self.bwd_w = GemmOp(lib, ws, a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
+                                    splits=pick_splits(_tiles(K + ones, N, vec), B),
+                                    a_rowoff=_dev_i32(np.arange(B) * K, device), a_coloff=_dev_i32(np.arange(K), device),
+                                    a_rows=B, a_cols=K, a_vec4=vec, a_src=x)
+                if not ones:
+                    self.db_args = (dy, B, N, db)
+                    ws.require(1024 * N)
+        self.bwd_x = None
+        self.perm = None
+        if need_dx:
+            assert pl.dy is not None and tl.channels_ok(N) and tl.width_ok(Ca), "tiled data gradient: unsupported shape"
+            # per-pixel transposed kernels: wT[p][n, c] = W[p * Ca + c, n]
+            w_index = np.arange(K * N).reshape(npix, Ca, N)
+            self.perm = _dev_i32(w_index.transpose(0, 2, 1).reshape(-1), device)
+            self.wT = torch.empty(npix * N * Ca, dtype=torch.float32, device=device)
+            self.wT_planes = tl.PlaneBuf(npix * N, Ca, device)
+            rowmap = None
+            if npix > 1:
+                qq, bb = np.meshgrid(np.arange(npix), np.arange(B), indexing="ij")
+                rowmap = _dev_i32((bb * npix + qq).reshape(-1), device)
+            self.bwd_x = tl.masked_forward_op(lib, ws, B, device, pl.dy, N, self.wT_planes, Ca,
+                                              [[(0, q)] for q in range(npix)], npix, dx, Ca,
+                                              x if prev_act else None, prev_act, rowmap, pl.dx)
 
     def forward(self):
         self.fwd.run()
@@ -221,10 +223,13 @@ class Dense(object):
                 dy, B, N, db = self.db_args
                 _lib.check(self.lib.cb200_colsum(dy.data_ptr(), B, N, db.data_ptr(), self.ws.ptr(), st))
         if self.bwd_x is not None:
-            pl = self.wT_planes
-            _lib.check(self.lib.cb200_transpose(self.w.data_ptr(), self.K, self.N, self.wT.data_ptr(),
-                                                pl.data_ptr() if pl is not None else None,
-                                                pl.shape[1] if pl is not None else 0, st))
+            if self.tiled_x:
+                _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), self.perm.data_ptr(), self.perm.numel(),
+                                                      self.wT.data_ptr(), self.wT_planes.ptr, self.wT_planes.stride,
+                                                      self.wT_planes.cols, st))
+            else:
+                _lib.check(self.lib.cb200_transpose(self.w.data_ptr(), self.K, self.N, self.wT.data_ptr(), None, 0,
+                                                    st))
             self.bwd_x.run()
 
 
@@ -248,12 +253,31 @@ class Conv2d(object):
     def out_elems(self):
         return self.OH * self.OW * self.N
 
+    def out_pixels(self):
+        return self.OH * self.OW
+
     def prepare(self, lib, ws, B, device, x, y, w, b, dw, db, dy, dx, x_is_u8=False, lut=None, need_dx=True,
-                prev_act=0, dx_accumulate=False, planes=False):
+                prev_act=0, dx_accumulate=False, planes=None):
         assert not dx_accumulate, "accumulating data gradients is only wired for Dense layers"
         H, W, C, N, KH, KW, S, OH, OW, K = self.H, self.W, self.C, self.N, self.KH, self.KW, self.S, self.OH, \
             self.OW, self.K
         M = B * OH * OW
+        self.lib, self.ws, self.w = lib, ws, w
+        self.classes = []
+        self.bwd_x = None
+        self.db_args = None
+        pl = planes
+        if (pl is not None and pl.x is not None and not x_is_u8 and B % 32 == 0 and pl.w_ptr and tl.width_ok(N) and
+                tl.channels_ok(C) and pl.x.cols == C and pl.x.npix == H * W):
+            self._prepare_tiled(lib, ws, B, device, x, y, w, b, dw, db, dy, dx, need_dx, prev_act, pl)
+            return
+        # no input planes (the uint8 frames of the first layer): register-staged cb200_gemm; the output planes are
+        # written by its epilogue (plane row = pixel * B + b), the weight gradient reads dY's planes as its B operand
+        yp = dict(c_planes=pl.y.ptr, c_plane_stride=pl.y.stride, c_plane_cols=N, c_prow_npix=OH * OW,
+                  c_prow_batch=B) if (pl is not None and pl.y is not None) else {}
+        gp = dict(b_planes=pl.dy.ptr, b_plane_stride=pl.dy.stride, b_prow_npix=OH * OW, b_prow_batch=B) \
+            if (pl is not None and pl.dy is not None) else {}
+        wp = dict(b_planes=pl.w_ptr, b_plane_stride=pl.w_stride) if (pl is not None and pl.w_ptr and K % 8 == 0) else {}
         bb, oy, ox = np.meshgrid(np.arange(B), np.arange(OH), np.arange(OW), indexing="ij")
         rowoff = (((bb * H + oy * S) * W + ox * S) * C).reshape(-1)
         ky, kx, cc = np.meshgrid(np.arange(KH), np.arange(KW), np.arange(C), indexing="ij")
@@ -261,22 +285,17 @@ class Conv2d(object):
         assert rowoff.max() + coloff.max() < 2 ** 31
         vec = int(C % 4 == 0)          # (kx, c) runs are contiguous: groups of 4 channels never straddle a pixel
         common = dict(a_rowoff=_dev_i32(rowoff, device), a_coloff=_dev_i32(coloff, device), a_rows=M, a_cols=K,
-                      a_src=x, a_lut=lut if x_is_u8 else None, a_vec4=vec, a_u8_div=_u8_div(lut, x_is_u8),
-                      a_vec8=int(C % 8 == 0), use_planes=planes)
+                      a_src=x, a_lut=lut if x_is_u8 else None, a_vec4=vec, a_u8_div=_u8_div(lut, x_is_u8))
         self.fwd = GemmOp(lib, ws, a_transposed=0, b=w, ldb=N, n=N, c=y, ldc=N, bias=b, act=self.act,
-                          splits=pick_splits(_tiles(M, N, vec), K), **common)
+                          splits=pick_splits(_tiles(M, N, vec), K), **common, **yp, **wp)
         self.bwd_w = None
-        self.db_args = None
         if dw is not None and dy is not None:
             ones = int(bool(vec) and _bias_rides_along(dw, db, K, N))
             self.bwd_w = GemmOp(lib, ws, a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
-                                splits=pick_splits(_tiles(K + ones, N, vec), M, min_chunk=512), **common)
+                                splits=pick_splits(_tiles(K + ones, N, vec), M, min_chunk=512), **common, **gp)
             if not ones:
                 self.db_args = (dy, M, N, db)
                 ws.require(1024 * N)
-        self.lib, self.ws = lib, ws
-        self.w = w
-        self.classes = []
         if not need_dx:
             return
         # transposed convolution, gather form, one GEMM per stride-parity class of input pixels
@@ -300,15 +319,57 @@ class Conv2d(object):
                 perm = w_index[S * a_ + py, S * t_ + px, :, n_]          # [TA, TB, N, C]
                 perm = perm.reshape(-1)
                 wt = torch.empty((TA * TB * N, C), dtype=torch.float32, device=device)
-                wt_planes = PLANES.register(wt) if planes else None
                 op = GemmOp(lib, ws, a_src=dy, a_rowoff=_dev_i32(ro, device), a_coloff=_dev_i32(co, device),
                             a_rowinfo=_dev_i32(rinfo, device), a_colinfo=_dev_i32(cinfo, device), a_oh=OH, a_ow=OW,
                             a_rows=B * IH * IW, a_cols=TA * TB * N, a_transposed=0, a_vec4=int(N % 4 == 0),
-                            a_vec8=int(N % 8 == 0), use_planes=planes,
                             b=wt, ldb=C, n=C, c=dx, ldc=C,
                             mask_y=x if prev_act else None, mask_act=prev_act, c_rowmap=_dev_i32(rowmap, device),
                             splits=pick_splits(_tiles(B * IH * IW, C, N % 4 == 0), TA * TB * N))
-                self.classes.append((op, wt, _dev_i32(perm, device), wt_planes))
+                self.classes.append((op, wt, _dev_i32(perm, device)))
+
+    def _prepare_tiled(self, lib, ws, B, device, x, y, w, b, dw, db, dy, dx, need_dx, prev_act, pl):
+        """input available as planes [H * W * B, C]: forward, weight gradient and data gradient as multi-tap GEMMs"""
+        H, W, C, N, KH, KW, S, OH, OW = self.H, self.W, self.C, self.N, self.KH, self.KW, self.S, self.OH, self.OW
+        T, nq = KH * KW, OH * OW
+        taps = [(ky, kx) for ky in range(KH) for kx in range(KW)]
+        pix_in = np.zeros((T, nq), dtype=np.int64)                  # input pixel under tap t at output pixel q
+        for t, (ky, kx) in enumerate(taps):
+            oy, ox = np.meshgrid(np.arange(OH), np.arange(OW), indexing="ij")
+            pix_in[t] = ((oy * S + ky) * W + (ox * S + kx)).reshape(-1)
+        qq, bb = np.meshgrid(np.arange(nq), np.arange(B), indexing="ij")
+        rowmap_out = _dev_i32((bb * nq + qq).reshape(-1), device)   # plane row q * B + b -> NHWC row b * nq + q
+        self.fwd = tl.forward_op(lib, ws, B, device, pl.x, C, pl.w_ptr, pl.w_stride, N,
+                                 [[(int(pix_in[t, q]), t) for t in range(T)] for q in range(nq)], nq, y, N, b,
+                                 self.act, rowmap_out, pl.y)
+        self.bwd_w = None
+        if dw is not None and dy is not None:
+            assert pl.dy is not None, "tiled conv weight gradient needs the planes of dY"
+            self.bwd_w = tl.wgrad_op(lib, ws, B, device, pl.x, C, pl.dy, N, pix_in, T, nq, dw)
+            self.db_args = (dy, B * nq, N, db)
+            ws.require(1024 * N)
+        if not need_dx:
+            return
+        assert pl.dy is not None and tl.channels_ok(N) and tl.width_ok(C), "tiled data gradient: unsupported shape"
+        # gather form over INPUT pixels: only the taps whose output pixel exists are listed
+        lists = []
+        for iy in range(H):
+            for ix in range(W):
+                ent = []
+                for t, (ky, kx) in enumerate(taps):
+                    dy_, dx_ = iy - ky, ix - kx
+                    if dy_ % S == 0 and dx_ % S == 0 and 0 <= dy_ // S < OH and 0 <= dx_ // S < OW:
+                        ent.append(((dy_ // S) * OW + dx_ // S, t))
+                lists.append(ent)
+        # per-tap transposed kernels wT[t][n, c] = W[ky, kx, c, n]
+        w_index = np.arange(T * C * N).reshape(T, C, N)
+        self.perm = _dev_i32(w_index.transpose(0, 2, 1).reshape(-1), device)
+        self.wT = torch.empty(T * N * C, dtype=torch.float32, device=device)
+        self.wT_planes = tl.PlaneBuf(T * N, C, device)
+        npix = H * W
+        qq, bb = np.meshgrid(np.arange(npix), np.arange(B), indexing="ij")
+        rowmap_in = _dev_i32((bb * npix + qq).reshape(-1), device)
+        self.bwd_x = tl.masked_forward_op(lib, ws, B, device, pl.dy, N, self.wT_planes, C, lists, npix, dx, C,
+                                          x if prev_act else None, prev_act, rowmap_in, pl.dx)
 
     def forward(self):
         self.fwd.run()
@@ -320,8 +381,12 @@ class Conv2d(object):
             if self.db_args is not None:
                 dy, M, N, db = self.db_args
                 _lib.check(self.lib.cb200_colsum(dy.data_ptr(), M, N, db.data_ptr(), self.ws.ptr(), st))
-        for op, wt, perm, pl in self.classes:
+        for op, wt, perm in self.classes:
             _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), perm.data_ptr(), perm.numel(), wt.data_ptr(),
-                                                  pl.data_ptr() if pl is not None else None,
-                                                  pl.shape[1] if pl is not None else 0, st))
+                                                  None, 0, 0, st))
             op.run()
+        if self.bwd_x is not None:
+            _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), self.perm.data_ptr(), self.perm.numel(),
+                                                  self.wT.data_ptr(), self.wT_planes.ptr, self.wT_planes.stride,
+                                                  self.wT_planes.cols, st))
+            self.bwd_x.run()

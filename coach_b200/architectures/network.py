@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 from coach_b200 import _lib
-from coach_b200.architectures.layers import ACT, PLANES, Workspace
+from coach_b200.architectures import tiled as tl
+from coach_b200.architectures.layers import ACT, Workspace
 
 
 class ParamStore(object):
@@ -30,7 +31,7 @@ class ParamStore(object):
             raise RuntimeError("ParamStore is finalised")
         n = int(np.prod(shape)) if len(shape) else 1
         # keep every tensor 32-byte aligned inside the flat buffer (vector loads in the kernels; 16-byte aligned
-        # rows in the bf16 planes that shadow the buffer, layers.PlaneRegistry)
+        # core-matrix rows in the bf16 planes that shadow the buffer, architectures/tiled.py)
         self.size = (self.size + 7) // 8 * 8
         self.entries[name] = (self.size, tuple(shape))
         self.size += n
@@ -93,11 +94,11 @@ class Sequential(object):
             self.names.append([store.add(base + "/" + pname, shape) for pname, shape in layer.param_shapes])
 
     def instantiate(self, lib, ws, B, x, theta, grad=None, x_is_u8=False, lut=None, need_input_grad=False,
-                    input_act=0, train=False, dx_in=None, dx_accumulate=False, planes=False):
+                    input_act=0, train=False, dx_in=None, dx_accumulate=False, theta_planes=None):
         """need_input_grad: also produce the gradient wrt the (pre-activation of the) input, masked by
         ``input_act``' evaluated on x; it is written (or, with dx_accumulate, added) to ``dx_in``."""
         return SequentialInstance(self, lib, ws, B, x, theta, grad, x_is_u8, lut, need_input_grad, input_act, train,
-                                  dx_in, dx_accumulate, planes)
+                                  dx_in, dx_accumulate, theta_planes)
 
 
 class SequentialInstance(object):
@@ -105,7 +106,7 @@ class SequentialInstance(object):
     pre-activation gradient buffers and prepares the backward ops (gradients land in ``grad``)."""
 
     def __init__(self, seq, lib, ws, B, x, theta, grad, x_is_u8, lut, need_input_grad, input_act, train,
-                 dx_in=None, dx_accumulate=False, planes=False):
+                 dx_in=None, dx_accumulate=False, theta_planes=None):
         import copy
         self.seq, self.B = seq, B
         dev = theta.device
@@ -122,13 +123,18 @@ class SequentialInstance(object):
             dz = torch.empty_like(y) if train else None
             self.acts.append(y)
             self.dzs.append(dz)
-            # planes=True: the hidden activations / pre-activation gradients are produced by GEMM epilogues only and
-            # consumed by GEMMs, so they carry bf16 planes (the caller keeps the parameter planes current).  The
-            # last layer's output and gradient are touched by head kernels and stay plain fp32.
-            if planes and i + 1 < len(self.layers):
-                PLANES.register(y)
-                if dz is not None:
-                    PLANES.register(dz)
+        # theta_planes (tiled.ThetaPlanes): run on pre-split bf16 operands.  Hidden activations / pre-activation
+        # gradients are produced by GEMM epilogues only and consumed by GEMMs, so they carry planes [pixels * B,
+        # channels]; the last layer's output and gradient are touched by head kernels and stay plain fp32.
+        self.act_planes = [None] * len(self.layers)
+        self.dz_planes = [None] * len(self.layers)
+        if theta_planes is not None and B % 32 == 0:
+            for i, layer in enumerate(self.layers[:-1]):
+                npix, ch = layer.out_pixels(), layer.N
+                if ch % 8 == 0:
+                    self.act_planes[i] = tl.PlaneBuf(npix * B, ch, dev, npix=npix)
+                    if train:
+                        self.dz_planes[i] = tl.PlaneBuf(npix * B, ch, dev, npix=npix)
         for i, layer in enumerate(self.layers):
             wname, bname = seq.names[i]
             w, b = store.view(theta, wname), store.view(theta, bname)
@@ -137,23 +143,28 @@ class SequentialInstance(object):
             first = i == 0
             dx = (self.dx_in if first else self.dzs[i - 1]) if train else None
             need_dx = train and (not first or need_input_grad)
+            ctx = None
+            if theta_planes is not None and B % 32 == 0:
+                ctx = tl.PlaneCtx(x=None if first else self.act_planes[i - 1], y=self.act_planes[i],
+                                  dy=self.dz_planes[i], dx=None if first else self.dz_planes[i - 1],
+                                  w_ptr=theta_planes.ptr(wname) if theta_planes.has(wname) else 0,
+                                  w_stride=theta_planes.stride)
             if train:
                 layer.prepare(lib, ws, B, dev, prev, self.acts[i], w, b, dw, db, self.dzs[i], dx,
                               x_is_u8=(x_is_u8 and first), lut=lut, need_dx=need_dx, prev_act=prev_act,
-                              dx_accumulate=(dx_accumulate and first), planes=planes)
+                              dx_accumulate=(dx_accumulate and first), planes=ctx)
             else:
-                self._prepare_fwd_only(layer, lib, ws, B, dev, prev, self.acts[i], w, b, x_is_u8 and first, lut,
-                                       planes)
+                self._prepare_fwd_only(layer, lib, ws, B, dev, prev, self.acts[i], w, b, x_is_u8 and first, lut, ctx)
             prev, prev_act = self.acts[i], layer.act
         self.out = self.acts[-1]
         self.d_out = self.dzs[-1]
         self.train = train
 
     @staticmethod
-    def _prepare_fwd_only(layer, lib, ws, B, dev, x, y, w, b, x_is_u8, lut, planes=False):
+    def _prepare_fwd_only(layer, lib, ws, B, dev, x, y, w, b, x_is_u8, lut, ctx=None):
         # reuse prepare() with dummy gradient tensors but drop the backward ops: forward descriptors are identical
         layer.prepare(lib, ws, B, dev, x, y, w, b, None, None, None, None, x_is_u8=x_is_u8, lut=lut, need_dx=False,
-                      planes=planes)
+                      planes=ctx)
 
     def forward(self):
         for layer in self.layers:

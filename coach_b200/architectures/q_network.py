@@ -13,7 +13,8 @@ import numpy as np
 import torch
 
 from coach_b200 import _lib
-from coach_b200.architectures.layers import PLANES, Conv2d, Dense, Workspace
+from coach_b200.architectures import tiled as tl
+from coach_b200.architectures.layers import Conv2d, Dense, Workspace
 from coach_b200.architectures.network import ParamStore, Sequential, make_u8_lut
 
 
@@ -63,13 +64,12 @@ class QNetworkInstance(object):
         self.net, self.lib, self.B = net, lib, B
         dev = net.device
         x_is_u8 = x.dtype == torch.uint8
-        # bf16 operand planes for the tensor-core GEMMs (layers.PlaneRegistry): the parameter planes are re-derived
-        # from theta at the start of every forward (one launch), so any writer of theta -- Adam, a target-network
-        # copy, a checkpoint load -- is covered; activations / gradients get theirs from the GEMM epilogues.
-        self.theta = theta
-        self.use_planes = B >= 128 and PLANES.register(theta) is not None
+        # Large batches run the trunk on pre-split bf16 operands (architectures/tiled.py).  The parameter planes are
+        # re-derived from theta at the start of every forward (one launch), so any writer of theta -- Adam, a target
+        # network copy, polyak, a checkpoint load -- is covered.
+        self.theta_planes = tl.ThetaPlanes(lib, net.store, theta) if (B >= 128 and B % 32 == 0) else None
         self.trunk = net.trunk.instantiate(lib, ws, B, x, theta, grad, x_is_u8=x_is_u8, lut=net.lut, train=train,
-                                           planes=self.use_planes)
+                                           theta_planes=self.theta_planes)
         if not net.dueling:
             self.q = self.trunk.out
             self.dq = self.trunk.d_out
@@ -85,8 +85,8 @@ class QNetworkInstance(object):
         self.dq = torch.empty_like(self.q) if train else None
 
     def forward(self):
-        if self.use_planes:
-            PLANES.refresh(self.lib, self.theta)
+        if self.theta_planes is not None:
+            self.theta_planes.refresh()
         self.trunk.forward()
         if self.net.dueling:
             self.v.forward()

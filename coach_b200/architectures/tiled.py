@@ -1,0 +1,201 @@
+"""Pre-split operand planes and the multi-tap tensor-core GEMM calls (include/coach_b200.h: cb200_gemm_tiled).
+
+The tensor-core path of the learn step computes fp32 products as 3 x BF16 operand splits.  Splitting inside every GEMM
+costs more than the GEMM, so every tensor that feeds a GEMM is kept, next to its fp32 form, as three bf16 "planes" in
+the 8x8 core-tiled format of csrc/nn_gemm.cuh (``tiled_elem``): activations / gradients as [pixel * batch + b, channel]
+matrices written by the producing GEMM's epilogue, parameters re-derived from theta once per forward
+(``ThetaPlanes.refresh``), per-tap transposed kernels by the permute kernel.  ``build_*`` below turn a layer geometry
+into the tap lists of cb200_gemm_tiled:
+
+  conv forward   C[q*B + b, n]      = sum_taps    X[pix_in(q, tap)*B + b, :] W_tap          (mode 0)
+  conv dX        dX[q_in*B + b, c]  = sum_valid   dY[pix_out(q_in, tap)*B + b, :] W_tap^T    (mode 0, gather form)
+  conv dW        dW[tap*C + c, n]   = sum_q sum_b X[pix_in(q, tap)*B + b, c] dY[q*B + b, n]  (mode 1)
+
+Dense layers are the one-pixel case; a dense layer on a flattened conv map has one tap per pixel.
+Reference semantics: rl_coach/architectures/tensorflow_components/layers.py:108-183 (+ tf.gradients).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from coach_b200 import _lib
+
+
+def _dev_i32(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
+
+
+class PlaneBuf(object):
+    """bf16 hi / mid / lo planes of a [rows, cols] matrix (rows = npix * batch) in the core-tiled format"""
+
+    def __init__(self, rows, cols, device, npix=1):
+        assert rows % 8 == 0 and cols % 8 == 0, (rows, cols)
+        self.rows, self.cols, self.npix = int(rows), int(cols), int(npix)
+        self.t = torch.zeros((3, self.rows * self.cols), dtype=torch.bfloat16, device=device)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+    @property
+    def stride(self):
+        return self.rows * self.cols
+
+    def load(self, lib, m):
+        """planes <- split of an fp32 [rows, cols] matrix (tests, host-written inputs)"""
+        m = m.contiguous().view(self.rows, self.cols).float()
+        seg = torch.tensor([[0, self.rows, self.cols, 0]], dtype=torch.int64, device=m.device)
+        _lib.check(lib.cb200_split_planes(m.data_ptr(), self.ptr, self.stride, seg.data_ptr(), 1,
+                                          self.rows * self.cols, _lib.current_stream()))
+        torch.cuda.current_stream().synchronize()      # m / seg are temporaries
+        return self
+
+    def to_dense(self):
+        """fp32 [rows, cols] reconstruction hi + mid + lo (tests)"""
+        v = (self.t[0].float() + self.t[1].float()) + self.t[2].float()
+        v = v.view(self.rows // 8, self.cols // 8, 8, 8).permute(0, 2, 1, 3)
+        return v.reshape(self.rows, self.cols)
+
+
+def channels_ok(c):
+    """a_cols constraint of cb200_gemm_tiled"""
+    return c in (32, 64, 128) or (c > 128 and c % 128 == 0)
+
+
+def width_ok(n):
+    """n constraint of cb200_gemm_tiled"""
+    return n == 32 or (n > 0 and n % 64 == 0)
+
+
+class ThetaPlanes(object):
+    """Planes of every 2-D-able kernel of a flat parameter buffer, at the kernels' own element offsets.  ``refresh``
+    re-derives all of them from the current fp32 values in one launch (start of every forward: covers Adam, target
+    network copies, polyak, checkpoint loads)."""
+
+    def __init__(self, lib, store, theta):
+        self.lib, self.store, self.theta = lib, store, theta
+        self.planes = torch.zeros((3, store.size), dtype=torch.bfloat16, device=theta.device)
+        segs, self.max_elems = [], 0
+        for name, (off, shape) in store.entries.items():
+            if not name.endswith("kernel") or len(shape) < 2:
+                continue
+            rows, cols = int(np.prod(shape[:-1])), int(shape[-1])
+            if rows % 8 or cols % 8 or off % 8:
+                continue
+            segs.append((off, rows, cols, off))
+            self.max_elems = max(self.max_elems, rows * cols)
+        self.names = set(n for n in store.entries)
+        self.segs = torch.tensor(segs, dtype=torch.int64, device=theta.device) if segs else None
+        self.eligible = {store_off for (store_off, _, _, _) in segs}
+
+    def has(self, name):
+        return self.store.entries[name][0] in self.eligible
+
+    def ptr(self, name):
+        return self.planes.data_ptr() + 2 * self.store.entries[name][0]
+
+    @property
+    def stride(self):
+        return self.store.size
+
+    def refresh(self):
+        if self.segs is not None:
+            _lib.check(self.lib.cb200_split_planes(self.theta.data_ptr(), self.planes.data_ptr(), self.stride,
+                                                   self.segs.data_ptr(), self.segs.shape[0], self.max_elems,
+                                                   _lib.current_stream()))
+
+
+class PlaneCtx(object):
+    """What one layer needs to run on pre-split operands."""
+
+    def __init__(self, x=None, y=None, dy=None, dx=None, w_ptr=0, w_stride=0):
+        self.x, self.y, self.dy, self.dx = x, y, dy, dx       # PlaneBuf or None
+        self.w_ptr, self.w_stride = w_ptr, w_stride           # planes of this layer's kernel inside ThetaPlanes
+
+
+def pick_splits_tiled(tiles, total_chunks, sm=148):
+    """reduction slices of a tiled GEMM: at most 32 chunks per slice (TMEM accumulation cap, csrc/nn_gemm_tc.cuh),
+    more when the tile count alone does not fill the machine"""
+    need = (total_chunks + 31) // 32
+    if tiles >= sm:
+        return int(max(1, need))
+    s = max(1, (2 * sm + tiles - 1) // tiles)
+    s = min(s, max(1, total_chunks // 4))
+    return int(max(s, need))
+
+
+class TGemmOp(object):
+    """A prepared cb200_gemm_tiled call."""
+
+    def __init__(self, lib, ws, **fields):
+        self.lib, self.ws = lib, ws
+        self.keep = []
+        self.desc = _lib.TGemmDesc()
+        for k, v in fields.items():
+            if torch.is_tensor(v):
+                self.keep.append(v)
+                v = v.data_ptr()
+            elif isinstance(v, PlaneBuf):
+                self.keep.append(v)
+                v = v.ptr
+            setattr(self.desc, k, v)
+        d = self.desc
+        rows = d.num_q * d.batch if d.mode == 0 else d.taps * d.a_cols
+        if d.splits > 1:
+            ws.require(d.splits * rows * d.n)
+
+    def run(self):
+        if self.desc.splits > 1:
+            self.desc.workspace = self.ws.ptr()
+        _lib.check(self.lib.cb200_gemm_tiled(ctypes.byref(self.desc), _lib.current_stream()))
+
+
+def _tiles0(num_q, B, n):
+    bn = 32 if n <= 32 else (128 if n % 128 == 0 else 64)
+    return num_q * ((B + 127) // 128) * ((n + bn - 1) // bn)
+
+
+def _tiles1(rows, n):
+    bn = 32 if n <= 32 else (128 if n % 128 == 0 else 64)
+    return ((rows + 127) // 128) * ((n + bn - 1) // bn)
+
+
+def forward_op(lib, ws, B, device, x, Ca, w_ptr, w_stride, N, lists, num_q, c, ldc, bias, act, rowmap, y_planes):
+    """mode 0 with explicit per-pixel tap lists: `lists[q]` = [(a_pix, w_blk), ...]"""
+    ptr = np.zeros(num_q + 1, dtype=np.int64)
+    flat = []
+    for q in range(num_q):
+        flat.extend(lists[q])
+        ptr[q + 1] = len(flat)
+    max_len = int(np.max(np.diff(ptr))) if num_q else 0
+    flat = np.asarray(flat, dtype=np.int32).reshape(-1, 2) if flat else np.zeros((1, 2), dtype=np.int32)
+    total = max_len * (Ca // 32)
+    return TGemmOp(lib, ws, mode=0, batch=B, a_planes=x, a_plane_stride=x.stride, a_cols=Ca, b_planes=w_ptr,
+                   b_plane_stride=w_stride, n=N, list_ptr=_dev_i32(ptr, device), list=_dev_i32(flat, device),
+                   max_list_len=max_len, num_q=num_q, taps=0, c=c, ldc=ldc, bias=bias, act=act,
+                   c_rowmap=rowmap, splits=pick_splits_tiled(_tiles0(num_q, B, N), total),
+                   c_planes=y_planes if y_planes is not None else None,
+                   c_plane_stride=y_planes.stride if y_planes is not None else 0,
+                   c_plane_cols=N if y_planes is not None else 0)
+
+
+def masked_forward_op(lib, ws, B, device, x, Ca, w_buf, N, lists, num_q, c, ldc, mask_y, mask_act, rowmap, y_planes):
+    """data-gradient flavour: no bias / activation, previous layer's activation derivative in the epilogue"""
+    op = forward_op(lib, ws, B, device, x, Ca, w_buf.ptr, w_buf.stride, N, lists, num_q, c, ldc, None, 0, rowmap,
+                    y_planes)
+    op.keep.append(w_buf)
+    if mask_y is not None and mask_act:
+        op.keep.append(mask_y)
+        op.desc.mask_y = mask_y.data_ptr()
+        op.desc.mask_act = mask_act
+    return op
+
+
+def wgrad_op(lib, ws, B, device, x, Ca, g, N, a_pix, taps, num_q, dw):
+    """mode 1: dw [taps * Ca, N] row-major fp32"""
+    total = num_q * (B // 32)
+    return TGemmOp(lib, ws, mode=1, batch=B, a_planes=x, a_plane_stride=x.stride, a_cols=Ca, b_planes=g,
+                   b_plane_stride=g.stride, n=N, a_pix=_dev_i32(np.asarray(a_pix).reshape(-1), device), num_q=num_q,
+                   taps=taps, max_list_len=0, c=dw, ldc=N, act=0,
+                   splits=pick_splits_tiled(_tiles1(taps * Ca, N), total))

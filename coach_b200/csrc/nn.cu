@@ -1,5 +1,5 @@
 // coach_b200/csrc/nn.cu -- C-ABI entry points of the dense contractions of the learn step (see nn_gemm.cuh).
-#include "nn_gemm_tc.cuh"
+#include "nn_gemm_tiled.cuh"
 
 namespace cb200 {
 namespace gemm {
@@ -11,7 +11,8 @@ using CfgSmall = Cfg<32, 32, 16, 4, 4>;  // 64 threads: small-batch MLPs
 static EpiParams make_epi(const cb200_gemm_desc& d, int splits) {
     return EpiParams{d.c,        d.ldc,       d.bias, d.act,        d.mask_y,
                      d.mask_act, d.c_rowmap,  d.workspace, splits,  d.accumulate,
-                     static_cast<uint16_t*>(d.c_planes), d.c_plane_stride};
+                     static_cast<uint16_t*>(d.c_planes), d.c_plane_stride, d.c_plane_cols, d.c_prow_npix,
+                     d.c_prow_batch};
 }
 
 template <class C, bool kT>
@@ -89,10 +90,10 @@ static int launch_tc(const cb200_gemm_desc& d, int M, int R, int splits, int r_p
         configured = true;
     }
     dim3 grid((M + kTcBM - 1) / kTcBM, (d.n + BN - 1) / BN, splits);
-    const bool bp = d.b_planes != nullptr && d.n % 8 == 0 && d.ldb % 8 == 0;
+    const bool bp = d.b_planes != nullptr && d.n % 8 == 0 && d.ldb == d.n && R % 8 == 0;
     gemm_tc_kernel<BN, kT, kU8><<<grid, 128, smem, st>>>(a, d.b, d.ldb, ep, M, d.n, R, r_per_split, d.a_u8_div,
                                                          bp ? static_cast<const uint16_t*>(d.b_planes) : nullptr,
-                                                         d.b_plane_stride);
+                                                         d.b_plane_stride, d.b_prow_npix, d.b_prow_batch);
     count_launch();
     if (splits > 1) {
         launch_split_reduce(ep, M, d.n, st);
@@ -102,52 +103,42 @@ static int launch_tc(const cb200_gemm_desc& d, int M, int R, int splits, int r_p
 }
 
 template <int BN, bool kT>
-static int launch_tc_planes(const cb200_gemm_desc& d, int M, int R, int splits, int r_per_split, cudaStream_t st) {
-    FastA a;
-    a.src = d.a_src;
-    a.lut = nullptr;
-    a.rowoff = d.a_rowoff;
-    a.coloff = d.a_coloff;
-    a.rowinfo = d.a_rowinfo;
-    a.colinfo = d.a_colinfo;
-    a.oh = d.a_oh;
-    a.ow = d.a_ow;
-    a.rows = d.a_rows;
-    a.cols = d.a_cols;
-    a.ones_col = (kT && d.a_ones_col) ? d.a_cols : -1;
-    const EpiParams ep = make_epi(d, splits);
-    PlaneOperands pl{static_cast<const uint16_t*>(d.a_planes), d.a_plane_stride,
-                     static_cast<const uint16_t*>(d.b_planes), d.b_plane_stride};
-    const int slice = kT ? r_per_split : (r_per_split + 7) / 8;
-    const size_t smem = tc_planes_smem_bytes<BN>(slice, d.a_rowinfo != nullptr);
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(gemm_tc_planes_kernel<BN, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+static int launch_tiled(const TiledParams& tp, const EpiParams& ep, int M, int gx, int splits, cudaStream_t st) {
+    constexpr size_t smem = TiledCfg<BN>::kSmemBytes;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tc_tiled_kernel<BN, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return -1;
-        configured = smem;
+        configured = true;
     }
-    dim3 grid((M + kTcBM - 1) / kTcBM, (d.n + BN - 1) / BN, splits);
-    gemm_tc_planes_kernel<BN, kT><<<grid, 128, smem, st>>>(a, pl, d.ldb, ep, M, d.n, R, r_per_split, slice);
+    dim3 grid(gx, (tp.n + BN - 1) / BN, splits);
+    gemm_tc_tiled_kernel<BN, kT><<<grid, 192, smem, st>>>(tp, ep, M);
     count_launch();
     if (splits > 1) {
-        launch_split_reduce(ep, M, d.n, st);
+        launch_split_reduce(ep, M, tp.n, st);
         count_launch();
     }
     return 0;
 }
 
-__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int64_t n,
-                                                           uint16_t* __restrict__ planes, int64_t stride) {
-    // 8 elements per thread (n % 8 == 0, 16-byte aligned planes): two 128-bit loads, three 128-bit stores
-    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n;
-         i += (int64_t)gridDim.x * blockDim.x * 8) {
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + i));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+// fp32 row-major matrices [rows, cols] -> tiled planes.  One launch converts a list of matrices that live in one fp32
+// buffer (the parameter buffer): segment k = (src offset, rows, cols, plane offset), all in elements.
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, uint16_t* __restrict__ planes,
+                                                           int64_t stride, const int64_t* __restrict__ segs) {
+    const int64_t* sg = segs + 4 * blockIdx.y;
+    const int64_t soff = sg[0], rows = sg[1], cols = sg[2], poff = sg[3];
+    const int64_t groups = rows * (cols >> 3);             // one thread per (row, 8 columns) = one core-matrix row
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = g / (cols >> 3), c8 = g % (cols >> 3);
+        const float* p = src + soff + r * cols + c8 * 8;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
         const Split8 sp = split8(v0, v1);
-        *reinterpret_cast<uint4*>(planes + i) = sp.h;
-        *reinterpret_cast<uint4*>(planes + stride + i) = sp.m;
-        *reinterpret_cast<uint4*>(planes + 2 * stride + i) = sp.l;
+        uint16_t* d = planes + poff + tiled_elem((size_t)r, (int)(c8 * 8), (int)cols);
+        *reinterpret_cast<uint4*>(d) = sp.h;
+        *reinterpret_cast<uint4*>(d + stride) = sp.m;
+        *reinterpret_cast<uint4*>(d + 2 * stride) = sp.l;
     }
 }
 
@@ -196,11 +187,15 @@ __global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ p
 
 __global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ src, const int32_t* __restrict__ table,
                                                       int64_t n, float* __restrict__ dst, uint16_t* __restrict__ planes,
-                                                      int64_t stride) {
+                                                      int64_t stride, int plane_cols) {
+    // planes: dst seen as a [n / plane_cols, plane_cols] matrix in the tiled format
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float v = __ldg(src + __ldg(table + i));
         dst[i] = v;
-        if (planes) split3(v, planes[i], planes[stride + i], planes[2 * stride + i]);
+        if (planes) {
+            uint16_t* p = planes + tiled_elem((size_t)(i / plane_cols), (int)(i % plane_cols), plane_cols);
+            split3(v, p[0], p[stride], p[2 * stride]);
+        }
     }
 }
 
@@ -218,9 +213,9 @@ __global__ void transpose_kernel(const float* __restrict__ src, int64_t rows, in
         if (r < rows && c < cols) {
             const float v = tile[threadIdx.x][i];
             dst[c * rows + r] = v;
-            if (planes) {
-                const int64_t e = c * rows + r;
-                split3(v, planes[e], planes[stride + e], planes[2 * stride + e]);
+            if (planes) {       // dst [cols, rows] in the tiled format
+                uint16_t* p = planes + tiled_elem((size_t)c, (int)r, (int)rows);
+                split3(v, p[0], p[stride], p[2 * stride]);
             }
         }
     }
@@ -258,23 +253,6 @@ int cb200_gemm(const cb200_gemm_desc* d, void* stream) {
                     ((reinterpret_cast<uintptr_t>(d->c) | reinterpret_cast<uintptr_t>(d->mask_y) |
                       reinterpret_cast<uintptr_t>(d->bias)) & 15) == 0 &&
                     r_per_split <= gemm::kTcMaxSlice;
-    const bool planes = tc && d->a_planes && d->b_planes && d->a_vec8 && !d->a_lut && d->a_cols % 8 == 0 &&
-                        d->n % 8 == 0 && d->ldb % 8 == 0 && tune_get("gemm_planes", 1, 0, 1) != 0 &&
-                        ((reinterpret_cast<uintptr_t>(d->a_planes) | reinterpret_cast<uintptr_t>(d->b_planes)) & 15) == 0 &&
-                        d->a_plane_stride % 8 == 0 && d->b_plane_stride % 8 == 0;
-    if (planes) {
-        int rc;
-#define CB200_TCP(BN_)                                                                 \
-    (tr ? gemm::launch_tc_planes<BN_, true>(*d, M, R, splits, r_per_split, st)        \
-        : gemm::launch_tc_planes<BN_, false>(*d, M, R, splits, r_per_split, st))
-        if (d->n <= 32) rc = CB200_TCP(32);
-        else if (d->n <= 64) rc = CB200_TCP(64);
-        else rc = CB200_TCP(128);
-#undef CB200_TCP
-        CB200_CHECK_ARG(rc == 0, "could not configure shared memory for the tcgen05 planes kernel");
-        CB200_CHECK_LAUNCH();
-        return CB200_OK;
-    }
     if (tc) {
         // uint8 A with a declared divisor: the integers are contracted exactly from one bf16 plane
         const bool u8 = d->a_lut != nullptr && d->a_u8_div > 0.f;
@@ -333,15 +311,82 @@ int cb200_tc_prof_read(unsigned long long* out16, int reset) {
 }
 #endif
 
-int cb200_split_planes(const float* src, int64_t n, void* planes, int64_t plane_stride, void* stream) {
-    CB200_CHECK_ARG(src && planes && n > 0 && n % 8 == 0 && plane_stride >= n && plane_stride % 8 == 0,
-                    "bad arguments (n and plane_stride must be multiples of 8)");
+int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
+    CB200_CHECK_ARG(d != nullptr, "null descriptor");
+    CB200_CHECK_ARG(d->mode == 0 || d->mode == 1, "mode must be 0 or 1");
+    CB200_CHECK_ARG(d->a_planes && d->b_planes && d->c, "null operand pointer");
+    CB200_CHECK_ARG(d->batch > 0 && d->batch % 32 == 0, "batch must be a multiple of 32");
+    CB200_CHECK_ARG(d->a_cols > 0 && d->a_cols % 32 == 0 && (d->a_cols <= 128 ? 128 % d->a_cols == 0 : d->a_cols % 128 == 0),
+                    "a_cols must be 32, 64, 128 or a multiple of 128");
+    CB200_CHECK_ARG(d->n == 32 || (d->n > 0 && d->n % 64 == 0), "n must be 32 or a multiple of 64");
+    CB200_CHECK_ARG(d->ldc >= d->n && d->ldc % 4 == 0, "ldc");
+    CB200_CHECK_ARG(((reinterpret_cast<uintptr_t>(d->a_planes) | reinterpret_cast<uintptr_t>(d->b_planes) |
+                      reinterpret_cast<uintptr_t>(d->c_planes) | reinterpret_cast<uintptr_t>(d->c) |
+                      reinterpret_cast<uintptr_t>(d->bias) | reinterpret_cast<uintptr_t>(d->mask_y)) & 15) == 0,
+                    "operands must be 16-byte aligned");
+    CB200_CHECK_ARG(d->a_plane_stride % 8 == 0 && d->b_plane_stride % 8 == 0 && d->c_plane_stride % 8 == 0, "plane strides");
+    CB200_CHECK_ARG(!d->c_planes || d->c_plane_cols == d->n, "c_plane_cols must equal n");
+    gemm::TiledParams tp;
+    tp.mode = d->mode;
+    tp.batch = d->batch;
+    tp.a = static_cast<const uint16_t*>(d->a_planes);
+    tp.a_stride = d->a_plane_stride;
+    tp.a_cols = d->a_cols;
+    tp.b = static_cast<const uint16_t*>(d->b_planes);
+    tp.b_stride = d->b_plane_stride;
+    tp.n = d->n;
+    tp.list_ptr = d->list_ptr;
+    tp.list = reinterpret_cast<const int2*>(d->list);
+    tp.a_pix = d->a_pix;
+    tp.num_q = d->num_q;
+    tp.taps = d->taps;
+    int M, gx, total;
+    if (d->mode == 0) {
+        CB200_CHECK_ARG(d->list_ptr && d->list && d->num_q > 0 && d->max_list_len > 0, "mode 0 needs the tap lists");
+        M = d->num_q * d->batch;
+        gx = d->num_q * ((d->batch + 127) / 128);
+        total = d->max_list_len * (d->a_cols / 32);
+    } else {
+        CB200_CHECK_ARG(d->a_pix && d->num_q > 0 && d->taps > 0, "mode 1 needs the tap / pixel table");
+        M = d->taps * d->a_cols;
+        gx = (M + 127) / 128;
+        total = d->num_q * (d->batch / 32);
+    }
+    int splits = d->splits > 1 ? d->splits : 1;
+    int cps = (total + splits - 1) / splits;
+    splits = (total + cps - 1) / cps;
+    // the TMEM accumulators add with truncation: at most 64 accumulating MMAs (32 chunks) per launch slice
+    CB200_CHECK_ARG(cps <= 32, "too few splits: more than 32 reduction chunks (1024 terms) per slice");
+    CB200_CHECK_ARG(splits == 1 || d->workspace, "split reduction needs a workspace");
+    tp.chunks_per_split = cps;
+    const gemm::EpiParams ep{d->c,        d->ldc,      d->bias,      d->act,  d->mask_y,
+                             d->mask_act, d->c_rowmap, d->workspace, splits,  0,
+                             static_cast<uint16_t*>(d->c_planes), d->c_plane_stride, d->c_plane_cols, 0, 0};
+    cudaStream_t st = as_stream(stream);
+    int rc;
+#define CB200_TL(BN_) \
+    (d->mode ? gemm::launch_tiled<BN_, true>(tp, ep, M, gx, splits, st) : gemm::launch_tiled<BN_, false>(tp, ep, M, gx, splits, st))
+    if (d->n <= 32) rc = CB200_TL(32);
+    else if (d->n <= 64 || d->n % 128 != 0) rc = CB200_TL(64);
+    else rc = CB200_TL(128);
+#undef CB200_TL
+    CB200_CHECK_ARG(rc == 0, "could not configure shared memory for the tiled tcgen05 kernel");
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_split_planes(const float* src, void* planes, int64_t plane_stride, const int64_t* d_segments, int num_segments,
+                       int64_t max_segment_elems, void* stream) {
+    CB200_CHECK_ARG(src && planes && d_segments && num_segments > 0 && max_segment_elems > 0 && plane_stride % 8 == 0,
+                    "bad arguments");
     CB200_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(planes)) & 15) == 0,
                     "src and planes must be 16-byte aligned");
-    int64_t grid = (n / 8 + 255) / 256;
-    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
-    gemm::split_planes_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(src, n, static_cast<uint16_t*>(planes),
-                                                                             plane_stride);
+    int64_t gx = (max_segment_elems / 8 + 255) / 256;
+    if (gx > (int64_t)sm_count() * 4) gx = (int64_t)sm_count() * 4;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)num_segments);
+    gemm::split_planes_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, static_cast<uint16_t*>(planes), plane_stride,
+                                                                   d_segments);
     count_launch();
     CB200_CHECK_LAUNCH();
     return CB200_OK;
@@ -361,12 +406,14 @@ int cb200_colsum(const float* x, int64_t rows, int64_t cols, float* out, float* 
 }
 
 int cb200_permute_f32(const float* src, const int32_t* table, int64_t n, float* dst, void* dst_planes,
-                      int64_t plane_stride, void* stream) {
+                      int64_t plane_stride, int32_t plane_cols, void* stream) {
+    CB200_CHECK_ARG(!dst_planes || (plane_cols > 0 && plane_cols % 8 == 0 && n % (8 * (int64_t)plane_cols) == 0),
+                    "planes: dst must be a [multiple of 8, plane_cols] matrix");
     CB200_CHECK_ARG(src && table && dst && n > 0, "bad arguments");
     int64_t grid = (n + 255) / 256;
     if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
-    gemm::permute_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(src, table, n, dst,
-                                                                        static_cast<uint16_t*>(dst_planes), plane_stride);
+    gemm::permute_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(
+        src, table, n, dst, static_cast<uint16_t*>(dst_planes), plane_stride, plane_cols);
     count_launch();
     CB200_CHECK_LAUNCH();
     return CB200_OK;

@@ -174,9 +174,26 @@ struct EpiParams {
     float* partial;            // splits > 1: raw partial sums [splits][M][N]
     int splits;
     int accumulate;            // c += v instead of c = v (after bias/act/mask); used by multi-class data gradients
-    uint16_t* c_planes;        // optional bf16 hi / mid / lo planes of c (same element indexing), see split3()
+    uint16_t* c_planes;        // optional bf16 hi / mid / lo planes of c in the 8x8 core-tiled format (tiled_elem)
     int64_t c_plane_stride;    // elements between planes
+    int c_plane_cols;          // columns of the tiled plane matrix (= n of this GEMM)
+    int c_prow_npix;           // > 0: output row m = b * npix + q  (NHWC order) lands in plane row q * batch + b
+    int c_prow_batch;          //      (pixel-major, batch-inner order of the planes); 0: plane row = m
 };
+
+// Plane format.  A logical [rows, cols] matrix (both multiples of 8) is stored as 8x8 "core matrices" of 128 contiguous
+// bytes, core (r / 8, c / 8) at ((r / 8) * (cols / 8) + c / 8) * 64 elements, element (r % 8, c % 8) inside it
+// row-major.  This is exactly the unit the tcgen05 shared-memory descriptors address without swizzling (K-major A with
+// M = rows, K = cols; MN-major A^T / B with K = rows, MN = cols all read the same 128 bytes), so any operand tile is a
+// handful of contiguous runs of cores that a 1-D bulk copy (TMA) moves without touching a register.
+// Activations / gradients use rows = pixel * batch + b (pixel-major, batch-inner), cols = channels: the im2col tile of
+// one tap is then 128 consecutive rows of the plane matrix.
+__device__ __forceinline__ size_t tiled_elem(size_t prow, int col, int pcols) {
+    return ((prow >> 3) * (size_t)(pcols >> 3) + (size_t)(col >> 3)) * 64 + (prow & 7) * 8 + (col & 7);
+}
+__device__ __forceinline__ size_t plane_row(size_t m, int npix, int batch) {
+    return npix > 0 ? (m % (size_t)npix) * (size_t)batch + m / (size_t)npix : m;
+}
 
 // Exact 3-way bf16 split of an fp32 value (truncation): x == hi + mid + lo, each the upper half-word of an fp32.
 // The tensor-core GEMM (nn_gemm_tc.cuh) consumes operands in this form; producers that know their output feeds another
@@ -200,7 +217,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int m, int n
     if (ep.accumulate) v += *dst;
     *dst = v;
     if (ep.c_planes) {
-        uint16_t* p = ep.c_planes + row * ep.ldc + n;
+        uint16_t* p = ep.c_planes + tiled_elem(plane_row((size_t)m, ep.c_prow_npix, ep.c_prow_batch), n, ep.c_plane_cols);
         split3(v, p[0], p[ep.c_plane_stride], p[2 * ep.c_plane_stride]);
     }
 }

@@ -27,11 +27,10 @@
 // for the stage).
 //
 // PLANES.  A producer that knows its output feeds another GEMM writes the bf16 hi / mid / lo planes next to the fp32
-// result (EpiParams::c_planes; weights are split once per step by cb200_split_planes).  When both operands come with
-// planes (a_planes, b_planes, a_vec8) the loader does no arithmetic at all: gemm_tc_planes_kernel moves 16-byte core
-// matrix rows global -> shared with cp.async through a 3-stage ring, invalid taps zero-filled by the copy itself.
-// The register-staged kernel below remains for uint8 sources (exact path), LUT sources and plane-less fp32 operands;
-// it accepts B planes too (conv1: weights / dY), which removes the B-side split.
+// result (EpiParams::c_planes, 8x8 core-tiled format of nn_gemm.cuh; weights are split once per step by
+// cb200_split_planes).  GEMMs whose operands both have planes run in nn_gemm_tiled.cuh (bulk-copy fed, no conversion
+// work).  The register-staged kernel below remains for uint8 sources (exact path), LUT sources and plane-less fp32
+// operands; it accepts B planes too (conv1: weights / dY), which removes the B-side split.
 //
 // CTA = 128 threads = one 128 x BN output tile.  Two shared-memory stages: while the tensor core works on chunk c
 // (asynchronously, tracked by tcgen05.commit -> mbarrier), all threads convert chunk c+1.  Thread t owns output row t
@@ -137,8 +136,8 @@ __device__ __forceinline__ bool tap_ok(int ri, int ci, int oh, int ow) {
 // fp32 result (+ bf16 planes) or split-R partial
 template <int BN>
 __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_main, uint32_t tmem_corr, bool have_acc,
-                                            int m0, int n0, int M, int N, int split, bool u8, float a_u8_div,
-                                            int unscaled_row) {
+                                            int m0, int n0, int M, int m_end, int N, int split, bool u8,
+                                            float a_u8_div, int unscaled_row) {
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m = m0 + tid;
     const bool scale_row = u8 && m != unscaled_row;
@@ -160,7 +159,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_m
 #pragma unroll
             for (int j = 0; j < 8; ++j) vm[j] = vc[j] = 0u;
         }
-        if (m < M) {
+        if (m < m_end) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -202,17 +201,13 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_m
                     for (int j = 0; j < 8; ++j) dst[j] = v[j];
                 }
                 if (ep.c_planes && ep.splits <= 1) {
-                    uint16_t* p = ep.c_planes + elem;
-                    if ((elem & 7) == 0) {
-                        const Split8 sp = split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
-                        *reinterpret_cast<uint4*>(p) = sp.h;
-                        *reinterpret_cast<uint4*>(p + ep.c_plane_stride) = sp.m;
-                        *reinterpret_cast<uint4*>(p + 2 * ep.c_plane_stride) = sp.l;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            split3(v[j], p[j], p[ep.c_plane_stride + j], p[2 * ep.c_plane_stride + j]);
-                    }
+                    // one core-matrix row (8 columns of one plane row) = 16 bytes per plane
+                    uint16_t* p = ep.c_planes +
+                                  tiled_elem(plane_row((size_t)m, ep.c_prow_npix, ep.c_prow_batch), nb, ep.c_plane_cols);
+                    const Split8 sp = split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+                    *reinterpret_cast<uint4*>(p) = sp.h;
+                    *reinterpret_cast<uint4*>(p + ep.c_plane_stride) = sp.m;
+                    *reinterpret_cast<uint4*>(p + 2 * ep.c_plane_stride) = sp.l;
                 }
             } else {
 #pragma unroll
@@ -239,7 +234,8 @@ constexpr size_t tc_smem_bytes() {
 template <int BN, bool kTransA, bool kU8>
 __global__ void __launch_bounds__(128) gemm_tc_kernel(FastA a, const float* __restrict__ b, int ldb, EpiParams ep,
                                                       int M, int N, int R, int r_per_split, float a_u8_div,
-                                                      const uint16_t* __restrict__ b_planes, int64_t b_plane_stride) {
+                                                      const uint16_t* __restrict__ b_planes, int64_t b_plane_stride,
+                                                      int b_prow_npix, int b_prow_batch) {
     constexpr int NA = kU8 ? 1 : 3;                       // bf16 planes of the A operand
     constexpr int A_SPLIT = kTcBM * kTcBK * 2;            // bytes of one bf16 plane of the A chunk (8 KB)
     constexpr int B_SPLIT = BN * kTcBK * 2;
@@ -412,8 +408,8 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(FastA a, const float* __re
             const uint4 zq = make_uint4(0u, 0u, 0u, 0u);
             uint4 q0 = zq, q1 = zq, q2 = zq;
             if (r < r_hi && n < N) {
-                if (b_planes) {                                   // N % 8 == 0: the 8 columns are all inside
-                    const uint16_t* p = b_planes + (size_t)r * ldb + n;
+                if (b_planes) {                                   // tiled planes of B [R, ldb]: one core-matrix row
+                    const uint16_t* p = b_planes + tiled_elem(plane_row((size_t)r, b_prow_npix, b_prow_batch), n, ldb);
                     q0 = __ldg(reinterpret_cast<const uint4*>(p));
                     q1 = __ldg(reinterpret_cast<const uint4*>(p + b_plane_stride));
                     q2 = __ldg(reinterpret_cast<const uint4*>(p + 2 * b_plane_stride));
@@ -503,264 +499,8 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(FastA a, const float* __re
         mbar_wait(done_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, N, split, kU8, a_u8_div,
+    tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, M, N, split, kU8, a_u8_div,
                     (kU8 && kTransA) ? a.ones_col : -1);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_main), "r"(TMEM_COLS));
-    }
-}
-
-// =====================================================================================================================
-// Both operands pre-split (bf16 hi / mid / lo planes with the fp32 tensors' element indexing): pure data movement.
-// =====================================================================================================================
-constexpr int kPlStages = 3;
-
-#ifdef CB200_TC_PROF
-// build-time instrumentation (python -m coach_b200.build with CB200_EXTRA_NVCC_FLAGS=-DCB200_TC_PROF): cycles thread 0
-// of CTA (0,0,0) spends in each phase of the chunk loop, read back with cb200_tc_prof_read (tools/tc_phase_probe.py)
-__device__ unsigned long long g_tc_prof[16];
-#define TC_PROF_T(var) const long long var = clock64()
-#define TC_PROF_ADD(i, a, b) \
-    if (prof_on) g_tc_prof[i] += (unsigned long long)((b) - (a))
-#else
-#define TC_PROF_T(var)
-#define TC_PROF_ADD(i, a, b)
-#endif
-
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
-    // 16-byte global -> shared copy; src-size 0 zero-fills the destination without reading (invalid taps, tails)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 16 : 0)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-struct PlaneOperands {
-    const uint16_t* a;         // planes of the A source
-    int64_t a_stride;
-    const uint16_t* b;         // planes of B [R, ldb]
-    int64_t b_stride;
-};
-
-template <int BN>
-constexpr size_t tc_planes_stage_bytes() {
-    return (size_t)3 * kTcBM * kTcBK * 2 + 3 * BN * kTcBK * 2;
-}
-// dynamic shared memory: stages | barriers (64 B) | tab_off [slice] | tab_info [slice] (only with validity tables)
-template <int BN>
-inline size_t tc_planes_smem_bytes(int slice_entries, bool has_info) {
-    return kPlStages * tc_planes_stage_bytes<BN>() + 64 + (has_info ? 2 : 1) * sizeof(int32_t) * (size_t)slice_entries;
-}
-
-template <int BN, bool kTransA>
-__global__ void __launch_bounds__(128) gemm_tc_planes_kernel(FastA a, PlaneOperands pl, int ldb, EpiParams ep, int M,
-                                                             int N, int R, int r_per_split, int slice_entries) {
-    constexpr int A_SPLIT = kTcBM * kTcBK * 2;
-    constexpr int B_SPLIT = BN * kTcBK * 2;
-    constexpr int STAGE = 3 * A_SPLIT + 3 * B_SPLIT;
-    constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + kPlStages * STAGE);      // [kPlStages]
-    uint64_t* done_bar = empty_bar + kPlStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
-    int32_t* tab_off = reinterpret_cast<int32_t*>(smem + kPlStages * STAGE + 64);
-    int32_t* tab_info = tab_off + slice_entries;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * BN;
-    const int split = blockIdx.z;
-    const int r_lo = split * r_per_split;
-    const int r_hi = min(R, r_lo + r_per_split);
-    const bool has_info = a.rowinfo != nullptr;
-
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    if (tid == 0) {
-        for (int s = 0; s < kPlStages; ++s) mbar_init(empty_bar + s, 1);
-        mbar_init(done_bar, 1);
-        fence_mbar_init();
-    }
-    // K-major: one table entry per group of 8 reduction indices; MN-major: one per reduction row
-    if (!kTransA) {
-        for (int j = tid; 8 * j < r_hi - r_lo; j += 128) {
-            tab_off[j] = __ldg(a.coloff + r_lo + 8 * j);
-            if (has_info) tab_info[j] = __ldg(a.colinfo + r_lo + 8 * j);
-        }
-    } else {
-        for (int j = tid; j < r_hi - r_lo; j += 128) {
-            tab_off[j] = __ldg(a.rowoff + r_lo + j);
-            if (has_info) tab_info[j] = __ldg(a.rowinfo + r_lo + j);
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_main = *tmem_slot;
-    const uint32_t tmem_corr = tmem_main + BN;
-    const uint32_t idesc = umma_instr_desc_bf16(BN, kTransA ? 1 : 0, 1);
-
-    // item -> thread mapping as in gemm_tc_kernel (a quarter-warp fills one 128-byte core matrix)
-    const int kgrp = lane >> 3;
-    int fix_off[4] = {-1, -1, -1, -1};     // K-major: rowoff[m_i];  MN-major: [0] = coloff[k] (or -2: the ones row)
-    int fix_info[4] = {0, 0, 0, 0};
-    if (!kTransA) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = m0 + 8 * warp + (lane & 7) + 32 * i;
-            if (m < a.rows) {
-                fix_off[i] = __ldg(a.rowoff + m);
-                if (has_info) fix_info[i] = __ldg(a.rowinfo + m);
-            }
-        }
-    } else {
-        const int k = m0 + 8 * (tid >> 3);
-        if (k < a.cols) {
-            fix_off[0] = __ldg(a.coloff + k);
-            if (has_info) fix_info[0] = __ldg(a.colinfo + k);
-        } else if (k == a.ones_col) {
-            fix_off[0] = -2;
-        }
-    }
-    constexpr int NG = BN / 8;
-    constexpr int NB_IT = kTcBK * NG / 128;
-    static_assert(kTcBK * NG % 128 == 0, "B loader shape");
-    const uint32_t smem_base = smem_u32(smem);
-
-    auto issue = [&](int c, int s) {
-        const int r0 = r_lo + c * kTcBK;
-        const uint32_t sA = smem_base + s * STAGE, sB = sA + 3 * A_SPLIT;
-        if (!kTransA) {
-            const int ra = r0 + kgrp * 8;
-            const int ja = (ra - r_lo) >> 3;
-            const bool in = ra < r_hi;
-            const int ca = in ? tab_off[ja] : 0;
-            const int ia = (in && has_info) ? tab_info[ja] : 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int rr = 8 * warp + (lane & 7) + 32 * i;
-                const uint32_t off = kgrp * (kTcBM / 8) * 128 + (rr >> 3) * 128 + (rr & 7) * 16;
-                const bool ok = in && fix_off[i] >= 0 && (!has_info || tap_ok(fix_info[i], ia, a.oh, a.ow));
-                const uint16_t* src = pl.a + (ok ? (int64_t)(fix_off[i] + ca) : 0);
-                cp_async16(sA + off, src, ok);
-                cp_async16(sA + A_SPLIT + off, src + pl.a_stride, ok);
-                cp_async16(sA + 2 * A_SPLIT + off, src + 2 * pl.a_stride, ok);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int mrow = r0 + 8 * i + (tid & 7);
-                const uint32_t off = i * (kTcBM / 8) * 128 + (tid >> 3) * 128 + (tid & 7) * 16;
-                const bool in = mrow < r_hi;
-                if (fix_off[0] == -2) {
-                    // bias-gradient row: A^T element 1.0 in the group's first column (bf16 0x3F80 in the hi plane)
-                    uint8_t* g = smem + s * STAGE + off;
-                    *reinterpret_cast<uint4*>(g) = make_uint4(in ? 0x3F80u : 0u, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(g + A_SPLIT) = make_uint4(0u, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(g + 2 * A_SPLIT) = make_uint4(0u, 0u, 0u, 0u);
-                    continue;
-                }
-                bool ok = in && fix_off[0] >= 0;
-                int64_t e = 0;
-                if (ok) {
-                    if (has_info && !tap_ok(tab_info[mrow - r_lo], fix_info[0], a.oh, a.ow)) ok = false;
-                    else e = (int64_t)tab_off[mrow - r_lo] + fix_off[0];
-                }
-                const uint16_t* src = pl.a + e;
-                cp_async16(sA + off, src, ok);
-                cp_async16(sA + A_SPLIT + off, src + pl.a_stride, ok);
-                cp_async16(sA + 2 * A_SPLIT + off, src + 2 * pl.a_stride, ok);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < NB_IT; ++i) {
-            const int it = tid + i * 128;
-            const int kk = (it & 7) + 8 * (it / (8 * NG)), g = (it >> 3) % NG;
-            const int r = r0 + kk, n = n0 + 8 * g;
-            const uint32_t off = (kk >> 3) * NG * 128 + g * 128 + (kk & 7) * 16;
-            const bool ok = r < r_hi && n < N;
-            const uint16_t* src = pl.b + (ok ? ((int64_t)r * ldb + n) : 0);
-            cp_async16(sB + off, src, ok);
-            cp_async16(sB + B_SPLIT + off, src + pl.b_stride, ok);
-            cp_async16(sB + 2 * B_SPLIT + off, src + 2 * pl.b_stride, ok);
-        }
-    };
-
-    const int nchunks = (r_hi - r_lo + kTcBK - 1) / kTcBK;
-#ifdef CB200_TC_PROF
-    const bool prof_on = tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-#endif
-    TC_PROF_T(tp0);
-#pragma unroll
-    for (int p = 0; p < kPlStages - 1; ++p) {
-        if (p < nchunks) issue(p, p);
-        cp_async_commit();
-    }
-    TC_PROF_T(tp1);
-    TC_PROF_ADD(0, tp0, tp1);
-    for (int c = 0; c < nchunks; ++c) {
-        const int s = c % kPlStages;
-        TC_PROF_T(t0);
-        cp_async_wait<kPlStages - 2>();       // this thread's copies of chunk c have landed
-        TC_PROF_T(t1);
-        fence_proxy_async_smem();             // ... and are visible to the tensor core (async proxy)
-        __syncthreads();                      // ... as are everybody else's
-        TC_PROF_T(t2);
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            constexpr uint32_t A_LBO = (kTcBM / 8) * 128, B_LBO = (BN / 8) * 128, SBO = 128;
-            const uint32_t a_base = smem_base + s * STAGE, b_base = a_base + 3 * A_SPLIT;
-#pragma unroll
-            for (int ks = 0; ks < kTcBK / 16; ++ks) {
-                const uint32_t ao = ks * 2 * A_LBO, bo = ks * 2 * B_LBO;
-                auto desc_a = [&](int sp) { return umma_smem_desc(a_base + sp * A_SPLIT + ao, A_LBO, SBO); };
-                auto desc_b = [&](int sp) { return umma_smem_desc(b_base + sp * B_SPLIT + bo, B_LBO, SBO); };
-                const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
-                umma_bf16(tmem_main, desc_a(0), desc_b(0), idesc, first);          // a1 b1
-                umma_bf16(tmem_corr, desc_a(0), desc_b(2), idesc, first);          // a1 b3
-                umma_bf16(tmem_corr, desc_a(2), desc_b(0), idesc, 1u);             // a3 b1
-                umma_bf16(tmem_corr, desc_a(1), desc_b(1), idesc, 1u);             // a2 b2
-                umma_bf16(tmem_corr, desc_a(0), desc_b(1), idesc, 1u);             // a1 b2
-                umma_bf16(tmem_corr, desc_a(1), desc_b(0), idesc, 1u);             // a2 b1
-            }
-            umma_commit(empty_bar + s);
-            if (c == nchunks - 1) umma_commit(done_bar);
-        }
-        TC_PROF_T(t3);
-        // refill the stage chunk c-1 used (its MMAs were issued one iteration ago) with chunk c + kPlStages - 1
-        const int nc = c + kPlStages - 1;
-        if (nc < nchunks) {
-            if (c >= 1) mbar_wait(empty_bar + (c - 1) % kPlStages, (uint32_t)(((c - 1) / kPlStages) & 1));
-        }
-        TC_PROF_T(t4);
-        if (nc < nchunks) issue(nc, nc % kPlStages);
-        cp_async_commit();
-        TC_PROF_T(t5);
-        TC_PROF_ADD(1, t0, t1);
-        TC_PROF_ADD(2, t1, t2);
-        TC_PROF_ADD(3, t2, t3);
-        TC_PROF_ADD(4, t3, t4);
-        TC_PROF_ADD(5, t4, t5);
-        TC_PROF_ADD(6, t0 - 1, t0);      // chunk count
-    }
-    TC_PROF_T(tq0);
-    if (nchunks > 0) {
-        mbar_wait(done_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    TC_PROF_T(tq1);
-    tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, N, split, false, 1.f, -1);
-    TC_PROF_T(tq2);
-    TC_PROF_ADD(7, tq0, tq1);
-    TC_PROF_ADD(8, tq1, tq2);
-    TC_PROF_ADD(9, tp0, tq2);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {

@@ -1,0 +1,264 @@
+// coach_b200/csrc/nn_gemm_tiled.cuh -- tensor-core GEMMs whose operands are pre-split bf16 planes in the 8x8
+// core-tiled format (nn_gemm.cuh: tiled_elem): convolutions and dense layers as "multi-tap" contractions.
+//
+// Activations / gradients are plane matrices with rows = pixel * batch + b (pixel-major, batch-inner) and cols =
+// channels; weights are stacks of [rows, n] blocks.  Two contraction shapes cover the whole learn step:
+//
+//   mode 0 (forward / data gradient; A is K-major):
+//       C[q * B + b, n] = sum over the tap list of output pixel q, entries (a_pix, w_blk):
+//                            sum_c  A[a_pix * B + b, c] * W[w_blk][c, n]
+//     conv forward   : q = output pixel, one entry per kernel tap (a_pix = the input pixel under the tap)
+//     conv data grad : q = INPUT pixel, entries = the taps whose output pixel exists (gather form: no zero padding, no
+//                      stride-class decomposition -- invalid taps are simply not in the list), W = per-tap W^T
+//     dense          : one pixel, one entry; a dense layer on a flattened conv map = one entry per pixel
+//   mode 1 (weight gradient; A^T is MN-major):
+//       C[t * Ca + c, n] = sum_q sum_b  A[a_pix(t, q) * B + b, c] * G[q * B + b, n]
+//
+// A CTA owns one 128 x BN output tile: 128 consecutive batch rows of one pixel (mode 0) or 128 rows of the stacked
+// per-tap weight matrix (mode 1).  Because of the plane format every operand chunk (32 reduction indices) is a few
+// contiguous runs of 128-byte core matrices, so the PRODUCER warp moves it with 1-D bulk copies (cp.async.bulk,
+// completion counted in bytes on an mbarrier -- the TMA engine, no registers, no shared-memory stores by threads), the
+// MMA warp (one elected thread) issues the 3xBF16 product set of nn_gemm_tc.cuh as soon as the "full" barrier of a
+// stage flips and releases the stage through tcgen05.commit -> "empty" barrier, and the four EPILOGUE warps drain
+// the TMEM accumulators at the end (tc_epilogue: bias / activation / derivative mask, fp32 result + planes).
+//
+// Shared-memory operand layouts (no swizzle; LBO = step between core matrices along K, SBO = along M / N):
+//   A  K-major  [128 rows, 32 k] : core (rg, kg) at rg * 512 + kg * 128          LBO = 128,  SBO = 512
+//   A^T MN-major [128 m,   32 k] : core (kg, mg) at kg * 2048 + mg * 128         LBO = 2048, SBO = 128
+//   B  MN-major [32 k, BN n]     : core (kg, ng) at kg * (BN/8) * 128 + ng * 128 LBO = BN * 16, SBO = 128
+#pragma once
+#include "nn_gemm_tc.cuh"
+
+namespace cb200 {
+namespace gemm {
+
+#ifdef CB200_TC_PROF
+// build-time instrumentation (CB200_EXTRA_NVCC_FLAGS=-DCB200_TC_PROF python -m coach_b200.build --force): cycles the
+// producer lane 0 / the MMA thread / epilogue thread 0 of CTA (0,0,0) spend per phase; read with cb200_tc_prof_read
+// (tools/tc_phase_probe.py)
+__device__ unsigned long long g_tc_prof[16];
+#define TC_PROF_T(var) const long long var = clock64()
+#define TC_PROF_ADD(i, a, b) \
+    if (prof_on) g_tc_prof[i] += (unsigned long long)((b) - (a))
+#else
+#define TC_PROF_T(var)
+#define TC_PROF_ADD(i, a, b)
+#endif
+
+struct TiledParams {
+    int mode;
+    int batch;                 // B, multiple of 32
+    const uint16_t* a;         // planes of the A matrix [a_pixels * B, a_cols]
+    long long a_stride;
+    int a_cols;                // Ca, multiple of 32
+    const uint16_t* b;         // mode 0: weight blocks [blocks][Ca, n];  mode 1: G [q_pixels * B, n]
+    long long b_stride;
+    int n;
+    const int32_t* list_ptr;   // mode 0: [num_q + 1]
+    const int2* list;          // mode 0: (a_pix, w_blk)
+    const int32_t* a_pix;      // mode 1: [taps * num_q]
+    int num_q, taps;
+    int chunks_per_split;
+};
+
+template <int BN>
+struct TiledCfg {
+    static constexpr int kStages = BN == 128 ? 4 : 3;
+    static constexpr size_t kSmemBytes = (size_t)kStages * (3 * kTcBM * kTcBK * 2 + 3 * BN * kTcBK * 2) + 128;
+};
+
+template <int BN, bool kTransA>
+__global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(TiledParams tp, EpiParams ep, int M) {
+    constexpr int S = TiledCfg<BN>::kStages;
+    constexpr int A_SPLIT = kTcBM * kTcBK * 2;            // 8 KB per plane
+    constexpr int B_SPLIT = BN * kTcBK * 2;
+    constexpr int STAGE = 3 * A_SPLIT + 3 * B_SPLIT;
+    constexpr int B_KG = (BN / 8) * 128;                  // bytes of one k-group (8 reduction rows) of the B tile
+    constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * STAGE);     // [S]
+    uint64_t* empty_bar = full_bar + S;                                    // [S]
+    uint64_t* done_bar = empty_bar + S;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int B = tp.batch, Ca = tp.a_cols, N = tp.n;
+    const int n0 = blockIdx.y * BN;
+    const int split = blockIdx.z;
+
+    // ---- tile decode ----------------------------------------------------------------------------------------------
+    int q = 0, b0 = 0, m0, m_end, total, list_lo = 0;
+    const int kc_per = Ca / kTcBK;                        // mode 0: chunks per tap
+    const int bc_per = B / kTcBK;                         // mode 1: chunks per pixel
+    if (!kTransA) {
+        const int tiles_per_q = (B + kTcBM - 1) / kTcBM;
+        q = blockIdx.x / tiles_per_q;
+        b0 = (blockIdx.x % tiles_per_q) * kTcBM;
+        m0 = q * B + b0;
+        m_end = q * B + B;
+        list_lo = __ldg(tp.list_ptr + q);
+        total = (__ldg(tp.list_ptr + q + 1) - list_lo) * kc_per;
+    } else {
+        m0 = blockIdx.x * kTcBM;
+        m_end = M;
+        total = tp.num_q * bc_per;
+    }
+    const int c_lo = split * tp.chunks_per_split;
+    const int c_hi = min(total, c_lo + tp.chunks_per_split);
+    const int nchunks = max(0, c_hi - c_lo);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_mbar_init();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_main = *tmem_slot;
+    const uint32_t tmem_corr = tmem_main + BN;
+#ifdef CB200_TC_PROF
+    const bool cta0 = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#endif
+
+    if (warp == 4) {
+        // ================= producer: bulk copies of the operand cores into the stage ring =========================
+#ifdef CB200_TC_PROF
+        const bool prof_on = cta0 && lane == 0;
+#endif
+        const int nrg = kTransA ? 0 : min(kTcBM / 8, (B - b0) / 8);            // valid 8-row groups of the A tile
+        // mode 1: taps covered by this M tile, and the channel range inside a tap
+        const int taps_in_tile = kTransA ? (Ca >= kTcBM ? 1 : min(kTcBM / Ca, tp.taps - m0 / Ca)) : 0;
+        const int t0 = kTransA ? m0 / Ca : 0;
+        const int cw = kTransA ? min(Ca, kTcBM) : 0;                           // channels per tap inside the tile
+        const int c0 = kTransA ? m0 % Ca : 0;
+        const uint32_t a_bytes = kTransA ? (uint32_t)(taps_in_tile * 4 * (cw / 8) * 128) : (uint32_t)(nrg * 512);
+        const uint32_t tx_bytes = 3u * (a_bytes + (uint32_t)B_SPLIT);
+        for (int j = 0; j < nchunks; ++j) {
+            const int s = j % S, u = j / S;
+            TC_PROF_T(t0c);
+            if (u > 0) mbar_wait(empty_bar + s, (uint32_t)((u - 1) & 1));      // MMAs that read this stage are done
+            TC_PROF_T(t1c);
+            uint8_t* sA = smem + s * STAGE;
+            uint8_t* sB = sA + 3 * A_SPLIT;
+            uint64_t* bar = full_bar + s;
+            if (lane == 0) mbar_expect_tx(bar, tx_bytes);
+            __syncwarp();
+            const int cj = c_lo + j;
+            size_t b_core;                                  // first core of the B run of k-group 0
+            if (!kTransA) {
+                const int e = cj / kc_per, kc = cj % kc_per;
+                const int2 ent = __ldg(tp.list + list_lo + e);
+                const size_t rg0 = ((size_t)ent.x * B + b0) >> 3;
+                if (Ca == kTcBK) {
+                    // the whole [rows, 32] tile is one contiguous run of cores
+                    if (lane < 3)
+                        bulk_g2s(sA + lane * A_SPLIT, tp.a + lane * tp.a_stride + rg0 * 4 * 64, (uint32_t)(nrg * 512), bar);
+                } else {
+                    for (int idx = lane; idx < 3 * 16; idx += 32) {
+                        const int p = idx >> 4, i = idx & 15;
+                        if (i < nrg)
+                            bulk_g2s(sA + p * A_SPLIT + i * 512,
+                                     tp.a + p * tp.a_stride + ((rg0 + i) * (size_t)(Ca >> 3) + (size_t)kc * 4) * 64, 512u,
+                                     bar);
+                    }
+                }
+                b_core = ((size_t)ent.y * Ca + (size_t)kc * kTcBK) / 8 * (size_t)(N >> 3) + (size_t)(n0 >> 3);
+            } else {
+                const int qq = cj / bc_per, bc = cj % bc_per;
+                // A^T: per tap of the tile, 4 k-groups (8 batch rows each) x a run of cw / 8 cores
+                for (int idx = lane; idx < 3 * 4 * taps_in_tile; idx += 32) {
+                    const int p = idx / (4 * taps_in_tile), r = idx % (4 * taps_in_tile);
+                    const int tt = r >> 2, kg = r & 3;
+                    const int apix = __ldg(tp.a_pix + (size_t)(t0 + tt) * tp.num_q + qq);
+                    const size_t rg = (((size_t)apix * B + (size_t)bc * kTcBK) >> 3) + kg;
+                    bulk_g2s(sA + p * A_SPLIT + kg * 2048 + tt * (Ca >> 3) * 128,
+                             tp.a + p * tp.a_stride + (rg * (size_t)(Ca >> 3) + (size_t)(c0 >> 3)) * 64,
+                             (uint32_t)((cw >> 3) * 128), bar);
+                }
+                b_core = ((((size_t)qq * B + (size_t)bc * kTcBK) >> 3)) * (size_t)(N >> 3) + (size_t)(n0 >> 3);
+            }
+            if (lane >= 16 && lane < 28) {
+                const int l = lane - 16, p = l >> 2, kg = l & 3;
+                bulk_g2s(sB + p * B_SPLIT + kg * B_KG, tp.b + p * tp.b_stride + (b_core + (size_t)kg * (N >> 3)) * 64,
+                         (uint32_t)B_KG, bar);
+            }
+            TC_PROF_T(t2c);
+            TC_PROF_ADD(0, t0c, t1c);      // producer: wait for a free stage
+            TC_PROF_ADD(1, t1c, t2c);      // producer: issue the copies
+            TC_PROF_ADD(2, t0c - 1, t0c);  // chunk count
+        }
+    } else if (warp == 5) {
+        // ================= MMA issuer ===============================================================================
+#ifdef CB200_TC_PROF
+        const bool prof_on = cta0 && lane == 0;
+#endif
+        const uint32_t idesc = umma_instr_desc_bf16(BN, kTransA ? 1 : 0, 1);
+        constexpr uint32_t A_LBO = kTransA ? 2048u : 128u, A_SBO = kTransA ? 128u : 512u;
+        constexpr uint32_t A_KS = kTransA ? 2u * 2048u : 256u;                 // bytes per k16 step
+        constexpr uint32_t B_LBO = (uint32_t)B_KG, B_SBO = 128u, B_KS = 2u * (uint32_t)B_KG;
+        const uint64_t a_hi = umma_smem_desc(0u, A_LBO, A_SBO), b_hi = umma_smem_desc(0u, B_LBO, B_SBO);
+        const uint32_t smem_base = smem_u32(smem);
+        for (int j = 0; j < nchunks; ++j) {
+            const int s = j % S, u = j / S;
+            TC_PROF_T(t0m);
+            mbar_wait(full_bar + s, (uint32_t)(u & 1));                        // the bulk copies of this stage landed
+            TC_PROF_T(t1m);
+            if (lane == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_base = smem_base + s * STAGE, b_base = a_base + 3 * A_SPLIT;
+#pragma unroll
+                for (int ks = 0; ks < kTcBK / 16; ++ks) {
+                    const uint64_t a0 = a_hi | (uint64_t)((a_base + ks * A_KS) >> 4);
+                    const uint64_t b0d = b_hi | (uint64_t)((b_base + ks * B_KS) >> 4);
+                    const uint64_t a1 = a0 + (A_SPLIT >> 4), a2 = a0 + 2 * (A_SPLIT >> 4);
+                    const uint64_t b1 = b0d + (B_SPLIT >> 4), b2 = b0d + 2 * (B_SPLIT >> 4);
+                    const uint32_t first = (j == 0 && ks == 0) ? 0u : 1u;
+                    umma_bf16(tmem_main, a0, b0d, idesc, first);       // a1 b1
+                    umma_bf16(tmem_corr, a0, b2, idesc, first);        // a1 b3
+                    umma_bf16(tmem_corr, a2, b0d, idesc, 1u);          // a3 b1
+                    umma_bf16(tmem_corr, a1, b1, idesc, 1u);           // a2 b2
+                    umma_bf16(tmem_corr, a0, b1, idesc, 1u);           // a1 b2
+                    umma_bf16(tmem_corr, a1, b0d, idesc, 1u);          // a2 b1
+                }
+                umma_commit(empty_bar + s);
+                if (j == nchunks - 1) umma_commit(done_bar);
+            }
+            __syncwarp();
+            TC_PROF_T(t2m);
+            TC_PROF_ADD(3, t0m, t1m);      // MMA thread: wait for data
+            TC_PROF_ADD(4, t1m, t2m);      // MMA thread: issue
+        }
+    } else {
+        // ================= epilogue warps (TMEM lanes 0..127) =====================================================
+#ifdef CB200_TC_PROF
+        const bool prof_on = cta0 && tid == 0;
+#endif
+        TC_PROF_T(t0e);
+        if (nchunks > 0) {
+            mbar_wait(done_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        TC_PROF_T(t1e);
+        tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, m_end, N, split, false, 1.f, -1);
+        TC_PROF_T(t2e);
+        TC_PROF_ADD(5, t0e, t1e);          // main loop as seen by the epilogue warps
+        TC_PROF_ADD(6, t1e, t2e);          // epilogue
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_main), "r"(TMEM_COLS));
+    }
+}
+
+}  // namespace gemm
+}  // namespace cb200

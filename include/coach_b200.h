@@ -179,26 +179,70 @@ typedef struct cb200_gemm_desc {
     float a_u8_div;             /* uint8 A only, 0 = not declared: the caller states a_lut[v] == (float)v / a_u8_div.  */
                                 /*    The tensor-core path then contracts the raw integers (exact in bf16) and divides */
                                 /*    each accumulated sum by a_u8_div once; other paths read a_lut and ignore this.   */
-    /* pre-split operands ("planes"): three bf16 arrays (hi, mid, lo; x == hi + mid + lo exactly, truncation split) */
-    /* indexed like the fp32 array they shadow, plane p at planes + p * plane_stride elements.  Optional; when A and  */
-    /* B both have them the tensor-core path moves operands with cp.async and does no conversion work.  The caller   */
-    /* guarantees they are current (cb200_split_planes, or produced by a GEMM through c_planes).                      */
-    const void* a_planes;       /* planes of a_src (fp32 sources only)                                              */
-    int64_t a_plane_stride;
-    const void* b_planes;       /* planes of b                                                                      */
+    /* bf16 operand planes (hi, mid, lo; x == hi + mid + lo exactly) in the 8x8 core-tiled format: a [rows, cols]    */
+    /* matrix stores element (r, c) of plane p at                                                                    */
+    /*     planes + p * plane_stride + ((r / 8) * (cols / 8) + c / 8) * 64 + (r % 8) * 8 + c % 8                     */
+    /* Activations / gradients use rows = pixel * batch + b.  Consumed natively by cb200_gemm_tiled; this entry point */
+    /* can read B planes (conv1: weights, dY) and write the planes of its result.                                    */
+    const void* b_planes;       /* planes of b [R, n] (ldb == n)                                                     */
     int64_t b_plane_stride;
+    int32_t b_prow_npix;        /* > 0: reduction row r = b * npix + q (NHWC) is plane row q * b_prow_batch + b       */
+    int32_t b_prow_batch;
     void* c_planes;             /* if set, the epilogue also writes the planes of the final c values                */
     int64_t c_plane_stride;
-    int32_t a_vec8;             /* like a_vec4 for groups of 8: aligned groups of 8 column indices are contiguous,   */
-                                /*    a_cols % 8 == 0, every a_rowoff / a_coloff group start % 8 == 0                */
+    int32_t c_plane_cols;       /* columns of the plane matrix (= n)                                                */
+    int32_t c_prow_npix;        /* > 0: output row m = b * npix + q is plane row q * c_prow_batch + b; 0: row m       */
+    int32_t c_prow_batch;
 } cb200_gemm_desc;
 
 int cb200_gemm(const cb200_gemm_desc* h_desc, void* stream);
 
-/* planes[p * plane_stride + i] = p-th bf16 piece of src[i] (p = 0 hi, 1 mid, 2 lo); n, plane_stride % 8 == 0, both
- * pointers 16-byte aligned.  Used for the parameter buffers once per step (the activations get their planes from the
- * producing GEMM's epilogue). */
-int cb200_split_planes(const float* src, int64_t n, void* planes, int64_t plane_stride, void* stream);
+/* =====================================================================================================================
+ * Tensor-core GEMMs on pre-split operands (csrc/nn_gemm_tiled.cuh).  Convolutions and dense layers as "multi-tap"
+ * contractions over plane matrices (rows = pixel * batch + b, cols = channels; weights = stacks of [a_cols, n] blocks):
+ *   mode 0: C[q * B + b, :] = sum over the tap list of output pixel q, entries (a_pix, w_blk):
+ *                                A[a_pix * B + b, :] * W[w_blk]                (forward, data gradient)
+ *   mode 1: C[t * a_cols + c, :] = sum_q sum_b A[a_pix[t * num_q + q] * B + b, c] * G[q * B + b, :]   (weight gradient)
+ * Replaces, for layers whose input already lives on the device as planes, the same reference code as cb200_gemm
+ * (layers.py:108-183 forward, tf.gradients backward).  Operands move by 1-D bulk copies (TMA); 3xBF16 products with
+ * fp32 TMEM accumulation, at most 32 reduction chunks of 32 per launch slice (use `splits`).
+ * ===================================================================================================================*/
+typedef struct cb200_tgemm_desc {
+    int32_t mode;
+    int32_t batch;              /* B, multiple of 32                                                                 */
+    const void* a_planes;       /* planes of A [a_pixels * B, a_cols]                                                */
+    int64_t a_plane_stride;
+    int32_t a_cols;             /* 32, 64, 128 or a multiple of 128                                                  */
+    const void* b_planes;       /* mode 0: weight blocks [blocks][a_cols, n];  mode 1: G [num_q * B, n]               */
+    int64_t b_plane_stride;
+    int32_t n;                  /* 32 or a multiple of 64                                                            */
+    const int32_t* list_ptr;    /* mode 0: [num_q + 1] offsets into list                                             */
+    const int32_t* list;        /* mode 0: pairs (a_pix, w_blk)                                                      */
+    int32_t max_list_len;       /* mode 0: longest tap list                                                          */
+    const int32_t* a_pix;       /* mode 1: [taps * num_q] input pixel under tap t at output pixel q                  */
+    int32_t num_q;
+    int32_t taps;
+    /* output / epilogue: as in cb200_gemm_desc; rows of C are q * B + b (mode 0) or t * a_cols + c (mode 1)          */
+    float* c;
+    int32_t ldc;
+    const float* bias;
+    int32_t act;
+    const float* mask_y;
+    int32_t mask_act;
+    const int32_t* c_rowmap;    /* e.g. q * B + b -> b * num_q + q to store NHWC                                      */
+    float* workspace;
+    int32_t splits;
+    void* c_planes;             /* tiled planes of C with plane row = C row, c_plane_cols == n                       */
+    int64_t c_plane_stride;
+    int32_t c_plane_cols;
+} cb200_tgemm_desc;
+
+int cb200_gemm_tiled(const cb200_tgemm_desc* h_desc, void* stream);
+
+/* fp32 row-major matrices -> tiled planes, one launch for a list of matrices inside one fp32 buffer (the parameter
+ * buffer, once per step): d_segments[k] = {src offset, rows, cols, plane offset} in elements (device memory). */
+int cb200_split_planes(const float* src, void* planes, int64_t plane_stride, const int64_t* d_segments,
+                       int32_t num_segments, int64_t max_segment_elems, void* stream);
 
 /* out[j] = sum_i x[i, j] for x [rows, cols] (bias gradients: tf.gradients wrt the bias of Dense / Conv2d), reduced in a
  * fixed order (two deterministic stages; `workspace` >= 1024 * cols floats). */
@@ -207,7 +251,8 @@ int cb200_colsum(const float* x, int64_t rows, int64_t cols, float* out, float* 
 /* dst[i] = src[table[i]], i < n  (fp32; static permutations of weight tensors for the data-gradient GEMMs, e.g. the
  * per-stride-class [taps*N, Cin] matrices of the transposed convolution) */
 int cb200_permute_f32(const float* src, const int32_t* table, int64_t n, float* dst, void* dst_planes,
-                      int64_t plane_stride, void* stream);   /* dst_planes optional (NULL): also write dst's planes */
+                      int64_t plane_stride, int32_t plane_cols, void* stream);
+                      /* dst_planes optional (NULL): also write dst, seen as [n / plane_cols, plane_cols], as planes */
 
 /* dst[c, r] = src[r, c]  (fp32; pre-transposition of weight matrices for the data-gradient GEMMs) */
 int cb200_transpose(const float* src, int64_t rows, int64_t cols, float* dst, void* dst_planes, int64_t plane_stride,

