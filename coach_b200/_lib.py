@@ -30,7 +30,8 @@ class GemmDesc(ctypes.Structure):
                 ("a_vec4", ctypes.c_int32), ("a_ones_col", ctypes.c_int32), ("a_u8_div", c_float),
                 ("b_planes", c_void_p), ("b_plane_stride", c_i64), ("b_prow_npix", ctypes.c_int32),
                 ("b_prow_batch", ctypes.c_int32), ("c_planes", c_void_p), ("c_plane_stride", c_i64),
-                ("c_plane_cols", ctypes.c_int32), ("c_prow_npix", ctypes.c_int32), ("c_prow_batch", ctypes.c_int32)]
+                ("c_plane_cols", ctypes.c_int32), ("c_prow_npix", ctypes.c_int32), ("c_prow_batch", ctypes.c_int32),
+                ("a_lda", ctypes.c_int32)]
 
 
 class TGemmDesc(ctypes.Structure):
@@ -41,7 +42,9 @@ class TGemmDesc(ctypes.Structure):
                 ("num_q", ctypes.c_int32), ("taps", ctypes.c_int32), ("c", c_void_p), ("ldc", ctypes.c_int32),
                 ("bias", c_void_p), ("act", ctypes.c_int32), ("mask_y", c_void_p), ("mask_act", ctypes.c_int32),
                 ("c_rowmap", c_void_p), ("workspace", c_void_p), ("splits", ctypes.c_int32), ("c_planes", c_void_p),
-                ("c_plane_stride", c_i64), ("c_plane_cols", ctypes.c_int32)]
+                ("c_plane_stride", c_i64), ("c_plane_cols", ctypes.c_int32), ("a_num_planes", ctypes.c_int32),
+                ("a_u8_div", c_float), ("a_rows", c_i64), ("b_rows", c_i64),
+                ("tmap_key", ctypes.c_uint64), ("tmap_storage", ctypes.c_uint8 * (2 * 128 + 64))]
 
 
 class Column(ctypes.Structure):
@@ -75,6 +78,7 @@ PROTOTYPES = {
     "cb200_colsum": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p]),
     "cb200_permute_f32": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "cb200_gemm_tiled": (c_int, [c_void_p, c_void_p]),
+    "cb200_u8_s2d_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cb200_transpose": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_void_p]),
     "cb200_split_planes": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_int, c_i64, c_void_p]),
     "cb200_dqn_td_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_i64,
@@ -177,3 +181,9 @@ def make_columns(pairs):
     for k, (s, d, rb) in enumerate(pairs):
         arr[k].src, arr[k].dst, arr[k].row_bytes = s, d, rb
     return arr, len(pairs)
+
+
+def tune_default(name, default):
+    """host-side feature switches: environment variable CB200_<NAME> overrides the default (benchmark A/B runs)"""
+    v = os.environ.get("CB200_" + name.upper())
+    return int(v) if v is not None else default

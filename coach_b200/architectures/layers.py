@@ -101,11 +101,14 @@ def _tiles(M, N, fast=True):
     return ((M + 127) // 128) * ((N + bn - 1) // bn)
 
 
-def _bias_rides_along(dw, db, K, N):
+def _bias_rides_along(dw, db, K, N, skinny=False):
     """True when the bias gradient is stored right behind the kernel gradient (flat ParamStore layout)."""
     bm = 256 if N <= 32 else 128          # row tile of the kernel that will run; only use slack of the last tile
-    return (dw is not None and db is not None and N % 4 == 0 and K % 4 == 0 and K + 1 > 64 and K % bm != 0 and
-            db.data_ptr() == dw.data_ptr() + K * N * 4)
+    if dw is None or db is None or db.data_ptr() != dw.data_ptr() + K * N * 4:
+        return False
+    if N <= 8 and skinny:                 # skinny weight-gradient kernel: the extra row is a block of its own
+        return True
+    return N % 4 == 0 and K % 4 == 0 and K + 1 > 64 and K % bm != 0
 
 
 # =====================================================================================================================
@@ -148,12 +151,12 @@ class Dense(object):
         coloff = _dev_i32(np.arange(K), device)
         vec = int(K % 4 == 0)
         common = dict(a_rowoff=rowoff, a_coloff=coloff, a_rows=B, a_cols=K, a_vec4=vec, a_src=x,
-                      a_lut=lut if x_is_u8 else None, a_u8_div=_u8_div(lut, x_is_u8))
+                      a_lut=lut if x_is_u8 else None, a_u8_div=_u8_div(lut, x_is_u8), a_lda=0 if x_is_u8 else K)
         self.fwd = GemmOp(lib, ws, a_transposed=0, b=w, ldb=N, n=N, c=y, ldc=N, bias=b, act=self.act,
                           splits=pick_splits(_tiles(B, N, vec), K), **common, **yp)
         self.bwd_w = None
         if dw is not None and dy is not None:
-            ones = int(bool(vec) and _bias_rides_along(dw, db, K, N))
+            ones = int(bool(vec) and _bias_rides_along(dw, db, K, N, skinny=not x_is_u8))
             self.bwd_w = GemmOp(lib, ws, a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
                                 splits=pick_splits(_tiles(K + ones, N, vec), B), **common)
             if not ones:
@@ -166,7 +169,7 @@ class Dense(object):
             ro = _dev_i32(np.arange(B) * N, device)
             co = _dev_i32(np.arange(N), device)
             self.bwd_x = GemmOp(lib, ws, a_src=dy, a_rowoff=ro, a_coloff=co, a_rows=B, a_cols=N, a_transposed=0,
-                                a_vec4=int(N % 4 == 0), b=self.wT, ldb=K, n=K, c=dx, ldc=K,
+                                a_vec4=int(N % 4 == 0), a_lda=N, b=self.wT, ldb=K, n=K, c=dx, ldc=K,
                                 mask_y=x if prev_act else None, mask_act=prev_act,
                                 accumulate=int(bool(dx_accumulate)),
                                 splits=pick_splits(_tiles(B, K, N % 4 == 0), N), **dxp)
@@ -266,10 +269,17 @@ class Conv2d(object):
         self.classes = []
         self.bwd_x = None
         self.db_args = None
+        self.s2d = None
         pl = planes
         if (pl is not None and pl.x is not None and not x_is_u8 and B % 32 == 0 and pl.w_ptr and tl.width_ok(N) and
                 tl.channels_ok(C) and pl.x.cols == C and pl.x.npix == H * W):
             self._prepare_tiled(lib, ws, B, device, x, y, w, b, dw, db, dy, dx, need_dx, prev_act, pl)
+            return
+        div = _u8_div(lut, x_is_u8)
+        if (pl is not None and x_is_u8 and div > 0 and B % 32 == 0 and pl.y is not None and KH % S == 0 and
+                KW % S == 0 and H % S == 0 and W % S == 0 and tl.channels_ok(S * S * C) and tl.width_ok(N) and
+                not need_dx and _lib.tune_default("conv_s2d", 1)):
+            self._prepare_s2d(lib, ws, B, device, x, y, w, b, dw, db, dy, pl, div)
             return
         # no input planes (the uint8 frames of the first layer): register-staged cb200_gemm; the output planes are
         # written by its epilogue (plane row = pixel * B + b), the weight gradient reads dY's planes as its B operand
@@ -327,6 +337,40 @@ class Conv2d(object):
                             splits=pick_splits(_tiles(B * IH * IW, C, N % 4 == 0), TA * TB * N))
                 self.classes.append((op, wt, _dev_i32(perm, device)))
 
+    def _prepare_s2d(self, lib, ws, B, device, x, y, w, b, dw, db, dy, pl, div):
+        """uint8 frames, kernel size a multiple of the stride: the space-to-depth(S) view of the input (one exact
+        bf16 plane, cb200_u8_s2d_planes) turns the layer into a (K/S) x (K/S) stride-1 convolution over S*S*C
+        channels -- a multi-tap tensor-core GEMM like every other layer, with 3 products instead of 6."""
+        H, W, C, N, KH, KW, S, OH, OW = self.H, self.W, self.C, self.N, self.KH, self.KW, self.S, self.OH, self.OW
+        Hs, Ws, Cs, TH, TW = H // S, W // S, S * S * C, KH // S, KW // S
+        T, nq = TH * TW, OH * OW
+        self.s2d = (x, tl.PlaneBuf(Hs * Ws * B, Cs, device, npix=Hs * Ws, nplanes=1), B)
+        # rows of the s2d kernel matrix: (tap (ty, tx), (dy, dx, c)) <- original row (ky, kx, c) = (S ty + dy, ...)
+        ty, tx, dy_, dx_, cc = np.meshgrid(np.arange(TH), np.arange(TW), np.arange(S), np.arange(S), np.arange(C),
+                                           indexing="ij")
+        orig_row = (((S * ty + dy_) * KW + (S * tx + dx_)) * C + cc).reshape(-1)            # [T * Cs]
+        self.w_s2d = torch.empty(T * Cs * N, dtype=torch.float32, device=device)
+        self.w_s2d_planes = tl.PlaneBuf(T * Cs, N, device)
+        self.w_perm = _dev_i32((orig_row[:, None] * N + np.arange(N)[None, :]).reshape(-1), device)
+        pix_in = np.zeros((T, nq), dtype=np.int64)
+        for t in range(T):
+            oy, ox = np.meshgrid(np.arange(OH), np.arange(OW), indexing="ij")
+            pix_in[t] = ((oy + t // TW) * Ws + (ox + t % TW)).reshape(-1)
+        qq, bb = np.meshgrid(np.arange(nq), np.arange(B), indexing="ij")
+        rowmap_out = _dev_i32((bb * nq + qq).reshape(-1), device)
+        xp = self.s2d[1]
+        self.fwd = tl.forward_op(lib, ws, B, device, xp, Cs, self.w_s2d_planes.ptr, self.w_s2d_planes.stride, N,
+                                 [[(int(pix_in[t, q]), t) for t in range(T)] for q in range(nq)], nq, y, N, b,
+                                 self.act, rowmap_out, pl.y, w_rows=T * Cs, a_u8_div=div)
+        self.fwd.keep.append(self.w_s2d_planes)
+        self.bwd_w = None
+        if dw is not None and dy is not None:
+            assert pl.dy is not None, "s2d conv weight gradient needs the planes of dY"
+            self.bwd_w = tl.wgrad_op(lib, ws, B, device, xp, Cs, pl.dy, N, pix_in, T, nq, dw, a_u8_div=div,
+                                     c_rowmap=_dev_i32(orig_row, device))
+            self.db_args = (dy, B * nq, N, db)
+            ws.require(1024 * N)
+
     def _prepare_tiled(self, lib, ws, B, device, x, y, w, b, dw, db, dy, dx, need_dx, prev_act, pl):
         """input available as planes [H * W * B, C]: forward, weight gradient and data gradient as multi-tap GEMMs"""
         H, W, C, N, KH, KW, S, OH, OW = self.H, self.W, self.C, self.N, self.KH, self.KW, self.S, self.OH, self.OW
@@ -372,6 +416,13 @@ class Conv2d(object):
                                           x if prev_act else None, prev_act, rowmap_in, pl.dx)
 
     def forward(self):
+        if self.s2d is not None:
+            st = _lib.current_stream()
+            x, xp, B = self.s2d
+            _lib.check(self.lib.cb200_u8_s2d_planes(x.data_ptr(), B, self.H, self.W, self.C, self.S, xp.ptr, st))
+            _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), self.w_perm.data_ptr(), self.w_perm.numel(),
+                                                  self.w_s2d.data_ptr(), self.w_s2d_planes.ptr,
+                                                  self.w_s2d_planes.stride, self.w_s2d_planes.cols, st))
         self.fwd.run()
 
     def backward(self, weights=True):

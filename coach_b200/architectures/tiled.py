@@ -29,10 +29,10 @@ def _dev_i32(a, device):
 class PlaneBuf(object):
     """bf16 hi / mid / lo planes of a [rows, cols] matrix (rows = npix * batch) in the core-tiled format"""
 
-    def __init__(self, rows, cols, device, npix=1):
+    def __init__(self, rows, cols, device, npix=1, nplanes=3):
         assert rows % 8 == 0 and cols % 8 == 0, (rows, cols)
-        self.rows, self.cols, self.npix = int(rows), int(cols), int(npix)
-        self.t = torch.zeros((3, self.rows * self.cols), dtype=torch.bfloat16, device=device)
+        self.rows, self.cols, self.npix, self.nplanes = int(rows), int(cols), int(npix), int(nplanes)
+        self.t = torch.zeros((self.nplanes, self.rows * self.cols), dtype=torch.bfloat16, device=device)
 
     @property
     def ptr(self):
@@ -53,7 +53,9 @@ class PlaneBuf(object):
 
     def to_dense(self):
         """fp32 [rows, cols] reconstruction hi + mid + lo (tests)"""
-        v = (self.t[0].float() + self.t[1].float()) + self.t[2].float()
+        v = self.t[0].float()
+        if self.nplanes == 3:
+            v = (v + self.t[1].float()) + self.t[2].float()
         v = v.view(self.rows // 8, self.cols // 8, 8, 8).permute(0, 2, 1, 3)
         return v.reshape(self.rows, self.cols)
 
@@ -161,7 +163,8 @@ def _tiles1(rows, n):
     return ((rows + 127) // 128) * ((n + bn - 1) // bn)
 
 
-def forward_op(lib, ws, B, device, x, Ca, w_ptr, w_stride, N, lists, num_q, c, ldc, bias, act, rowmap, y_planes):
+def forward_op(lib, ws, B, device, x, Ca, w_ptr, w_stride, N, lists, num_q, c, ldc, bias, act, rowmap, y_planes,
+               w_rows=None, **extra):
     """mode 0 with explicit per-pixel tap lists: `lists[q]` = [(a_pix, w_blk), ...]"""
     ptr = np.zeros(num_q + 1, dtype=np.int64)
     flat = []
@@ -173,17 +176,18 @@ def forward_op(lib, ws, B, device, x, Ca, w_ptr, w_stride, N, lists, num_q, c, l
     total = max_len * (Ca // 32)
     return TGemmOp(lib, ws, mode=0, batch=B, a_planes=x, a_plane_stride=x.stride, a_cols=Ca, b_planes=w_ptr,
                    b_plane_stride=w_stride, n=N, list_ptr=_dev_i32(ptr, device), list=_dev_i32(flat, device),
-                   max_list_len=max_len, num_q=num_q, taps=0, c=c, ldc=ldc, bias=bias, act=act,
+                   max_list_len=max_len, num_q=num_q, taps=0, c=c, ldc=ldc, bias=bias, act=act, a_rows=x.rows,
+                   b_rows=int(w_rows if w_rows is not None else (int(flat[:, 1].max()) + 1) * Ca),
                    c_rowmap=rowmap, splits=pick_splits_tiled(_tiles0(num_q, B, N), total),
                    c_planes=y_planes if y_planes is not None else None,
                    c_plane_stride=y_planes.stride if y_planes is not None else 0,
-                   c_plane_cols=N if y_planes is not None else 0)
+                   c_plane_cols=N if y_planes is not None else 0, a_num_planes=x.nplanes, **extra)
 
 
 def masked_forward_op(lib, ws, B, device, x, Ca, w_buf, N, lists, num_q, c, ldc, mask_y, mask_act, rowmap, y_planes):
     """data-gradient flavour: no bias / activation, previous layer's activation derivative in the epilogue"""
     op = forward_op(lib, ws, B, device, x, Ca, w_buf.ptr, w_buf.stride, N, lists, num_q, c, ldc, None, 0, rowmap,
-                    y_planes)
+                    y_planes, w_rows=w_buf.rows)
     op.keep.append(w_buf)
     if mask_y is not None and mask_act:
         op.keep.append(mask_y)
@@ -192,10 +196,10 @@ def masked_forward_op(lib, ws, B, device, x, Ca, w_buf, N, lists, num_q, c, ldc,
     return op
 
 
-def wgrad_op(lib, ws, B, device, x, Ca, g, N, a_pix, taps, num_q, dw):
+def wgrad_op(lib, ws, B, device, x, Ca, g, N, a_pix, taps, num_q, dw, **extra):
     """mode 1: dw [taps * Ca, N] row-major fp32"""
     total = num_q * (B // 32)
     return TGemmOp(lib, ws, mode=1, batch=B, a_planes=x, a_plane_stride=x.stride, a_cols=Ca, b_planes=g,
                    b_plane_stride=g.stride, n=N, a_pix=_dev_i32(np.asarray(a_pix).reshape(-1), device), num_q=num_q,
-                   taps=taps, max_list_len=0, c=dw, ldc=N, act=0,
-                   splits=pick_splits_tiled(_tiles1(taps * Ca, N), total))
+                   taps=taps, max_list_len=0, c=dw, ldc=N, act=0, a_rows=x.rows, b_rows=g.rows,
+                   splits=pick_splits_tiled(_tiles1(taps * Ca, N), total), a_num_planes=x.nplanes, **extra)

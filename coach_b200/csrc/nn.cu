@@ -1,4 +1,5 @@
 // coach_b200/csrc/nn.cu -- C-ABI entry points of the dense contractions of the learn step (see nn_gemm.cuh).
+#include "nn_gemm_skinny.cuh"
 #include "nn_gemm_tiled.cuh"
 
 namespace cb200 {
@@ -102,18 +103,49 @@ static int launch_tc(const cb200_gemm_desc& d, int M, int R, int splits, int r_p
     return 0;
 }
 
-template <int BN, bool kT>
-static int launch_tiled(const TiledParams& tp, const EpiParams& ep, int M, int gx, int splits, cudaStream_t st) {
-    constexpr size_t smem = TiledCfg<BN>::kSmemBytes;
+// ---- tensor maps of plane sets -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// planes of a [rows, cols] matrix in the core-tiled format as a 4-D tensor (64 | cols / 8 | rows / 8 | 3) with box
+// (64, box_cores, box_groups, 3)
+static bool make_plane_map(CUtensorMap* map, const void* planes, int64_t plane_stride, int64_t rows, int cols,
+                           int box_cores, int box_groups, int nplanes = 3) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[4] = {64, (cuuint64_t)(cols / 8), (cuuint64_t)(rows / 8), (cuuint64_t)nplanes};
+    const cuuint64_t strides[3] = {128, (cuuint64_t)(cols / 8) * 128, (cuuint64_t)plane_stride * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)box_cores, (cuuint32_t)box_groups, (cuuint32_t)nplanes};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(planes), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, bool kT, int NA>
+static int launch_tiled(const CUtensorMap& tmA, const CUtensorMap& tmB, const TiledParams& tp, const EpiParams& ep,
+                        int M, int gx, int splits, cudaStream_t st) {
+    constexpr size_t smem = TiledCfg<BN, NA>::kSmemBytes;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc_tiled_kernel<BN, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(gemm_tc_tiled_kernel<BN, kT, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return -1;
         configured = true;
     }
     dim3 grid(gx, (tp.n + BN - 1) / BN, splits);
-    gemm_tc_tiled_kernel<BN, kT><<<grid, 192, smem, st>>>(tp, ep, M);
+    gemm_tc_tiled_kernel<BN, kT, NA><<<grid, 192, smem, st>>>(tmA, tmB, tp, ep, M);
     count_launch();
     if (splits > 1) {
         launch_split_reduce(ep, M, tp.n, st);
@@ -142,6 +174,26 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
     }
 }
 
+// uint8 NHWC frames -> ONE exact bf16 plane of the space-to-depth view: pixel (Y, X) = (y / S, x / S), channel
+// ((y % S) * S + x % S) * C + c, plane row (Y * (W / S) + X) * B + b.  A K x K stride-S convolution (K % S == 0) is a
+// (K / S) x (K / S) stride-1 convolution of that view, whose channel count S * S * C (64 for Atari) suits the tiled
+// tensor-core kernel.  One thread per (b, Y, X, y % S): S * C consecutive bytes -> S * C bf16.
+__global__ void __launch_bounds__(256) u8_s2d_planes_kernel(const uint8_t* __restrict__ x, int B, int H, int W, int C,
+                                                            int S, uint16_t* __restrict__ plane) {
+    const int Hs = H / S, Ws = W / S, Cs = S * S * C, run = S * C;       // run: bytes per (pixel, y % S), multiple of 8
+    const int64_t total = (int64_t)B * Hs * Ws * S;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int dy = (int)(t % S);
+        const int X = (int)((t / S) % Ws), Y = (int)((t / S / Ws) % Hs), b = (int)(t / S / Ws / Hs);
+        const uint8_t* src = x + (((size_t)b * H + (size_t)Y * S + dy) * W + (size_t)X * S) * C;
+        const size_t prow = ((size_t)Y * Ws + X) * B + b;
+        for (int g = 0; g < run; g += 8) {
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(src + g));
+            *reinterpret_cast<uint4*>(plane + tiled_elem(prow, dy * run + g, Cs)) = u8x8_to_bf16(w.x, w.y);
+        }
+    }
+}
+
 // ---- small helpers -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ x, int64_t rows, int64_t cols,
                                                      float* __restrict__ part, int nslab) {
@@ -166,12 +218,13 @@ __global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ x
         part[(int64_t)slab * cols + col] = s;
     }
 }
-__global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ part, int64_t cols, int nslab,
-                                                     float* __restrict__ out) {
-    // same thread shape as stage 1: RL row lanes x CW columns, lanes folded in a fixed order
-    __shared__ float red[256];
+__global__ void __launch_bounds__(1024) colsum_stage2(const float* __restrict__ part, int64_t cols, int nslab,
+                                                      float* __restrict__ out) {
+    // 1024 threads = RL row lanes x CW columns (up to 1024 partial rows: 32 per lane for a 32-column matrix), lanes
+    // folded in a fixed order
+    __shared__ float red[1024];
     const int cw = cols < 256 ? (int)cols : 256;
-    const int rl = 256 / cw;
+    const int rl = 1024 / cw;
     const int c_local = threadIdx.x % cw, lane_r = threadIdx.x / cw;
     const int64_t col = (int64_t)blockIdx.x * cw + c_local;
     float s = 0.f;
@@ -244,9 +297,37 @@ int cb200_gemm(const cb200_gemm_desc* d, void* stream) {
     r_per_split = (r_per_split + 15) / 16 * 16;
     splits = (R + r_per_split - 1) / r_per_split;
     cudaStream_t st = as_stream(stream);
+    // skinny dense products (heads): dedicated kernels, no split reduction
+    if (d->a_lda > 0 && !d->a_lut && !d->a_rowinfo && !d->c_rowmap && tune_get("gemm_skinny", 1, 0, 1) != 0) {
+        const float* a = static_cast<const float*>(d->a_src);
+        const bool al16 = (reinterpret_cast<uintptr_t>(a) & 15) == 0 && d->a_lda % 4 == 0;
+        const gemm::EpiParams ep = gemm::make_epi(*d, 1);
+        if (!tr && d->n <= 8 && R % 4 == 0 && al16) {
+            gemm::skinny_n_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(a, d->a_lda, d->b, d->ldb, ep, M, d->n, R);
+            count_launch();
+            CB200_CHECK_LAUNCH();
+            return CB200_OK;
+        }
+        if (!tr && R <= 8 && d->n % 4 == 0 && d->ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(d->b) & 15) == 0) {
+            const int64_t groups = (int64_t)M * (d->n / 4);
+            gemm::skinny_r_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(a, d->a_lda, d->b, d->ldb, ep, M,
+                                                                                     d->n, R);
+            count_launch();
+            CB200_CHECK_LAUNCH();
+            return CB200_OK;
+        }
+        if (tr && d->n <= 8) {
+            const int kblocks = (d->a_cols + 31) / 32;
+            gemm::skinny_tn_kernel<<<(unsigned)(kblocks + (ones ? 1 : 0)), 1024, 0, st>>>(
+                a, d->a_lda, d->b, d->ldb, ep, d->a_rows, d->a_cols, d->n, d->a_cols);
+            count_launch();
+            CB200_CHECK_LAUNCH();
+            return CB200_OK;
+        }
+    }
     const bool fast = d->a_vec4 && d->n % 4 == 0 && d->ldb % 4 == 0 && d->a_cols % 4 == 0 &&
                       (reinterpret_cast<uintptr_t>(d->b) & 15) == 0 && M > 64;
-    CB200_CHECK_ARG(!ones || fast, "a_ones_col needs the vectorised path (a_vec4, n % 4 == 0, more than 64 rows)");
+    CB200_CHECK_ARG(!ones || fast, "a_ones_col needs the vectorised or the skinny path");
     // tensor-core path (tcgen05): operands split into 3 x bf16, fp32 accumulation in TMEM; the reduction length per
     // launch is capped (split-R) because the TMEM accumulator truncates -- see nn_gemm_tc.cuh
     const bool tc = fast && d->n % 16 == 0 && d->n >= 16 && tune_get("gemm_tc", 1, 0, 1) != 0 && d->ldc % 4 == 0 &&
@@ -341,6 +422,24 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
     tp.num_q = d->num_q;
     tp.taps = d->taps;
     int M, gx, total;
+    CB200_CHECK_ARG(d->a_rows > 0 && d->a_rows % 8 == 0 && d->b_rows > 0 && d->b_rows % 8 == 0, "a_rows / b_rows");
+    const int bn = d->n <= 32 ? 32 : ((d->n <= 64 || d->n % 128 != 0) ? 64 : 128);
+    const int na = d->a_num_planes == 1 ? 1 : 3;
+    CB200_CHECK_ARG(na == 3 || d->a_u8_div > 0.f, "a single A plane means raw uint8 values: a_u8_div must be set");
+    // the tensor maps depend only on the descriptor: built on the first call, kept in the descriptor
+    cb200_tgemm_desc* md = const_cast<cb200_tgemm_desc*>(d);
+    CUtensorMap* maps =
+        reinterpret_cast<CUtensorMap*>((reinterpret_cast<uintptr_t>(md->tmap_storage) + 63) & ~(uintptr_t)63);
+    const uint64_t key = (uint64_t)(reinterpret_cast<uintptr_t>(d->a_planes) ^ (reinterpret_cast<uintptr_t>(d->b_planes) << 1) ^ 1);
+    if (md->tmap_key != key) {
+        bool ok = gemm::make_plane_map(maps + 1, d->b_planes, d->b_plane_stride, d->b_rows, d->n, bn / 8, 4);
+        if (d->mode == 0)
+            ok = ok && gemm::make_plane_map(maps + 0, d->a_planes, d->a_plane_stride, d->a_rows, d->a_cols, 4, 16, na);
+        else
+            maps[0] = maps[1];
+        CB200_CHECK_ARG(ok, "cuTensorMapEncodeTiled failed (driver too old or bad plane geometry)");
+        md->tmap_key = key;
+    }
     if (d->mode == 0) {
         CB200_CHECK_ARG(d->list_ptr && d->list && d->num_q > 0 && d->max_list_len > 0, "mode 0 needs the tap lists");
         M = d->num_q * d->batch;
@@ -359,18 +458,37 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
     CB200_CHECK_ARG(cps <= 32, "too few splits: more than 32 reduction chunks (1024 terms) per slice");
     CB200_CHECK_ARG(splits == 1 || d->workspace, "split reduction needs a workspace");
     tp.chunks_per_split = cps;
+    tp.a_u8_div = d->a_u8_div;
     const gemm::EpiParams ep{d->c,        d->ldc,      d->bias,      d->act,  d->mask_y,
                              d->mask_act, d->c_rowmap, d->workspace, splits,  0,
                              static_cast<uint16_t*>(d->c_planes), d->c_plane_stride, d->c_plane_cols, 0, 0};
     cudaStream_t st = as_stream(stream);
     int rc;
 #define CB200_TL(BN_) \
-    (d->mode ? gemm::launch_tiled<BN_, true>(tp, ep, M, gx, splits, st) : gemm::launch_tiled<BN_, false>(tp, ep, M, gx, splits, st))
-    if (d->n <= 32) rc = CB200_TL(32);
-    else if (d->n <= 64 || d->n % 128 != 0) rc = CB200_TL(64);
+    (na == 1 ? (d->mode ? gemm::launch_tiled<BN_, true, 1>(maps[0], maps[1], tp, ep, M, gx, splits, st)   \
+                        : gemm::launch_tiled<BN_, false, 1>(maps[0], maps[1], tp, ep, M, gx, splits, st)) \
+             : (d->mode ? gemm::launch_tiled<BN_, true, 3>(maps[0], maps[1], tp, ep, M, gx, splits, st)   \
+                        : gemm::launch_tiled<BN_, false, 3>(maps[0], maps[1], tp, ep, M, gx, splits, st)))
+    if (bn == 32) rc = CB200_TL(32);
+    else if (bn == 64) rc = CB200_TL(64);
     else rc = CB200_TL(128);
 #undef CB200_TL
     CB200_CHECK_ARG(rc == 0, "could not configure shared memory for the tiled tcgen05 kernel");
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_u8_s2d_planes(const void* x, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t s, void* plane,
+                        void* stream) {
+    CB200_CHECK_ARG(x && plane && batch > 0 && batch % 8 == 0 && s > 0 && h % s == 0 && w % s == 0, "bad geometry");
+    CB200_CHECK_ARG((s * c) % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(plane)) & 15) == 0,
+                    "s * c must be a multiple of 8 and the buffers 16-byte aligned");
+    const int64_t total = (int64_t)batch * (h / s) * (w / s) * s;
+    int64_t grid = (total + 255) / 256;
+    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+    gemm::u8_s2d_planes_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(static_cast<const uint8_t*>(x), batch, h, w,
+                                                                               c, s, static_cast<uint16_t*>(plane));
+    count_launch();
     CB200_CHECK_LAUNCH();
     return CB200_OK;
 }
@@ -394,12 +512,17 @@ int cb200_split_planes(const float* src, void* planes, int64_t plane_stride, con
 
 int cb200_colsum(const float* x, int64_t rows, int64_t cols, float* out, float* workspace, void* stream) {
     CB200_CHECK_ARG(x && out && workspace && rows > 0 && cols > 0, "bad arguments");
-    int nslab = (int)((rows + 255) / 256);
+    // slabs of about 8 rows per row lane (256 / min(cols, 256) lanes): enough blocks to fill the machine even for the
+    // short, wide matrices of the dense layers; workspace holds <= 1024 partial rows
+    const int64_t cw = cols < 256 ? cols : 256;
+    const int64_t rl = 256 / cw;
+    int nslab = (int)((rows + rl * 8 - 1) / (rl * 8));
     if (nslab > 1024) nslab = 1024;
+    if (nslab < 1) nslab = 1;
     cudaStream_t st = as_stream(stream);
     dim3 g1((unsigned)((cols + 255) / 256), nslab);
     gemm::colsum_stage1<<<g1, 256, 0, st>>>(x, rows, cols, workspace, nslab);
-    gemm::colsum_stage2<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(workspace, cols, nslab, out);
+    gemm::colsum_stage2<<<(unsigned)((cols + 255) / 256), 1024, 0, st>>>(workspace, cols, nslab, out);
     count_launch(2);
     CB200_CHECK_LAUNCH();
     return CB200_OK;

@@ -302,26 +302,29 @@ __global__ void __launch_bounds__(256) split_reduce_kernel(EpiParams ep, int M, 
         epilogue_store(ep, (int)(i / N), (int)(i % N), v);
     }
 }
-// many splits, few outputs (conv1 weight gradient: 291 partial tiles of 257 x 32): one warp per 4 outputs would still
-// walk 291 partials serially, so the splits are strided over the lanes of a warp and folded in a fixed order
-// (lane-strided partial sums, then a fixed shuffle tree) -- deterministic, but a different association than the
-// serial kernels, selected only by the split count.
+// many splits (weight gradients: 56 ... 291 partial tiles): a block owns 32 consecutive outputs; its 8 warps walk the
+// splits 8 apart with fully coalesced 128-byte reads, and the 8 partial sums are folded in a fixed order --
+// deterministic, but a different association than the serial kernels, selected only by the split count.
 __global__ void __launch_bounds__(256) split_reduce_wide_kernel(EpiParams ep, int M, int N) {
+    __shared__ float red[8][32];
     const int64_t total = (int64_t)M * N;
-    const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= total) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + lane;
     float v = 0.f;
-    for (int s = lane; s < ep.splits; s += 32) v += ep.partial[(size_t)s * total + i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) epilogue_store(ep, (int)(i / N), (int)(i % N), v);
+    if (i < total)
+        for (int s = w; s < ep.splits; s += 8) v += ep.partial[(size_t)s * total + i];
+    red[w][lane] = v;
+    __syncthreads();
+    if (w == 0 && i < total) {
+        for (int k = 1; k < 8; ++k) v += red[k][lane];
+        epilogue_store(ep, (int)(i / N), (int)(i % N), v);
+    }
 }
 
 inline void launch_split_reduce(const EpiParams& ep, int M, int N, cudaStream_t st) {
     const int64_t total = (int64_t)M * N;
-    if (ep.splits >= 64 && total <= (1 << 16)) {
-        split_reduce_wide_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(ep, M, N);
+    if (ep.splits >= 16 && total <= (1 << 16)) {
+        split_reduce_wide_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(ep, M, N);
     } else if (N % 4 == 0 && total % 4 == 0 && (reinterpret_cast<uintptr_t>(ep.partial) & 15) == 0) {
         split_reduce_kernel<true><<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(ep, M, N);
     } else {

@@ -134,6 +134,13 @@ __device__ __forceinline__ bool tap_ok(int ri, int ci, int oh, int ow) {
 
 // thread = output row (TMEM lane): tcgen05.ld -> (1 / a_u8_div) -> bias / activation / activation-derivative mask ->
 // fp32 result (+ bf16 planes) or split-R partial
+#define CB200_TMEM_LD16(arr, addr)                                                                                   \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                 : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]),    \
+                   "=r"(arr[7]), "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]),               \
+                   "=r"(arr[13]), "=r"(arr[14]), "=r"(arr[15])                                                          \
+                 : "r"(addr))
+
 template <int BN>
 __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_main, uint32_t tmem_corr, bool have_acc,
                                             int m0, int n0, int M, int m_end, int N, int split, bool u8,
@@ -141,70 +148,75 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_m
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m = m0 + tid;
     const bool scale_row = u8 && m != unscaled_row;
+    const bool live = m < m_end;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // everything that depends only on the row (the asm memory clobbers below would otherwise force re-evaluation)
+    const bool vec = !ep.accumulate && (N % 8 == 0);
+    const size_t part_row = ((size_t)split * M + (live ? m : 0)) * N;
+    size_t c_row = 0, p_row = 0;
+    if (live && ep.splits <= 1) {
+        c_row = (ep.c_rowmap ? (size_t)__ldg(ep.c_rowmap + m) : (size_t)m) * ep.ldc;
+        if (ep.c_planes) p_row = plane_row((size_t)m, ep.c_prow_npix, ep.c_prow_batch);
+    }
+    const size_t p_base = ep.c_planes ? (p_row >> 3) * (size_t)(ep.c_plane_cols >> 3) * 64 + (p_row & 7) * 8 : 0;
 #pragma unroll 1
-    for (int col = 0; col < BN; col += 8) {
-        uint32_t vm[8], vc[8];
+    for (int col = 0; col < BN; col += 16) {
+        uint32_t vm[16], vc[16];
         if (have_acc) {
-            const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(vm[0]), "=r"(vm[1]), "=r"(vm[2]), "=r"(vm[3]), "=r"(vm[4]), "=r"(vm[5]), "=r"(vm[6]),
-                           "=r"(vm[7])
-                         : "r"(tmem_main + lane_base + (uint32_t)col));
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(vc[0]), "=r"(vc[1]), "=r"(vc[2]), "=r"(vc[3]), "=r"(vc[4]), "=r"(vc[5]), "=r"(vc[6]),
-                           "=r"(vc[7])
-                         : "r"(tmem_corr + lane_base + (uint32_t)col));
+            CB200_TMEM_LD16(vm, tmem_main + lane_base + (uint32_t)col);
+            CB200_TMEM_LD16(vc, tmem_corr + lane_base + (uint32_t)col);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) vm[j] = vc[j] = 0u;
+            for (int j = 0; j < 16; ++j) vm[j] = vc[j] = 0u;
         }
-        if (m < m_end) {
-            float v[8];
+        if (!live) continue;
+        float v[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                v[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
-                if (scale_row) v[j] = __fdiv_rn(v[j], a_u8_div);
-            }
-            const int nb = n0 + col;
-            if (nb + 8 <= N && !ep.accumulate) {
-                // 2 x 128-bit stores per 8 columns (rows of C / the partial buffer are 16-byte aligned: N % 16 == 0)
+        for (int j = 0; j < 16; ++j) {
+            v[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+            if (scale_row) v[j] = __fdiv_rn(v[j], a_u8_div);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int nb = n0 + col + 8 * h;
+            float* w = v + 8 * h;
+            if (nb >= N) continue;
+            if (vec) {
+                // 2 x 128-bit stores per 8 columns (rows of C / the partial buffer are 16-byte aligned)
                 float* dst;
-                size_t elem = 0;
                 if (ep.splits > 1) {
-                    dst = ep.partial + ((size_t)split * M + m) * N + nb;
+                    dst = ep.partial + part_row + nb;
                 } else {
-                    const size_t row = ep.c_rowmap ? (size_t)__ldg(ep.c_rowmap + m) : (size_t)m;
-                    elem = row * ep.ldc + nb;
+                    const size_t elem = c_row + nb;
                     dst = ep.c + elem;
                     if (ep.bias) {
                         const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb));
                         const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + 4));
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                        w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
+                        w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
+                    for (int j = 0; j < 8; ++j) w[j] = apply_act(w[j], ep.act);
                     if (ep.mask_y) {
                         const float4 y0 = *reinterpret_cast<const float4*>(ep.mask_y + elem);
                         const float4 y1 = *reinterpret_cast<const float4*>(ep.mask_y + elem + 4);
                         const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_output(yy[j], ep.mask_act);
+                        for (int j = 0; j < 8; ++j) w[j] *= act_grad_from_output(yy[j], ep.mask_act);
                     }
                 }
                 if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    *reinterpret_cast<float4*>(dst) = make_float4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(w[4], w[5], w[6], w[7]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = v[j];
+                    for (int j = 0; j < 8; ++j) dst[j] = w[j];
                 }
                 if (ep.c_planes && ep.splits <= 1) {
                     // one core-matrix row (8 columns of one plane row) = 16 bytes per plane
-                    uint16_t* p = ep.c_planes +
-                                  tiled_elem(plane_row((size_t)m, ep.c_prow_npix, ep.c_prow_batch), nb, ep.c_plane_cols);
-                    const Split8 sp = split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+                    uint16_t* p = ep.c_planes + p_base + (size_t)(nb >> 3) * 64;
+                    const Split8 sp = split8(make_float4(w[0], w[1], w[2], w[3]), make_float4(w[4], w[5], w[6], w[7]));
                     *reinterpret_cast<uint4*>(p) = sp.h;
                     *reinterpret_cast<uint4*>(p + ep.c_plane_stride) = sp.m;
                     *reinterpret_cast<uint4*>(p + 2 * ep.c_plane_stride) = sp.l;
@@ -215,9 +227,9 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_m
                     const int n = nb + j;
                     if (n >= N) continue;
                     if (ep.splits > 1)
-                        ep.partial[((size_t)split * M + m) * N + n] = v[j];
+                        ep.partial[part_row + n] = w[j];
                     else
-                        epilogue_store(ep, m, n, v[j]);
+                        epilogue_store(ep, m, n, w[j]);
                 }
             }
         }

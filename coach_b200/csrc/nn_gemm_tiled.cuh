@@ -22,11 +22,20 @@
 // stage flips and releases the stage through tcgen05.commit -> "empty" barrier, and the four EPILOGUE warps drain
 // the TMEM accumulators at the end (tc_epilogue: bias / activation / derivative mask, fp32 result + planes).
 //
+// Tensor maps.  A plane set is a 4-D bf16 tensor (64 elements of a core | cores per 8-row group | row groups | 3
+// planes); one TMA tile operation with box (64, cores, row groups, 3) fetches the hi / mid / lo planes of a whole
+// operand chunk and lands them densely -- exactly the layouts below.  Mode 0 needs TWO operations per chunk (A, B),
+// mode 1 one for G plus 1-D bulk copies for the A^T runs (one per tap and 8-row group: taps sit at unrelated pixels
+// and the M direction must stay uniformly strided in shared memory).  A TMA operation costs ~60 cycles of issue on
+// an SM whatever its size (measured, profiles/), which is what makes few large operations matter.
+//
 // Shared-memory operand layouts (no swizzle; LBO = step between core matrices along K, SBO = along M / N):
 //   A  K-major  [128 rows, 32 k] : core (rg, kg) at rg * 512 + kg * 128          LBO = 128,  SBO = 512
 //   A^T MN-major [128 m,   32 k] : core (kg, mg) at kg * 2048 + mg * 128         LBO = 2048, SBO = 128
 //   B  MN-major [32 k, BN n]     : core (kg, ng) at kg * (BN/8) * 128 + ng * 128 LBO = BN * 16, SBO = 128
 #pragma once
+#include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint in nn.cu)
+
 #include "nn_gemm_tc.cuh"
 
 namespace cb200 {
@@ -59,20 +68,34 @@ struct TiledParams {
     const int32_t* a_pix;      // mode 1: [taps * num_q]
     int num_q, taps;
     int chunks_per_split;
+    float a_u8_div;            // NA == 1: A holds raw uint8 values (exact in bf16); every sum is divided by this
 };
 
-template <int BN>
+// NA = planes of the A operand: 3 (fp32 split) or 1 (uint8 values, exact: 3 products instead of 6)
+template <int BN, int NA>
 struct TiledCfg {
     static constexpr int kStages = BN == 128 ? 4 : 3;
-    static constexpr size_t kSmemBytes = (size_t)kStages * (3 * kTcBM * kTcBK * 2 + 3 * BN * kTcBK * 2) + 128;
+    static constexpr size_t kSmemBytes = (size_t)kStages * (NA * kTcBM * kTcBK * 2 + 3 * BN * kTcBK * 2) + 128;
 };
 
-template <int BN, bool kTransA>
-__global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(TiledParams tp, EpiParams ep, int M) {
-    constexpr int S = TiledCfg<BN>::kStages;
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+        "[%6];" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// tmA: planes of A with box (64, 4, 16, NA) (mode 0 only); tmB: planes of the B operand with box (64, BN / 8, 4, 3)
+template <int BN, bool kTransA, int NA>
+__global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB, TiledParams tp,
+                                                            EpiParams ep, int M) {
+    constexpr int S = TiledCfg<BN, NA>::kStages;
     constexpr int A_SPLIT = kTcBM * kTcBK * 2;            // 8 KB per plane
     constexpr int B_SPLIT = BN * kTcBK * 2;
-    constexpr int STAGE = 3 * A_SPLIT + 3 * B_SPLIT;
+    constexpr int STAGE = NA * A_SPLIT + 3 * B_SPLIT;
     constexpr int B_KG = (BN / 8) * 128;                  // bytes of one k-group (8 reduction rows) of the B tile
     constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -134,48 +157,41 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(TiledParams tp, EpiP
 #ifdef CB200_TC_PROF
         const bool prof_on = cta0 && lane == 0;
 #endif
-        const int nrg = kTransA ? 0 : min(kTcBM / 8, (B - b0) / 8);            // valid 8-row groups of the A tile
         // mode 1: taps covered by this M tile, and the channel range inside a tap
         const int taps_in_tile = kTransA ? (Ca >= kTcBM ? 1 : min(kTcBM / Ca, tp.taps - m0 / Ca)) : 0;
         const int t0 = kTransA ? m0 / Ca : 0;
         const int cw = kTransA ? min(Ca, kTcBM) : 0;                           // channels per tap inside the tile
         const int c0 = kTransA ? m0 % Ca : 0;
-        const uint32_t a_bytes = kTransA ? (uint32_t)(taps_in_tile * 4 * (cw / 8) * 128) : (uint32_t)(nrg * 512);
-        const uint32_t tx_bytes = 3u * (a_bytes + (uint32_t)B_SPLIT);
+        // a tensor-map box always delivers (and counts) its full size, rows past the batch included
+        const uint32_t a_bytes = kTransA ? (uint32_t)(taps_in_tile * 4 * (cw / 8) * 128) : (uint32_t)A_SPLIT;
+        const uint32_t tx_bytes = (uint32_t)NA * a_bytes + 3u * (uint32_t)B_SPLIT;
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            if (!kTransA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        }
         for (int j = 0; j < nchunks; ++j) {
             const int s = j % S, u = j / S;
             TC_PROF_T(t0c);
             if (u > 0) mbar_wait(empty_bar + s, (uint32_t)((u - 1) & 1));      // MMAs that read this stage are done
             TC_PROF_T(t1c);
             uint8_t* sA = smem + s * STAGE;
-            uint8_t* sB = sA + 3 * A_SPLIT;
+            uint8_t* sB = sA + NA * A_SPLIT;
             uint64_t* bar = full_bar + s;
             if (lane == 0) mbar_expect_tx(bar, tx_bytes);
             __syncwarp();
             const int cj = c_lo + j;
-            size_t b_core;                                  // first core of the B run of k-group 0
             if (!kTransA) {
-                const int e = cj / kc_per, kc = cj % kc_per;
-                const int2 ent = __ldg(tp.list + list_lo + e);
-                const size_t rg0 = ((size_t)ent.x * B + b0) >> 3;
-                if (Ca == kTcBK) {
-                    // the whole [rows, 32] tile is one contiguous run of cores
-                    if (lane < 3)
-                        bulk_g2s(sA + lane * A_SPLIT, tp.a + lane * tp.a_stride + rg0 * 4 * 64, (uint32_t)(nrg * 512), bar);
-                } else {
-                    for (int idx = lane; idx < 3 * 16; idx += 32) {
-                        const int p = idx >> 4, i = idx & 15;
-                        if (i < nrg)
-                            bulk_g2s(sA + p * A_SPLIT + i * 512,
-                                     tp.a + p * tp.a_stride + ((rg0 + i) * (size_t)(Ca >> 3) + (size_t)kc * 4) * 64, 512u,
-                                     bar);
-                    }
+                if (lane == 0) {
+                    const int e = cj / kc_per, kc = cj % kc_per;
+                    const int2 ent = __ldg(tp.list + list_lo + e);
+                    tma_load_4d(sA, &tmA, 0, kc * 4, (int)(((size_t)ent.x * B + b0) >> 3), 0, bar);
+                    tma_load_4d(sB, &tmB, 0, n0 >> 3, (ent.y * Ca + kc * kTcBK) >> 3, 0, bar);
                 }
-                b_core = ((size_t)ent.y * Ca + (size_t)kc * kTcBK) / 8 * (size_t)(N >> 3) + (size_t)(n0 >> 3);
             } else {
                 const int qq = cj / bc_per, bc = cj % bc_per;
+                if (lane == 0) tma_load_4d(sB, &tmB, 0, n0 >> 3, (int)(((size_t)qq * B + (size_t)bc * kTcBK) >> 3), 0, bar);
                 // A^T: per tap of the tile, 4 k-groups (8 batch rows each) x a run of cw / 8 cores
-                for (int idx = lane; idx < 3 * 4 * taps_in_tile; idx += 32) {
+                for (int idx = lane; idx < NA * 4 * taps_in_tile; idx += 32) {
                     const int p = idx / (4 * taps_in_tile), r = idx % (4 * taps_in_tile);
                     const int tt = r >> 2, kg = r & 3;
                     const int apix = __ldg(tp.a_pix + (size_t)(t0 + tt) * tp.num_q + qq);
@@ -184,12 +200,6 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(TiledParams tp, EpiP
                              tp.a + p * tp.a_stride + (rg * (size_t)(Ca >> 3) + (size_t)(c0 >> 3)) * 64,
                              (uint32_t)((cw >> 3) * 128), bar);
                 }
-                b_core = ((((size_t)qq * B + (size_t)bc * kTcBK) >> 3)) * (size_t)(N >> 3) + (size_t)(n0 >> 3);
-            }
-            if (lane >= 16 && lane < 28) {
-                const int l = lane - 16, p = l >> 2, kg = l & 3;
-                bulk_g2s(sB + p * B_SPLIT + kg * B_KG, tp.b + p * tp.b_stride + (b_core + (size_t)kg * (N >> 3)) * 64,
-                         (uint32_t)B_KG, bar);
             }
             TC_PROF_T(t2c);
             TC_PROF_ADD(0, t0c, t1c);      // producer: wait for a free stage
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(TiledParams tp, EpiP
             TC_PROF_T(t1m);
             if (lane == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_base = smem_base + s * STAGE, b_base = a_base + 3 * A_SPLIT;
+                const uint32_t a_base = smem_base + s * STAGE, b_base = a_base + NA * A_SPLIT;
 #pragma unroll
                 for (int ks = 0; ks < kTcBK / 16; ++ks) {
                     const uint64_t a0 = a_hi | (uint64_t)((a_base + ks * A_KS) >> 4);
@@ -224,10 +234,12 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(TiledParams tp, EpiP
                     const uint32_t first = (j == 0 && ks == 0) ? 0u : 1u;
                     umma_bf16(tmem_main, a0, b0d, idesc, first);       // a1 b1
                     umma_bf16(tmem_corr, a0, b2, idesc, first);        // a1 b3
-                    umma_bf16(tmem_corr, a2, b0d, idesc, 1u);          // a3 b1
-                    umma_bf16(tmem_corr, a1, b1, idesc, 1u);           // a2 b2
+                    if (NA == 3) {
+                        umma_bf16(tmem_corr, a2, b0d, idesc, 1u);      // a3 b1
+                        umma_bf16(tmem_corr, a1, b1, idesc, 1u);       // a2 b2
+                    }
                     umma_bf16(tmem_corr, a0, b1, idesc, 1u);           // a1 b2
-                    umma_bf16(tmem_corr, a1, b0d, idesc, 1u);          // a2 b1
+                    if (NA == 3) umma_bf16(tmem_corr, a1, b0d, idesc, 1u);   // a2 b1
                 }
                 umma_commit(empty_bar + s);
                 if (j == nchunks - 1) umma_commit(done_bar);
@@ -248,7 +260,7 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(TiledParams tp, EpiP
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         TC_PROF_T(t1e);
-        tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, m_end, N, split, false, 1.f, -1);
+        tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, m_end, N, split, NA == 1, tp.a_u8_div, -1);
         TC_PROF_T(t2e);
         TC_PROF_ADD(5, t0e, t1e);          // main loop as seen by the epilogue warps
         TC_PROF_ADD(6, t1e, t2e);          // epilogue

@@ -193,6 +193,8 @@ typedef struct cb200_gemm_desc {
     int32_t c_plane_cols;       /* columns of the plane matrix (= n)                                                */
     int32_t c_prow_npix;        /* > 0: output row m = b * npix + q is plane row q * c_prow_batch + b; 0: row m       */
     int32_t c_prow_batch;
+    int32_t a_lda;              /* > 0: A is a plain row-major fp32 matrix with this leading dimension (the tables   */
+                                /*    say the same); lets products with n <= 8 or a_cols <= 8 take the skinny kernels */
 } cb200_gemm_desc;
 
 int cb200_gemm(const cb200_gemm_desc* h_desc, void* stream);
@@ -235,9 +237,23 @@ typedef struct cb200_tgemm_desc {
     void* c_planes;             /* tiled planes of C with plane row = C row, c_plane_cols == n                       */
     int64_t c_plane_stride;
     int32_t c_plane_cols;
+    int32_t a_num_planes;       /* 3 (0 = 3): fp32 split;  1: A holds raw uint8 values as ONE exact bf16 plane, every    */
+    float a_u8_div;             /*    accumulated sum is divided by a_u8_div (x / 255 input rescale, embedder.py:103)  */
+    int64_t a_rows;             /* rows of the A plane matrix (a_pixels * B) and of the B operand's plane matrix      */
+    int64_t b_rows;             /*   (mode 0: blocks * a_cols, mode 1: num_q * B): bounds of the TMA tensor maps      */
+    /* private: TMA tensor maps of the operands, built by the first call with this descriptor (keep the descriptor    */
+    /* alive and unchanged between calls; zero-initialise)                                                            */
+    uint64_t tmap_key;
+    uint8_t tmap_storage[2 * 128 + 64];
 } cb200_tgemm_desc;
 
 int cb200_gemm_tiled(const cb200_tgemm_desc* h_desc, void* stream);
+
+/* uint8 NHWC frames [batch, h, w, c] -> one exact bf16 plane of the space-to-depth(s) view: plane row
+ * ((y / s) * (w / s) + x / s) * batch + b, column ((y % s) * s + x % s) * c + ch; [h/s * w/s * batch, s*s*c] tiled.
+ * Turns the strided first convolution (Atari: 8x8 stride 4 on 84x84x4) into a 2x2 stride-1 one on 64 channels. */
+int cb200_u8_s2d_planes(const void* x, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t s, void* plane,
+                        void* stream);
 
 /* fp32 row-major matrices -> tiled planes, one launch for a list of matrices inside one fp32 buffer (the parameter
  * buffer, once per step): d_segments[k] = {src offset, rows, cols, plane offset} in elements (device memory). */
