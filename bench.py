@@ -227,6 +227,32 @@ def run_device(args):
     learn_us = float(np.mean([b.elapsed_time(c) for _, b, c in ev])) * 1e3
     ms_total = parallel.max_over_ranks(ms_total, device)
 
+    # ---- per-launch timing of the dominant kernel family (the tiled tcgen05 GEMMs): one traced step lists the
+    # launches, then every distinct prepared call is timed with CUDA events on the launching stream over 10
+    # back-to-back launches (the step itself has host-side bubbles between some launches, which per-launch events
+    # inside the step would count as kernel time).  Operands are in the L2 state the step leaves them in.
+    from coach_b200.architectures.tiled import TGemmOp
+    gemm_ops = {}
+    if rank == 0 and not args.no_tc:
+        TGemmOp.trace = []
+        one_step(False)
+        torch.cuda.synchronize()
+        trace, TGemmOp.trace = TGemmOp.trace, None
+        for op, _, _ in trace:
+            rec = gemm_ops.setdefault(id(op), {"op": op, "tag": op.tag, "macs": op.macs, "nprod": op.nprod, "n": 0})
+            rec["n"] += 1
+        for rec in gemm_ops.values():
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(2):
+                rec["op"].run()
+            a.record()
+            for _ in range(10):
+                rec["op"].run()
+            b.record()
+            torch.cuda.synchronize()
+            rec["us"] = a.elapsed_time(b) * 1e2          # ms / 10 launches -> us
+    barrier()
+
     # ---- end-to-end leg through the public API with host buffers ---------------------------------------------------
     rng = np.random.RandomState(7 + rank)
     pool = host_transitions(rng, 64)
@@ -255,6 +281,19 @@ def run_device(args):
     steps_per_s = world * K / (ms_total * 1e-3)
     gather_gbs = GATHER_BYTES / gather_us / 1e3
     gemm_tflops = 2.0 * MACS_PER_SAMPLE * BATCH / (learn_us * 1e-6) / 1e12
+    # dominant kernel family: every launch of gemm_tc_tiled_kernel in one step.  "achieved" counts the bf16
+    # tensor-core FLOPs actually ISSUED (6 products per fp32 multiply-accumulate, 3 for the exact uint8 operand): that
+    # is what the tensor pipe executes; the useful fp32-equivalent rate is reported next to it.
+    ops = []
+    for rec in gemm_ops.values():
+        us = rec["us"]
+        ops.append({"op": rec["tag"], "us": round(us, 1), "launches_per_step": rec["n"],
+                    "issued_tflops": round(2.0 * rec["macs"] * rec["nprod"] / us / 1e6, 1),
+                    "fp32_equiv_tflops": round(2.0 * rec["macs"] / us / 1e6, 1)})
+    tl_us = sum(o["us"] * o["launches_per_step"] for o in ops)
+    tl_issued = sum(2.0 * r["macs"] * r["nprod"] * r["n"] for r in gemm_ops.values())
+    tl_useful = sum(2.0 * r["macs"] * r["n"] for r in gemm_ops.values())
+    tiled_tflops = tl_issued / tl_us / 1e6 if tl_us else 0.0
     line = {
         "metric": "learn_from_batch steps/sec (DQN PER batch 512)", "value": round(steps_per_s, 2),
         "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 4),
@@ -271,7 +310,20 @@ def run_device(args):
                 "d2h_bytes_per_step": d2h, "steps": Ke,
                 "what": "per step: 4 host Transitions store()d + train(fetch=True) reading the loss back"},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "per_sample_gather_kernel (fused sum-tree descent + IS weights + TMA bulk-copy gather)",
+        "roofline": {"kernel": "gemm_tc_tiled_kernel (multi-tap tcgen05 GEMM on TMA-fed bf16 planes; all %d launches of a "
+                               "step, conv / dense forward, data and weight gradients)" % sum(
+                                   o["launches_per_step"] for o in ops),
+                     "bound": "tensor", "achieved": round(tiled_tflops, 1), "peak": pk["bf16_tflops_sustained"],
+                     "unit": "TFLOP/s", "frac": round(tiled_tflops / pk["bf16_tflops_sustained"], 4),
+                     "peak_kind": pk_kind + " (sustained dense bf16, kernel timed inside the step)",
+                     "us_per_step": round(tl_us, 1), "share_of_step": round(tl_us / (ms_total / K * 1e3), 3),
+                     "algorithmic_flops_per_step": tl_issued, "fp32_equivalent_tflops": round(tl_useful / tl_us / 1e6, 1)
+                     if tl_us else 0.0,
+                     "what": "achieved = bf16 tensor-core FLOPs issued (3xBF16 split: 6 products per fp32 MAC, 3 for "
+                             "the exact uint8 operand) / CUDA-event time of the launches (each prepared call timed over "
+                             "10 back-to-back launches incl. its split-reduce pass, weighted by launches per step)",
+                     "traffic": TRAFFIC_NCU.get("gemm_tc_tiled"), "ops": ops},
+        "roofline_gather": {"kernel": "per_sample_gather_kernel (fused sum-tree descent + IS weights + TMA bulk-copy gather)",
                      "bound": "hbm", "achieved": round(gather_gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": round(gather_gbs / pk["hbm_gbs"], 4), "peak_kind": pk_kind + " (burst copy)",
                      "us_per_launch": round(gather_us, 2), "algorithmic_bytes": GATHER_BYTES,

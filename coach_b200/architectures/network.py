@@ -155,6 +155,10 @@ class SequentialInstance(object):
                               dx_accumulate=(dx_accumulate and first), planes=ctx)
             else:
                 self._prepare_fwd_only(layer, lib, ws, B, dev, prev, self.acts[i], w, b, x_is_u8 and first, lut, ctx)
+            for attr in ("fwd", "bwd_w", "bwd_x"):
+                op = getattr(layer, attr, None)
+                if isinstance(op, tl.TGemmOp):
+                    op.tag = "%s_%d.%s" % (type(layer).__name__, i, attr)
             prev, prev_act = self.acts[i], layer.act
         self.out = self.acts[-1]
         self.d_out = self.dzs[-1]

@@ -128,10 +128,15 @@ def pick_splits_tiled(tiles, total_chunks, sm=148):
 
 
 class TGemmOp(object):
-    """A prepared cb200_gemm_tiled call."""
+    """A prepared cb200_gemm_tiled call.  ``macs`` = multiply-accumulates of the contraction, ``nprod`` = bf16 tensor-core
+    products issued per multiply (6: 3xBF16 split of both operands, 3: exact uint8 A)."""
+
+    trace = None          # bench.py: a list -> (op, start event, end event) is appended around every launch
 
     def __init__(self, lib, ws, **fields):
         self.lib, self.ws = lib, ws
+        self.macs = int(fields.pop("macs", 0))
+        self.tag = fields.pop("tag", "")
         self.keep = []
         self.desc = _lib.TGemmDesc()
         for k, v in fields.items():
@@ -147,9 +152,20 @@ class TGemmOp(object):
         if d.splits > 1:
             ws.require(d.splits * rows * d.n)
 
+    @property
+    def nprod(self):
+        return 3 if self.desc.a_num_planes == 1 else 6
+
     def run(self):
         if self.desc.splits > 1:
             self.desc.workspace = self.ws.ptr()
+        if TGemmOp.trace is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(self.lib.cb200_gemm_tiled(ctypes.byref(self.desc), _lib.current_stream()))
+            e1.record()
+            TGemmOp.trace.append((self, e0, e1))
+            return
         _lib.check(self.lib.cb200_gemm_tiled(ctypes.byref(self.desc), _lib.current_stream()))
 
 
@@ -174,6 +190,7 @@ def forward_op(lib, ws, B, device, x, Ca, w_ptr, w_stride, N, lists, num_q, c, l
     max_len = int(np.max(np.diff(ptr))) if num_q else 0
     flat = np.asarray(flat, dtype=np.int32).reshape(-1, 2) if flat else np.zeros((1, 2), dtype=np.int32)
     total = max_len * (Ca // 32)
+    extra.setdefault("macs", int(ptr[-1]) * Ca * B * N)
     return TGemmOp(lib, ws, mode=0, batch=B, a_planes=x, a_plane_stride=x.stride, a_cols=Ca, b_planes=w_ptr,
                    b_plane_stride=w_stride, n=N, list_ptr=_dev_i32(ptr, device), list=_dev_i32(flat, device),
                    max_list_len=max_len, num_q=num_q, taps=0, c=c, ldc=ldc, bias=bias, act=act, a_rows=x.rows,
@@ -199,6 +216,7 @@ def masked_forward_op(lib, ws, B, device, x, Ca, w_buf, N, lists, num_q, c, ldc,
 def wgrad_op(lib, ws, B, device, x, Ca, g, N, a_pix, taps, num_q, dw, **extra):
     """mode 1: dw [taps * Ca, N] row-major fp32"""
     total = num_q * (B // 32)
+    extra.setdefault("macs", taps * Ca * N * num_q * B)
     return TGemmOp(lib, ws, mode=1, batch=B, a_planes=x, a_plane_stride=x.stride, a_cols=Ca, b_planes=g,
                    b_plane_stride=g.stride, n=N, a_pix=_dev_i32(np.asarray(a_pix).reshape(-1), device), num_q=num_q,
                    taps=taps, max_list_len=0, c=dw, ldc=N, act=0, a_rows=x.rows, b_rows=g.rows,
