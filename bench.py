@@ -233,11 +233,13 @@ def run_device(args):
     # inside the step would count as kernel time).  Operands are in the L2 state the step leaves them in.
     from coach_b200.architectures.tiled import TGemmOp
     gemm_ops = {}
-    if rank == 0 and not args.no_tc:
+    if not args.no_tc:
         TGemmOp.trace = []
-        one_step(False)
+        one_step(False)                                # every rank: the step contains the gradient all-reduce
         torch.cuda.synchronize()
         trace, TGemmOp.trace = TGemmOp.trace, None
+        if rank != 0:
+            trace = []
         for op, _, _ in trace:
             rec = gemm_ops.setdefault(id(op), {"op": op, "tag": op.tag, "macs": op.macs, "nprod": op.nprod, "n": 0})
             rec["n"] += 1
@@ -343,10 +345,12 @@ def run_device(args):
     }
     line["cpu_baseline"] = cpu_reference(steps=args.cpu_steps, warmup=1, quiet=True)
     print(json.dumps(line))
+    sys.stdout.flush()
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)
-TRAFFIC_NCU = {"per_sample_gather": 30270000}
+# (gemm_tc_tiled: sum over the 15 launches of one step, profiles/ncu_tiled_gemm_r1k_summary.txt -- cold caches under ncu)
+TRAFFIC_NCU = {"per_sample_gather": 30270000, "gemm_tc_tiled": 498600000}
 
 
 # =====================================================================================================================
@@ -465,6 +469,9 @@ def main():
         run_reference(args)
     else:
         run_device(args)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
