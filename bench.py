@@ -193,6 +193,7 @@ def run_device(args):
         one_step(False)
     barrier()
     launches0 = lib.cb200_launch_count()
+    graph_launches0 = agent.graph_kernel_launches     # kernels run through CUDA-graph replays of the learn step
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -221,7 +222,7 @@ def run_device(args):
     agent.sample_batch = orig_sample
     mem.kernel_events = None
     ms_total = t0.elapsed_time(t1)
-    launches = lib.cb200_launch_count() - launches0
+    launches = lib.cb200_launch_count() - launches0 + agent.graph_kernel_launches - graph_launches0
     clocks = sampler.stop() if rank == 0 else None
     gather_us = float(np.mean([a.elapsed_time(b) for a, b, _ in ev])) * 1e3
     learn_us = float(np.mean([b.elapsed_time(c) for _, b, c in ev])) * 1e3
@@ -235,7 +236,9 @@ def run_device(args):
     gemm_ops = {}
     if not args.no_tc:
         TGemmOp.trace = []
+        graph_mode, agent.use_graph = agent.use_graph, False     # the trace needs the eager launch path
         one_step(False)                                # every rank: the step contains the gradient all-reduce
+        agent.use_graph = graph_mode
         torch.cuda.synchronize()
         trace, TGemmOp.trace = TGemmOp.trace, None
         if rank != 0:
@@ -306,6 +309,7 @@ def run_device(args):
                                   int(np.log2(mem.power_of_2_size))),
                    "parallelism": "dp%d (one replay shard per GPU, flat fp32 gradient all-reduce over NCCL)" % world,
                    "l2": "inputs (ring) >> L2, no flush needed", "priority_mode": mem.priority_mode,
+                   "cuda_graph": bool(agent.use_graph),
                    "l2_persist_tree_top": not args.no_l2_persist},
         "clocks": clocks,
         "e2e": {"value": round(world * Ke / (e2e_ms * 1e-3), 2), "unit": "steps/s", "h2d_bytes_per_step": h2d,

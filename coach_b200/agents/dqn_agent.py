@@ -87,6 +87,11 @@ class QNetworkWrapper(object):
         self.beta2_power = np.float32(params.adam_optimizer_beta2)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=device)
         self.has_target = self.theta_target is not None
+        # device copy of the running powers: the optimizer step then has constant launch parameters and the whole
+        # learn step can be captured in a CUDA graph (cb200_adam_tf_dev)
+        self.adam_state = torch.tensor([params.adam_optimizer_beta1, params.adam_optimizer_beta2],
+                                       dtype=torch.float32, device=device)
+        self.device_adam_state = False
 
     def sync(self):
         """online -> target hard copy (network_wrapper.py:94-107)."""
@@ -106,6 +111,13 @@ class QNetworkWrapper(object):
         p = self.params
         if p.optimizer_type != 'Adam':
             raise NotImplementedError("only the Adam optimizer of the DQN presets is implemented on device")
+        if self.device_adam_state:
+            _lib.check(self.lib.cb200_adam_tf_dev(self.theta.data_ptr(), self.store.m.data_ptr(),
+                                                  self.store.v.data_ptr(), self.store.grad.data_ptr(), n,
+                                                  float(p.learning_rate), float(p.adam_optimizer_beta1),
+                                                  float(p.adam_optimizer_beta2), float(p.optimizer_epsilon),
+                                                  self.adam_state.data_ptr(), st))
+            return
         _lib.check(self.lib.cb200_adam_tf(self.theta.data_ptr(), self.store.m.data_ptr(), self.store.v.data_ptr(),
                                           self.store.grad.data_ptr(), n, float(p.learning_rate),
                                           float(p.adam_optimizer_beta1), float(p.adam_optimizer_beta2),
@@ -162,6 +174,15 @@ class DQNAgent(object):
         self._pr_host = torch.zeros(B, dtype=torch.float64, pin_memory=pin)
         self._pa_dev = torch.zeros(B, dtype=torch.float64, device=dev)
         self._pr_dev = torch.zeros(B, dtype=torch.float64, device=dev)
+        # CUDA graphs of the learn step (own minibatch buffers only): forward + TD targets | loss + backward + clip
+        # [+ Adam when there is no all-reduce in between].  Every launch parameter of those kernels is constant from
+        # step to step, so two graph launches replace ~45 kernel launches; the first steps run eagerly (they build
+        # the TMA tensor maps, size the workspace and configure shared memory).
+        self.use_graph = bool(_lib.tune_default("dqn_graph", 1)) and dev.type == "cuda" and B >= 128
+        self.networks["main"].device_adam_state = self.use_graph
+        self._graphs = None
+        self._eager_steps = 0
+        self.graph_kernel_launches = 0            # kernels executed through graph replays (bench.py gpu_launches)
         # counters of agents/agent.py:112-135
         self.training_iteration = 0
         self.total_steps_counter = 0
@@ -208,35 +229,30 @@ class DQNAgent(object):
         """memory sample straight into the persistent minibatch buffers"""
         return self.memory.sample_batch(self.batch_size, out=self.batch_buffers)
 
-    def learn_from_batch(self, batch, fetch=True):
+    def _part_forward(self, cols, per_libm):
+        """target / online forward passes, TD targets and errors (dqn_agent.py:87-103); kernels and one D2H copy"""
         lib, st = self.lib, _lib.current_stream()
         net = self.networks["main"]
-        B, A = self.batch_size, self.num_actions
-        cols = batch.columns
-        for k in ("state:observation", "next_state:observation"):
-            if cols[k].data_ptr() != self.batch_buffers[k].data_ptr():
-                self.batch_buffers[k].copy_(cols[k])             # foreign batch: stage it (device -> device)
         q_next = net.target_s2.forward()                          # dqn_agent.py:87-90
         q_online = net.online_s.forward()
         q_select = net.online_s2.forward() if self.double_dqn else q_next      # ddqn_agent.py:42-43
         _lib.check(lib.cb200_dqn_td_targets(q_next.data_ptr(), q_select.data_ptr(), q_online.data_ptr(),
                                             cols["action"].data_ptr(), cols["reward"].data_ptr(),
-                                            cols["game_over"].data_ptr(), float(self.ap.algorithm.discount), B, A,
-                                            self.targets.data_ptr(), self.td_err.data_ptr(), st))
-        # value_optimization_agent.py:74-80: priorities from the pre-update errors, weights from the batch
-        per = isinstance(self.memory, PrioritizedExperienceReplay)
-        weights, ev = None, None
-        if per:
-            weights = cols["weight32"] if "weight32" in cols else cols["weight"].to(torch.float32)
-            if self.memory.priority_mode == "libm":
-                self._td_host.copy_(self.td_err, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record()
+                                            cols["game_over"].data_ptr(), float(self.ap.algorithm.discount),
+                                            self.batch_size, self.num_actions, self.targets.data_ptr(),
+                                            self.td_err.data_ptr(), st))
+        if per_libm:
+            self._td_host.copy_(self.td_err, non_blocking=True)
+
+    def _part_backward(self, weights, with_optimizer):
+        """head loss, backward pass, global norm / clipping [, optimizer]"""
+        lib, st = self.lib, _lib.current_stream()
+        net = self.networks["main"]
         huber = 1 if net.params.replace_mse_with_huber_loss else 0
-        _lib.check(lib.cb200_regression_head_loss_grad(q_online.data_ptr(), self.targets.data_ptr(),
-                                                       weights.data_ptr() if weights is not None else None, B, A,
-                                                       huber, 1.0, net.online_s.dq.data_ptr(),
-                                                       self.loss_dev.data_ptr(), st))
+        _lib.check(lib.cb200_regression_head_loss_grad(net.online_s.q.data_ptr(), self.targets.data_ptr(),
+                                                       weights.data_ptr() if weights is not None else None,
+                                                       self.batch_size, self.num_actions, huber, 1.0,
+                                                       net.online_s.dq.data_ptr(), self.loss_dev.data_ptr(), st))
         net.online_s.backward()
         n = net.store.size
         _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(), st))
@@ -246,9 +262,60 @@ class DQNAgent(object):
                 raise NotImplementedError("only ClipByGlobalNorm is implemented on device")
             _lib.check(lib.cb200_clip_by_global_norm(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), float(clip),
                                                      st))
-        scaler = parallel.allreduce_gradients(
-            net.store.grad, net.params.scale_down_gradients_by_number_of_workers_for_sync_training)
-        net.apply_gradients(scaler)
+        if with_optimizer:
+            net.apply_gradients(1.0)
+
+    def _capture(self, cols, weights, per_libm, single):
+        c0 = self.lib.cb200_launch_count()
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(ga):
+            self._part_forward(cols, per_libm)
+        c1 = self.lib.cb200_launch_count()
+        with torch.cuda.graph(gb):
+            self._part_backward(weights, single)
+        c2 = self.lib.cb200_launch_count()
+        self._graphs = (ga, gb, int(c1 - c0), int(c2 - c1))
+
+    def learn_from_batch(self, batch, fetch=True):
+        net = self.networks["main"]
+        cols = batch.columns
+        own = all(cols[k].data_ptr() == self.batch_buffers[k].data_ptr()
+                  for k in ("state:observation", "next_state:observation", "action", "reward", "game_over"))
+        for k in ("state:observation", "next_state:observation"):
+            if cols[k].data_ptr() != self.batch_buffers[k].data_ptr():
+                self.batch_buffers[k].copy_(cols[k])             # foreign batch: stage it (device -> device)
+        # value_optimization_agent.py:74-80: priorities from the pre-update errors, weights from the batch
+        per = isinstance(self.memory, PrioritizedExperienceReplay)
+        weights = None
+        if per:
+            weights = cols["weight32"] if "weight32" in cols else cols["weight"].to(torch.float32)
+            own = own and weights.data_ptr() == self.batch_buffers["weight32"].data_ptr()
+        per_libm = per and self.memory.priority_mode == "libm"
+        single = not parallel.is_distributed()                    # no all-reduce between backward and optimizer
+        graph = self.use_graph and own and self._eager_steps >= 2
+        if graph and self._graphs is None:
+            self._capture(cols, weights, per_libm, single)
+        ev = None
+        if graph:
+            ga, gb, na, nb = self._graphs
+            ga.replay()
+            if per_libm:
+                ev = torch.cuda.Event()
+                ev.record()
+            gb.replay()
+            self.graph_kernel_launches += na + nb
+        else:
+            self._part_forward(cols, per_libm)
+            if per_libm:
+                ev = torch.cuda.Event()
+                ev.record()
+            self._part_backward(weights, False)
+            self._eager_steps += 1
+        if not (graph and single):
+            scaler = parallel.allreduce_gradients(
+                net.store.grad, net.params.scale_down_gradients_by_number_of_workers_for_sync_training)
+            net.apply_gradients(scaler)
         if per:
             if ev is not None:
                 ev.synchronize()                                  # GPU is busy with the backward pass meanwhile

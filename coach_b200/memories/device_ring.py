@@ -67,6 +67,7 @@ class DeviceTransitionRing(object):
         self.specs = None
         self.columns = None          # name -> uint8 [capacity, row_bytes] on device
         self.stage_rows = int(stage_rows)
+        self._table_cache = {}
         self._stage_host = None      # name -> pinned uint8 [stage_rows, row_bytes]
         self._stage_dev = None
         self._pending = 0
@@ -80,10 +81,12 @@ class DeviceTransitionRing(object):
             return
         self.specs = specs
         self.columns, self._stage_host, self._stage_dev = OrderedDict(), OrderedDict(), OrderedDict()
+        self._stage_np = {}
         pin = self.device.type == "cuda"
         for name, sp in specs.items():
             self.columns[name] = torch.empty((self.capacity, sp.row_bytes), dtype=torch.uint8, device=self.device)
             self._stage_host[name] = torch.empty((self.stage_rows, sp.row_bytes), dtype=torch.uint8, pin_memory=pin)
+            self._stage_np[name] = self._stage_host[name].numpy()      # same memory, no per-store tensor objects
             self._stage_dev[name] = torch.empty((self.stage_rows, sp.row_bytes), dtype=torch.uint8,
                                                 device=self.device)
 
@@ -114,7 +117,7 @@ class DeviceTransitionRing(object):
             if a.shape != sp.shape:
                 raise ValueError("transition field %s has shape %s, the replay was created with %s"
                                  % (name, a.shape, sp.shape))
-            self._stage_host[name][r].numpy()[:] = a.reshape(-1).view(np.uint8)
+            self._stage_np[name][r] = a.reshape(-1).view(np.uint8)
         self._pending += 1
         return self._pending >= min(self.stage_rows, self.capacity)
 
@@ -191,9 +194,17 @@ class DeviceTransitionRing(object):
         return out
 
     def column_table(self, out):
-        pairs = [(self.columns[name].data_ptr(), out[name].data_ptr(), sp.row_bytes)
-                 for name, sp in self.specs.items()]
-        return _lib.make_columns(pairs)
+        # the agents sample into the same persistent buffers every step: build the ctypes table once per buffer set
+        key = tuple(out[name].data_ptr() for name in self.specs)
+        hit = self._table_cache.get(key)
+        if hit is None:
+            pairs = [(self.columns[name].data_ptr(), out[name].data_ptr(), sp.row_bytes)
+                     for name, sp in self.specs.items()]
+            hit = self._table_cache[key] = _lib.make_columns(pairs)
+            if len(self._table_cache) > 64:
+                self._table_cache.clear()
+                self._table_cache[key] = hit
+        return hit
 
     def gather(self, idx, out=None):
         """out[c][i] = column c of slot idx[i]; idx int64 CUDA tensor."""

@@ -70,6 +70,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         self._maximal_priority = 1.0
         self._maxp_stale = False
         self._list_len = 0                  # len(self.transitions) of the reference (doubled, capped)
+        self._u_ring = {}                   # batch size -> rotating pinned / device buffers of the uniform draws
 
     def _init_trees(self):
         _lib.check(self.lib.cb200_per_init(self.sum_tree.data_ptr(), self.min_tree.data_ptr(),
@@ -187,10 +188,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         if uniforms is None:
             rnd = random.random
             uniforms = [rnd() for _ in range(size)]
-        u_host = torch.tensor(uniforms, dtype=torch.float64)
-        if self.device.type == "cuda":
-            u_host = u_host.pin_memory()
-        u = u_host.to(self.device, non_blocking=True)
+        u = self._upload_uniforms(uniforms, size)
         if out is None:
             out = self.ring.alloc_batch(size)
         for k, dt in (("idx", torch.int64), ("weight", torch.float64), ("weight32", torch.float32)):
@@ -208,6 +206,26 @@ class PrioritizedExperienceReplay(ExperienceReplay):
             ke[1].record()
         self.beta.step()                                                                 # :255
         return DeviceBatch(dict(out), size)
+
+    def _upload_uniforms(self, uniforms, size):
+        """host draws -> device through a small ring of persistent pinned buffers (no allocation per call; a buffer
+        is reused only after the copy that read it has completed)"""
+        if self.device.type != "cuda":
+            return torch.tensor(uniforms, dtype=torch.float64)
+        ring = self._u_ring.get(size)
+        if ring is None:
+            ring = self._u_ring[size] = {"i": 0, "slots": [
+                (torch.empty(size, dtype=torch.float64, pin_memory=True),
+                 torch.empty(size, dtype=torch.float64, device=self.device), [None]) for _ in range(4)]}
+        host, dev, ev = ring["slots"][ring["i"]]
+        ring["i"] = (ring["i"] + 1) % len(ring["slots"])
+        if ev[0] is not None:
+            ev[0].synchronize()
+        host.numpy()[:] = uniforms
+        dev.copy_(host, non_blocking=True)
+        ev[0] = torch.cuda.Event()
+        ev[0].record()
+        return dev
 
     def sample_indices(self, size: int, uniforms=None):
         """Descent + weights only (no gather): returns (idx int64, weight float64) CUDA tensors."""

@@ -33,6 +33,10 @@ def init_from_env(backend=None):
     return world()
 
 
+def is_distributed() -> bool:
+    return world()[1] > 1
+
+
 def allreduce_gradients(flat_grad: torch.Tensor, scale_down: bool = True) -> float:
     """Sums the flat gradient buffer over all ranks in place and returns the scaler the optimizer step must apply
     (1/world when averaging, else 1)."""

@@ -349,3 +349,37 @@ def test_target_network_cadence_and_polyak():
         agent.train()
         synced.append(bool(torch.equal(net.theta, net.theta_target)))
     assert synced == [False, False, True, False, False, True, False]
+
+
+def test_dqn_graph_replay_matches_eager(monkeypatch):
+    """the CUDA-graph replay of the learn step (agents/dqn_agent.py) is bit-identical to the eager launch sequence"""
+    import random
+    results = []
+    for graph in (0, 1):
+        monkeypatch.setenv("CB200_DQN_GRAPH", str(graph))
+        torch.manual_seed(0)
+        agent = _make_agent((84, 84, 4), 6, 128, False, True, True, None, True, seed=5)
+        assert agent.use_graph == bool(graph)
+        rng = np.random.RandomState(3)
+        n = 512
+        agent.memory.store_columns({
+            "state:observation": rng.randint(0, 256, (n, 84, 84, 4)).astype(np.uint8),
+            "next_state:observation": rng.randint(0, 256, (n, 84, 84, 4)).astype(np.uint8),
+            "action": rng.randint(0, 6, n).astype(np.int64), "reward": rng.randint(-1, 2, n).astype(np.float64),
+            "game_over": (rng.rand(n) < 0.1).astype(np.uint8)})
+        agent.memory.update_priorities(np.arange(n), np.abs(rng.randn(n)))
+        losses = []
+        for step in range(6):                       # 2 eager steps, capture, 3 replays
+            random.seed(20 + step)
+            np.random.seed(20 + step)
+            batch = agent.sample_batch()
+            loss, _, _ = agent.learn_from_batch(batch)
+            losses.append(loss)
+        torch.cuda.synchronize()
+        if graph:
+            assert agent._graphs is not None and agent.graph_kernel_launches > 0
+        store = agent.net_def.store
+        results.append((losses, store.theta.clone(), agent.memory.sum_tree.clone()))
+    assert results[0][0] == results[1][0]
+    assert torch.equal(results[0][1], results[1][1])
+    assert torch.equal(results[0][2], results[1][2])
