@@ -101,6 +101,11 @@ def _tiles(M, N, fast=True):
     return ((M + 127) // 128) * ((N + bn - 1) // bn)
 
 
+def _bias_behind(dw, db, K, N):
+    """the bias gradient is stored right behind the kernel gradient (flat ParamStore layout): one more GEMM row"""
+    return dw is not None and db is not None and db.data_ptr() == dw.data_ptr() + K * N * 4
+
+
 def _bias_rides_along(dw, db, K, N, skinny=False):
     """True when the bias gradient is stored right behind the kernel gradient (flat ParamStore layout)."""
     bm = 256 if N <= 32 else 128          # row tile of the kernel that will run; only use slack of the last tile
@@ -185,9 +190,12 @@ class Dense(object):
         self.bwd_w = None
         if dw is not None and dy is not None:
             if pl.dy is not None:
-                self.bwd_w = tl.wgrad_op(lib, ws, B, device, xp, Ca, pl.dy, N, np.arange(npix), npix, 1, dw)
-                self.db_args = (dy, B, N, db)
-                ws.require(1024 * N)
+                fused = _bias_behind(dw, db, K, N)        # bias gradient as one more row of the same GEMM
+                self.bwd_w = tl.wgrad_op(lib, ws, B, device, xp, Ca, pl.dy, N, np.arange(npix), npix, 1, dw,
+                                         bias_row=int(fused))
+                if not fused:
+                    self.db_args = (dy, B, N, db)
+                    ws.require(1024 * N)
             else:       # the gradient of this layer's output has no planes (written by a head kernel)
                 vec = int(K % 4 == 0)
                 ones = int(bool(vec) and _bias_rides_along(dw, db, K, N))
@@ -366,10 +374,13 @@ class Conv2d(object):
         self.bwd_w = None
         if dw is not None and dy is not None:
             assert pl.dy is not None, "s2d conv weight gradient needs the planes of dY"
+            fused = _bias_behind(dw, db, T * Cs, N)
             self.bwd_w = tl.wgrad_op(lib, ws, B, device, xp, Cs, pl.dy, N, pix_in, T, nq, dw, a_u8_div=div,
-                                     c_rowmap=_dev_i32(orig_row, device))
-            self.db_args = (dy, B * nq, N, db)
-            ws.require(1024 * N)
+                                     c_rowmap=_dev_i32(np.concatenate([orig_row, [T * Cs]]), device),
+                                     bias_row=int(fused))
+            if not fused:
+                self.db_args = (dy, B * nq, N, db)
+                ws.require(1024 * N)
 
     def _prepare_tiled(self, lib, ws, B, device, x, y, w, b, dw, db, dy, dx, need_dx, prev_act, pl):
         """input available as planes [H * W * B, C]: forward, weight gradient and data gradient as multi-tap GEMMs"""
@@ -388,9 +399,11 @@ class Conv2d(object):
         self.bwd_w = None
         if dw is not None and dy is not None:
             assert pl.dy is not None, "tiled conv weight gradient needs the planes of dY"
-            self.bwd_w = tl.wgrad_op(lib, ws, B, device, pl.x, C, pl.dy, N, pix_in, T, nq, dw)
-            self.db_args = (dy, B * nq, N, db)
-            ws.require(1024 * N)
+            fused = _bias_behind(dw, db, T * C, N)
+            self.bwd_w = tl.wgrad_op(lib, ws, B, device, pl.x, C, pl.dy, N, pix_in, T, nq, dw, bias_row=int(fused))
+            if not fused:
+                self.db_args = (dy, B * nq, N, db)
+                ws.require(1024 * N)
         if not need_dx:
             return
         assert pl.dy is not None and tl.channels_ok(N) and tl.width_ok(C), "tiled data gradient: unsupported shape"

@@ -148,7 +148,7 @@ class TGemmOp(object):
                 v = v.ptr
             setattr(self.desc, k, v)
         d = self.desc
-        rows = d.num_q * d.batch if d.mode == 0 else d.taps * d.a_cols
+        rows = d.num_q * d.batch if d.mode == 0 else d.taps * d.a_cols + (1 if d.bias_row else 0)
         if d.splits > 1:
             ws.require(d.splits * rows * d.n)
 

@@ -450,6 +450,7 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
         M = d->taps * d->a_cols;
         gx = (M + 127) / 128;
         total = d->num_q * (d->batch / 32);
+        if (d->bias_row) M += 1;          // rows of the result (and of the split partials); tiles still cover M - 1
     }
     int splits = d->splits > 1 ? d->splits : 1;
     int cps = (total + splits - 1) / splits;
@@ -459,6 +460,7 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
     CB200_CHECK_ARG(splits == 1 || d->workspace, "split reduction needs a workspace");
     tp.chunks_per_split = cps;
     tp.a_u8_div = d->a_u8_div;
+    tp.bias_row = d->mode == 1 ? d->bias_row : 0;
     const gemm::EpiParams ep{d->c,        d->ldc,      d->bias,      d->act,  d->mask_y,
                              d->mask_act, d->c_rowmap, d->workspace, splits,  0,
                              static_cast<uint16_t*>(d->c_planes), d->c_plane_stride, d->c_plane_cols, 0, 0};

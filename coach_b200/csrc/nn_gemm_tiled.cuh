@@ -69,13 +69,14 @@ struct TiledParams {
     int num_q, taps;
     int chunks_per_split;
     float a_u8_div;            // NA == 1: A holds raw uint8 values (exact in bf16); every sum is divided by this
+    int bias_row;              // mode 1: also produce row M = sum over all rows of G (the bias gradient)
 };
 
 // NA = planes of the A operand: 3 (fp32 split) or 1 (uint8 values, exact: 3 products instead of 6)
 template <int BN, int NA>
 struct TiledCfg {
     static constexpr int kStages = BN == 128 ? 4 : 3;
-    static constexpr size_t kSmemBytes = (size_t)kStages * (NA * kTcBM * kTcBK * 2 + 3 * BN * kTcBK * 2) + 128;
+    static constexpr size_t kSmemBytes = (size_t)kStages * (NA * kTcBM * kTcBK * 2 + 3 * BN * kTcBK * 2) + 128 + 4096;
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -97,14 +98,20 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
     constexpr int B_SPLIT = BN * kTcBK * 2;
     constexpr int STAGE = NA * A_SPLIT + 3 * B_SPLIT;
     constexpr int B_KG = (BN / 8) * 128;                  // bytes of one k-group (8 reduction rows) of the B tile
-    constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * STAGE);     // [S]
     uint64_t* empty_bar = full_bar + S;                                    // [S]
     uint64_t* done_bar = empty_bar + S;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+    uint8_t* ones_tile = smem + S * STAGE + 128;          // 4 KB: a [128 x 16] A^T operand of bf16 1.0 (bias row)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Bias gradient (mode 1): the CTAs of the first M tile also accumulate ones^T * G in two more TMEM accumulators --
+    // every row of that product is sum_rows G[row, :], the epilogue keeps row 0.  Three extra MMAs per k16 step in
+    // 1 / gridDim.x of the CTAs replace a separate column-sum pass over dY.
+    const bool bias_cta = kTransA && tp.bias_row != 0 && blockIdx.x == 0;
+    const uint32_t tmem_cols_needed = (bias_cta ? 4u : 2u) * BN;
+    const uint32_t TMEM_COLS = tmem_cols_needed <= 32 ? 32u : (tmem_cols_needed <= 64 ? 64u : (tmem_cols_needed <= 128 ? 128u : (tmem_cols_needed <= 256 ? 256u : 512u)));
     const int B = tp.batch, Ca = tp.a_cols, N = tp.n;
     const int n0 = blockIdx.y * BN;
     const int split = blockIdx.z;
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
         total = (__ldg(tp.list_ptr + q + 1) - list_lo) * kc_per;
     } else {
         m0 = blockIdx.x * kTcBM;
-        m_end = M;
+        m_end = M - (tp.bias_row ? 1 : 0);       // the bias row is not part of any tile
         total = tp.num_q * bc_per;
     }
     const int c_lo = split * tp.chunks_per_split;
@@ -143,11 +150,18 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
         mbar_init(done_bar, 1);
         fence_mbar_init();
     }
+    if (bias_cta && tid < 128) {
+        // 2048 bf16 ones, 16 per thread; generic-proxy stores made visible to the tensor core (async proxy)
+        uint4* o = reinterpret_cast<uint4*>(ones_tile) + 2 * tid;
+        o[0] = o[1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        fence_proxy_async_smem();
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_main = *tmem_slot;
     const uint32_t tmem_corr = tmem_main + BN;
+    const uint32_t tmem_bias_main = tmem_main + 2 * BN, tmem_bias_corr = tmem_main + 3 * BN;
 #ifdef CB200_TC_PROF
     const bool cta0 = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 #endif
@@ -240,6 +254,12 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
                     }
                     umma_bf16(tmem_corr, a0, b1, idesc, 1u);           // a1 b2
                     if (NA == 3) umma_bf16(tmem_corr, a1, b0d, idesc, 1u);   // a2 b1
+                    if (bias_cta) {
+                        const uint64_t od = umma_smem_desc(smem_u32(ones_tile), 2048u, 128u);
+                        umma_bf16(tmem_bias_main, od, b0d, idesc, first);      // 1 g1
+                        umma_bf16(tmem_bias_corr, od, b2, idesc, first);       // 1 g3
+                        umma_bf16(tmem_bias_corr, od, b1, idesc, 1u);          // 1 g2
+                    }
                 }
                 umma_commit(empty_bar + s);
                 if (j == nchunks - 1) umma_commit(done_bar);
@@ -261,6 +281,33 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
         }
         TC_PROF_T(t1e);
         tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, m_end, N, split, NA == 1, tp.a_u8_div, -1);
+        if (bias_cta && warp == 0) {
+            // row `m_end` (= taps * Ca) of the result: lane 0 owns TMEM lane 0 of the bias accumulators
+#pragma unroll 1
+            for (int col = 0; col < BN; col += 16) {
+                uint32_t vm[16], vc[16];
+                if (nchunks > 0) {
+                    CB200_TMEM_LD16(vm, tmem_bias_main + (uint32_t)col);
+                    CB200_TMEM_LD16(vc, tmem_bias_corr + (uint32_t)col);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) vm[j] = vc[j] = 0u;
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + col + j;
+                        if (n >= N) continue;
+                        const float v = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+                        if (ep.splits > 1)
+                            ep.partial[((size_t)split * M + m_end) * N + n] = v;
+                        else
+                            epilogue_store(ep, m_end, n, v);
+                    }
+                }
+            }
+        }
         TC_PROF_T(t2e);
         TC_PROF_ADD(5, t0e, t1e);          // main loop as seen by the epilogue warps
         TC_PROF_ADD(6, t1e, t2e);          // epilogue

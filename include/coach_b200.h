@@ -237,6 +237,8 @@ typedef struct cb200_tgemm_desc {
     void* c_planes;             /* tiled planes of C with plane row = C row, c_plane_cols == n                       */
     int64_t c_plane_stride;
     int32_t c_plane_cols;
+    int32_t bias_row;           /* mode 1: 1 = also produce row taps * a_cols = sum over all rows of G (the bias gradient, */
+                                /*    stored right behind the kernel gradient); c / workspace / c_rowmap have one more row  */
     int32_t a_num_planes;       /* 3 (0 = 3): fp32 split;  1: A holds raw uint8 values as ONE exact bf16 plane, every    */
     float a_u8_div;             /*    accumulated sum is divided by a_u8_div (x / 255 input rescale, embedder.py:103)  */
     int64_t a_rows;             /* rows of the A plane matrix (a_pixels * B) and of the B operand's plane matrix      */

@@ -57,7 +57,8 @@ def test_dense_forward_backward(B, K, N, act, planes):
     dy = torch.randn(B, N, generator=g)
     xd, wd, bd, dyd = x.to(dev), w.to(dev), b.to(dev), dy.to(dev)
     y = torch.empty(B, N, device=dev)
-    dw, db, dx = torch.empty(K, N, device=dev), torch.empty(N, device=dev), torch.empty(B, K, device=dev)
+    flat = torch.empty(K * N + N, device=dev)          # bias gradient right behind the kernel gradient (ParamStore)
+    dw, db, dx = flat[:K * N].view(K, N), flat[K * N:], torch.empty(B, K, device=dev)
     ws = Workspace(dev)
     layer = Dense(K, N, act)
     ctx = None
@@ -112,7 +113,8 @@ def test_conv_forward_backward(B, H, C, N, K, S, u8, planes):
     dy = torch.randn(B, OH, OH, N, generator=g)
     xd, wd, bd, dyd = x.to(dev), w.to(dev), b.to(dev), dy.to(dev)
     y = torch.empty(B, OH * OH * N, device=dev)
-    dw, db = torch.empty(K, K, C, N, device=dev), torch.empty(N, device=dev)
+    flat = torch.empty(K * K * C * N + N, device=dev)  # bias gradient right behind the kernel gradient (ParamStore)
+    dw, db = flat[:K * K * C * N].view(K, K, C, N), flat[K * K * C * N:]
     dx = torch.empty(B, H * H * C, device=dev)
     ws = Workspace(dev)
     ctx = None
