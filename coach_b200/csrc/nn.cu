@@ -1,6 +1,6 @@
 // coach_b200/csrc/nn.cu -- C-ABI entry points of the dense contractions of the learn step (see nn_gemm.cuh).
 #include "nn_gemm_skinny.cuh"
-#include "nn_gemm_tiled.cuh"
+#include "nn_gemm_tiled_persist.cuh"
 
 namespace cb200 {
 namespace gemm {
@@ -192,6 +192,29 @@ __global__ void __launch_bounds__(256) u8_s2d_planes_kernel(const uint8_t* __res
             *reinterpret_cast<uint4*>(plane + tiled_elem(prow, dy * run + g, Cs)) = u8x8_to_bf16(w.x, w.y);
         }
     }
+}
+
+template <int BN, bool kT, int NA>
+static int launch_tiled_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const TiledParams& tp,
+                                const EpiParams& ep, int M, int gx, int splits, cudaStream_t st) {
+    constexpr size_t smem = PersistCfg<BN, NA>::kSmemBytes;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tc_tiled_persist_kernel<BN, kT, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    UnitGrid ug{gx, (tp.n + BN - 1) / BN, splits};
+    const int units = ug.gx * ug.gy * ug.gz;
+    const int grid = units < sm_count() ? units : sm_count();
+    gemm_tc_tiled_persist_kernel<BN, kT, NA><<<grid, kPsThreads, smem, st>>>(tmA, tmB, tp, ep, M, ug);
+    count_launch();
+    if (splits > 1) {
+        launch_split_reduce(ep, M, tp.n, st);
+        count_launch();
+    }
+    return 0;
 }
 
 // ---- small helpers -------------------------------------------------------------------------------------------------
@@ -471,9 +494,24 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
                         : gemm::launch_tiled<BN_, false, 1>(maps[0], maps[1], tp, ep, M, gx, splits, st)) \
              : (d->mode ? gemm::launch_tiled<BN_, true, 3>(maps[0], maps[1], tp, ep, M, gx, splits, st)   \
                         : gemm::launch_tiled<BN_, false, 3>(maps[0], maps[1], tp, ep, M, gx, splits, st)))
-    if (bn == 32) rc = CB200_TL(32);
+#define CB200_TP(BN_)                                                                                            \
+    (na == 1 ? (d->mode ? gemm::launch_tiled_persist<BN_, true, 1>(maps[0], maps[1], tp, ep, M, gx, splits, st)   \
+                        : gemm::launch_tiled_persist<BN_, false, 1>(maps[0], maps[1], tp, ep, M, gx, splits, st)) \
+             : (d->mode ? gemm::launch_tiled_persist<BN_, true, 3>(maps[0], maps[1], tp, ep, M, gx, splits, st)   \
+                        : gemm::launch_tiled_persist<BN_, false, 3>(maps[0], maps[1], tp, ep, M, gx, splits, st)))
+    // persistent schedule (epilogue of unit i under the main loop of unit i+1) unless the bias row would need more
+    // than the 512 TMEM columns for two accumulator sets
+    // (measured, profiles/README.md: on the step's shapes the persistent schedule is not faster yet -- one producer warp
+    // and one MMA thread per SM instead of two of each -- so it is opt-in: cb200_tune("gemm_persistent", 1))
+    const bool persist = tune_get("gemm_persistent", 0, 0, 1) != 0 && !(tp.bias_row && bn == 128);
+    if (persist) {
+        if (bn == 32) rc = CB200_TP(32);
+        else if (bn == 64) rc = CB200_TP(64);
+        else rc = CB200_TP(128);
+    } else if (bn == 32) rc = CB200_TL(32);
     else if (bn == 64) rc = CB200_TL(64);
     else rc = CB200_TL(128);
+#undef CB200_TP
 #undef CB200_TL
     CB200_CHECK_ARG(rc == 0, "could not configure shared memory for the tiled tcgen05 kernel");
     CB200_CHECK_LAUNCH();

@@ -144,8 +144,10 @@ __device__ __forceinline__ bool tap_ok(int ri, int ci, int oh, int ow) {
 template <int BN>
 __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_main, uint32_t tmem_corr, bool have_acc,
                                             int m0, int n0, int M, int m_end, int N, int split, bool u8,
-                                            float a_u8_div, int unscaled_row) {
-    const int tid = threadIdx.x, warp = tid >> 5;
+                                            float a_u8_div, int unscaled_row, int col_lo = 0, int col_hi = BN) {
+    // row = TMEM lane = thread index modulo 128 (a warp reaches the lane quadrant 32 * (warp % 4)); a second group
+    // of four warps may take the other half of the columns [col_lo, col_hi)
+    const int tid = threadIdx.x & 127, warp = tid >> 5;
     const int m = m0 + tid;
     const bool scale_row = u8 && m != unscaled_row;
     const bool live = m < m_end;
@@ -160,7 +162,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_m
     }
     const size_t p_base = ep.c_planes ? (p_row >> 3) * (size_t)(ep.c_plane_cols >> 3) * 64 + (p_row & 7) * 8 : 0;
 #pragma unroll 1
-    for (int col = 0; col < BN; col += 16) {
+    for (int col = col_lo; col < col_hi; col += 16) {
         uint32_t vm[16], vc[16];
         if (have_acc) {
             CB200_TMEM_LD16(vm, tmem_main + lane_base + (uint32_t)col);

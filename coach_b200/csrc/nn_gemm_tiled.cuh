@@ -204,8 +204,10 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
             } else {
                 const int qq = cj / bc_per, bc = cj % bc_per;
                 if (lane == 0) tma_load_4d(sB, &tmB, 0, n0 >> 3, (int)(((size_t)qq * B + (size_t)bc * kTcBK) >> 3), 0, bar);
-                // A^T: per tap of the tile, 4 k-groups (8 batch rows each) x a run of cw / 8 cores
-                for (int idx = lane; idx < NA * 4 * taps_in_tile; idx += 32) {
+                // A^T: per tap of the tile, 4 k-groups (8 batch rows each) x a run of cw / 8 cores.  A bulk copy costs
+                // ~60 cycles of issue in the issuing warp whatever its size, so the runs are dealt out over five
+                // warps: this one and the four epilogue warps, which are idle until the accumulators are complete.
+                for (int idx = lane; idx < NA * 4 * taps_in_tile; idx += 5 * 32) {
                     const int p = idx / (4 * taps_in_tile), r = idx % (4 * taps_in_tile);
                     const int tt = r >> 2, kg = r & 3;
                     const int apix = __ldg(tp.a_pix + (size_t)(t0 + tt) * tp.num_q + qq);
@@ -274,6 +276,30 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
 #ifdef CB200_TC_PROF
         const bool prof_on = cta0 && tid == 0;
 #endif
+        if (kTransA) {
+            // main loop: help the producer with the A^T bulk copies (slots 1..4 of the five-way deal)
+            const int taps_in_tile = Ca >= kTcBM ? 1 : min(kTcBM / Ca, tp.taps - m0 / Ca);
+            const int t0 = m0 / Ca, cw = min(Ca, kTcBM), c0 = m0 % Ca;
+            for (int j = 0; j < nchunks; ++j) {
+                const int s = j % S, u = j / S;
+                if ((warp + 1) * 32 >= NA * 4 * taps_in_tile) break;           // nothing dealt to this warp
+                if (u > 0) mbar_wait(empty_bar + s, (uint32_t)((u - 1) & 1));
+                uint8_t* sA = smem + s * STAGE;
+                uint64_t* bar = full_bar + s;
+                const int cj = c_lo + j;
+                const int qq = cj / bc_per, bc = cj % bc_per;
+                for (int idx = (warp + 1) * 32 + lane; idx < NA * 4 * taps_in_tile; idx += 5 * 32) {
+                    const int p = idx / (4 * taps_in_tile), r = idx % (4 * taps_in_tile);
+                    const int tt = r >> 2, kg = r & 3;
+                    const int apix = __ldg(tp.a_pix + (size_t)(t0 + tt) * tp.num_q + qq);
+                    const size_t rg = (((size_t)apix * B + (size_t)bc * kTcBK) >> 3) + kg;
+                    bulk_g2s(sA + p * A_SPLIT + kg * 2048 + tt * (Ca >> 3) * 128,
+                             tp.a + p * tp.a_stride + (rg * (size_t)(Ca >> 3) + (size_t)(c0 >> 3)) * 64,
+                             (uint32_t)((cw >> 3) * 128), bar);
+                }
+                __syncwarp();
+            }
+        }
         TC_PROF_T(t0e);
         if (nchunks > 0) {
             mbar_wait(done_bar, 0);
