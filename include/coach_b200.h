@@ -36,8 +36,11 @@ const char* cb200_last_error(void);
 int64_t cb200_launch_count(void);
 /* Multiprocessor count and compute capability of the current device (any pointer may be NULL). */
 int cb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
-/* Runtime tuning knobs (benchmark sweeps): "gather_stages" (smem stages per CTA, default 6),
- * "gather_ctas_per_sm" (persistent gather grid = SMs x this, default 2). Unknown keys are stored and ignored. */
+/* Runtime switches for benchmark A/B runs (unknown keys are stored and ignored):
+ *   "gather_ctas_per_sm" (persistent gather grid = SMs x this, default 4), "gather_stages" (0 = automatic)
+ *   "gemm_tc" (1)          tcgen05 path of cb200_gemm; 0 = fp32 CUDA-core kernels only
+ *   "gemm_skinny" (1)      dedicated kernels for products with n <= 8 or k <= 8
+ *   "gemm_persistent" (0)  persistent schedule of cb200_gemm_tiled (two TMEM accumulator sets, 8 epilogue warps) */
 int cb200_tune(const char* key, int value);
 
 /* =====================================================================================================================
@@ -93,8 +96,9 @@ int cb200_per_store(double* sum_tree, double* min_tree, double* max_tree, int32_
  *   idx_out     int64[n]  leaf indices (bit-exact)
  *   w_out       double[n] normalised importance weights ((nt*P)^-beta / max_w); w32_out float[n] the same rounded
  *               once to fp32 (what the TF placeholder receives); either may be NULL
- * One warp per sample; each round fetches a 5-level sub-tree (62 nodes) with two coalesced loads per lane and walks
- * it with shuffles, so a 2^20-leaf descent costs 4 dependent memory round trips instead of 20. */
+ * One warp per sample; each round fetches a 7-level sub-tree (254 nodes, 8 coalesced loads per lane) into a per-warp
+ * shared-memory scratch and replays the reference's comparisons from it, so a 2^20-leaf descent costs 3 dependent
+ * memory round trips instead of 20. */
 int cb200_per_sample(const double* sum_tree, const double* min_tree, int64_t size, const double* u, int64_t n,
                      int64_t nt, double beta, int64_t* idx_out, double* w_out, float* w32_out, void* stream);
 
