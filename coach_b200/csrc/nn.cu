@@ -145,7 +145,7 @@ static int launch_tiled(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ti
         configured = true;
     }
     dim3 grid(gx, (tp.n + BN - 1) / BN, splits);
-    gemm_tc_tiled_kernel<BN, kT, NA><<<grid, 192, smem, st>>>(tmA, tmB, tp, ep, M);
+    gemm_tc_tiled_kernel<BN, kT, NA><<<grid, kTlThreads, smem, st>>>(tmA, tmB, tp, ep, M);
     count_launch();
     if (splits > 1) {
         launch_split_reduce(ep, M, tp.n, st);

@@ -73,6 +73,11 @@ struct TiledParams {
 };
 
 // NA = planes of the A operand: 3 (fp32 split) or 1 (uint8 values, exact: 3 products instead of 6)
+// warps 0-7: epilogue (two per TMEM lane quadrant, half of the tile's columns each; in mode 1 they also help issuing
+// bulk copies during the main loop), warp 8: producer, warp 9: MMA issuer
+constexpr int kTlThreads = 320;
+constexpr int kTlProducerWarp = 8, kTlMmaWarp = 9;
+
 template <int BN, int NA>
 struct TiledCfg {
     static constexpr int kStages = BN == 128 ? 4 : 3;
@@ -90,7 +95,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 
 // tmA: planes of A with box (64, 4, 16, NA) (mode 0 only); tmB: planes of the B operand with box (64, BN / 8, 4, 3)
 template <int BN, bool kTransA, int NA>
-__global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kTlThreads) gemm_tc_tiled_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB, TiledParams tp,
                                                             EpiParams ep, int M) {
     constexpr int S = TiledCfg<BN, NA>::kStages;
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
         mbar_init(done_bar, 1);
         fence_mbar_init();
     }
-    if (bias_cta && tid < 128) {
+    if (bias_cta && tid < 128) {     // (any 128 threads)
         // 2048 bf16 ones, 16 per thread; generic-proxy stores made visible to the tensor core (async proxy)
         uint4* o = reinterpret_cast<uint4*>(ones_tile) + 2 * tid;
         o[0] = o[1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -166,7 +171,7 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
     const bool cta0 = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 #endif
 
-    if (warp == 4) {
+    if (warp == kTlProducerWarp) {
         // ================= producer: bulk copies of the operand cores into the stage ring =========================
 #ifdef CB200_TC_PROF
         const bool prof_on = cta0 && lane == 0;
@@ -205,9 +210,9 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
                 const int qq = cj / bc_per, bc = cj % bc_per;
                 if (lane == 0) tma_load_4d(sB, &tmB, 0, n0 >> 3, (int)(((size_t)qq * B + (size_t)bc * kTcBK) >> 3), 0, bar);
                 // A^T: per tap of the tile, 4 k-groups (8 batch rows each) x a run of cw / 8 cores.  A bulk copy costs
-                // ~60 cycles of issue in the issuing warp whatever its size, so the runs are dealt out over five
-                // warps: this one and the four epilogue warps, which are idle until the accumulators are complete.
-                for (int idx = lane; idx < NA * 4 * taps_in_tile; idx += 5 * 32) {
+                // ~60 cycles of issue in the issuing warp whatever its size, so the runs are dealt out over nine
+                // warps: this one and the eight epilogue warps, which are idle until the accumulators are complete.
+                for (int idx = lane; idx < NA * 4 * taps_in_tile; idx += 9 * 32) {
                     const int p = idx / (4 * taps_in_tile), r = idx % (4 * taps_in_tile);
                     const int tt = r >> 2, kg = r & 3;
                     const int apix = __ldg(tp.a_pix + (size_t)(t0 + tt) * tp.num_q + qq);
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
             TC_PROF_ADD(1, t1c, t2c);      // producer: issue the copies
             TC_PROF_ADD(2, t0c - 1, t0c);  // chunk count
         }
-    } else if (warp == 5) {
+    } else if (warp == kTlMmaWarp) {
         // ================= MMA issuer ===============================================================================
 #ifdef CB200_TC_PROF
         const bool prof_on = cta0 && lane == 0;
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
         const bool prof_on = cta0 && tid == 0;
 #endif
         if (kTransA) {
-            // main loop: help the producer with the A^T bulk copies (slots 1..4 of the five-way deal)
+            // main loop: help the producer with the A^T bulk copies (slots 1..8 of the nine-way deal)
             const int taps_in_tile = Ca >= kTcBM ? 1 : min(kTcBM / Ca, tp.taps - m0 / Ca);
             const int t0 = m0 / Ca, cw = min(Ca, kTcBM), c0 = m0 % Ca;
             for (int j = 0; j < nchunks; ++j) {
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
                 uint64_t* bar = full_bar + s;
                 const int cj = c_lo + j;
                 const int qq = cj / bc_per, bc = cj % bc_per;
-                for (int idx = (warp + 1) * 32 + lane; idx < NA * 4 * taps_in_tile; idx += 5 * 32) {
+                for (int idx = (warp + 1) * 32 + lane; idx < NA * 4 * taps_in_tile; idx += 9 * 32) {
                     const int p = idx / (4 * taps_in_tile), r = idx % (4 * taps_in_tile);
                     const int tt = r >> 2, kg = r & 3;
                     const int apix = __ldg(tp.a_pix + (size_t)(t0 + tt) * tp.num_q + qq);
@@ -306,7 +311,11 @@ __global__ void __launch_bounds__(192) gemm_tc_tiled_kernel(const __grid_constan
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         TC_PROF_T(t1e);
-        tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, m_end, N, split, NA == 1, tp.a_u8_div, -1);
+        {
+            const int half = warp >> 2;                        // warps 0-3: low half of the columns, 4-7: high half
+            tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, m_end, N, split, NA == 1, tp.a_u8_div, -1,
+                            half * (BN / 2), half * (BN / 2) + BN / 2);
+        }
         if (bias_cta && warp == 0) {
             // row `m_end` (= taps * Ca) of the result: lane 0 owns TMEM lane 0 of the bias accumulators
 #pragma unroll 1
