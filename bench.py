@@ -353,8 +353,8 @@ def run_device(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)
-# (gemm_tc_tiled: sum over the 15 launches of one step, profiles/ncu_tiled_gemm_r1k_summary.txt -- cold caches under ncu)
-TRAFFIC_NCU = {"per_sample_gather": 30270000, "gemm_tc_tiled": 498600000}
+# (gemm_tc_tiled: sum over the 15 launches of one step, profiles/ncu_tiled_gemm_r1p_summary.txt -- cold caches under ncu)
+TRAFFIC_NCU = {"per_sample_gather": 30270000, "gemm_tc_tiled": 500000000}
 
 
 # =====================================================================================================================
