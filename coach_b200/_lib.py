@@ -75,6 +75,7 @@ PROTOTYPES = {
     "cb200_per_sample_gather": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_double, c_void_p,
                                         c_void_p, c_void_p, ctypes.POINTER(Column), c_int, c_void_p]),
     "cb200_scatter_ring": (c_int, [ctypes.POINTER(Column), c_int, c_i64, c_i64, c_i64, c_void_p]),
+    "cb200_scatter_ring_packed": (c_int, [ctypes.POINTER(Column), c_int, c_i64, c_i64, c_i64, c_i64, c_void_p]),
     "cb200_gemm": (c_int, [ctypes.POINTER(GemmDesc), c_void_p]),
     "cb200_colsum": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p]),
     "cb200_permute_f32": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_void_p]),

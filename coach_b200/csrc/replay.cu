@@ -468,6 +468,35 @@ __global__ void __launch_bounds__(256) scatter_ring_kernel(uint8_t* ring, const 
     }
 }
 
+// all columns of a packed staging area in ONE launch: staged record i holds column c at staged[c] + i * staged_stride
+struct ScatterPacked {
+    uint8_t* ring[CB200_MAX_COLUMNS];
+    const uint8_t* staged[CB200_MAX_COLUMNS];
+    int64_t row_bytes[CB200_MAX_COLUMNS];
+    int piece_start[CB200_MAX_COLUMNS + 1];      // prefix sums of the 4 KB pieces per row
+    int n_cols;
+    int64_t staged_stride;
+};
+__global__ void __launch_bounds__(256) scatter_ring_packed_kernel(ScatterPacked sp, int64_t cursor, int64_t capacity,
+                                                                  int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int total = sp.piece_start[sp.n_cols];
+    for (int64_t w = warp; w < n * total; w += nwarps) {
+        const int64_t i = w / total;
+        const int pp = (int)(w - i * total);
+        int c = 0;
+#pragma unroll
+        for (int q = 1; q < CB200_MAX_COLUMNS; ++q)
+            if (q < sp.n_cols && pp >= sp.piece_start[q]) c = q;
+        const int64_t off = (int64_t)(pp - sp.piece_start[c]) * 4096;
+        const int64_t bytes = (off + 4096 <= sp.row_bytes[c]) ? 4096 : (sp.row_bytes[c] - off);
+        const int64_t slot = (cursor + i) % capacity;
+        warp_copy_row(sp.ring[c] + slot * sp.row_bytes[c] + off, sp.staged[c] + i * sp.staged_stride + off, bytes, lane);
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------
 #define g_tune_ctas_per_sm (cb200::tune_get("gather_ctas_per_sm", 4, 1, 16))
 
@@ -760,6 +789,39 @@ int cb200_scatter_ring(const cb200_column* h_columns, int n_columns, int64_t cur
         CB200_LAUNCH(scatter_ring_kernel, grid, 256, 0, st, static_cast<uint8_t*>(const_cast<void*>(col.src)),
                      static_cast<const uint8_t*>(col.dst), col.row_bytes, cursor, capacity, n, piece, pieces);
     }
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_scatter_ring_packed(const cb200_column* h_columns, int n_columns, int64_t staged_stride, int64_t cursor,
+                              int64_t capacity, int64_t n, void* stream) {
+    CB200_CHECK_ARG(h_columns && n_columns > 0 && n_columns <= CB200_MAX_COLUMNS, "bad column table");
+    CB200_CHECK_ARG(capacity > 0 && cursor >= 0 && cursor < capacity && n >= 0 && n <= capacity && staged_stride > 0,
+                    "bad ring arguments");
+    if (n == 0) return CB200_OK;
+    ScatterPacked sp;
+    sp.n_cols = n_columns;
+    sp.staged_stride = staged_stride;
+    sp.piece_start[0] = 0;
+    for (int c = 0; c < n_columns; ++c) {
+        const cb200_column& col = h_columns[c];
+        CB200_CHECK_ARG(col.src && col.dst && col.row_bytes > 0 && col.row_bytes <= staged_stride, "bad column entry");
+        sp.ring[c] = static_cast<uint8_t*>(const_cast<void*>(col.src));
+        sp.staged[c] = static_cast<const uint8_t*>(col.dst);
+        sp.row_bytes[c] = col.row_bytes;
+        sp.piece_start[c + 1] = sp.piece_start[c] + (int)((col.row_bytes + 4095) / 4096);
+    }
+    for (int c = n_columns; c < CB200_MAX_COLUMNS; ++c) {
+        sp.ring[c] = nullptr;
+        sp.staged[c] = nullptr;
+        sp.row_bytes[c] = 0;
+        sp.piece_start[c + 1] = sp.piece_start[n_columns];
+    }
+    const int64_t warps = n * sp.piece_start[n_columns];
+    unsigned grid = (unsigned)((warps + 7) / 8);
+    const unsigned cap = (unsigned)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    CB200_LAUNCH(scatter_ring_packed_kernel, grid, 256, 0, as_stream(stream), sp, cursor, capacity, n);
     CB200_CHECK_LAUNCH();
     return CB200_OK;
 }

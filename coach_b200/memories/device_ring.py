@@ -83,12 +83,21 @@ class DeviceTransitionRing(object):
         self.columns, self._stage_host, self._stage_dev = OrderedDict(), OrderedDict(), OrderedDict()
         self._stage_np = {}
         pin = self.device.type == "cuda"
+        # staging area: ONE pinned record per staged transition (columns at 16-byte aligned offsets inside it), so a
+        # flush is one H2D copy of the used prefix plus one scatter launch for all columns
+        self._rec_off, off = {}, 0
+        for name, sp in specs.items():
+            self._rec_off[name] = off
+            off = (off + sp.row_bytes + 15) // 16 * 16
+        self._rec_bytes = off
+        self._stage_host_all = torch.zeros((self.stage_rows, self._rec_bytes), dtype=torch.uint8, pin_memory=pin)
+        self._stage_dev_all = torch.empty((self.stage_rows, self._rec_bytes), dtype=torch.uint8, device=self.device)
+        host_np = self._stage_host_all.numpy()
         for name, sp in specs.items():
             self.columns[name] = torch.empty((self.capacity, sp.row_bytes), dtype=torch.uint8, device=self.device)
-            self._stage_host[name] = torch.empty((self.stage_rows, sp.row_bytes), dtype=torch.uint8, pin_memory=pin)
-            self._stage_np[name] = self._stage_host[name].numpy()      # same memory, no per-store tensor objects
-            self._stage_dev[name] = torch.empty((self.stage_rows, sp.row_bytes), dtype=torch.uint8,
-                                                device=self.device)
+            o = self._rec_off[name]
+            self._stage_np[name] = host_np[:, o:o + sp.row_bytes]      # same memory, no per-store tensor objects
+        self._flush_table = None
 
     def hbm_bytes(self):
         return 0 if self.columns is None else sum(c.numel() for c in self.columns.values())
@@ -127,12 +136,18 @@ class DeviceTransitionRing(object):
         if n == 0:
             return self.cursor, 0
         first = self.cursor
-        pairs = []
-        for name in self.specs:
-            self._stage_dev[name][:n].copy_(self._stage_host[name][:n], non_blocking=True)
-            pairs.append((self.columns[name].data_ptr(), self._stage_dev[name].data_ptr(),
-                          self.specs[name].row_bytes))
-        self._scatter(pairs, n)
+        self._stage_dev_all[:n].copy_(self._stage_host_all[:n], non_blocking=True)
+        if self._flush_table is None:
+            base = self._stage_dev_all.data_ptr()
+            pairs = [(self.columns[name].data_ptr(), base + self._rec_off[name], sp.row_bytes)
+                     for name, sp in self.specs.items()]
+            self._flush_table = [_lib.make_columns(pairs[k:k + _lib.CB200_MAX_COLUMNS])
+                                 for k in range(0, len(pairs), _lib.CB200_MAX_COLUMNS)]
+        for arr, cnt in self._flush_table:
+            _lib.check(self.lib.cb200_scatter_ring_packed(arr, cnt, self._rec_bytes, self.cursor, self.capacity, n,
+                                                          _lib.current_stream()))
+        self.cursor = (self.cursor + n) % self.capacity
+        self.count = min(self.count + n, self.capacity)
         self._pending = 0
         if self.device.type == "cuda":
             self._flush_event = torch.cuda.Event()

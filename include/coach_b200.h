@@ -132,6 +132,12 @@ int cb200_per_sample_gather(const double* sum_tree, const double* min_tree, int6
 int cb200_scatter_ring(const cb200_column* h_columns, int n_columns, int64_t cursor, int64_t capacity, int64_t n,
                        void* stream);
 
+/* Same append for a PACKED staging area, all columns in one launch: column c of staged record i is at
+ * h_columns[c].dst + i * staged_stride (the host staging area of DeviceRing.store is one pinned record per transition,
+ * so a flush is one H2D copy and one kernel). */
+int cb200_scatter_ring_packed(const cb200_column* h_columns, int n_columns, int64_t staged_stride, int64_t cursor,
+                              int64_t capacity, int64_t n, void* stream);
+
 
 /* =====================================================================================================================
  * Learn step: dense contractions.  One primitive ("gather-GEMM") covers conv forward (implicit im2col over NHWC),
