@@ -174,6 +174,7 @@ class DQNAgent(object):
         self._pr_host = torch.zeros(B, dtype=torch.float64, pin_memory=pin)
         self._pa_dev = torch.zeros(B, dtype=torch.float64, device=dev)
         self._pr_dev = torch.zeros(B, dtype=torch.float64, device=dev)
+        self._fetch_host = torch.zeros(2, dtype=torch.float32, pin_memory=pin)
         # CUDA graphs of the learn step (own minibatch buffers only): forward + TD targets | loss + backward + clip
         # [+ Adam when there is no all-reduce in between].  Every launch parameter of those kernels is constant from
         # step to step, so two graph launches replace ~45 kernel launches; the first steps run eagerly (they build
@@ -328,8 +329,12 @@ class DQNAgent(object):
             else:
                 self.memory.update_priorities(cols["idx"], self.td_err)
         if fetch:
-            loss = float(self.loss_dev.item())
-            return loss, [loss], float(torch.sqrt(net.sumsq).item())
+            # one synchronisation for both scalars (loss, squared gradient norm) through a pinned pair
+            self._fetch_host[0:1].copy_(self.loss_dev, non_blocking=True)
+            self._fetch_host[1:2].copy_(net.sumsq, non_blocking=True)
+            torch.cuda.current_stream().synchronize() if self.device.type == "cuda" else None
+            loss = float(self._fetch_host[0])
+            return loss, [loss], float(np.sqrt(np.float32(self._fetch_host[1])))
         return self.loss_dev, [self.loss_dev], net.sumsq
 
     def train(self, fetch=True):
