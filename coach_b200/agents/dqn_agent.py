@@ -101,25 +101,26 @@ class QNetworkWrapper(object):
         _lib.check(self.lib.cb200_polyak(self.theta_target.data_ptr(), self.theta.data_ptr(), self.store.size,
                                          float(rate), _lib.current_stream()))
 
-    def apply_gradients(self, scaler=1.0):
+    def apply_gradients(self, scaler=1.0, grad=None):
         """clip is applied by the caller (accumulate_gradients side in the reference); here: optional rescale,
-        then the optimizer (architecture.py:469-521)."""
+        then the optimizer (architecture.py:469-521).  grad: flat gradient buffer to apply (default: store.grad)."""
         st = _lib.current_stream()
         n = self.store.size
+        grad = self.store.grad if grad is None else grad
         if scaler != 1.0:
-            _lib.check(self.lib.cb200_scale(self.store.grad.data_ptr(), n, float(scaler), st))
+            _lib.check(self.lib.cb200_scale(grad.data_ptr(), n, float(scaler), st))
         p = self.params
         if p.optimizer_type != 'Adam':
             raise NotImplementedError("only the Adam optimizer of the DQN presets is implemented on device")
         if self.device_adam_state:
             _lib.check(self.lib.cb200_adam_tf_dev(self.theta.data_ptr(), self.store.m.data_ptr(),
-                                                  self.store.v.data_ptr(), self.store.grad.data_ptr(), n,
+                                                  self.store.v.data_ptr(), grad.data_ptr(), n,
                                                   float(p.learning_rate), float(p.adam_optimizer_beta1),
                                                   float(p.adam_optimizer_beta2), float(p.optimizer_epsilon),
                                                   self.adam_state.data_ptr(), st))
             return
         _lib.check(self.lib.cb200_adam_tf(self.theta.data_ptr(), self.store.m.data_ptr(), self.store.v.data_ptr(),
-                                          self.store.grad.data_ptr(), n, float(p.learning_rate),
+                                          grad.data_ptr(), n, float(p.learning_rate),
                                           float(p.adam_optimizer_beta1), float(p.adam_optimizer_beta2),
                                           float(p.optimizer_epsilon), float(self.beta1_power),
                                           float(self.beta2_power), st))
@@ -182,6 +183,7 @@ class DQNAgent(object):
         self.use_graph = bool(_lib.tune_default("dqn_graph", 1)) and dev.type == "cuda" and B >= 128
         self.networks["main"].device_adam_state = self.use_graph
         self._graphs = None
+        self._grad_sync = None                    # exchange buffer of the overlapped gradient all-reduce
         self._eager_steps = 0
         self.graph_kernel_launches = 0            # kernels executed through graph replays (bench.py gpu_launches)
         # counters of agents/agent.py:112-135
@@ -245,16 +247,25 @@ class DQNAgent(object):
         if per_libm:
             self._td_host.copy_(self.td_err, non_blocking=True)
 
-    def _part_backward(self, weights, with_optimizer):
-        """head loss, backward pass, global norm / clipping [, optimizer]"""
+    def _part_backward(self, weights, with_optimizer, part="all"):
+        """head loss, backward pass, global norm / clipping [, optimizer].  part: "all", or "top" (loss + dense
+        layers) / "bottom" (conv layers + norm) when the all-reduce of the dense gradients overlaps the rest"""
         lib, st = self.lib, _lib.current_stream()
         net = self.networks["main"]
-        huber = 1 if net.params.replace_mse_with_huber_loss else 0
-        _lib.check(lib.cb200_regression_head_loss_grad(net.online_s.q.data_ptr(), self.targets.data_ptr(),
-                                                       weights.data_ptr() if weights is not None else None,
-                                                       self.batch_size, self.num_actions, huber, 1.0,
-                                                       net.online_s.dq.data_ptr(), self.loss_dev.data_ptr(), st))
-        net.online_s.backward()
+        if part != "bottom":
+            huber = 1 if net.params.replace_mse_with_huber_loss else 0
+            _lib.check(lib.cb200_regression_head_loss_grad(net.online_s.q.data_ptr(), self.targets.data_ptr(),
+                                                           weights.data_ptr() if weights is not None else None,
+                                                           self.batch_size, self.num_actions, huber, 1.0,
+                                                           net.online_s.dq.data_ptr(), self.loss_dev.data_ptr(),
+                                                           st))
+        if part == "top":
+            net.online_s.backward_top()
+            return
+        if part == "bottom":
+            net.online_s.backward_bottom()
+        else:
+            net.online_s.backward()
         n = net.store.size
         _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(), st))
         clip = net.params.clip_gradients
@@ -266,17 +277,42 @@ class DQNAgent(object):
         if with_optimizer:
             net.apply_gradients(1.0)
 
-    def _capture(self, cols, weights, per_libm, single):
+    def _capture(self, cols, weights, per_libm, single, overlap):
         c0 = self.lib.cb200_launch_count()
-        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        ga, gb, gb2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), None
         torch.cuda.synchronize()
         with torch.cuda.graph(ga):
             self._part_forward(cols, per_libm)
         c1 = self.lib.cb200_launch_count()
-        with torch.cuda.graph(gb):
-            self._part_backward(weights, single)
+        if overlap:
+            gb2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb):
+                self._part_backward(weights, False, "top")
+            with torch.cuda.graph(gb2):
+                self._part_backward(weights, False, "bottom")
+        else:
+            with torch.cuda.graph(gb):
+                self._part_backward(weights, single)
         c2 = self.lib.cb200_launch_count()
-        self._graphs = (ga, gb, int(c1 - c0), int(c2 - c1))
+        self._graphs = (ga, gb, gb2, int(c1 - c0), int(c2 - c1))
+
+    def _overlapped_allreduce_begin(self):
+        """dense-layer gradients (the tail of the flat buffer, ~95 % of it) are final: copy them to the exchange
+        buffer and start their all-reduce; it runs on NCCL's stream under the conv backward pass"""
+        net = self.networks["main"]
+        off = net.online_s.grad_split_offset()
+        self._grad_sync[off:].copy_(net.store.grad[off:])
+        return off, torch.distributed.all_reduce(self._grad_sync[off:], async_op=True)
+
+    def _overlapped_allreduce_end(self, off, work):
+        net = self.networks["main"]
+        self._grad_sync[:off].copy_(net.store.grad[:off])
+        work2 = torch.distributed.all_reduce(self._grad_sync[:off], async_op=True)
+        work.wait()
+        work2.wait()
+        ws = torch.distributed.get_world_size()
+        scaler = 1.0 / ws if net.params.scale_down_gradients_by_number_of_workers_for_sync_training else 1.0
+        net.apply_gradients(scaler, grad=self._grad_sync)
 
     def learn_from_batch(self, batch, fetch=True):
         net = self.networks["main"]
@@ -294,26 +330,46 @@ class DQNAgent(object):
             own = own and weights.data_ptr() == self.batch_buffers["weight32"].data_ptr()
         per_libm = per and self.memory.priority_mode == "libm"
         single = not parallel.is_distributed()                    # no all-reduce between backward and optimizer
+        # several ranks, no global-norm clipping (which needs the complete local gradient first), plain Q head: the
+        # all-reduce of the dense layers' gradients can run under the conv backward pass (CB200_DQN_OVERLAP_ALLREDUCE=1).
+        # Bit-identical (tools/check_allreduce_overlap.py) but measured 1 % SLOWER at 2 and 4 GPUs (profiles/README.md):
+        # the 6.75 MB all-reduce over NVSwitch is shorter than the two extra copies and launches, so it is opt-in.
+        clip = net.params.clip_gradients
+        overlap = (not single) and not (clip is not None and clip != 0) and not self.net_def.dueling and \
+            bool(_lib.tune_default("dqn_overlap_allreduce", 0))
+        if overlap and self._grad_sync is None:
+            self._grad_sync = torch.zeros_like(net.store.grad)
         graph = self.use_graph and own and self._eager_steps >= 2
         if graph and self._graphs is None:
-            self._capture(cols, weights, per_libm, single)
+            self._capture(cols, weights, per_libm, single, overlap)
         ev = None
+        pending = None
         if graph:
-            ga, gb, na, nb = self._graphs
+            ga, gb, gb2, na, nb = self._graphs
             ga.replay()
             if per_libm:
                 ev = torch.cuda.Event()
                 ev.record()
             gb.replay()
+            if gb2 is not None:
+                pending = self._overlapped_allreduce_begin()
+                gb2.replay()
             self.graph_kernel_launches += na + nb
         else:
             self._part_forward(cols, per_libm)
             if per_libm:
                 ev = torch.cuda.Event()
                 ev.record()
-            self._part_backward(weights, False)
+            if overlap:
+                self._part_backward(weights, False, "top")
+                pending = self._overlapped_allreduce_begin()
+                self._part_backward(weights, False, "bottom")
+            else:
+                self._part_backward(weights, False)
             self._eager_steps += 1
-        if not (graph and single):
+        if pending is not None:
+            self._overlapped_allreduce_end(*pending)
+        elif not (graph and single):
             scaler = parallel.allreduce_gradients(
                 net.store.grad, net.params.scale_down_gradients_by_number_of_workers_for_sync_training)
             net.apply_gradients(scaler)

@@ -175,10 +175,12 @@ class SequentialInstance(object):
             layer.forward()
         return self.out
 
-    def backward(self, weights=True):
-        """weights=False: data gradients only (d(out)/d(input), e.g. dQ/da through the critic)"""
-        for layer in reversed(self.layers):
-            layer.backward(weights)
+    def backward(self, weights=True, layers=None):
+        """weights=False: data gradients only (d(out)/d(input), e.g. dQ/da through the critic).  layers=(lo, hi): only
+        layers lo <= i < hi, last first (lets a caller start the all-reduce of the top layers' gradients early)."""
+        lo, hi = (0, len(self.layers)) if layers is None else layers
+        for i in reversed(range(lo, hi)):
+            self.layers[i].backward(weights)
 
 
 def make_u8_lut(device, rescale=255.0, offset=0.0):

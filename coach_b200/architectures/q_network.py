@@ -96,6 +96,20 @@ class QNetworkInstance(object):
                                                           _lib.current_stream()))
         return self.q
 
+    def backward_top(self):
+        """plain Q head only: the dense layers (middleware + head) of the trunk, which hold ~95 % of the parameters;
+        their gradients are complete -- and can be all-reduced -- while ``backward_bottom`` still runs"""
+        assert not self.net.dueling
+        n = len(self.trunk.layers)
+        self.trunk.backward(layers=(self.net.n_embedder, n))
+
+    def backward_bottom(self):
+        self.trunk.backward(layers=(0, self.net.n_embedder))
+
+    def grad_split_offset(self):
+        """element offset in the flat gradient buffer where the top (dense) layers' gradients start"""
+        return self.net.store.entries[self.net.trunk.names[self.net.n_embedder][0]][0]
+
     def backward(self):
         """expects d(loss)/dq in self.dq; leaves all parameter gradients in the grad buffer"""
         if self.net.dueling:
