@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcoach_b200.so")
+# CB200_LIB_PATH: load another build of the same library (the -DCB200_TC_PROF instrumented one of tools/tc_phase_probe.py)
+LIB_PATH = os.environ.get("CB200_LIB_PATH") or os.path.join(_HERE, "lib", "libcoach_b200.so")
 
 c_void_p = ctypes.c_void_p
 c_i64 = ctypes.c_int64
