@@ -160,6 +160,15 @@ class SequentialInstance(object):
                 if isinstance(op, tl.TGemmOp):
                     op.tag = "%s_%d.%s" % (type(layer).__name__, i, attr)
             prev, prev_act = self.acts[i], layer.act
+        # Forward-only instances (target networks): a hidden activation whose consumer reads its planes needs no fp32
+        # copy -- the epilogue is bound by write bandwidth, and the fp32 result is 40 % of what it writes.
+        if not train:
+            for i in range(len(self.layers) - 1):
+                op, nxt = getattr(self.layers[i], "fwd", None), self.layers[i + 1]
+                if isinstance(op, tl.TGemmOp) and isinstance(getattr(nxt, "fwd", None), tl.TGemmOp) and \
+                        op.desc.c_planes and nxt.fwd.desc.a_num_planes == 3:
+                    op.desc.c = None
+                    self.acts[i] = None          # not produced: fail loudly if anything asks for it
         self.out = self.acts[-1]
         self.d_out = self.dzs[-1]
         self.train = train

@@ -418,7 +418,7 @@ int cb200_tc_prof_read(unsigned long long* out16, int reset) {
 int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
     CB200_CHECK_ARG(d != nullptr, "null descriptor");
     CB200_CHECK_ARG(d->mode == 0 || d->mode == 1, "mode must be 0 or 1");
-    CB200_CHECK_ARG(d->a_planes && d->b_planes && d->c, "null operand pointer");
+    CB200_CHECK_ARG(d->a_planes && d->b_planes && (d->c || (d->c_planes && !d->mask_y)), "null operand pointer");
     CB200_CHECK_ARG(d->batch > 0 && d->batch % 32 == 0, "batch must be a multiple of 32");
     CB200_CHECK_ARG(d->a_cols > 0 && d->a_cols % 32 == 0 && (d->a_cols <= 128 ? 128 % d->a_cols == 0 : d->a_cols % 128 == 0),
                     "a_cols must be 32, 64, 128 or a multiple of 128");

@@ -213,9 +213,11 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int m, int n
     if (ep.bias) v += __ldg(ep.bias + n);
     v = apply_act(v, ep.act);
     if (ep.mask_y) v *= act_grad_from_output(ep.mask_y[row * ep.ldc + n], ep.mask_act);
-    float* dst = ep.c + row * ep.ldc + n;
-    if (ep.accumulate) v += *dst;
-    *dst = v;
+    if (ep.c) {             // c may be omitted when only the planes of the result are consumed (forward-only networks)
+        float* dst = ep.c + row * ep.ldc + n;
+        if (ep.accumulate) v += *dst;
+        *dst = v;
+    }
     if (ep.c_planes) {
         uint16_t* p = ep.c_planes + tiled_elem(plane_row((size_t)m, ep.c_prow_npix, ep.c_prow_batch), n, ep.c_plane_cols);
         split3(v, p[0], p[ep.c_plane_stride], p[2 * ep.c_plane_stride]);

@@ -235,6 +235,7 @@ typedef struct cb200_tgemm_desc {
     int32_t num_q;
     int32_t taps;
     /* output / epilogue: as in cb200_gemm_desc; rows of C are q * B + b (mode 0) or t * a_cols + c (mode 1)          */
+    /* c may be NULL when c_planes is set: only the planes of the result are produced (forward-only networks)         */
     float* c;
     int32_t ldc;
     const float* bias;
