@@ -5,8 +5,14 @@ the embedders' input rescale (``embedders/embedder.py:103-104``).  Data layout i
 conv kernels HWIO (= a row-major [KH*KW*Cin, N] matrix), dense kernels [in, out]; VALID padding
 (``tf.layers.conv2d`` default).
 
-Every contraction is ONE C-ABI call whose descriptor -- index tables included -- is built once per (layer, batch size)
-and reused every step: forward, weight gradient (A^T * dZ with a fixed-order split reduction over the batch*pixels
+Two execution forms, chosen per layer when it is prepared.  With operand planes (``planes=tiled.PlaneCtx``, batch a
+multiple of 32, channel counts the tensor-core kernel supports) forward, weight gradient and data gradient are
+multi-tap tcgen05 GEMMs on pre-split bf16 operands (``architectures/tiled.py``, cb200_gemm_tiled); the uint8 first
+convolution runs on the space-to-depth view of the frames (``_prepare_s2d``).  Otherwise -- small batches, odd shapes,
+the skinny Q head -- the gather-GEMM below.
+
+Gather-GEMM: every contraction is ONE C-ABI call whose descriptor -- index tables included -- is built once per (layer,
+batch size) and reused every step: forward, weight gradient (A^T * dZ with a fixed-order split reduction over the batch*pixels
 axis; the bias gradient rides along as one extra output row when the bias gradient sits right behind the kernel
 gradient in the flat buffer), data gradient (dense: dZ * W^T; conv: transposed convolution in gather form, one call
 per stride-parity class, with the previous layer's activation derivative fused into the epilogue).

@@ -13,8 +13,10 @@
 // [R, N]; the epilogue adds bias, applies the activation or an activation-derivative mask, remaps output rows
 // (c_rowmap) or writes split-R partial sums that a second deterministic kernel reduces in fixed order.
 //
-// fp32 FFMA on the CUDA cores: the reference trains in fp32 and the parity bar is 1e-5 relative, which TF32 / BF16
-// tensor-core operands do not meet without 3-way operand splitting ("learn step").
+// This file: the fp32 FFMA (CUDA-core) kernels, the shared epilogue and the plane format.  The reference trains in
+// fp32 and the parity bar is 1e-5 relative, which TF32 / BF16 tensor-core operands only meet with 3-way operand
+// splitting: that path is nn_gemm_tc.cuh (operands staged by the threads) and nn_gemm_tiled*.cuh (pre-split planes
+// fed by TMA); the kernels here serve the shapes without a tensor-core form and the small batches.
 //
 // Tile: BM x BN outputs per CTA, reduction chunk BK, TM x TN outputs per thread.  Shared tiles are reduction-major
 // (As[BK][BM], Bs[BK][BN]) and double buffered: operands of chunk c+1 are fetched into registers before the FMAs of
