@@ -43,7 +43,8 @@ class TGemmDesc(ctypes.Structure):
                 ("num_q", ctypes.c_int32), ("taps", ctypes.c_int32), ("c", c_void_p), ("ldc", ctypes.c_int32),
                 ("bias", c_void_p), ("act", ctypes.c_int32), ("mask_y", c_void_p), ("mask_act", ctypes.c_int32),
                 ("c_rowmap", c_void_p), ("workspace", c_void_p), ("splits", ctypes.c_int32), ("c_planes", c_void_p),
-                ("c_plane_stride", c_i64), ("c_plane_cols", ctypes.c_int32), ("bias_row", ctypes.c_int32),
+                ("c_plane_stride", c_i64), ("c_plane_cols", ctypes.c_int32), ("mask_planes", c_void_p),
+                ("mask_plane_stride", c_i64), ("bias_row", ctypes.c_int32),
                 ("a_num_planes", ctypes.c_int32),
                 ("a_u8_div", c_float), ("a_rows", c_i64), ("b_rows", c_i64),
                 ("tmap_key", ctypes.c_uint64), ("tmap_storage", ctypes.c_uint8 * (2 * 128 + 64))]

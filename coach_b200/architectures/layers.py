@@ -227,7 +227,7 @@ class Dense(object):
                 rowmap = _dev_i32((bb * npix + qq).reshape(-1), device)
             self.bwd_x = tl.masked_forward_op(lib, ws, B, device, pl.dy, N, self.wT_planes, Ca,
                                               [[(0, q)] for q in range(npix)], npix, dx, Ca,
-                                              x if prev_act else None, prev_act, rowmap, pl.dx)
+                                              x if prev_act else None, prev_act, rowmap, pl.dx, mask_planes=pl.x)
 
     def forward(self):
         self.fwd.run()
@@ -432,7 +432,7 @@ class Conv2d(object):
         qq, bb = np.meshgrid(np.arange(npix), np.arange(B), indexing="ij")
         rowmap_in = _dev_i32((bb * npix + qq).reshape(-1), device)
         self.bwd_x = tl.masked_forward_op(lib, ws, B, device, pl.dy, N, self.wT_planes, C, lists, npix, dx, C,
-                                          x if prev_act else None, prev_act, rowmap_in, pl.dx)
+                                          x if prev_act else None, prev_act, rowmap_in, pl.dx, mask_planes=pl.x)
 
     def forward(self):
         if self.s2d is not None:

@@ -162,13 +162,32 @@ class SequentialInstance(object):
             prev, prev_act = self.acts[i], layer.act
         # Forward-only instances (target networks): a hidden activation whose consumer reads its planes needs no fp32
         # copy -- the epilogue is bound by write bandwidth, and the fp32 result is 40 % of what it writes.
-        if not train:
+        def tiled(op):
+            return isinstance(op, tl.TGemmOp)
+
+        for i in range(len(self.layers) - 1):
+            op, nxt = getattr(self.layers[i], "fwd", None), self.layers[i + 1]
+            if not (tiled(op) and op.desc.c_planes and tiled(getattr(nxt, "fwd", None)) and
+                    nxt.fwd.desc.a_num_planes == 3):
+                continue
+            # the next layer reads this activation as planes in its forward; in training it must also do so in its
+            # weight gradient and take the derivative mask of its data gradient from the planes
+            bw, bx = getattr(nxt, "bwd_w", None), getattr(nxt, "bwd_x", None)
+            if train and not (tiled(bw) and (bx is None or (tiled(bx) and not bx.desc.mask_y))):
+                continue
+            op.desc.c = None
+            self.acts[i] = None                  # not produced: fail loudly if anything asks for it
+        if train:
+            # pre-activation gradients: dz[i] is written by layer i+1's data-gradient GEMM and read by layer i's
+            # weight / data gradients; when both read planes (and the bias gradient rides in the GEMM), no fp32 copy
             for i in range(len(self.layers) - 1):
-                op, nxt = getattr(self.layers[i], "fwd", None), self.layers[i + 1]
-                if isinstance(op, tl.TGemmOp) and isinstance(getattr(nxt, "fwd", None), tl.TGemmOp) and \
-                        op.desc.c_planes and nxt.fwd.desc.a_num_planes == 3:
-                    op.desc.c = None
-                    self.acts[i] = None          # not produced: fail loudly if anything asks for it
+                cur, nxt = self.layers[i], self.layers[i + 1]
+                prod = getattr(nxt, "bwd_x", None)
+                bw, bx = getattr(cur, "bwd_w", None), getattr(cur, "bwd_x", None)
+                if tiled(prod) and prod.desc.c_planes and tiled(bw) and bw.desc.bias_row and \
+                        getattr(cur, "db_args", None) is None and (bx is None or tiled(bx)):
+                    prod.desc.c = None
+                    self.dzs[i] = None
         self.out = self.acts[-1]
         self.d_out = self.dzs[-1]
         self.train = train

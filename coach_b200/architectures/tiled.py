@@ -201,12 +201,20 @@ def forward_op(lib, ws, B, device, x, Ca, w_ptr, w_stride, N, lists, num_q, c, l
                    c_plane_cols=N if y_planes is not None else 0, a_num_planes=x.nplanes, **extra)
 
 
-def masked_forward_op(lib, ws, B, device, x, Ca, w_buf, N, lists, num_q, c, ldc, mask_y, mask_act, rowmap, y_planes):
-    """data-gradient flavour: no bias / activation, previous layer's activation derivative in the epilogue"""
+def masked_forward_op(lib, ws, B, device, x, Ca, w_buf, N, lists, num_q, c, ldc, mask_y, mask_act, rowmap, y_planes,
+                      mask_planes=None):
+    """data-gradient flavour: no bias / activation, previous layer's activation derivative in the epilogue -- read
+    from the activation's planes when they exist (``mask_planes``, same geometry as the result), else from fp32"""
     op = forward_op(lib, ws, B, device, x, Ca, w_buf.ptr, w_buf.stride, N, lists, num_q, c, ldc, None, 0, rowmap,
                     y_planes, w_rows=w_buf.rows)
     op.keep.append(w_buf)
-    if mask_y is not None and mask_act:
+    if mask_act and mask_planes is not None and mask_planes.nplanes == 3 and mask_planes.cols == N:
+        op.keep.append(mask_planes)
+        op.desc.mask_planes = mask_planes.ptr
+        op.desc.mask_plane_stride = mask_planes.stride
+        op.desc.mask_act = mask_act
+        op.desc.c_plane_cols = N
+    elif mask_y is not None and mask_act:
         op.keep.append(mask_y)
         op.desc.mask_y = mask_y.data_ptr()
         op.desc.mask_act = mask_act

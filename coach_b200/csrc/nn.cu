@@ -13,7 +13,7 @@ static EpiParams make_epi(const cb200_gemm_desc& d, int splits) {
     return EpiParams{d.c,        d.ldc,       d.bias, d.act,        d.mask_y,
                      d.mask_act, d.c_rowmap,  d.workspace, splits,  d.accumulate,
                      static_cast<uint16_t*>(d.c_planes), d.c_plane_stride, d.c_plane_cols, d.c_prow_npix,
-                     d.c_prow_batch};
+                     d.c_prow_batch, nullptr, 0};
 }
 
 template <class C, bool kT>
@@ -419,6 +419,9 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
     CB200_CHECK_ARG(d != nullptr, "null descriptor");
     CB200_CHECK_ARG(d->mode == 0 || d->mode == 1, "mode must be 0 or 1");
     CB200_CHECK_ARG(d->a_planes && d->b_planes && (d->c || (d->c_planes && !d->mask_y)), "null operand pointer");
+    CB200_CHECK_ARG(!d->mask_planes || (d->c_plane_cols == d->n && d->mask_plane_stride % 8 == 0 &&
+                                        (reinterpret_cast<uintptr_t>(d->mask_planes) & 15) == 0),
+                    "mask_planes need c_plane_cols == n and 16-byte alignment");
     CB200_CHECK_ARG(d->batch > 0 && d->batch % 32 == 0, "batch must be a multiple of 32");
     CB200_CHECK_ARG(d->a_cols > 0 && d->a_cols % 32 == 0 && (d->a_cols <= 128 ? 128 % d->a_cols == 0 : d->a_cols % 128 == 0),
                     "a_cols must be 32, 64, 128 or a multiple of 128");
@@ -486,7 +489,8 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
     tp.bias_row = d->mode == 1 ? d->bias_row : 0;
     const gemm::EpiParams ep{d->c,        d->ldc,      d->bias,      d->act,  d->mask_y,
                              d->mask_act, d->c_rowmap, d->workspace, splits,  0,
-                             static_cast<uint16_t*>(d->c_planes), d->c_plane_stride, d->c_plane_cols, 0, 0};
+                             static_cast<uint16_t*>(d->c_planes), d->c_plane_stride, d->c_plane_cols, 0, 0,
+                             static_cast<const uint16_t*>(d->mask_planes), d->mask_plane_stride};
     cudaStream_t st = as_stream(stream);
     int rc;
 #define CB200_TL(BN_) \

@@ -181,7 +181,17 @@ struct EpiParams {
     int c_plane_cols;          // columns of the tiled plane matrix (= n of this GEMM)
     int c_prow_npix;           // > 0: output row m = b * npix + q  (NHWC order) lands in plane row q * batch + b
     int c_prow_batch;          //      (pixel-major, batch-inner order of the planes); 0: plane row = m
+    const uint16_t* mask_planes;   // optional: the activation whose derivative masks the result, given as tiled planes of
+    int64_t mask_plane_stride;     // the SAME geometry as the result (replaces mask_y: no fp32 copy of it is needed)
 };
+
+// activation output y rebuilt from its planes for the derivative mask: relu only asks y > 0, which the hi plane answers
+// (hi == 0 with y > 0 would need y < 2^-133); tanh needs the value
+__device__ __forceinline__ float mask_from_planes(const uint16_t* p, int64_t stride, int act) {
+    const float hi = __uint_as_float((uint32_t)p[0] << 16);
+    if (act == CB200_ACT_RELU) return hi;
+    return (hi + __uint_as_float((uint32_t)p[stride] << 16)) + __uint_as_float((uint32_t)p[2 * stride] << 16);
+}
 
 // Plane format.  A logical [rows, cols] matrix (both multiples of 8) is stored as 8x8 "core matrices" of 128 contiguous
 // bytes, core (r / 8, c / 8) at ((r / 8) * (cols / 8) + c / 8) * 64 elements, element (r % 8, c % 8) inside it
@@ -214,7 +224,13 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int m, int n
     const size_t row = ep.c_rowmap ? (size_t)__ldg(ep.c_rowmap + m) : (size_t)m;
     if (ep.bias) v += __ldg(ep.bias + n);
     v = apply_act(v, ep.act);
-    if (ep.mask_y) v *= act_grad_from_output(ep.mask_y[row * ep.ldc + n], ep.mask_act);
+    if (ep.mask_planes)
+        v *= act_grad_from_output(
+            mask_from_planes(ep.mask_planes + tiled_elem(plane_row((size_t)m, ep.c_prow_npix, ep.c_prow_batch), n,
+                                                         ep.c_plane_cols),
+                             ep.mask_plane_stride, ep.mask_act),
+            ep.mask_act);
+    else if (ep.mask_y) v *= act_grad_from_output(ep.mask_y[row * ep.ldc + n], ep.mask_act);
     if (ep.c) {             // c may be omitted when only the planes of the result are consumed (forward-only networks)
         float* dst = ep.c + row * ep.ldc + n;
         if (ep.accumulate) v += *dst;

@@ -158,9 +158,10 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_m
     size_t c_row = 0, p_row = 0;
     if (live && ep.splits <= 1) {
         c_row = (ep.c_rowmap ? (size_t)__ldg(ep.c_rowmap + m) : (size_t)m) * ep.ldc;
-        if (ep.c_planes) p_row = plane_row((size_t)m, ep.c_prow_npix, ep.c_prow_batch);
+        if (ep.c_planes || ep.mask_planes) p_row = plane_row((size_t)m, ep.c_prow_npix, ep.c_prow_batch);
     }
-    const size_t p_base = ep.c_planes ? (p_row >> 3) * (size_t)(ep.c_plane_cols >> 3) * 64 + (p_row & 7) * 8 : 0;
+    const size_t p_base =
+        (ep.c_planes || ep.mask_planes) ? (p_row >> 3) * (size_t)(ep.c_plane_cols >> 3) * 64 + (p_row & 7) * 8 : 0;
 #pragma unroll 1
     for (int col = col_lo; col < col_hi; col += 16) {
         uint32_t vm[16], vc[16];
@@ -200,7 +201,22 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_m
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) w[j] = apply_act(w[j], ep.act);
-                    if (ep.mask_y) {
+                    if (ep.mask_planes) {
+                        // mask from the planes of the activation (same tiled geometry as the result)
+                        const uint16_t* mp = ep.mask_planes + p_base + (size_t)(nb >> 3) * 64;
+                        const uint4 h = *reinterpret_cast<const uint4*>(mp);
+                        float yy[8] = {__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u),
+                                       __uint_as_float(h.y << 16), __uint_as_float(h.y & 0xffff0000u),
+                                       __uint_as_float(h.z << 16), __uint_as_float(h.z & 0xffff0000u),
+                                       __uint_as_float(h.w << 16), __uint_as_float(h.w & 0xffff0000u)};
+                        if (ep.mask_act != CB200_ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                yy[j] = mask_from_planes(mp + j, ep.mask_plane_stride, ep.mask_act);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w[j] *= act_grad_from_output(yy[j], ep.mask_act);
+                    } else if (ep.mask_y) {
                         const float4 y0 = *reinterpret_cast<const float4*>(ep.mask_y + elem);
                         const float4 y1 = *reinterpret_cast<const float4*>(ep.mask_y + elem + 4);
                         const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};

@@ -248,6 +248,8 @@ typedef struct cb200_tgemm_desc {
     void* c_planes;             /* tiled planes of C with plane row = C row, c_plane_cols == n                       */
     int64_t c_plane_stride;
     int32_t c_plane_cols;
+    const void* mask_planes;    /* optional, instead of mask_y: the masking activation as tiled planes with the geometry */
+    int64_t mask_plane_stride;  /*    of the result (rows q * B + b, n columns); c_plane_cols must be set to n            */
     int32_t bias_row;           /* mode 1: 1 = also produce row taps * a_cols = sum over all rows of G (the bias gradient, */
                                 /*    stored right behind the kernel gradient); c / workspace / c_rowmap have one more row  */
     int32_t a_num_planes;       /* 3 (0 = 3): fp32 split;  1: A holds raw uint8 values as ONE exact bf16 plane, every    */
