@@ -207,7 +207,8 @@ __device__ __forceinline__ size_t plane_row(size_t m, int npix, int batch) {
     return npix > 0 ? (m % (size_t)npix) * (size_t)batch + m / (size_t)npix : m;
 }
 
-// Exact 3-way bf16 split of an fp32 value (truncation): x == hi + mid + lo, each the upper half-word of an fp32.
+// Exact 3-way bf16 split of an fp32 value (truncation): x == hi + mid + lo, each the upper half-word of an fp32
+// (exact for |x| >= 2^-110 and for 0; tinier values lose less than 2^-133, tests/test_tiled_host.py).
 // The tensor-core GEMM (nn_gemm_tc.cuh) consumes operands in this form; producers that know their output feeds another
 // GEMM write the planes next to the fp32 result so that consumers need no conversion work.
 __device__ __forceinline__ void split3(float x, uint16_t& h, uint16_t& m, uint16_t& l) {

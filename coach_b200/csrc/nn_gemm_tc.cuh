@@ -91,7 +91,8 @@ struct Split8 {
 };
 __device__ __forceinline__ Split8 split8(const float4& lo4, const float4& hi4) {
     // Truncation split: hi = top 8 significant bits of x, mid = top 8 of the (exact) remainder, lo = the rest (<= 8
-    // bits, exact).  x == hi + mid + lo exactly for every finite fp32, and each piece is a bf16 (upper half-word).
+    // bits, exact).  x == hi + mid + lo exactly for |x| >= 2^-110 (below that `lo` is an fp32 denormal whose low
+    // half-word is cut: absolute error < 2^-133), and each piece is a bf16 (upper half-word).
     const float x[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
     uint32_t hb[8], mb[8], lb[8];
 #pragma unroll

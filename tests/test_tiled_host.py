@@ -166,3 +166,26 @@ def test_dense_on_flattened_conv_map():
     wT = w.reshape(-1)[layer.perm.numpy()].reshape(npix, N, C)
     # result rows (pixel, b) are mapped to the NHWC rows b * npix + pixel of the [B, npix * C] gradient
     np.testing.assert_allclose(_mode0(layer.bwd_x, dy, wT, B).reshape(B, K), dy @ w.T, rtol=1e-9, atol=1e-9)
+
+
+def test_truncation_split_is_exact():
+    """numpy restatement of csrc/nn_gemm.cuh split3 / nn_gemm_tc.cuh split8: hi = upper half-word of x, mid = upper
+    half-word of the (exact) remainder, lo = upper half-word of the rest.  x == hi + mid + lo exactly whenever
+    |x| >= 2^-110 (or x == 0); for smaller magnitudes `lo` is an fp32 denormal whose low half-word is cut, an absolute
+    error below 2^-133"""
+    rng = np.random.RandomState(0)
+    bits = rng.randint(0, 2 ** 32, size=1 << 20, dtype=np.uint64).astype(np.uint32)
+    special = np.array([0x00000000, 0x80000000, 0x00000001, 0x007fffff, 0x00800000, 0x7f7fffff, 0xff7fffff, 0x3f800000,
+                        0x3f7fffff, 0x33800000], dtype=np.uint32)                  # zeros, denormals, extremes
+    x = np.concatenate([bits, special]).view(np.float32)
+    x = x[np.isfinite(x)]
+    hi = (x.view(np.uint32) & np.uint32(0xffff0000)).view(np.float32)
+    r1 = x - hi                                                                     # exact: at most 16 significant bits
+    mid = (r1.view(np.uint32) & np.uint32(0xffff0000)).view(np.float32)
+    lo = ((r1 - mid).view(np.uint32) & np.uint32(0xffff0000)).view(np.float32)      # what the kernels store
+    rebuilt = (hi.astype(np.float64) + mid.astype(np.float64)) + lo.astype(np.float64)
+    normal = (np.abs(x) >= 2.0 ** -110) | (x == 0)
+    assert normal.sum() > 900000
+    assert np.array_equal(rebuilt[normal], x[normal].astype(np.float64))
+    assert np.array_equal(((hi + mid) + lo)[normal], x[normal])                     # also in fp32 arithmetic
+    assert np.all(np.abs(rebuilt[~normal] - x[~normal].astype(np.float64)) < 2.0 ** -133)
