@@ -171,6 +171,8 @@ def run_device(args):
     device = torch.device("cuda", local)
     lib = _lib.load()
     lib.cb200_tune(b"gemm_tc", 0 if args.no_tc else 1)
+    if args.no_tc:
+        os.environ["CB200_GEMM_TILED"] = "0"      # no pre-split planes / tiled tcgen05 GEMMs either
     random.seed(1000 + rank)
     np.random.seed(1000 + rank)
     agent = build_device_agent(args.capacity, 100 + rank, device)

@@ -67,7 +67,9 @@ class QNetworkInstance(object):
         # Large batches run the trunk on pre-split bf16 operands (architectures/tiled.py).  The parameter planes are
         # re-derived from theta at the start of every forward (one launch), so any writer of theta -- Adam, a target
         # network copy, polyak, a checkpoint load -- is covered.
-        self.theta_planes = tl.ThetaPlanes(lib, net.store, theta) if (B >= 128 and B % 32 == 0) else None
+        # (CB200_GEMM_TILED=0 keeps every layer on the gather-GEMM of cb200_gemm: A/B runs, bench.py --no-tc)
+        self.theta_planes = tl.ThetaPlanes(lib, net.store, theta) \
+            if (B >= 128 and B % 32 == 0 and _lib.tune_default("gemm_tiled", 1)) else None
         self.trunk = net.trunk.instantiate(lib, ws, B, x, theta, grad, x_is_u8=x_is_u8, lut=net.lut, train=train,
                                            theta_planes=self.theta_planes)
         if not net.dueling:
