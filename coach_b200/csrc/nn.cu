@@ -180,16 +180,31 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 // tensor-core kernel.  One thread per (b, Y, X, y % S): S * C consecutive bytes -> S * C bf16.
 __global__ void __launch_bounds__(256) u8_s2d_planes_kernel(const uint8_t* __restrict__ x, int B, int H, int W, int C,
                                                             int S, uint16_t* __restrict__ plane) {
+    // Thread = (8-batch block, Y, pair of X, y % S, b % 8) with b % 8 fastest: the 8 lanes of a quarter-warp write the
+    // 8 rows of one core matrix (128 contiguous bytes), and every thread reads the S * C bytes of two neighbouring
+    // pixels' rows (a full 32-byte sector for the Atari 4 x 4 x 4 block).
     const int Hs = H / S, Ws = W / S, Cs = S * S * C, run = S * C;       // run: bytes per (pixel, y % S), multiple of 8
-    const int64_t total = (int64_t)B * Hs * Ws * S;
+    const int Wp = (Ws + 1) / 2;
+    const int64_t total = (int64_t)(B / 8) * Hs * Wp * S * 8;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int dy = (int)(t % S);
-        const int X = (int)((t / S) % Ws), Y = (int)((t / S / Ws) % Hs), b = (int)(t / S / Ws / Hs);
-        const uint8_t* src = x + (((size_t)b * H + (size_t)Y * S + dy) * W + (size_t)X * S) * C;
-        const size_t prow = ((size_t)Y * Ws + X) * B + b;
-        for (int g = 0; g < run; g += 8) {
-            const uint2 w = __ldg(reinterpret_cast<const uint2*>(src + g));
-            *reinterpret_cast<uint4*>(plane + tiled_elem(prow, dy * run + g, Cs)) = u8x8_to_bf16(w.x, w.y);
+        const int b8 = (int)(t & 7);
+        int64_t r = t >> 3;
+        const int dy = (int)(r % S);
+        r /= S;
+        const int xp = (int)(r % Wp);
+        r /= Wp;
+        const int Y = (int)(r % Hs);
+        const int b = (int)(r / Hs) * 8 + b8;
+#pragma unroll
+        for (int xi = 0; xi < 2; ++xi) {
+            const int X = 2 * xp + xi;
+            if (X >= Ws) break;
+            const uint8_t* src = x + (((size_t)b * H + (size_t)Y * S + dy) * W + (size_t)X * S) * C;
+            const size_t prow = ((size_t)Y * Ws + X) * B + b;
+            for (int g = 0; g < run; g += 8) {
+                const uint2 w = __ldg(reinterpret_cast<const uint2*>(src + g));
+                *reinterpret_cast<uint4*>(plane + tiled_elem(prow, dy * run + g, Cs)) = u8x8_to_bf16(w.x, w.y);
+            }
         }
     }
 }
@@ -527,7 +542,7 @@ int cb200_u8_s2d_planes(const void* x, int32_t batch, int32_t h, int32_t w, int3
     CB200_CHECK_ARG(x && plane && batch > 0 && batch % 8 == 0 && s > 0 && h % s == 0 && w % s == 0, "bad geometry");
     CB200_CHECK_ARG((s * c) % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(plane)) & 15) == 0,
                     "s * c must be a multiple of 8 and the buffers 16-byte aligned");
-    const int64_t total = (int64_t)batch * (h / s) * (w / s) * s;
+    const int64_t total = (int64_t)batch * (h / s) * ((w / s + 1) / 2) * s;
     int64_t grid = (total + 255) / 256;
     if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
     gemm::u8_s2d_planes_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(static_cast<const uint8_t*>(x), batch, h, w,
