@@ -189,3 +189,30 @@ def test_truncation_split_is_exact():
     assert np.array_equal(rebuilt[normal], x[normal].astype(np.float64))
     assert np.array_equal(((hi + mid) + lo)[normal], x[normal])                     # also in fp32 arithmetic
     assert np.all(np.abs(rebuilt[~normal] - x[~normal].astype(np.float64)) < 2.0 ** -133)
+
+
+def test_theta_planes_cover_the_tensor_core_layers_of_the_atari_network():
+    """parameter planes: every kernel whose [rows, cols] form is a multiple of 8 both ways gets a segment at its own
+    (8-aligned) offset of the flat buffer; the skinny Q head (512 x 6) stays fp32 only"""
+    from coach_b200.architectures.q_network import QNetworkDef
+    lib = _lib.load()
+    net = QNetworkDef("cpu", (84, 84, 4), 6)
+    tp = tl.ThetaPlanes(lib, net.store, net.store.theta)
+    segs = {int(o): (int(r), int(c)) for o, r, c, _ in tp.segs.tolist()}
+    shapes = sorted(segs.values())
+    assert shapes == sorted([(256, 32), (512, 64), (576, 64), (3136, 512)])
+    for name, (off, shape) in net.store.entries.items():
+        assert off % 8 == 0, name
+        if name.endswith("kernel"):
+            assert tp.has(name) == (int(np.prod(shape[:-1])) % 8 == 0 and shape[-1] % 8 == 0), name
+    head = [n for n in net.store.entries if n.endswith("kernel")][-1]
+    assert not tp.has(head) and net.store.entries[head][1] == (512, 6)
+    assert tp.stride == net.store.size and tp.max_elems == 3136 * 512
+
+
+@pytest.mark.parametrize("tiles,total", [(324, 16), (196, 18), (16, 98), (4, 1296), (5, 784), (100, 16), (1600, 8)])
+def test_split_choice_respects_the_accumulation_cap(tiles, total):
+    """at most 32 reduction chunks (64 accumulating MMAs) per launch slice, whatever the tile count"""
+    s = tl.pick_splits_tiled(tiles, total)
+    cps = -(-total // s)
+    assert 1 <= s <= max(1, total) and cps <= 32
