@@ -349,7 +349,8 @@ def run_device(args):
         "share_of_step": {"sample_gather": round(gather_us / (gather_us + learn_us), 4),
                           "learn": round(learn_us / (gather_us + learn_us), 4)},
     }
-    line["cpu_baseline"] = cpu_reference(steps=args.cpu_steps, warmup=1, quiet=True)
+    if world == 1:          # the CPU baseline is reported by the single-GPU run only
+        line["cpu_baseline"] = cpu_reference(steps=args.cpu_steps, warmup=1, quiet=True)
     print(json.dumps(line))
     sys.stdout.flush()
 
