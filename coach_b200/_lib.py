@@ -117,7 +117,7 @@ PROTOTYPES = {
     "cb200_ac_td_targets": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int32, c_i64, c_double, ctypes.c_int32,
                                     ctypes.c_int32, c_double, c_double, c_void_p, c_void_p]),
     "cb200_min2": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
-    "cb200_td3_smooth_actions": (c_int, [c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_void_p]),
+    "cb200_td3_smooth_actions": (c_int, [c_void_p, c_void_p, c_i64, c_double, c_double, c_double, c_void_p]),
     "cb200_gae_scan": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
     "cb200_standardize": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),

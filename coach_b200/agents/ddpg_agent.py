@@ -231,6 +231,8 @@ class DDPGAgent(object):
         self.batch_buffers = {"state:observation": f32(B, D), "next_state:observation": f32(B, D),
                               "action": f32(B, A), "reward": torch.zeros(B, dtype=torch.float64, device=dev),
                               "game_over": torch.zeros(B, dtype=torch.uint8, device=dev)}
+        if hasattr(self.memory, "declare_schema") and self.memory.ring.specs is None:
+            self.memory.declare_schema(self.batch_buffers)       # store(Transition) casts gym's float64 to these dtypes
         s, s2 = self.batch_buffers["state:observation"], self.batch_buffers["next_state:observation"]
         self.actor_target_s2 = self.actor_seq.instantiate(self.lib, self.ws, B, s2, self.actor.target)
         self.actor_online_s = self.actor_seq.instantiate(self.lib, self.ws, B, s, sa.theta, sa.grad, train=True)
@@ -239,7 +241,7 @@ class DDPGAgent(object):
         self.critic_pi = _CriticBinding(self, sc.theta, sc.grad, False, True)
         self.td_targets = f32(B, 1)
         self.q_min = f32(B, 1)
-        self.noise = f32(B, A)
+        self.noise = torch.zeros((B, A), dtype=torch.float64, device=dev)
         self.loss_dev = [f32(1), f32(1)]
         self.training_iteration = 0
         self.total_steps_counter = 0
@@ -382,7 +384,7 @@ class TD3Agent(DDPGAgent):
         self.actor_online_s.forward()
         if noise is None:
             noise = np.random.normal(0, alg.policy_noise, (B, A))
-        self.noise.copy_(torch.as_tensor(np.asarray(noise), dtype=torch.float32))
+        self.noise.copy_(torch.as_tensor(np.asarray(noise, dtype=np.float64)))
         _lib.check(lib.cb200_td3_smooth_actions(self.critic_target.act.data_ptr(), self.noise.data_ptr(), B * A,
                                                 float(alg.noise_clipping), self.action_low, self.action_high, st))
         q1, q2 = self.critic_target.forward()

@@ -21,8 +21,8 @@ import torch
 from coach_b200 import _lib
 from coach_b200.architectures.layers import Workspace
 from coach_b200.architectures.q_network import QNetworkDef
-from coach_b200.base_parameters import (AgentParameters, AlgorithmParameters, EnvironmentSteps, NetworkParameters,
-                                        TrainingSteps)
+from coach_b200.base_parameters import (AgentParameters, AlgorithmParameters, EnvironmentSteps, MiddlewareScheme,
+                                        NetworkParameters, TrainingSteps)
 from coach_b200.memories.experience_replay import ExperienceReplayParameters
 from coach_b200.memories.prioritized_experience_replay import PrioritizedExperienceReplay
 from coach_b200.utils import dynamic_import_and_instantiate_module_from_params
@@ -158,9 +158,17 @@ class DQNAgent(object):
             "weight": torch.ones(B, dtype=torch.float64, device=dev),
             "weight32": torch.ones(B, dtype=torch.float32, device=dev),
         }
+        # the ring's column layout = the agent's batch buffers, fixed before the first store: store(Transition) then
+        # casts what the environment hands out (gym: float64) instead of the gather overrunning float32 buffers
+        if hasattr(self.memory, "declare_schema") and self.memory.ring.specs is None:
+            self.memory.declare_schema({k: self.batch_buffers[k] for k in
+                                        ("state:observation", "next_state:observation", "action", "reward",
+                                         "game_over")})
         dueling = "DuelingQHead" in getattr(net_params, "heads_parameters", ["QHead"])
         gen = torch.Generator().manual_seed(int(seed)) if seed is not None else None
-        self.net_def = QNetworkDef(dev, self.observation_shape, A, dueling=dueling)
+        scheme = getattr(getattr(net_params, "middleware_parameters", None), "scheme", MiddlewareScheme.Medium)
+        self.net_def = QNetworkDef(dev, self.observation_shape, A, dueling=dueling,
+                                   middleware_units=MiddlewareScheme.units[getattr(scheme, "value", scheme)])
         self.net_def.store.init_glorot(gen)
         self.networks = {"main": QNetworkWrapper(self.lib, self.net_def, net_params, B, self.batch_buffers,
                                                  self.double_dqn, dev)}

@@ -140,6 +140,8 @@ class SoftActorCriticAgent(object):
         self.batch_buffers = {"state:observation": f32(B, D), "next_state:observation": f32(B, D),
                               "action": f32(B, A), "reward": torch.zeros(B, dtype=torch.float64, device=dev),
                               "game_over": torch.zeros(B, dtype=torch.uint8, device=dev)}
+        if hasattr(self.memory, "declare_schema") and self.memory.ring.specs is None:
+            self.memory.declare_schema(self.batch_buffers)       # store(Transition) casts gym's float64 to these dtypes
         s, s2 = self.batch_buffers["state:observation"], self.batch_buffers["next_state:observation"]
         self.policy_inst = self.policy_seq.instantiate(self.lib, self.ws, B, s, sp.theta, sp.grad, train=True)
         self.sampled = f32(B, A)

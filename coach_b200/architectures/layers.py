@@ -158,6 +158,12 @@ class Dense(object):
             if (pl is not None and pl.y is not None) else {}
         dxp = dict(c_planes=pl.dx.ptr, c_plane_stride=pl.dx.stride, c_plane_cols=K) \
             if (pl is not None and pl.dx is not None and pl.dx.npix == 1) else {}
+        if need_dx and pl is not None and pl.dx is not None and pl.dx.npix != 1:
+            # the producer of this gradient would have to write pixel-major planes of a flattened conv map, which only
+            # the tiled data-gradient GEMM does: fail instead of leaving the consumer's planes stale
+            raise NotImplementedError("Dense(%d -> %d) on a %d-pixel conv map has no tensor-core form (n must be 32 or a "
+                                      "multiple of 64): its data gradient cannot feed the conv layer's operand planes"
+                                      % (K, N, pl.dx.npix))
         rowoff = _dev_i32(np.arange(B) * K, device)
         coloff = _dev_i32(np.arange(K), device)
         vec = int(K % 4 == 0)

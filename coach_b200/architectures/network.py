@@ -94,11 +94,16 @@ class Sequential(object):
             self.names.append([store.add(base + "/" + pname, shape) for pname, shape in layer.param_shapes])
 
     def instantiate(self, lib, ws, B, x, theta, grad=None, x_is_u8=False, lut=None, need_input_grad=False,
-                    input_act=0, train=False, dx_in=None, dx_accumulate=False, theta_planes=None):
+                    input_act=0, train=False, dx_in=None, dx_accumulate=False, theta_planes=None, x_planes=None,
+                    last_planes=False, dz_planes_map=None):
         """need_input_grad: also produce the gradient wrt the (pre-activation of the) input, masked by
-        ``input_act``' evaluated on x; it is written (or, with dx_accumulate, added) to ``dx_in``."""
+        ``input_act``' evaluated on x; it is written (or, with dx_accumulate, added) to ``dx_in``.
+        x_planes: operand planes of the input (a PlaneBuf written by whoever produces x); last_planes: the last
+        layer's output / pre-activation gradient carry planes too (their consumers / producers are tiled GEMMs of
+        another chain); dz_planes_map {layer index: planes}: use these planes for that layer's pre-activation gradient
+        (several chains sharing one plane matrix so that ONE GEMM can contract over all of them)."""
         return SequentialInstance(self, lib, ws, B, x, theta, grad, x_is_u8, lut, need_input_grad, input_act, train,
-                                  dx_in, dx_accumulate, theta_planes)
+                                  dx_in, dx_accumulate, theta_planes, x_planes, last_planes, dz_planes_map)
 
 
 class SequentialInstance(object):
@@ -106,7 +111,8 @@ class SequentialInstance(object):
     pre-activation gradient buffers and prepares the backward ops (gradients land in ``grad``)."""
 
     def __init__(self, seq, lib, ws, B, x, theta, grad, x_is_u8, lut, need_input_grad, input_act, train,
-                 dx_in=None, dx_accumulate=False, theta_planes=None):
+                 dx_in=None, dx_accumulate=False, theta_planes=None, x_planes=None, last_planes=False,
+                 dz_planes_map=None):
         import copy
         self.seq, self.B = seq, B
         dev = theta.device
@@ -129,12 +135,12 @@ class SequentialInstance(object):
         self.act_planes = [None] * len(self.layers)
         self.dz_planes = [None] * len(self.layers)
         if theta_planes is not None and B % 32 == 0:
-            for i, layer in enumerate(self.layers[:-1]):
+            for i, layer in enumerate(self.layers if last_planes else self.layers[:-1]):
                 npix, ch = layer.out_pixels(), layer.N
                 if ch % 8 == 0:
                     self.act_planes[i] = tl.PlaneBuf(npix * B, ch, dev, npix=npix)
                     if train:
-                        self.dz_planes[i] = tl.PlaneBuf(npix * B, ch, dev, npix=npix)
+                        self.dz_planes[i] = (dz_planes_map or {}).get(i) or tl.PlaneBuf(npix * B, ch, dev, npix=npix)
         for i, layer in enumerate(self.layers):
             wname, bname = seq.names[i]
             w, b = store.view(theta, wname), store.view(theta, bname)
@@ -145,7 +151,7 @@ class SequentialInstance(object):
             need_dx = train and (not first or need_input_grad)
             ctx = None
             if theta_planes is not None and B % 32 == 0:
-                ctx = tl.PlaneCtx(x=None if first else self.act_planes[i - 1], y=self.act_planes[i],
+                ctx = tl.PlaneCtx(x=x_planes if first else self.act_planes[i - 1], y=self.act_planes[i],
                                   dy=self.dz_planes[i], dx=None if first else self.dz_planes[i - 1],
                                   w_ptr=theta_planes.ptr(wname) if theta_planes.has(wname) else 0,
                                   w_stride=theta_planes.stride)

@@ -3,7 +3,9 @@
 Structure and variable order follow the TF graph of the reference:
   embedder  -- image: Conv2d(32,8,4) Conv2d(64,4,2) Conv2d(64,3,1), ReLU, flatten (image_embedder.py:62-67, Medium);
                vector: Dense(256) ReLU (vector_embedder.py:58-61, Medium); input / 255 for images (embedder.py:103)
-  middleware-- Dense(512) ReLU (fc_middleware.py:66-69, Medium)
+  middleware-- Dense(512) ReLU (fc_middleware.py:66-69, Medium); MiddlewareScheme.Empty = no layer at all, the heads
+               read the flattened embedder output (fc_middleware.py:58-59; presets/Atari_Dueling_DDQN_with_PER_OpenAI.py:17:
+               the dueling towers sit directly on the 3136-wide conv map, 3,293,863 trainable parameters)
   head      -- QHead: Dense(num_actions) (q_head.py:52-54);
                DuelingQHead: V: Dense(512) ReLU, Dense(1); A: Dense(512) ReLU, Dense(num_actions);
                Q = V + (A - mean_a A) (dueling_q_head.py:33-47)
@@ -22,6 +24,12 @@ class QNetworkDef(object):
     """Parameter layout + layer chain; instances bind it to buffers (see QNetworkInstance)."""
 
     def __init__(self, device, observation_shape, num_actions, dueling=False, embedder="auto", middleware_units=512):
+        """middleware_units: width of one FC middleware layer, a tuple of widths, or None / () for MiddlewareScheme.Empty"""
+        if middleware_units is None:
+            middleware_units = ()
+        elif isinstance(middleware_units, int):
+            middleware_units = (middleware_units,)
+        self.middleware_units = tuple(int(u) for u in middleware_units)
         self.device = torch.device(device)
         self.obs_shape = tuple(observation_shape)
         self.num_actions = int(num_actions)
@@ -40,7 +48,10 @@ class QNetworkDef(object):
             layers.append(Dense(self.obs_shape[0], 256, "relu"))
             flat = 256
         self.n_embedder = len(layers)
-        layers.append(Dense(flat, middleware_units, "relu"))
+        for u in self.middleware_units:
+            layers.append(Dense(flat, u, "relu"))
+            flat = u
+        middleware_units = flat                 # width of what the head reads
         if not self.dueling:
             layers.append(Dense(middleware_units, self.num_actions, None))
             self.trunk = Sequential(layers, self.store, "main/online/network_0")
@@ -70,21 +81,73 @@ class QNetworkInstance(object):
         # (CB200_GEMM_TILED=0 keeps every layer on the gather-GEMM of cb200_gemm: A/B runs, bench.py --no-tc)
         self.theta_planes = tl.ThetaPlanes(lib, net.store, theta) \
             if (B >= 128 and B % 32 == 0 and _lib.tune_default("gemm_tiled", 1)) else None
+        # dueling towers directly on a conv map (MiddlewareScheme.Empty, the Atari dueling-DDQN preset): the towers'
+        # first layers are the two largest GEMMs of the network, so they run on the conv map's operand planes too
+        last = net.trunk.layers[-1]
+        self.towers_on_planes = bool(net.dueling and self.theta_planes is not None and not net.middleware_units and
+                                     net.is_image and tl.channels_ok(last.N) and tl.width_ok(last.N))
         self.trunk = net.trunk.instantiate(lib, ws, B, x, theta, grad, x_is_u8=x_is_u8, lut=net.lut, train=train,
-                                           theta_planes=self.theta_planes)
+                                           theta_planes=self.theta_planes, last_planes=self.towers_on_planes)
         if not net.dueling:
             self.q = self.trunk.out
             self.dq = self.trunk.d_out
             return
-        h = self.trunk.out                      # middleware output (post-ReLU)
+        h = self.trunk.out                      # what the head reads (post-ReLU): middleware or embedder output
         dh = self.trunk.d_out                   # gradient wrt its pre-activation
         relu = 1
+        self.q = torch.empty((B, net.num_actions), dtype=torch.float32, device=dev)
+        self.dq = torch.empty_like(self.q) if train else None
+        self.towers_dx = None
+        if self.towers_on_planes:
+            self._towers_on_conv_map(lib, ws, B, h, dh, theta, grad, train)
+            return
         self.v = net.v_tower.instantiate(lib, ws, B, h, theta, grad, need_input_grad=train, input_act=relu,
                                          train=train, dx_in=dh, dx_accumulate=False)
         self.a = net.a_tower.instantiate(lib, ws, B, h, theta, grad, need_input_grad=train, input_act=relu,
                                          train=train, dx_in=dh, dx_accumulate=True)
-        self.q = torch.empty((B, net.num_actions), dtype=torch.float32, device=dev)
-        self.dq = torch.empty_like(self.q) if train else None
+
+    def _towers_on_conv_map(self, lib, ws, B, h, dh, theta, grad, train):
+        """V / A towers as tiled GEMMs on the planes of the last conv map [npix * B, C].  Forward and weight gradients
+        are per tower; the data gradient into the conv map is ONE multi-tap GEMM over both towers: their
+        pre-activation gradients are the two "pixels" of one [2B, 512] plane matrix, the per-pixel transposed kernels
+        of both towers one weight stack, and every conv pixel's tap list has one entry per tower -- so the sum
+        dV W_v^T + dA W_a^T is accumulated in TMEM instead of by a second, accumulating pass."""
+        net, dev = self.net, self.net.device
+        xp = self.trunk.act_planes[-1]
+        npix, C = xp.npix, xp.cols
+        H1 = net.v_tower.layers[0].N                                   # 512
+        comb = tl.PlaneBuf(2 * B, H1, dev, npix=2) if train else None
+        maps = [({0: comb.view_rows(t * B, B)} if train else None) for t in range(2)]
+        self.v = net.v_tower.instantiate(lib, ws, B, h, theta, grad, input_act=1, train=train,
+                                         theta_planes=self.theta_planes, x_planes=xp, dz_planes_map=maps[0])
+        self.a = net.a_tower.instantiate(lib, ws, B, h, theta, grad, input_act=1, train=train,
+                                         theta_planes=self.theta_planes, x_planes=xp, dz_planes_map=maps[1])
+        assert self.v.layers[0].tiled_x and self.a.layers[0].tiled_x
+        if not train:
+            return
+        store = net.store
+        K = npix * C
+        w_index = np.arange(K * H1).reshape(npix, C, H1)
+        perm = torch.from_numpy(np.ascontiguousarray(w_index.transpose(0, 2, 1).reshape(-1), dtype=np.int32)).to(dev)
+        wT = torch.empty(2 * npix * H1 * C, dtype=torch.float32, device=dev)
+        wT_planes = tl.PlaneBuf(2 * npix * H1, C, dev)
+        w_src = [store.view(theta, seq.names[0][0]) for seq in (net.v_tower, net.a_tower)]
+        qq, bb = np.meshgrid(np.arange(npix), np.arange(B), indexing="ij")
+        rowmap = torch.from_numpy(np.ascontiguousarray((bb * npix + qq).reshape(-1), dtype=np.int32)).to(dev)
+        op = tl.masked_forward_op(lib, ws, B, dev, comb, H1, wT_planes, C,
+                                  [[(0, q), (1, npix + q)] for q in range(npix)], npix, dh, C, h, 1, rowmap,
+                                  self.trunk.dz_planes[-1], mask_planes=xp)
+        op.tag = "DuelingTowers.bwd_x"
+        self.towers_dx = (op, perm, wT, wT_planes, w_src, npix * H1)
+
+    def _run_towers_dx(self):
+        op, perm, wT, wT_planes, w_src, half = self.towers_dx
+        st = _lib.current_stream()
+        for t, w in enumerate(w_src):
+            pv = wT_planes.view_rows(t * half, half)
+            _lib.check(self.lib.cb200_permute_f32(w.data_ptr(), perm.data_ptr(), perm.numel(),
+                                                  wT.data_ptr() + 4 * t * perm.numel(), pv.ptr, pv.stride, pv.cols, st))
+        op.run()
 
     def forward(self):
         if self.theta_planes is not None:
@@ -120,4 +183,6 @@ class QNetworkInstance(object):
                                                           _lib.current_stream()))
             self.v.backward()      # writes d(middleware pre-activation)
             self.a.backward()      # accumulates into it
+            if self.towers_dx is not None:
+                self._run_towers_dx()      # both towers' data gradients into the conv map, one GEMM
         self.trunk.backward()

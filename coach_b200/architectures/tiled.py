@@ -42,6 +42,11 @@ class PlaneBuf(object):
     def stride(self):
         return self.rows * self.cols
 
+    def view_rows(self, lo, n, npix=1):
+        """rows [lo, lo + n) as a plane matrix of their own (same memory, same plane stride); lo, n multiples of 8"""
+        assert lo % 8 == 0 and n % 8 == 0 and 0 <= lo and lo + n <= self.rows
+        return PlaneView(self, lo, n, npix)
+
     def load(self, lib, m):
         """planes <- split of an fp32 [rows, cols] matrix (tests, host-written inputs)"""
         m = m.contiguous().view(self.rows, self.cols).float()
@@ -58,6 +63,27 @@ class PlaneBuf(object):
             v = (v + self.t[1].float()) + self.t[2].float()
         v = v.view(self.rows // 8, self.cols // 8, 8, 8).permute(0, 2, 1, 3)
         return v.reshape(self.rows, self.cols)
+
+
+class PlaneView(object):
+    """A run of 8-row groups of a PlaneBuf: in the core-tiled format whole row groups are contiguous inside a plane,
+    so the view is the parent's memory at an element offset, with the PARENT's plane stride."""
+
+    def __init__(self, parent, lo, n, npix=1):
+        self.parent, self.lo = parent, int(lo)
+        self.rows, self.cols, self.npix, self.nplanes = int(n), parent.cols, int(npix), parent.nplanes
+        self.t = parent.t                      # keeps the storage alive
+
+    @property
+    def ptr(self):
+        return self.parent.ptr + 2 * self.lo * self.cols
+
+    @property
+    def stride(self):
+        return self.parent.stride
+
+    def to_dense(self):
+        return self.parent.to_dense()[self.lo:self.lo + self.rows]
 
 
 def channels_ok(c):
@@ -143,7 +169,7 @@ class TGemmOp(object):
             if torch.is_tensor(v):
                 self.keep.append(v)
                 v = v.data_ptr()
-            elif isinstance(v, PlaneBuf):
+            elif isinstance(v, (PlaneBuf, PlaneView)):
                 self.keep.append(v)
                 v = v.ptr
             setattr(self.desc, k, v)

@@ -20,6 +20,21 @@ class EnvironmentEpisodes(StepMethod):
     pass
 
 
+class MiddlewareScheme(object):
+    """rl_coach/base_parameters.py:44-48; FC middleware layer lists of
+    architectures/tensorflow_components/middlewares/fc_middleware.py:56-80"""
+    Empty = "Empty"
+    Shallow = "Shallow"
+    Medium = "Medium"
+    Deep = "Deep"
+    units = {"Empty": (), "Shallow": (64,), "Medium": (512,), "Deep": (128, 128, 128)}
+
+
+class MiddlewareParameters(object):
+    def __init__(self, scheme=MiddlewareScheme.Medium):
+        self.scheme = scheme
+
+
 class AlgorithmParameters(object):
     def __init__(self):
         self.num_consecutive_playing_steps = EnvironmentSteps(1)
@@ -46,6 +61,7 @@ class NetworkParameters(object):
         self.replace_mse_with_huber_loss = False
         self.create_target_network = False
         self.scale_down_gradients_by_number_of_workers_for_sync_training = True
+        self.middleware_parameters = MiddlewareParameters()
 
 
 class AgentParameters(object):

@@ -200,13 +200,15 @@ __global__ void __launch_bounds__(256) min2_kernel(const float* __restrict__ a, 
     if (i < n) out[i] = fminf(a[i], b[i]);
 }
 
-// TD3 target policy smoothing (td3_agent.py:162-164): a = clip(a + clip(noise, -c, c), lo, hi), in place
-__global__ void __launch_bounds__(256) td3_smooth_kernel(float* __restrict__ actions, const float* __restrict__ noise,
-                                                         int64_t n, float noise_clip, float lo, float hi) {
+// TD3 target policy smoothing (td3_agent.py:162-164): a = clip(a + clip(noise, -c, c), lo, hi), in place.  The
+// reference adds the fp64 numpy draw to the fp32 network output in fp64, clips in fp64 and the result is rounded to
+// fp32 once when it is fed to the critic: same operations here (pinned by tests/golden/agent_prologues.npz).
+__global__ void __launch_bounds__(256) td3_smooth_kernel(float* __restrict__ actions, const double* __restrict__ noise,
+                                                         int64_t n, double noise_clip, double lo, double hi) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float nz = fminf(fmaxf(noise[i], -noise_clip), noise_clip);
-    actions[i] = fminf(fmaxf(actions[i] + nz, lo), hi);
+    const double nz = fmin(fmax(noise[i], -noise_clip), noise_clip);
+    actions[i] = (float)fmin(fmax(__dadd_rn((double)actions[i], nz), lo), hi);
 }
 
 // =====================================================================================================================
@@ -373,7 +375,7 @@ int cb200_min2(const float* a, const float* b, int64_t n, float* out, void* stre
     return CB200_OK;
 }
 
-int cb200_td3_smooth_actions(float* actions, const float* noise, int64_t n, float noise_clip, float lo, float hi,
+int cb200_td3_smooth_actions(float* actions, const double* noise, int64_t n, double noise_clip, double lo, double hi,
                              void* stream) {
     CB200_CHECK_ARG(actions && noise && n > 0, "bad arguments");
     CB200_LAUNCH(td3_smooth_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), actions, noise, n,

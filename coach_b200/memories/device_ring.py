@@ -99,6 +99,24 @@ class DeviceTransitionRing(object):
             self._stage_np[name] = host_np[:, o:o + sp.row_bytes]      # same memory, no per-store tensor objects
         self._flush_table = None
 
+    def declare_schema(self, columns):
+        """Fix the column layout before the first store: {name: (shape, numpy dtype)} or {name: batch tensor [n, ...]}.
+        ``store(Transition)`` then converts every field to the declared dtype (gym hands out float64 observations and
+        actions where the networks -- and the agents' persistent batch buffers -- are float32)."""
+        if self.specs is not None:
+            raise RuntimeError("the replay already holds transitions; the schema is fixed")
+        specs = OrderedDict()
+        for name, v in columns.items():
+            if torch.is_tensor(v):
+                dt = np.dtype(str(v.dtype).replace("torch.", "")) if v.dtype != torch.bool else np.dtype(np.uint8)
+                specs[name] = ColumnSpec(name, tuple(v.shape[1:]), dt)
+            else:
+                specs[name] = ColumnSpec(name, v[0], v[1])
+        for need in ("action", "reward", "game_over"):
+            if need not in specs:
+                raise ValueError("schema lacks the %r column" % need)
+        self.set_schema(specs)
+
     def hbm_bytes(self):
         return 0 if self.columns is None else sum(c.numel() for c in self.columns.values())
 
@@ -208,11 +226,22 @@ class DeviceTransitionRing(object):
             out[name] = torch.empty((n,) + sp.shape, dtype=sp.torch_dtype(), device=self.device)
         return out
 
-    def column_table(self, out):
-        # the agents sample into the same persistent buffers every step: build the ctypes table once per buffer set
-        key = tuple(out[name].data_ptr() for name in self.specs)
+    def column_table(self, out, n):
+        """ctypes gather table for ``n`` rows into ``out``.  The kernels write ``n * row_bytes`` bytes per column: a
+        destination of another dtype or size would be overrun (or read back reinterpreted), so every buffer is checked
+        against the ring's schema -- once per buffer set, the agents sample into the same persistent buffers."""
+        key = (int(n),) + tuple(out[name].data_ptr() for name in self.specs)
         hit = self._table_cache.get(key)
         if hit is None:
+            for name, sp in self.specs.items():
+                t = out[name]
+                if not (t.is_cuda == (self.device.type == "cuda") and t.is_contiguous()):
+                    raise ValueError("batch buffer %r must be a contiguous tensor on %s" % (name, self.device))
+                if t.dtype != sp.torch_dtype() or t.numel() * t.element_size() != n * sp.row_bytes:
+                    raise ValueError(
+                        "batch buffer %r is %s%s but the replay stores %s%s per transition (%d rows): declare the "
+                        "schema up front (memory.declare_schema) or store transitions in the agent's dtypes"
+                        % (name, t.dtype, tuple(t.shape), sp.dtype, sp.shape, n))
             pairs = [(self.columns[name].data_ptr(), out[name].data_ptr(), sp.row_bytes)
                      for name, sp in self.specs.items()]
             hit = self._table_cache[key] = _lib.make_columns(pairs)
@@ -226,6 +255,6 @@ class DeviceTransitionRing(object):
         n = idx.shape[0]
         if out is None:
             out = self.alloc_batch(n)
-        arr, cnt = self.column_table(out)
+        arr, cnt = self.column_table(out, n)
         _lib.check(self.lib.cb200_gather(arr, cnt, idx.data_ptr(), n, _lib.current_stream()))
         return out

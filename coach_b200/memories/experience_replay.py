@@ -76,6 +76,11 @@ class ExperienceReplay(Memory):
         if self.ring.count + self.ring._pending > self.ring.capacity:
             self._flush()
 
+    def declare_schema(self, columns: dict) -> None:
+        """Column layout of the ring ({name: (shape, dtype)} or the agent's batch buffers), fixed before the first store
+        so that ``store(Transition)`` casts to it (device_ring.DeviceTransitionRing.declare_schema)."""
+        self.ring.declare_schema(columns)
+
     def store_columns(self, columns: dict) -> None:
         """Batched ingest: {column name: array/tensor [n, ...]} with the ring's column names (see device_ring)."""
         self.assert_not_frozen()

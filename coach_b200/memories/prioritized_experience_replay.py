@@ -194,7 +194,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         for k, dt in (("idx", torch.int64), ("weight", torch.float64), ("weight32", torch.float32)):
             if k not in out:
                 out[k] = torch.empty(size, dtype=dt, device=self.device)
-        arr, cnt = self.ring.column_table(out)
+        arr, cnt = self.ring.column_table(out, size)
         ke = getattr(self, "kernel_events", None)      # (start, end) CUDA events recorded right around the launch
         if ke:
             ke[0].record()

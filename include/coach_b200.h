@@ -390,8 +390,10 @@ int cb200_ac_td_targets(const double* rewards, const uint8_t* game_overs, const 
 /* out = min(a, b) element-wise (clipped double-Q: td3_v_head.py:61, sac_q_head.py:84-86) */
 int cb200_min2(const float* a, const float* b, int64_t n, float* out, void* stream);
 
-/* TD3 target policy smoothing (td3_agent.py:162-164): a = clip(a + clip(noise, -noise_clip, noise_clip), lo, hi) */
-int cb200_td3_smooth_actions(float* actions, const float* noise, int64_t n, float noise_clip, float lo, float hi,
+/* TD3 target policy smoothing (td3_agent.py:162-164): a = clip(a + clip(noise, -noise_clip, noise_clip), lo, hi);
+ * noise is the fp64 np.random.normal draw, the sum and both clips are evaluated in fp64 like numpy does and rounded
+ * to fp32 once (bit-exact with the reference, tests/golden/agent_prologues.npz) */
+int cb200_td3_smooth_actions(float* actions, const double* noise, int64_t n, double noise_clip, double lo, double hi,
                              void* stream);
 
 /* SACPolicyHead (heads/sac_head.py:60-97).  head_out [batch, 2*action_dim] = [mu | raw log-sigma]; log-sigma is clipped

@@ -1,5 +1,7 @@
 """torch-CPU fp32/fp64 restatement of the actor-critic learn steps (ClippedPPO, DDPG, TD3, SAC).
-TEST INFRASTRUCTURE ONLY.  **Parity unpinned** (TensorFlow semantics restated; see oracle/nets.py header).
+TEST INFRASTRUCTURE ONLY.  The numpy prologues (TD targets, target-policy smoothing, advantage filling) are PINNED to the unmodified reference
+(tests/golden/agent_prologues.npz); the network arithmetic (layers, losses, gradients, Adam) is **parity unpinned**
+(TensorFlow semantics restated; see oracle/nets.py header).
 
 Sources restated
   ClippedPPO  agents/clipped_ppo_agent.py:157-308; heads/ppo_head.py:52-144; heads/v_head.py:35-51;
@@ -15,6 +17,7 @@ import numpy as np
 import torch
 
 from oracle.nets import AdamTF
+from oracle.rl_math import ac_td_targets, td3_smooth_actions
 
 EPS = 1e-15
 
@@ -123,13 +126,11 @@ def ddpg_td3_step(actor, actor_t, critic, critic_t, opt_a, opt_c, batch, discoun
     with torch.no_grad():
         next_actions = actor_forward(At, s2, scale)
         if twin:
-            nz = np.clip(np.asarray(noise, dtype=np.float64), -noise_clip, noise_clip)
-            next_actions = torch.clamp(next_actions + t(nz), low, high)
+            # pinned restatement (oracle/rl_math.py): fp64 sum / clips, rounded once to the compute dtype
+            next_actions = t(td3_smooth_actions(next_actions.numpy(), noise, noise_clip, low, high))
         qn = cf(Ct, s2, next_actions)
         q_next = torch.min(qn[0], qn[1]) if twin else qn[0]
-    r = np.asarray(batch["rewards"], dtype=np.float64).reshape(-1, 1)
-    d = np.asarray(batch["game_overs"]).reshape(-1, 1)
-    y = r + (1.0 - d) * discount * q_next.numpy().astype(np.float64 if dtype == torch.float64 else np.float32)
+    y = ac_td_targets(batch["rewards"], batch["game_overs"], q_next.numpy(), discount)
     y = t(y.astype(np.float32) if dtype == torch.float32 else y)
 
     def action_grad(Cp):

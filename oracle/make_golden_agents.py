@@ -1,0 +1,346 @@
+"""Pins the numpy prologues of the reference AGENTS: tests/golden/agent_prologues.npz.
+
+TensorFlow is absent, but everything an agent's ``learn_from_batch`` does *around* its network calls is numpy and
+imports under oracle/ref_loader.py.  Each function below calls the UNMODIFIED reference method with a stand-in
+``self`` whose ``networks`` return given arrays and record what they are handed:
+
+  DQNAgent.learn_from_batch / DDQNAgent.select_actions      rl_coach/agents/dqn_agent.py:81-113, ddqn_agent.py:42-43
+  ValueOptimizationAgent.update_transition_priorities_...   rl_coach/agents/value_optimization_agent.py:74-80
+  ClippedPPOAgent.fill_advantages                           rl_coach/agents/clipped_ppo_agent.py:157-207
+  DDPGAgent.learn_from_batch                                rl_coach/agents/ddpg_agent.py:137-195
+  TD3Agent.learn_from_batch                                 rl_coach/agents/td3_agent.py:148-209
+  SoftActorCriticAgent.learn_from_batch                     rl_coach/agents/soft_actor_critic_agent.py:168-280
+  Batch                                                     rl_coach/core_types.py:405-649
+
+The recorded arrays (TD targets handed to ``train_and_sync_networks``, priorities handed to the memory, advantages
+written into ``transition.info`` ...) are what the oracle restatement AND the CUDA kernels must reproduce bit for bit
+from the same inputs (tests/test_oracle_golden.py, tests/test_agent_prologues_gpu.py).
+
+Run in the build container only:   python -m oracle.make_golden_agents          TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+class _Sig(object):
+    def add_sample(self, *_a, **_k):
+        pass
+
+
+def _ref():
+    from oracle import ref_loader
+    ref_loader.load()
+
+
+def _transitions(rng, n, obs_shape, action, with_info=True, obs_dtype=np.float32):
+    from rl_coach.core_types import Transition
+    ts = []
+    for i in range(n):
+        if obs_dtype == np.uint8:
+            s = rng.randint(0, 256, obs_shape).astype(np.uint8)
+            s2 = rng.randint(0, 256, obs_shape).astype(np.uint8)
+        else:
+            s = rng.randn(*obs_shape).astype(obs_dtype)
+            s2 = rng.randn(*obs_shape).astype(obs_dtype)
+        a = int(rng.randint(0, action)) if isinstance(action, int) else rng.uniform(-1, 1, action[0]).astype(np.float32)
+        t = Transition(state={'observation': s}, action=a, reward=float(rng.randint(-1, 2) if isinstance(action, int)
+                                                                       else rng.randn()),
+                       next_state={'observation': s2}, game_over=bool(rng.rand() < 0.15))
+        if with_info:
+            t.info['idx'] = int(rng.randint(0, 1024))
+            t.info['weight'] = float(rng.rand() + 0.1)
+        ts.append(t)
+    return ts
+
+
+def _ap(keys=("observation",), **alg):
+    nw = SimpleNamespace(input_embedders_parameters={k: None for k in keys}, batch_size=alg.pop("batch_size", 64))
+    return nw, SimpleNamespace(**alg)
+
+
+# ---- DQN / DDQN ------------------------------------------------------------------------------------------------------
+def golden_dqn(out, rng, B=64, A=6):
+    from rl_coach.agents.dqn_agent import DQNAgent
+    from rl_coach.agents.ddqn_agent import DDQNAgent
+    from rl_coach.agents.value_optimization_agent import ValueOptimizationAgent
+    from rl_coach.core_types import Batch
+    from rl_coach.memories.non_episodic.prioritized_experience_replay import PrioritizedExperienceReplay
+    from rl_coach.memories.memory import MemoryGranularity
+    for tag, cls in (("dqn", DQNAgent), ("ddqn", DDQNAgent)):
+        ts = _transitions(rng, B, (4,), A)
+        batch = Batch(ts)
+        q_next = rng.randn(B, A).astype(np.float32)
+        q_online = rng.randn(B, A).astype(np.float32)
+        q_select = rng.randn(B, A).astype(np.float32)
+        q_select[5, 1] = q_select[5, 3] = q_select[5].max() + 1.0            # a tie: np.argmax takes the first
+        rec = {}
+        nw, alg = _ap(discount=0.99)
+        mem = PrioritizedExperienceReplay((MemoryGranularity.Transitions, 1024))
+        net = SimpleNamespace(
+            target_network="T", online_network=SimpleNamespace(predict=lambda states: q_select.copy()),
+            parallel_prediction=lambda pairs: (q_next.copy(), q_online.copy()),
+            train_and_sync_networks=lambda states, targets, importance_weights=None: (
+                rec.update(states=states, targets=np.array(targets), w=None if importance_weights is None
+                           else np.array(importance_weights)) or (0.0, [0.0], 0.0)))
+        calls = []
+        fake = SimpleNamespace(ap=SimpleNamespace(network_wrappers={'main': nw}, algorithm=alg),
+                               networks={'main': net}, q_values=_Sig(), memory=mem,
+                               call_memory=lambda f, args: calls.append((f, args)))
+        fake.select_actions = lambda ns, q: cls.select_actions(fake, ns, q)
+        fake.update_transition_priorities_and_get_weights = \
+            lambda e, b: ValueOptimizationAgent.update_transition_priorities_and_get_weights(fake, e, b)
+        cls.learn_from_batch(fake, batch)
+        assert calls[0][0] == 'update_priorities'
+        pidx, perr = calls[0][1]
+        out[tag + "_q_next"], out[tag + "_q_online"], out[tag + "_q_select"] = q_next, q_online, q_select
+        out[tag + "_actions"] = batch.actions().astype(np.int64)
+        out[tag + "_rewards"] = batch.rewards().astype(np.float64)
+        out[tag + "_game_overs"] = batch.game_overs().astype(np.uint8)
+        out[tag + "_targets"] = rec["targets"]                       # fp32 [B, A], what the train op is fed
+        out[tag + "_td_errors"] = np.array(perr, dtype=np.float64)   # what update_priorities is handed
+        out[tag + "_prio_idx"] = np.array(pidx, dtype=np.int64)
+        out[tag + "_weights"] = rec["w"]
+        assert rec["targets"].dtype == np.float32
+
+
+# ---- ClippedPPO fill_advantages --------------------------------------------------------------------------------------
+def golden_ppo(out, rng):
+    from rl_coach.agents.actor_critic_agent import ActorCriticAgent
+    from rl_coach.agents.clipped_ppo_agent import ClippedPPOAgent
+    from rl_coach.agents.policy_optimization_agent import PolicyGradientRescaler
+    from rl_coach.core_types import Batch
+    for k, (N, mb, tail) in enumerate([(300, 64, True), (256, 64, False), (97, 32, True)]):
+        ts = _transitions(rng, N, (17,), (6,), with_info=False)
+        for i, t in enumerate(ts):
+            t.game_over = bool(rng.rand() < 0.03)
+            t.n_step_discounted_rewards = 0.0
+        ts[-1].game_over = not tail            # tail=True: the rollout ends inside an episode (zip() truncation, :203)
+        if tail:
+            ts[N // 2].game_over = True
+        values = rng.randn(N, 1).astype(np.float32)
+        batch = Batch(ts)
+        nw, alg = _ap(discount=0.99, gae_lambda=0.95, estimate_state_value_using_gae=True, batch_size=mb)
+        seen = []
+
+        def predict(d):
+            start = sum(seen)
+            n = len(d['observation'])
+            seen.append(n)
+            return [values[start:start + n]]
+        fake = SimpleNamespace(ap=SimpleNamespace(network_wrappers={'main': nw}, algorithm=alg),
+                               networks={'main': SimpleNamespace(online_network=SimpleNamespace(predict=predict))},
+                               state_values=_Sig(), action_advantages=_Sig(),
+                               policy_gradient_rescaler=PolicyGradientRescaler.GAE)
+        fake.discount = lambda x, g: ActorCriticAgent.discount(fake, x, g)
+        fake.get_general_advantage_estimation_values = \
+            lambda r, v: ActorCriticAgent.get_general_advantage_estimation_values(fake, r, v)
+        ClippedPPOAgent.fill_advantages(fake, batch)
+        filled = [i for i, t in enumerate(ts) if 'advantage' in t.info]
+        assert filled == list(range(len(filled)))
+        out["ppo_values_%d" % k] = values
+        out["ppo_rewards_%d" % k] = batch.rewards().astype(np.float64)
+        out["ppo_game_overs_%d" % k] = batch.game_overs().astype(np.uint8)
+        out["ppo_adv_%d" % k] = np.array([ts[i].info['advantage'] for i in filled], dtype=np.float64)
+        out["ppo_vtgt_%d" % k] = np.array([ts[i].info['gae_based_value_target'] for i in filled], dtype=np.float64)
+        out["ppo_minibatch_%d" % k] = mb
+    out["ppo_cases"] = 3
+
+
+# ---- DDPG / TD3 ------------------------------------------------------------------------------------------------------
+def _critic_actor_stubs(rec, next_actions, actions_mean, q_outputs, action_grads):
+    class Critic(object):
+        def __init__(self):
+            self.target_network = SimpleNamespace(predict=self._target_predict)
+            self.online_network = SimpleNamespace(predict=self._online_predict,
+                                                  gradients_wrt_inputs=[{'action': 'g0'}, {'action': 'g1'},
+                                                                        {'action': 'g2'}, {'action': 'g3'}])
+
+        def _target_predict(self, inputs):
+            rec["target_critic_action"] = np.array(inputs['action'])
+            return q_outputs
+
+        def _online_predict(self, inputs, outputs=None):
+            rec["action_grad_fetch"] = outputs
+            rec["action_grad_action_input"] = np.array(inputs['action'])
+            return action_grads
+
+        def train_and_sync_networks(self, inputs, targets, **kw):
+            rec["critic_train_action"] = np.array(inputs['action'])
+            rec["td_targets"] = np.array(targets)
+            return 0.0, [0.0], 0.0
+
+    class Actor(object):
+        has_global = False
+        target_network = "T"
+
+        def __init__(self):
+            self.online_network = SimpleNamespace(predict=self._predict, gradients_weights_ph=["ph0"],
+                                                  weighted_gradients=["wg0"])
+
+        def parallel_prediction(self, pairs):
+            return next_actions.copy(), actions_mean.copy()
+
+        def _predict(self, states, outputs=None, initial_feed_dict=None):
+            rec["actor_feed"] = np.array(initial_feed_dict["ph0"])
+            return ["grads"]
+
+        def apply_gradients_to_online_network(self, grads, additional_inputs=None):
+            rec["actor_applied"] = True
+    return Critic(), Actor()
+
+
+def golden_ddpg_td3(out, rng, B=64, D=17, A=6):
+    from rl_coach.agents.ddpg_agent import DDPGAgent
+    from rl_coach.agents.td3_agent import TD3Agent
+    from rl_coach.core_types import Batch
+    from rl_coach.spaces import BoxActionSpace
+    cases = [("ddpg0", DDPGAgent, dict(clip_critic_targets=None, use_non_zero_discount_for_terminal_states=False)),
+             ("ddpg1", DDPGAgent, dict(clip_critic_targets=(-1.5, 1.5), use_non_zero_discount_for_terminal_states=False)),
+             ("ddpg2", DDPGAgent, dict(clip_critic_targets=None, use_non_zero_discount_for_terminal_states=True)),
+             ("td3", TD3Agent, dict(clip_critic_targets=None, use_non_zero_discount_for_terminal_states=False,
+                                    policy_noise=0.2, noise_clipping=0.5, update_policy_every_x_episode_steps=2))]
+    for tag, cls, alg_kw in cases:
+        ts = _transitions(rng, B, (D,), (A,), with_info=False)
+        batch = Batch(ts)
+        next_actions = rng.uniform(-1, 1, (B, A)).astype(np.float32)
+        actions_mean = rng.uniform(-1, 1, (B, A)).astype(np.float32)
+        q1 = (rng.randn(B, 1) * 3).astype(np.float32)
+        q2 = (rng.randn(B, 1) * 3).astype(np.float32)
+        q_outputs = [q1, q2, np.minimum(q1, q2), np.float32(q1.mean())] if cls is TD3Agent else [q1, np.float32(q1.mean())]
+        action_grads = rng.randn(B, A).astype(np.float32)
+        rec = {}
+        critic, actor = _critic_actor_stubs(rec, next_actions, actions_mean, q_outputs, action_grads)
+        nw, alg = _ap(discount=0.99, **alg_kw)
+        fake = SimpleNamespace(ap=SimpleNamespace(network_wrappers={'actor': nw, 'critic': nw}, algorithm=alg),
+                               networks={'actor': actor, 'critic': critic}, TD_targets_signal=_Sig(),
+                               training_iteration=0,
+                               spaces=SimpleNamespace(action=BoxActionSpace(A, -0.9, 0.9)))
+        seed = int(rng.randint(0, 2 ** 31 - 1))
+        np.random.seed(seed)
+        cls.learn_from_batch(fake, batch)
+        out[tag + "_next_actions"], out[tag + "_q1"], out[tag + "_q2"] = next_actions, q1, q2
+        out[tag + "_rewards"] = batch.rewards().astype(np.float64)
+        out[tag + "_game_overs"] = batch.game_overs().astype(np.uint8)
+        out[tag + "_td_targets"] = rec["td_targets"]                   # fp64 [B, 1] as handed to the train op
+        out[tag + "_actor_feed"] = rec["actor_feed"]                   # -action_gradients
+        out[tag + "_action_grads"] = action_grads
+        out[tag + "_critic_train_action"] = rec["critic_train_action"]
+        out[tag + "_batch_actions"] = batch.actions()
+        out[tag + "_grad_fetch"] = np.array([rec["action_grad_fetch"]])
+        out[tag + "_clip"] = np.array(alg_kw["clip_critic_targets"] or (0.0, 0.0), dtype=np.float64)
+        out[tag + "_nonzero_terminal"] = int(alg_kw["use_non_zero_discount_for_terminal_states"])
+        if cls is TD3Agent:
+            np.random.seed(seed)
+            out[tag + "_noise"] = np.random.normal(0, 0.2, next_actions.shape)       # the draw the agent consumed
+            out[tag + "_smoothed_actions"] = rec["target_critic_action"]              # after noise + clip to the space
+            out[tag + "_space"] = np.array([-0.9, 0.9])
+
+
+# ---- SAC -------------------------------------------------------------------------------------------------------------
+def golden_sac(out, rng, B=64, D=17, A=6):
+    from rl_coach.agents.soft_actor_critic_agent import SoftActorCriticAgent
+    from rl_coach.core_types import Batch
+    ts = _transitions(rng, B, (D,), (A,), with_info=False)
+    batch = Batch(ts)
+    rec = {}
+    mu, std = rng.randn(B, A).astype(np.float32), rng.rand(B, A).astype(np.float32)
+    raw, act = rng.randn(B, A).astype(np.float32), np.tanh(rng.randn(B, A)).astype(np.float32)
+    logp = rng.randn(B).astype(np.float32)
+    q_min = rng.randn(B, 1).astype(np.float32)
+    v_next = rng.randn(B, 1).astype(np.float32)
+    dlogp = [rng.randn(5, 3).astype(np.float32), rng.randn(3).astype(np.float32)]
+    dq = [rng.randn(5, 3).astype(np.float32), rng.randn(3).astype(np.float32)]
+    dq_da = rng.randn(B, A).astype(np.float32)
+
+    def policy_predict(inputs, outputs=None, initial_feed_dict=None):
+        if outputs is None:
+            return [mu, std, raw, act, logp, np.float32(logp.mean())]
+        if outputs == "wg5":
+            rec["dlogp_feed"] = np.array(initial_feed_dict["ph5"])
+            return dlogp
+        rec["dq_feed"] = np.array(initial_feed_dict["ph3"])
+        return dq
+    policy_net = SimpleNamespace(predict=policy_predict, gradients_weights_ph=["ph%d" % i for i in range(6)],
+                                 weighted_gradients=["wg%d" % i for i in range(6)],
+                                 apply_gradients=lambda g: rec.update(policy_grads=[np.array(x) for x in g]))
+    q_head = SimpleNamespace(q1_output="q1", q2_output="q2", q1_loss="l1", q2_loss="l2")
+
+    def q_predict(inputs, outputs=None):
+        if outputs is None:
+            rec["q_action_input"] = np.array(inputs['output_0_0'])
+            return [q_min]
+        if isinstance(outputs, list):
+            return q_min, q_min
+        return dq_da
+
+    def q_train(inputs, targets, additional_fetches=None):
+        rec["q_train_action"] = np.array(inputs['output_0_0'])
+        rec["td_targets"] = np.array(targets)
+        return 0.0, [0.0], 0.0, (0.0, 0.0)
+    q_net = SimpleNamespace(predict=q_predict, output_heads=[q_head], train_on_batch=q_train,
+                            gradients_wrt_inputs=[{}, {'output_0_0': 'gq'}])
+    v_wrap = SimpleNamespace(
+        online_network=SimpleNamespace(train_on_batch=lambda i, t: (rec.update(value_targets=np.array(t)) or [0.0])),
+        target_network=SimpleNamespace(predict=lambda i: v_next))
+    nw, alg = _ap(discount=0.99)
+    sig = _Sig()
+    fake = SimpleNamespace(ap=SimpleNamespace(network_wrappers={'v': nw, 'q': nw, 'policy': nw}, algorithm=alg),
+                           networks={'v': v_wrap, 'q': SimpleNamespace(online_network=q_net),
+                                     'policy': SimpleNamespace(online_network=policy_net)},
+                           policy_means=sig, policy_logsig=sig, policy_logprob_sampled=sig, q1_values=sig,
+                           q2_values=sig, policy_grads=sig, v_onl_ys=sig, v_tgt_ns=sig, TD_err1=sig, TD_err2=sig)
+    SoftActorCriticAgent.learn_from_batch(fake, batch)
+    out["sac_q_min"], out["sac_logp"], out["sac_v_next"] = q_min, logp, v_next
+    out["sac_rewards"] = batch.rewards().astype(np.float64)
+    out["sac_game_overs"] = batch.game_overs().astype(np.uint8)
+    out["sac_value_targets"] = rec["value_targets"]                      # [B, 1] = min Q(s, a~pi) - log pi
+    out["sac_td_targets"] = rec["td_targets"]                            # fp64 [B, 1]
+    out["sac_dlogp_feed"] = rec["dlogp_feed"]                            # scalar 1.0 (sum over the batch of mean log pi)
+    out["sac_dq_feed"], out["sac_dq_da"] = rec["dq_feed"], dq_da
+    for i in range(2):
+        out["sac_dlogp_%d" % i], out["sac_dq_%d" % i], out["sac_pgrad_%d" % i] = dlogp[i], dq[i], rec["policy_grads"][i]
+    out["sac_sampled_actions"], out["sac_q_action_input"] = act, rec["q_action_input"]
+
+
+# ---- Batch -----------------------------------------------------------------------------------------------------------
+def golden_batch(out, rng, n=24):
+    from rl_coach.core_types import Batch
+    ts = _transitions(rng, n, (3, 3, 2), 4, obs_dtype=np.uint8)
+    for i, t in enumerate(ts):
+        t.n_step_discounted_rewards = float(rng.randn())
+    b = Batch(ts)
+    out["batch_states"] = b.states(["observation"])["observation"]
+    out["batch_next_states"] = b.next_states(["observation"])["observation"]
+    out["batch_actions"], out["batch_actions_x"] = b.actions(), b.actions(expand_dims=True)
+    out["batch_rewards"], out["batch_rewards_x"] = b.rewards(), b.rewards(expand_dims=True)
+    out["batch_game_overs"], out["batch_game_overs_x"] = b.game_overs(), b.game_overs(expand_dims=True)
+    out["batch_nstep"] = b.n_step_discounted_rewards()
+    out["batch_idx"], out["batch_weight"] = b.info("idx"), b.info("weight")
+    b.slice(3, 11)
+    out["batch_slice_rewards"], out["batch_slice_states"] = b.rewards(), b.states(["observation"])["observation"]
+    out["batch_slice_size"] = b.size
+
+
+def main():
+    _ref()
+    rng = np.random.RandomState(20240)
+    out = {}
+    golden_dqn(out, rng)
+    golden_ppo(out, rng)
+    golden_ddpg_td3(out, rng)
+    golden_sac(out, rng)
+    golden_batch(out, rng)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "agent_prologues.npz"), **out)
+    print("agent_prologues", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -41,7 +41,9 @@ def huber(pred, label, delta=1.0):
 class QNetOracle(object):
     """Functional Q-network; ``params`` is an OrderedDict name -> tensor in creation order."""
 
-    def __init__(self, observation_shape, num_actions, dueling=False, dtype=torch.float32):
+    def __init__(self, observation_shape, num_actions, dueling=False, dtype=torch.float32, middleware=True):
+        """middleware=False: MiddlewareScheme.Empty (fc_middleware.py:58-59), the head reads the embedder output"""
+        self.middleware = middleware
         self.obs_shape = tuple(observation_shape)
         self.A = num_actions
         self.dueling = dueling
@@ -64,8 +66,9 @@ class QNetOracle(object):
         else:
             h = F.relu(h @ p[k] + p[k + 1])
             k += 2
-        h = F.relu(h @ p[k] + p[k + 1])                     # middleware Dense(512)
-        k += 2
+        if self.middleware:
+            h = F.relu(h @ p[k] + p[k + 1])                 # middleware Dense(512)
+            k += 2
         if not self.dueling:
             return h @ p[k] + p[k + 1]
         v = F.relu(h @ p[k] + p[k + 1]) @ p[k + 2] + p[k + 3]

@@ -4,6 +4,11 @@
   n_step_returns()     <- rl_coach/core_types.py:771-801
   RunningStats         <- rl_coach/utilities/shared_running_stats.py:115-164
   ppo_fill_advantages()<- rl_coach/agents/clipped_ppo_agent.py:157-207 (episode split, zero bootstrap, standardise)
+  ac_td_targets()      <- rl_coach/agents/ddpg_agent.py:152-161, td3_agent.py:170-179, soft_actor_critic_agent.py:259-260
+  td3_smooth_actions() <- rl_coach/agents/td3_agent.py:161-164 (+ spaces.py BoxActionSpace.clip_action_to_space)
+
+Pinned: every function here reproduces tests/golden/{rl_math,agent_prologues}.npz, which the UNMODIFIED reference
+generated (oracle/make_golden.py, oracle/make_golden_agents.py; tests/test_oracle_golden.py).
 """
 import numpy as np
 
@@ -98,3 +103,25 @@ def ppo_fill_advantages(rewards, values, game_overs, discount, lam):
     a = adv[:n_valid]
     adv[:n_valid] = (a - np.mean(a)) / np.std(a)
     return adv, tgt, n_valid
+
+
+def ac_td_targets(rewards, game_overs, q_next, discount, clip=None, use_non_zero_discount_for_terminal_states=False):
+    """Bootstrapped TD targets of the actor-critic agents: fp64 numpy broadcasting on the fp32 network output,
+    [B, 1].  The train op's float32 placeholder rounds the result once (np.float32(result))."""
+    r = np.asarray(rewards, dtype=np.float64).reshape(-1, 1)
+    d = np.asarray(game_overs).astype(bool).reshape(-1, 1)
+    q = np.asarray(q_next).reshape(-1, 1)
+    if use_non_zero_discount_for_terminal_states:
+        y = r + discount * q
+    else:
+        y = r + (1.0 - d) * discount * q
+    if clip:
+        y = np.clip(y, *clip)
+    return y
+
+
+def td3_smooth_actions(next_actions, noise, noise_clip, low, high):
+    """td3_agent.py:162-164: fp64 draw clipped, added to the fp32 target-actor output (promoted to fp64), clipped to
+    the action space; fp64 result (the critic's float32 placeholder rounds it once)."""
+    nz = np.asarray(noise, dtype=np.float64).clip(-noise_clip, noise_clip)
+    return np.clip(np.asarray(next_actions) + nz, low, high)

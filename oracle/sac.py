@@ -1,5 +1,6 @@
-"""torch-CPU restatement of the Soft Actor-Critic learn step.  TEST INFRASTRUCTURE ONLY; **parity unpinned**
-(TensorFlow semantics restated, see oracle/nets.py).
+"""torch-CPU restatement of the Soft Actor-Critic learn step.  TEST INFRASTRUCTURE ONLY.  TD / value targets are pinned to the
+unmodified reference (tests/golden/agent_prologues.npz); the network arithmetic is **parity unpinned** (TensorFlow
+semantics restated, see oracle/nets.py).
 
 Sources: agents/soft_actor_critic_agent.py:168-280; heads/sac_head.py:49-97 (policy: [mu | log sigma], clip [-20, 2],
 reparameterised sample, tanh squash + log-prob correction with eps 1e-6); heads/sac_q_head.py:59-119 (two Q heads,
@@ -14,6 +15,7 @@ import numpy as np
 import torch
 
 from oracle.actor_critic import mlp
+from oracle.rl_math import ac_td_targets
 
 LOG_SIG_MIN, LOG_SIG_MAX, EPS = -20.0, 2.0, 1e-6
 
@@ -77,9 +79,7 @@ def sac_step(policy, q, v, v_target, opt_p, opt_q, opt_v, batch, noise, discount
     # 5. Q
     with torch.no_grad():
         v_next = mlp(Vt[0:6], s2, ["relu", "relu", None])
-    r = np.asarray(batch["rewards"], dtype=np.float64).reshape(-1, 1)
-    d = np.asarray(batch["game_overs"]).reshape(-1, 1)
-    y = r + (1.0 - d) * discount * v_next.numpy()
+    y = ac_td_targets(batch["rewards"], batch["game_overs"], v_next.numpy(), discount)
     y = t(y.astype(np.float32) if dtype == torch.float32 else y)
     qa1, qa2 = q_heads(Q, s, a)
     q_loss = 0.5 * ((qa1 - y) ** 2).mean() + 0.5 * ((qa2 - y) ** 2).mean()

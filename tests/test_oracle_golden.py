@@ -136,3 +136,84 @@ def test_gae_nstep_runningstats(golden_dir):
         np.testing.assert_array_equal(rs.std, fx["rs_stds"][k])
     assert rs.count == float(fx["rs_count"])
     np.testing.assert_array_equal(rs.normalize(fx["rs_query"]), fx["rs_norm"])
+
+
+# ---- agent prologues (oracle/make_golden_agents.py: the reference agents' own learn_from_batch, stub networks) -------
+def test_dqn_ddqn_targets_match_reference_agents(golden_dir):
+    from oracle import nets as on
+    fx = np.load(os.path.join(golden_dir, "agent_prologues.npz"))
+    for tag in ("dqn", "ddqn"):
+        q_sel = fx[tag + "_q_select"] if tag == "ddqn" else fx[tag + "_q_next"]     # ddqn_agent.py:42-43
+        targets, td = on.dqn_targets(fx[tag + "_q_next"], q_sel, fx[tag + "_q_online"], fx[tag + "_actions"],
+                                     fx[tag + "_rewards"], fx[tag + "_game_overs"].astype(bool), 0.99)
+        np.testing.assert_array_equal(targets, fx[tag + "_targets"])           # what train_and_sync_networks was fed
+        np.testing.assert_array_equal(td, fx[tag + "_td_errors"])              # what update_priorities was handed
+        assert targets.dtype == np.float32 and fx[tag + "_weights"] is not None
+
+
+def test_ppo_fill_advantages_matches_reference_agent(golden_dir):
+    fx = np.load(os.path.join(golden_dir, "agent_prologues.npz"))
+    for k in range(int(fx["ppo_cases"])):
+        adv, tgt, n_valid = rl_math.ppo_fill_advantages(fx["ppo_rewards_%d" % k], fx["ppo_values_%d" % k][:, 0],
+                                                        fx["ppo_game_overs_%d" % k].astype(bool), 0.99, 0.95)
+        want_adv, want_tgt = fx["ppo_adv_%d" % k], fx["ppo_vtgt_%d" % k]
+        assert n_valid == len(want_adv)                        # trailing open episode gets nothing (zip(), :203)
+        np.testing.assert_allclose(adv[:n_valid], want_adv, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(tgt[:n_valid], want_tgt, rtol=1e-12, atol=1e-13)
+        assert np.all(np.isnan(adv[n_valid:]))
+
+
+def test_actor_critic_targets_match_reference_agents(golden_dir):
+    fx = np.load(os.path.join(golden_dir, "agent_prologues.npz"))
+    for tag in ("ddpg0", "ddpg1", "ddpg2", "td3"):
+        clip = tuple(fx[tag + "_clip"]) if fx[tag + "_clip"].any() else None
+        q = np.minimum(fx[tag + "_q1"], fx[tag + "_q2"]) if tag == "td3" else fx[tag + "_q1"]
+        y = rl_math.ac_td_targets(fx[tag + "_rewards"], fx[tag + "_game_overs"], q, 0.99, clip,
+                                  bool(fx[tag + "_nonzero_terminal"]))
+        np.testing.assert_array_equal(y, fx[tag + "_td_targets"])
+        # the actor is fed -dQ/da (ddpg_agent.py:181, td3_agent.py:196); the critic trains on the batch's own actions
+        np.testing.assert_array_equal(fx[tag + "_actor_feed"], -fx[tag + "_action_grads"])
+        np.testing.assert_array_equal(fx[tag + "_critic_train_action"], fx[tag + "_batch_actions"])
+    # DDPG takes dQ/da from critic output 1, TD3 from output 3 (mean of Q1)
+    assert str(fx["ddpg0_grad_fetch"][0]) == "g1" and str(fx["td3_grad_fetch"][0]) == "g3"
+    sm = rl_math.td3_smooth_actions(fx["td3_next_actions"], fx["td3_noise"], 0.5, *fx["td3_space"])
+    np.testing.assert_array_equal(sm, fx["td3_smoothed_actions"])
+    y = rl_math.ac_td_targets(fx["sac_rewards"], fx["sac_game_overs"], fx["sac_v_next"], 0.99)
+    np.testing.assert_array_equal(y, fx["sac_td_targets"])
+    np.testing.assert_array_equal((fx["sac_q_min"][:, 0] - fx["sac_logp"])[:, None], fx["sac_value_targets"])
+    assert float(fx["sac_dlogp_feed"]) == 1.0
+    np.testing.assert_array_equal(fx["sac_dq_feed"], fx["sac_dq_da"])
+    for i in range(2):       # policy gradient = d(mean log pi) - dq_dphi (soft_actor_critic_agent.py:231)
+        np.testing.assert_array_equal(fx["sac_pgrad_%d" % i], fx["sac_dlogp_%d" % i] - fx["sac_dq_%d" % i])
+    np.testing.assert_array_equal(fx["sac_q_action_input"], fx["sac_sampled_actions"])
+
+
+def test_batch_matches_reference_batch(golden_dir):
+    """core_types.py:405-649: AoS -> SoA, expand_dims, info, slice -- oracle restatement and the host Batch class"""
+    from coach_b200.core_types import Batch, Transition
+    fx = np.load(os.path.join(golden_dir, "agent_prologues.npz"))
+    n = len(fx["batch_rewards"])
+    ts = [Transition(state={"observation": fx["batch_states"][i]}, action=int(fx["batch_actions"][i]),
+                     reward=float(fx["batch_rewards"][i]), next_state={"observation": fx["batch_next_states"][i]},
+                     game_over=bool(fx["batch_game_overs"][i]),
+                     info={"idx": int(fx["batch_idx"][i]), "weight": float(fx["batch_weight"][i])}) for i in range(n)]
+    for i, t in enumerate(ts):
+        t.n_step_discounted_rewards = float(fx["batch_nstep"][i])
+    s, s2, a, r, d = om.batch_columns(ts)
+    b = Batch(ts)
+    for got, got2, key in ((s, b.states(["observation"])["observation"], "batch_states"),
+                           (s2, b.next_states(["observation"])["observation"], "batch_next_states"),
+                           (a, b.actions(), "batch_actions"), (r, b.rewards(), "batch_rewards"),
+                           (d, b.game_overs(), "batch_game_overs")):
+        for g in (got, got2):
+            assert g.dtype == fx[key].dtype and g.shape == fx[key].shape
+            np.testing.assert_array_equal(g, fx[key])
+    for key, got in (("batch_actions_x", b.actions(True)), ("batch_rewards_x", b.rewards(True)),
+                     ("batch_game_overs_x", b.game_overs(True)), ("batch_nstep", b.n_step_discounted_rewards()),
+                     ("batch_idx", b.info("idx")), ("batch_weight", b.info("weight"))):
+        assert got.shape == fx[key].shape
+        np.testing.assert_array_equal(got, fx[key])
+    b.slice(3, 11)
+    assert b.size == int(fx["batch_slice_size"])
+    np.testing.assert_array_equal(b.rewards(), fx["batch_slice_rewards"])
+    np.testing.assert_array_equal(b.states(["observation"])["observation"], fx["batch_slice_states"])
