@@ -47,7 +47,7 @@ class TGemmDesc(ctypes.Structure):
                 ("mask_plane_stride", c_i64), ("bias_row", ctypes.c_int32),
                 ("a_num_planes", ctypes.c_int32),
                 ("a_u8_div", c_float), ("a_rows", c_i64), ("b_rows", c_i64),
-                ("tmap_key", ctypes.c_uint64), ("tmap_storage", ctypes.c_uint8 * (2 * 128 + 64))]
+                ("b_interleaved", ctypes.c_int32), ("tmap_key", ctypes.c_uint64), ("tmap_storage", ctypes.c_uint8 * (2 * 128 + 64))]
 
 
 class Column(ctypes.Structure):
@@ -76,6 +76,12 @@ PROTOTYPES = {
     "cb200_gather": (c_int, [ctypes.POINTER(Column), c_int, c_void_p, c_i64, c_void_p]),
     "cb200_per_sample_gather": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_double, c_void_p,
                                         c_void_p, c_void_p, ctypes.POINTER(Column), c_int, c_void_p]),
+    "cb200_per_sample_gather_s2d": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_double, c_void_p,
+                                            c_void_p, c_void_p, ctypes.POINTER(Column), c_int, ctypes.c_int32,
+                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(Column),
+                                            c_int, c_void_p]),
+    "cb200_gather_s2d": (c_int, [c_void_p, c_i64, ctypes.POINTER(Column), c_int, ctypes.c_int32, ctypes.c_int32,
+                                 ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(Column), c_int, c_void_p]),
     "cb200_scatter_ring": (c_int, [ctypes.POINTER(Column), c_int, c_i64, c_i64, c_i64, c_void_p]),
     "cb200_scatter_ring_packed": (c_int, [ctypes.POINTER(Column), c_int, c_i64, c_i64, c_i64, c_i64, c_void_p]),
     "cb200_gemm": (c_int, [ctypes.POINTER(GemmDesc), c_void_p]),
@@ -152,6 +158,10 @@ def load():
         fn.argtypes = argtypes
     if lib.cb200_abi_version() != 1:
         raise ImportError("coach_b200: ABI version mismatch between _lib.py and libcoach_b200.so")
+    # CB200_TUNE_<KEY>=<int>: runtime knobs of the library (cb200_tune), e.g. CB200_TUNE_GEMM_PERSISTENT=0 for A/B runs
+    for k, v in os.environ.items():
+        if k.startswith("CB200_TUNE_"):
+            lib.cb200_tune(k[len("CB200_TUNE_"):].lower().encode(), int(v))
     _lib = lib
     return lib
 

@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from coach_b200 import _lib
+from coach_b200.architectures import tiled as tl
 from coach_b200.architectures.layers import Workspace
 from coach_b200.architectures.q_network import QNetworkDef
 from coach_b200.base_parameters import (AgentParameters, AlgorithmParameters, EnvironmentSteps, MiddlewareScheme,
@@ -71,13 +72,16 @@ class QNetworkWrapper(object):
     """online + target parameter buffers over one QNetworkDef (network_wrapper.py:31-116), with the three forward
     bindings a DQN step needs: online(s) [training], target(s'), online(s') [DDQN]."""
 
-    def __init__(self, lib, net_def, params: NetworkParameters, batch_size, batch_buffers, double_dqn, device):
+    def __init__(self, lib, net_def, params: NetworkParameters, batch_size, batch_buffers, double_dqn, device,
+                 input_planes=None):
         self.lib, self.net, self.params, self.B = lib, net_def, params, batch_size
         self.store = net_def.store
         self.ws = Workspace(device)
         self.theta = self.store.theta
         self.theta_target = self.store.new_buffer() if params.create_target_network else None
         s, s2 = batch_buffers["state:observation"], batch_buffers["next_state:observation"]
+        if input_planes is not None:         # fused input path: the replay hands over the s2d operand planes directly
+            s, s2 = input_planes["state:observation"], input_planes["next_state:observation"]
         self.online_s = net_def.instantiate(lib, self.ws, batch_size, s, self.theta, self.store.grad, train=True)
         self.target_s2 = net_def.instantiate(lib, self.ws, batch_size, s2, self.theta_target) \
             if self.theta_target is not None else None
@@ -170,8 +174,21 @@ class DQNAgent(object):
         self.net_def = QNetworkDef(dev, self.observation_shape, A, dueling=dueling,
                                    middleware_units=MiddlewareScheme.units[getattr(scheme, "value", scheme)])
         self.net_def.store.init_glorot(gen)
+        # Fused input path (image observations on the tensor-core path): the replay's sample kernel writes the
+        # space-to-depth bf16 plane the first convolution contracts -- no staged uint8 copy, no conversion pass.
+        self.s2d = None
+        first = self.net_def.trunk.layers[0]
+        if (self.net_def.is_image and B >= 128 and B % 32 == 0 and _lib.tune_default("gemm_tiled", 1) and
+                _lib.tune_default("conv_s2d", 1) and _lib.tune_default("fused_input", 1) and
+                first.KH % first.S == 0 and first.H % first.S == 0 and first.W % first.S == 0 and
+                (first.S * first.C) % 8 == 0 and tl.channels_ok(first.S * first.S * first.C)):
+            H, W, C, S = first.H, first.W, first.C, first.S
+            mk = lambda: tl.PlaneBuf((H // S) * (W // S) * B, S * S * C, dev, npix=(H // S) * (W // S), nplanes=1)  # noqa
+            self.s2d = {"columns": {"state:observation": mk(), "next_state:observation": mk()},
+                        "geometry": (H, W, C, S)}
         self.networks = {"main": QNetworkWrapper(self.lib, self.net_def, net_params, B, self.batch_buffers,
-                                                 self.double_dqn, dev)}
+                                                 self.double_dqn, dev,
+                                                 input_planes=self.s2d["columns"] if self.s2d else None)}
         if self.networks["main"].has_target:
             self.networks["main"].sync()
         self.targets = torch.zeros((B, A), dtype=torch.float32, device=dev)
@@ -238,6 +255,8 @@ class DQNAgent(object):
     # ---- the hot path ------------------------------------------------------------------------------------------------
     def sample_batch(self):
         """memory sample straight into the persistent minibatch buffers"""
+        if self.s2d is not None:
+            return self.memory.sample_batch(self.batch_size, out=self.batch_buffers, s2d=self.s2d)
         return self.memory.sample_batch(self.batch_size, out=self.batch_buffers)
 
     def _part_forward(self, cols, per_libm):
@@ -325,11 +344,19 @@ class DQNAgent(object):
     def learn_from_batch(self, batch, fetch=True):
         net = self.networks["main"]
         cols = batch.columns
-        own = all(cols[k].data_ptr() == self.batch_buffers[k].data_ptr()
-                  for k in ("state:observation", "next_state:observation", "action", "reward", "game_over"))
-        for k in ("state:observation", "next_state:observation"):
-            if cols[k].data_ptr() != self.batch_buffers[k].data_ptr():
+        img = ("state:observation", "next_state:observation")
+        own = all(cols[k].data_ptr() == self.batch_buffers[k].data_ptr() for k in ("action", "reward", "game_over"))
+        for k in img:
+            if self.s2d is not None:
+                if k in cols:      # a batch that carries uint8 frames (not sampled through the fused path): convert
+                    H, W, C, S = self.s2d["geometry"]
+                    x = cols[k].contiguous()
+                    _lib.check(self.lib.cb200_u8_s2d_planes(x.data_ptr(), self.batch_size, H, W, C, S,
+                                                            self.s2d["columns"][k].ptr, _lib.current_stream()))
+                    own = False
+            elif cols[k].data_ptr() != self.batch_buffers[k].data_ptr():
                 self.batch_buffers[k].copy_(cols[k])             # foreign batch: stage it (device -> device)
+                own = False
         # value_optimization_agent.py:74-80: priorities from the pre-update errors, weights from the batch
         per = isinstance(self.memory, PrioritizedExperienceReplay)
         weights = None

@@ -226,7 +226,7 @@ class Dense(object):
             w_index = np.arange(K * N).reshape(npix, Ca, N)
             self.perm = _dev_i32(w_index.transpose(0, 2, 1).reshape(-1), device)
             self.wT = torch.empty(npix * N * Ca, dtype=torch.float32, device=device)
-            self.wT_planes = tl.PlaneBuf(npix * N, Ca, device)
+            self.wT_planes = tl.PlaneBuf(npix * N, Ca, device, interleaved=tl.b_interleaved(Ca))
             rowmap = None
             if npix > 1:
                 qq, bb = np.meshgrid(np.arange(npix), np.arange(B), indexing="ij")
@@ -296,6 +296,9 @@ class Conv2d(object):
             self._prepare_tiled(lib, ws, B, device, x, y, w, b, dw, db, dy, dx, need_dx, prev_act, pl)
             return
         div = _u8_div(lut, x_is_u8)
+        if isinstance(x, tl.PlaneBuf):
+            assert (pl is not None and x_is_u8 and div > 0 and B % 32 == 0 and pl.y is not None and not need_dx), \
+                "a space-to-depth input plane needs the tensor-core form of the layer"
         if (pl is not None and x_is_u8 and div > 0 and B % 32 == 0 and pl.y is not None and KH % S == 0 and
                 KW % S == 0 and H % S == 0 and W % S == 0 and tl.channels_ok(S * S * C) and tl.width_ok(N) and
                 not need_dx and _lib.tune_default("conv_s2d", 1)):
@@ -307,7 +310,8 @@ class Conv2d(object):
                   c_prow_batch=B) if (pl is not None and pl.y is not None) else {}
         gp = dict(b_planes=pl.dy.ptr, b_plane_stride=pl.dy.stride, b_prow_npix=OH * OW, b_prow_batch=B) \
             if (pl is not None and pl.dy is not None) else {}
-        wp = dict(b_planes=pl.w_ptr, b_plane_stride=pl.w_stride) if (pl is not None and pl.w_ptr and K % 8 == 0) else {}
+        wp = dict(b_planes=pl.w_ptr, b_plane_stride=pl.w_stride) \
+            if (pl is not None and pl.w_ptr and K % 8 == 0 and pl.w_stride > 0) else {}
         bb, oy, ox = np.meshgrid(np.arange(B), np.arange(OH), np.arange(OW), indexing="ij")
         rowoff = (((bb * H + oy * S) * W + ox * S) * C).reshape(-1)
         ky, kx, cc = np.meshgrid(np.arange(KH), np.arange(KW), np.arange(C), indexing="ij")
@@ -364,13 +368,18 @@ class Conv2d(object):
         H, W, C, N, KH, KW, S, OH, OW = self.H, self.W, self.C, self.N, self.KH, self.KW, self.S, self.OH, self.OW
         Hs, Ws, Cs, TH, TW = H // S, W // S, S * S * C, KH // S, KW // S
         T, nq = TH * TW, OH * OW
-        self.s2d = (x, tl.PlaneBuf(Hs * Ws * B, Cs, device, npix=Hs * Ws, nplanes=1), B)
+        if isinstance(x, tl.PlaneBuf):
+            # the replay's fused gather already delivered the space-to-depth plane (cb200_per_sample_gather_s2d)
+            assert x.nplanes == 1 and x.rows == Hs * Ws * B and x.cols == Cs, "s2d plane geometry"
+            self.s2d = (None, x, B)
+        else:
+            self.s2d = (x, tl.PlaneBuf(Hs * Ws * B, Cs, device, npix=Hs * Ws, nplanes=1), B)
         # rows of the s2d kernel matrix: (tap (ty, tx), (dy, dx, c)) <- original row (ky, kx, c) = (S ty + dy, ...)
         ty, tx, dy_, dx_, cc = np.meshgrid(np.arange(TH), np.arange(TW), np.arange(S), np.arange(S), np.arange(C),
                                            indexing="ij")
         orig_row = (((S * ty + dy_) * KW + (S * tx + dx_)) * C + cc).reshape(-1)            # [T * Cs]
         self.w_s2d = torch.empty(T * Cs * N, dtype=torch.float32, device=device)
-        self.w_s2d_planes = tl.PlaneBuf(T * Cs, N, device)
+        self.w_s2d_planes = tl.PlaneBuf(T * Cs, N, device, interleaved=tl.b_interleaved(N))
         self.w_perm = _dev_i32((orig_row[:, None] * N + np.arange(N)[None, :]).reshape(-1), device)
         pix_in = np.zeros((T, nq), dtype=np.int64)
         for t in range(T):
@@ -433,7 +442,7 @@ class Conv2d(object):
         w_index = np.arange(T * C * N).reshape(T, C, N)
         self.perm = _dev_i32(w_index.transpose(0, 2, 1).reshape(-1), device)
         self.wT = torch.empty(T * N * C, dtype=torch.float32, device=device)
-        self.wT_planes = tl.PlaneBuf(T * N, C, device)
+        self.wT_planes = tl.PlaneBuf(T * N, C, device, interleaved=tl.b_interleaved(C))
         npix = H * W
         qq, bb = np.meshgrid(np.arange(npix), np.arange(B), indexing="ij")
         rowmap_in = _dev_i32((bb * npix + qq).reshape(-1), device)
@@ -444,7 +453,8 @@ class Conv2d(object):
         if self.s2d is not None:
             st = _lib.current_stream()
             x, xp, B = self.s2d
-            _lib.check(self.lib.cb200_u8_s2d_planes(x.data_ptr(), B, self.H, self.W, self.C, self.S, xp.ptr, st))
+            if x is not None:
+                _lib.check(self.lib.cb200_u8_s2d_planes(x.data_ptr(), B, self.H, self.W, self.C, self.S, xp.ptr, st))
             _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), self.w_perm.data_ptr(), self.w_perm.numel(),
                                                   self.w_s2d.data_ptr(), self.w_s2d_planes.ptr,
                                                   self.w_s2d_planes.stride, self.w_s2d_planes.cols, st))

@@ -154,7 +154,7 @@ class SequentialInstance(object):
                 ctx = tl.PlaneCtx(x=x_planes if first else self.act_planes[i - 1], y=self.act_planes[i],
                                   dy=self.dz_planes[i], dx=None if first else self.dz_planes[i - 1],
                                   w_ptr=theta_planes.ptr(wname) if theta_planes.has(wname) else 0,
-                                  w_stride=theta_planes.stride)
+                                  w_stride=theta_planes.stride_of(wname) if theta_planes.has(wname) else 0)
             if train:
                 layer.prepare(lib, ws, B, dev, prev, self.acts[i], w, b, dw, db, self.dzs[i], dx,
                               x_is_u8=(x_is_u8 and first), lut=lut, need_dx=need_dx, prev_act=prev_act,

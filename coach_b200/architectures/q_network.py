@@ -74,7 +74,7 @@ class QNetworkInstance(object):
     def __init__(self, net, lib, ws, B, x, theta, grad, train):
         self.net, self.lib, self.B = net, lib, B
         dev = net.device
-        x_is_u8 = x.dtype == torch.uint8
+        x_is_u8 = isinstance(x, tl.PlaneBuf) or x.dtype == torch.uint8      # PlaneBuf: s2d plane of the uint8 frames
         # Large batches run the trunk on pre-split bf16 operands (architectures/tiled.py).  The parameter planes are
         # re-derived from theta at the start of every forward (one launch), so any writer of theta -- Adam, a target
         # network copy, polyak, a checkpoint load -- is covered.
@@ -130,7 +130,7 @@ class QNetworkInstance(object):
         w_index = np.arange(K * H1).reshape(npix, C, H1)
         perm = torch.from_numpy(np.ascontiguousarray(w_index.transpose(0, 2, 1).reshape(-1), dtype=np.int32)).to(dev)
         wT = torch.empty(2 * npix * H1 * C, dtype=torch.float32, device=dev)
-        wT_planes = tl.PlaneBuf(2 * npix * H1, C, dev)
+        wT_planes = tl.PlaneBuf(2 * npix * H1, C, dev, interleaved=tl.b_interleaved(C))
         w_src = [store.view(theta, seq.names[0][0]) for seq in (net.v_tower, net.a_tower)]
         qq, bb = np.meshgrid(np.arange(npix), np.arange(B), indexing="ij")
         rowmap = torch.from_numpy(np.ascontiguousarray((bb * npix + qq).reshape(-1), dtype=np.int32)).to(dev)

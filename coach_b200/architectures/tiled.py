@@ -26,12 +26,22 @@ def _dev_i32(a, device):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
 
 
-class PlaneBuf(object):
-    """bf16 hi / mid / lo planes of a [rows, cols] matrix (rows = npix * batch) in the core-tiled format"""
+def b_interleaved(n):
+    """B operands of the N <= 64 tile width (cb200_gemm_tiled: bn = 32 / 64) use row-group interleaved planes: one
+    TMA box then delivers [b1 | b2 | b3] as ONE operand and the product set is three wide MMAs instead of six"""
+    return bool(_lib.tune_default("gemm_cat", 1)) and (n <= 64 or n % 128 != 0)
 
-    def __init__(self, rows, cols, device, npix=1, nplanes=3):
+
+class PlaneBuf(object):
+    """bf16 hi / mid / lo planes of a [rows, cols] matrix (rows = npix * batch) in the core-tiled format.
+    interleaved: (row group | plane | column core | 64) instead of three planes `rows * cols` apart -- the layout of
+    the B operands of the narrow GEMMs (``b_interleaved``); its plane stride is passed to the library as -1."""
+
+    def __init__(self, rows, cols, device, npix=1, nplanes=3, interleaved=False):
         assert rows % 8 == 0 and cols % 8 == 0, (rows, cols)
         self.rows, self.cols, self.npix, self.nplanes = int(rows), int(cols), int(npix), int(nplanes)
+        self.interleaved = bool(interleaved)
+        assert not self.interleaved or self.nplanes == 3
         self.t = torch.zeros((self.nplanes, self.rows * self.cols), dtype=torch.bfloat16, device=device)
 
     @property
@@ -40,7 +50,7 @@ class PlaneBuf(object):
 
     @property
     def stride(self):
-        return self.rows * self.cols
+        return -1 if self.interleaved else self.rows * self.cols
 
     def view_rows(self, lo, n, npix=1):
         """rows [lo, lo + n) as a plane matrix of their own (same memory, same plane stride); lo, n multiples of 8"""
@@ -50,14 +60,18 @@ class PlaneBuf(object):
     def load(self, lib, m):
         """planes <- split of an fp32 [rows, cols] matrix (tests, host-written inputs)"""
         m = m.contiguous().view(self.rows, self.cols).float()
-        seg = torch.tensor([[0, self.rows, self.cols, 0]], dtype=torch.int64, device=m.device)
-        _lib.check(lib.cb200_split_planes(m.data_ptr(), self.ptr, self.stride, seg.data_ptr(), 1,
+        seg = torch.tensor([[0, self.rows, self.cols, 0, int(self.interleaved)]], dtype=torch.int64, device=m.device)
+        _lib.check(lib.cb200_split_planes(m.data_ptr(), self.ptr, 0 if self.interleaved else self.stride, seg.data_ptr(), 1,
                                           self.rows * self.cols, _lib.current_stream()))
         torch.cuda.current_stream().synchronize()      # m / seg are temporaries
         return self
 
     def to_dense(self):
         """fp32 [rows, cols] reconstruction hi + mid + lo (tests)"""
+        if self.interleaved:
+            p = self.t.reshape(self.rows // 8, 3, self.cols // 8, 8, 8).float()
+            v = (p[:, 0] + p[:, 1]) + p[:, 2]
+            return v.permute(0, 2, 1, 3).reshape(self.rows, self.cols)
         v = self.t[0].float()
         if self.nplanes == 3:
             v = (v + self.t[1].float()) + self.t[2].float()
@@ -72,11 +86,12 @@ class PlaneView(object):
     def __init__(self, parent, lo, n, npix=1):
         self.parent, self.lo = parent, int(lo)
         self.rows, self.cols, self.npix, self.nplanes = int(n), parent.cols, int(npix), parent.nplanes
+        self.interleaved = parent.interleaved
         self.t = parent.t                      # keeps the storage alive
 
     @property
     def ptr(self):
-        return self.parent.ptr + 2 * self.lo * self.cols
+        return self.parent.ptr + 2 * self.lo * self.cols * (3 if self.interleaved else 1)
 
     @property
     def stride(self):
@@ -103,25 +118,42 @@ class ThetaPlanes(object):
 
     def __init__(self, lib, store, theta):
         self.lib, self.store, self.theta = lib, store, theta
-        self.planes = torch.zeros((3, store.size), dtype=torch.bfloat16, device=theta.device)
+        # one buffer of 6 * size elements.  Planar kernels: plane p of the tensor at `off` sits at p * size + off
+        # (first half).  Row-group interleaved kernels (narrow B operands, ``b_interleaved``): [3 off, 3 off + 3 rows
+        # cols) of the second half.
+        self.buf = torch.zeros(6 * store.size, dtype=torch.bfloat16, device=theta.device)
+        self.planes = self.buf[:3 * store.size].view(3, store.size)
+        self.planes_il = self.buf[3 * store.size:]
         segs, self.max_elems = [], 0
+        self.layout = {}
         for name, (off, shape) in store.entries.items():
             if not name.endswith("kernel") or len(shape) < 2:
                 continue
             rows, cols = int(np.prod(shape[:-1])), int(shape[-1])
             if rows % 8 or cols % 8 or off % 8:
                 continue
-            segs.append((off, rows, cols, off))
+            il = b_interleaved(cols)
+            segs.append((off, rows, cols, 3 * store.size + 3 * off if il else off, int(il)))
+            self.layout[off] = il
             self.max_elems = max(self.max_elems, rows * cols)
         self.names = set(n for n in store.entries)
         self.segs = torch.tensor(segs, dtype=torch.int64, device=theta.device) if segs else None
-        self.eligible = {store_off for (store_off, _, _, _) in segs}
+        self.eligible = {s[0] for s in segs}
 
     def has(self, name):
         return self.store.entries[name][0] in self.eligible
 
+    def interleaved(self, name):
+        return bool(self.layout.get(self.store.entries[name][0], False))
+
     def ptr(self, name):
-        return self.planes.data_ptr() + 2 * self.store.entries[name][0]
+        off = self.store.entries[name][0]
+        if self.layout.get(off, False):
+            return self.planes_il.data_ptr() + 2 * 3 * off
+        return self.planes.data_ptr() + 2 * off
+
+    def stride_of(self, name):
+        return -1 if self.interleaved(name) else self.store.size
 
     @property
     def stride(self):
@@ -139,13 +171,20 @@ class PlaneCtx(object):
 
     def __init__(self, x=None, y=None, dy=None, dx=None, w_ptr=0, w_stride=0):
         self.x, self.y, self.dy, self.dx = x, y, dy, dx       # PlaneBuf or None
-        self.w_ptr, self.w_stride = w_ptr, w_stride           # planes of this layer's kernel inside ThetaPlanes
+        # planes of this layer's kernel inside ThetaPlanes; w_stride -1 = row-group interleaved (``b_interleaved``)
+        self.w_ptr, self.w_stride = w_ptr, w_stride
+
+
+TILED_MAX_CHUNKS = 20
 
 
 def pick_splits_tiled(tiles, total_chunks, sm=148):
-    """reduction slices of a tiled GEMM: at most 32 chunks per slice (TMEM accumulation cap, csrc/nn_gemm_tc.cuh),
-    more when the tile count alone does not fill the machine"""
-    need = (total_chunks + 31) // 32
+    """reduction slices of a tiled GEMM: at most TILED_MAX_CHUNKS chunks (40 accumulating MMAs) per slice -- the TMEM
+    accumulator adds with truncation, a bias that grows linearly with the accumulation count (csrc/nn_gemm_tc.cuh;
+    measured in tests/test_learn_gpu.py: 18 chunks keep every gradient of the B = 512 step within 1e-5, the 32 chunks
+    the kernel would accept put the conv1 gradient of the dueling network at 3e-5) -- and more slices when the tile
+    count alone does not fill the machine"""
+    need = (total_chunks + TILED_MAX_CHUNKS - 1) // TILED_MAX_CHUNKS
     if tiles >= sm:
         return int(max(1, need))
     s = max(1, (2 * sm + tiles - 1) // tiles)
@@ -217,8 +256,10 @@ def forward_op(lib, ws, B, device, x, Ca, w_ptr, w_stride, N, lists, num_q, c, l
     flat = np.asarray(flat, dtype=np.int32).reshape(-1, 2) if flat else np.zeros((1, 2), dtype=np.int32)
     total = max_len * (Ca // 32)
     extra.setdefault("macs", int(ptr[-1]) * Ca * B * N)
+    il = int(w_stride == -1)
+    assert not il or b_interleaved(N), "interleaved B planes only for the narrow tile widths"
     return TGemmOp(lib, ws, mode=0, batch=B, a_planes=x, a_plane_stride=x.stride, a_cols=Ca, b_planes=w_ptr,
-                   b_plane_stride=w_stride, n=N, list_ptr=_dev_i32(ptr, device), list=_dev_i32(flat, device),
+                   b_plane_stride=0 if il else w_stride, b_interleaved=il, n=N, list_ptr=_dev_i32(ptr, device), list=_dev_i32(flat, device),
                    max_list_len=max_len, num_q=num_q, taps=0, c=c, ldc=ldc, bias=bias, act=act, a_rows=x.rows,
                    b_rows=int(w_rows if w_rows is not None else (int(flat[:, 1].max()) + 1) * Ca),
                    c_rowmap=rowmap, splits=pick_splits_tiled(_tiles0(num_q, B, N), total),

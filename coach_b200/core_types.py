@@ -167,9 +167,18 @@ class DeviceBatch(object):
     importance weights, ``'weight32'`` the same rounded once to float32).
     """
 
-    def __init__(self, columns: dict, size: int):
+    def __init__(self, columns: dict, size: int, lazy=None):
+        """lazy(name) -> tensor: materialises a column the sampler did not stage (the fused image path hands the frames
+        to the first convolution as operand planes and skips the uint8 copy; ``states()`` / ``column()`` gather it on
+        demand from the drawn slots)."""
         self.columns = columns
         self._size = size
+        self._lazy = lazy
+
+    def column(self, name):
+        if name not in self.columns and self._lazy is not None:
+            self.columns[name] = self._lazy(name)
+        return self.columns[name]
 
     @property
     def size(self) -> int:
@@ -179,6 +188,11 @@ class DeviceBatch(object):
         out = {}
         for key in fetches:
             name = prefix + key
+            if name not in self.columns and self._lazy is not None:
+                try:
+                    self.column(name)
+                except KeyError:
+                    pass
             if name in self.columns:
                 t = self.columns[name]
                 out[key] = t.unsqueeze(-1) if expand_dims else t
@@ -215,6 +229,9 @@ class DeviceBatch(object):
 
     def to_transitions(self) -> List[Transition]:
         """Host materialisation (device -> host copy of every column); API-compatibility path only."""
+        if self._lazy is not None:
+            for name in getattr(self._lazy, "names", ()):
+                self.column(name)
         host = {k: v.cpu().numpy() for k, v in self.columns.items()}
         out = []
         for i in range(self._size):

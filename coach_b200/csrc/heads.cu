@@ -187,8 +187,16 @@ __global__ void __launch_bounds__(256) ac_td_targets_kernel(const double* __rest
                                                             double clip_lo, double clip_hi, float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
-    const double nd = ignore_done ? 1.0 : __dsub_rn(1.0, dones[i] ? 1.0 : 0.0);
-    double y = __dadd_rn(rewards[i], __dmul_rn(__dmul_rn(nd, discount), (double)q_next[i * ld_q]));
+    double y;
+    if (ignore_done) {
+        // ddpg_agent.py:155: rewards + discount * q -- a Python float times a float32 array stays float32 in numpy, so
+        // this product is rounded to fp32 before the fp64 add (pinned by tests/golden/agent_prologues.npz, "ddpg2")
+        y = __dadd_rn(rewards[i], (double)__fmul_rn((float)discount, q_next[i * ld_q]));
+    } else {
+        // :157-158: (1.0 - game_overs) is a float64 array, the whole product is fp64
+        const double nd = __dsub_rn(1.0, dones[i] ? 1.0 : 0.0);
+        y = __dadd_rn(rewards[i], __dmul_rn(__dmul_rn(nd, discount), (double)q_next[i * ld_q]));
+    }
     if (use_clip) y = fmin(fmax(y, clip_lo), clip_hi);
     out[i] = (float)y;
 }

@@ -121,31 +121,40 @@ static EncodeTiledFn encode_tiled_fn() {
 // planes of a [rows, cols] matrix in the core-tiled format as a 4-D tensor (64 | cols / 8 | rows / 8 | 3) with box
 // (64, box_cores, box_groups, 3)
 static bool make_plane_map(CUtensorMap* map, const void* planes, int64_t plane_stride, int64_t rows, int cols,
-                           int box_cores, int box_groups, int nplanes = 3) {
+                           int box_cores, int box_groups, int nplanes = 3, bool interleaved = false) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
-    const cuuint64_t dims[4] = {64, (cuuint64_t)(cols / 8), (cuuint64_t)(rows / 8), (cuuint64_t)nplanes};
-    const cuuint64_t strides[3] = {128, (cuuint64_t)(cols / 8) * 128, (cuuint64_t)plane_stride * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)box_cores, (cuuint32_t)box_groups, (cuuint32_t)nplanes};
+    cuuint64_t dims[4] = {64, (cuuint64_t)(cols / 8), (cuuint64_t)(rows / 8), (cuuint64_t)nplanes};
+    cuuint64_t strides[3] = {128, (cuuint64_t)(cols / 8) * 128, (cuuint64_t)plane_stride * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_cores, (cuuint32_t)box_groups, (cuuint32_t)nplanes};
+    if (interleaved) {
+        // (64 | column cores | 3 planes | row groups): the box lands as [k-group][plane][column core]
+        dims[2] = 3;
+        dims[3] = (cuuint64_t)(rows / 8);
+        strides[1] = (cuuint64_t)(cols / 8) * 128;
+        strides[2] = 3 * (cuuint64_t)(cols / 8) * 128;
+        box[2] = 3;
+        box[3] = (cuuint32_t)box_groups;
+    }
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(planes), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, bool kT, int NA>
+template <int BN, bool kT, int NA, bool kCat = false>
 static int launch_tiled(const CUtensorMap& tmA, const CUtensorMap& tmB, const TiledParams& tp, const EpiParams& ep,
                         int M, int gx, int splits, cudaStream_t st) {
     constexpr size_t smem = TiledCfg<BN, NA>::kSmemBytes;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc_tiled_kernel<BN, kT, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(gemm_tc_tiled_kernel<BN, kT, NA, kCat>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return -1;
         configured = true;
     }
     dim3 grid(gx, (tp.n + BN - 1) / BN, splits);
-    gemm_tc_tiled_kernel<BN, kT, NA><<<grid, kTlThreads, smem, st>>>(tmA, tmB, tp, ep, M);
+    gemm_tc_tiled_kernel<BN, kT, NA, kCat><<<grid, kTlThreads, smem, st>>>(tmA, tmB, tp, ep, M);
     count_launch();
     if (splits > 1) {
         launch_split_reduce(ep, M, tp.n, st);
@@ -158,8 +167,9 @@ static int launch_tiled(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ti
 // buffer (the parameter buffer): segment k = (src offset, rows, cols, plane offset), all in elements.
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, uint16_t* __restrict__ planes,
                                                            int64_t stride, const int64_t* __restrict__ segs) {
-    const int64_t* sg = segs + 4 * blockIdx.y;
+    const int64_t* sg = segs + 5 * blockIdx.y;
     const int64_t soff = sg[0], rows = sg[1], cols = sg[2], poff = sg[3];
+    const bool il = sg[4] != 0;                            // row-group interleaved planes (tiled_elem_il)
     const int64_t groups = rows * (cols >> 3);             // one thread per (row, 8 columns) = one core-matrix row
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = g / (cols >> 3), c8 = g % (cols >> 3);
@@ -167,6 +177,14 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
         const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
         const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
         const Split8 sp = split8(v0, v1);
+        if (il) {
+            uint16_t* d = planes + poff + tiled_elem_il((size_t)r, (int)(c8 * 8), (int)cols, 0);
+            const size_t ps = (size_t)(cols >> 3) * 64;
+            *reinterpret_cast<uint4*>(d) = sp.h;
+            *reinterpret_cast<uint4*>(d + ps) = sp.m;
+            *reinterpret_cast<uint4*>(d + 2 * ps) = sp.l;
+            continue;
+        }
         uint16_t* d = planes + poff + tiled_elem((size_t)r, (int)(c8 * 8), (int)cols);
         *reinterpret_cast<uint4*>(d) = sp.h;
         *reinterpret_cast<uint4*>(d + stride) = sp.m;
@@ -209,13 +227,13 @@ __global__ void __launch_bounds__(256) u8_s2d_planes_kernel(const uint8_t* __res
     }
 }
 
-template <int BN, bool kT, int NA>
+template <int BN, bool kT, int NA, bool kCat = false>
 static int launch_tiled_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const TiledParams& tp,
                                 const EpiParams& ep, int M, int gx, int splits, cudaStream_t st) {
     constexpr size_t smem = PersistCfg<BN, NA>::kSmemBytes;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc_tiled_persist_kernel<BN, kT, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(gemm_tc_tiled_persist_kernel<BN, kT, NA, kCat>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return -1;
         configured = true;
@@ -223,7 +241,7 @@ static int launch_tiled_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, 
     UnitGrid ug{gx, (tp.n + BN - 1) / BN, splits};
     const int units = ug.gx * ug.gy * ug.gz;
     const int grid = units < sm_count() ? units : sm_count();
-    gemm_tc_tiled_persist_kernel<BN, kT, NA><<<grid, kPsThreads, smem, st>>>(tmA, tmB, tp, ep, M, ug);
+    gemm_tc_tiled_persist_kernel<BN, kT, NA, kCat><<<grid, kPsThreads, smem, st>>>(tmA, tmB, tp, ep, M, ug);
     count_launch();
     if (splits > 1) {
         launch_split_reduce(ep, M, tp.n, st);
@@ -283,7 +301,11 @@ __global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float v = __ldg(src + __ldg(table + i));
         dst[i] = v;
-        if (planes) {
+        if (planes && stride < 0) {          // row-group interleaved planes
+            uint16_t* p = planes + tiled_elem_il((size_t)(i / plane_cols), (int)(i % plane_cols), plane_cols, 0);
+            const size_t ps = (size_t)(plane_cols >> 3) * 64;
+            split3(v, p[0], p[ps], p[2 * ps]);
+        } else if (planes) {
             uint16_t* p = planes + tiled_elem((size_t)(i / plane_cols), (int)(i % plane_cols), plane_cols);
             split3(v, p[0], p[stride], p[2 * stride]);
         }
@@ -467,13 +489,17 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
     const int bn = d->n <= 32 ? 32 : ((d->n <= 64 || d->n % 128 != 0) ? 64 : 128);
     const int na = d->a_num_planes == 1 ? 1 : 3;
     CB200_CHECK_ARG(na == 3 || d->a_u8_div > 0.f, "a single A plane means raw uint8 values: a_u8_div must be set");
+    // row-group interleaved B planes: the three B planes reach shared memory as one [32 k, 3 n] operand and the 3xBF16
+    // product set is issued as 3 wide MMAs instead of 6 (half the shared-memory operand reads of the tensor pipe)
+    const bool cat = d->b_interleaved != 0;
+    CB200_CHECK_ARG(!cat || (d->mode == 0 && bn <= 64), "b_interleaved needs mode 0 and n <= 64 (or n % 128 != 0)");
     // the tensor maps depend only on the descriptor: built on the first call, kept in the descriptor
     cb200_tgemm_desc* md = const_cast<cb200_tgemm_desc*>(d);
     CUtensorMap* maps =
         reinterpret_cast<CUtensorMap*>((reinterpret_cast<uintptr_t>(md->tmap_storage) + 63) & ~(uintptr_t)63);
     const uint64_t key = (uint64_t)(reinterpret_cast<uintptr_t>(d->a_planes) ^ (reinterpret_cast<uintptr_t>(d->b_planes) << 1) ^ 1);
     if (md->tmap_key != key) {
-        bool ok = gemm::make_plane_map(maps + 1, d->b_planes, d->b_plane_stride, d->b_rows, d->n, bn / 8, 4);
+        bool ok = gemm::make_plane_map(maps + 1, d->b_planes, d->b_plane_stride, d->b_rows, d->n, bn / 8, 4, 3, cat);
         if (d->mode == 0)
             ok = ok && gemm::make_plane_map(maps + 0, d->a_planes, d->a_plane_stride, d->a_rows, d->a_cols, 4, 16, na);
         else
@@ -513,6 +539,12 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
                         : gemm::launch_tiled<BN_, false, 1>(maps[0], maps[1], tp, ep, M, gx, splits, st)) \
              : (d->mode ? gemm::launch_tiled<BN_, true, 3>(maps[0], maps[1], tp, ep, M, gx, splits, st)   \
                         : gemm::launch_tiled<BN_, false, 3>(maps[0], maps[1], tp, ep, M, gx, splits, st)))
+#define CB200_TLC(BN_) \
+    (na == 1 ? gemm::launch_tiled<BN_, false, 1, true>(maps[0], maps[1], tp, ep, M, gx, splits, st) \
+             : gemm::launch_tiled<BN_, false, 3, true>(maps[0], maps[1], tp, ep, M, gx, splits, st))
+#define CB200_TPC(BN_) \
+    (na == 1 ? gemm::launch_tiled_persist<BN_, false, 1, true>(maps[0], maps[1], tp, ep, M, gx, splits, st) \
+             : gemm::launch_tiled_persist<BN_, false, 3, true>(maps[0], maps[1], tp, ep, M, gx, splits, st))
 #define CB200_TP(BN_)                                                                                            \
     (na == 1 ? (d->mode ? gemm::launch_tiled_persist<BN_, true, 1>(maps[0], maps[1], tp, ep, M, gx, splits, st)   \
                         : gemm::launch_tiled_persist<BN_, false, 1>(maps[0], maps[1], tp, ep, M, gx, splits, st)) \
@@ -523,7 +555,10 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
     // (measured, profiles/README.md: on the step's shapes the persistent schedule is not faster yet -- one producer warp
     // and one MMA thread per SM instead of two of each -- so it is opt-in: cb200_tune("gemm_persistent", 1))
     const bool persist = tune_get("gemm_persistent", 0, 0, 1) != 0 && !(tp.bias_row && bn == 128);
-    if (persist) {
+    if (cat) {
+        if (persist) rc = bn == 32 ? CB200_TPC(32) : CB200_TPC(64);
+        else rc = bn == 32 ? CB200_TLC(32) : CB200_TLC(64);
+    } else if (persist) {
         if (bn == 32) rc = CB200_TP(32);
         else if (bn == 64) rc = CB200_TP(64);
         else rc = CB200_TP(128);
@@ -532,6 +567,8 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
     else rc = CB200_TL(128);
 #undef CB200_TP
 #undef CB200_TL
+#undef CB200_TLC
+#undef CB200_TPC
     CB200_CHECK_ARG(rc == 0, "could not configure shared memory for the tiled tcgen05 kernel");
     CB200_CHECK_LAUNCH();
     return CB200_OK;

@@ -203,6 +203,13 @@ __device__ __forceinline__ float mask_from_planes(const uint16_t* p, int64_t str
 __device__ __forceinline__ size_t tiled_elem(size_t prow, int col, int pcols) {
     return ((prow >> 3) * (size_t)(pcols >> 3) + (size_t)(col >> 3)) * 64 + (prow & 7) * 8 + (col & 7);
 }
+// "Row-group interleaved" planes (B operands of the N <= 64 forward / data-gradient GEMMs): the three planes of one
+// 8-row group sit next to each other -- (row group | plane | column core | 64) -- so that ONE TMA box delivers a
+// [k-group][plane][column core] tile, i.e. a single MN-major operand [32 k, 3 * n] = [b1 | b2 | b3] whose products with
+// one A plane are issued as one tcgen05.mma of triple width (nn_gemm_tiled.cuh, kCat).  Plane stride argument -1.
+__device__ __forceinline__ size_t tiled_elem_il(size_t prow, int col, int pcols, int plane) {
+    return (((prow >> 3) * 3 + (size_t)plane) * (size_t)(pcols >> 3) + (size_t)(col >> 3)) * 64 + (prow & 7) * 8 + (col & 7);
+}
 __device__ __forceinline__ size_t plane_row(size_t m, int npix, int batch) {
     return npix > 0 ? (m % (size_t)npix) * (size_t)batch + m / (size_t)npix : m;
 }

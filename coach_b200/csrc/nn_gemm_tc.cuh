@@ -145,7 +145,10 @@ __device__ __forceinline__ bool tap_ok(int ri, int ci, int oh, int ow) {
 template <int BN>
 __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_main, uint32_t tmem_corr, bool have_acc,
                                             int m0, int n0, int M, int m_end, int N, int split, bool u8,
-                                            float a_u8_div, int unscaled_row, int col_lo = 0, int col_hi = BN) {
+                                            float a_u8_div, int unscaled_row, int col_lo = 0, int col_hi = BN,
+                                            uint32_t tmem_corr2 = 0xffffffffu) {
+    // tmem_corr2: a second accumulator of correction products (kCat scheme of nn_gemm_tiled.cuh): value = main +
+    // (corr + corr2)
     // row = TMEM lane = thread index modulo 128 (a warp reaches the lane quadrant 32 * (warp % 4)); a second group
     // of four warps may take the other half of the columns [col_lo, col_hi)
     const int tid = threadIdx.x & 127, warp = tid >> 5;
@@ -169,7 +172,15 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& ep, uint32_t tmem_m
         if (have_acc) {
             CB200_TMEM_LD16(vm, tmem_main + lane_base + (uint32_t)col);
             CB200_TMEM_LD16(vc, tmem_corr + lane_base + (uint32_t)col);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (tmem_corr2 != 0xffffffffu) {
+                uint32_t vd[16];
+                CB200_TMEM_LD16(vd, tmem_corr2 + lane_base + (uint32_t)col);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) vc[j] = __float_as_uint(__uint_as_float(vc[j]) + __uint_as_float(vd[j]));
+            } else {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) vm[j] = vc[j] = 0u;

@@ -94,7 +94,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 }
 
 // tmA: planes of A with box (64, 4, 16, NA) (mode 0 only); tmB: planes of the B operand with box (64, BN / 8, 4, 3)
-template <int BN, bool kTransA, int NA>
+// kCat (mode 0, BN <= 64, row-group interleaved B planes): the B box lands as [k-group][plane][column core], one
+// MN-major operand [32 k, 3 BN] = [b1 | b2 | b3].  The product set becomes THREE tcgen05.mma per k16 step,
+//     a1 x [b1|b2|b3] (N = 3 BN) -> columns MAIN | CA | CB       a2 x [b1|b2] (N = 2 BN) -> CA | CB
+//     a3 x [b1]       (N = BN)   -> CA                            value = MAIN + (CA + CB)
+// i.e. the same six products with each A plane read from shared memory once per k-step instead of 3 / 2 / 1 times: an
+// SS-mode MMA of width 64 reads (128 + 64) x 16 x 2 B = 6 KB per 32 tensor cycles, 192 B/cycle against the 128 B/cycle
+// shared memory delivers -- the six narrow MMAs were bound by shared-memory reads, not by the tensor pipe.
+template <int BN, bool kTransA, int NA, bool kCat = false>
 __global__ void __launch_bounds__(kTlThreads) gemm_tc_tiled_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB, TiledParams tp,
                                                             EpiParams ep, int M) {
@@ -115,7 +122,8 @@ __global__ void __launch_bounds__(kTlThreads) gemm_tc_tiled_kernel(const __grid_
     // every row of that product is sum_rows G[row, :], the epilogue keeps row 0.  Three extra MMAs per k16 step in
     // 1 / gridDim.x of the CTAs replace a separate column-sum pass over dY.
     const bool bias_cta = kTransA && tp.bias_row != 0 && blockIdx.x == 0;
-    const uint32_t tmem_cols_needed = (bias_cta ? 4u : 2u) * BN;
+    static_assert(!kCat || (!kTransA && BN <= 64), "kCat: mode 0, BN <= 64");
+    const uint32_t tmem_cols_needed = kCat ? 3u * BN : (bias_cta ? 4u : 2u) * BN;
     const uint32_t TMEM_COLS = tmem_cols_needed <= 32 ? 32u : (tmem_cols_needed <= 64 ? 64u : (tmem_cols_needed <= 128 ? 128u : (tmem_cols_needed <= 256 ? 256u : 512u)));
     const int B = tp.batch, Ca = tp.a_cols, N = tp.n;
     const int n0 = blockIdx.y * BN;
@@ -204,7 +212,8 @@ __global__ void __launch_bounds__(kTlThreads) gemm_tc_tiled_kernel(const __grid_
                     const int e = cj / kc_per, kc = cj % kc_per;
                     const int2 ent = __ldg(tp.list + list_lo + e);
                     tma_load_4d(sA, &tmA, 0, kc * 4, (int)(((size_t)ent.x * B + b0) >> 3), 0, bar);
-                    tma_load_4d(sB, &tmB, 0, n0 >> 3, (ent.y * Ca + kc * kTcBK) >> 3, 0, bar);
+                    if (kCat) tma_load_4d(sB, &tmB, 0, n0 >> 3, 0, (ent.y * Ca + kc * kTcBK) >> 3, bar);
+                    else tma_load_4d(sB, &tmB, 0, n0 >> 3, (ent.y * Ca + kc * kTcBK) >> 3, 0, bar);
                 }
             } else {
                 const int qq = cj / bc_per, bc = cj % bc_per;
@@ -249,10 +258,20 @@ __global__ void __launch_bounds__(kTlThreads) gemm_tc_tiled_kernel(const __grid_
 #pragma unroll
                 for (int ks = 0; ks < kTcBK / 16; ++ks) {
                     const uint64_t a0 = a_hi | (uint64_t)((a_base + ks * A_KS) >> 4);
-                    const uint64_t b0d = b_hi | (uint64_t)((b_base + ks * B_KS) >> 4);
                     const uint64_t a1 = a0 + (A_SPLIT >> 4), a2 = a0 + 2 * (A_SPLIT >> 4);
-                    const uint64_t b1 = b0d + (B_SPLIT >> 4), b2 = b0d + 2 * (B_SPLIT >> 4);
                     const uint32_t first = (j == 0 && ks == 0) ? 0u : 1u;
+                    if (kCat) {
+                        // B stage = [k-group][plane][column core]: k-group stride 3 * B_KG, column-core stride 128
+                        const uint64_t bd = umma_smem_desc(b_base + ks * 2u * 3u * (uint32_t)B_KG, 3u * (uint32_t)B_KG, 128u);
+                        umma_bf16(tmem_main, a0, bd, umma_instr_desc_bf16(3 * BN, 0, 1), first);   // a1 [b1|b2|b3]
+                        if (NA == 3) {
+                            umma_bf16(tmem_main + BN, a1, bd, umma_instr_desc_bf16(2 * BN, 0, 1), 1u);   // a2 [b1|b2]
+                            umma_bf16(tmem_main + BN, a2, bd, umma_instr_desc_bf16(BN, 0, 1), 1u);       // a3 [b1]
+                        }
+                        continue;
+                    }
+                    const uint64_t b0d = b_hi | (uint64_t)((b_base + ks * B_KS) >> 4);
+                    const uint64_t b1 = b0d + (B_SPLIT >> 4), b2 = b0d + 2 * (B_SPLIT >> 4);
                     umma_bf16(tmem_main, a0, b0d, idesc, first);       // a1 b1
                     umma_bf16(tmem_corr, a0, b2, idesc, first);        // a1 b3
                     if (NA == 3) {
@@ -314,7 +333,7 @@ __global__ void __launch_bounds__(kTlThreads) gemm_tc_tiled_kernel(const __grid_
         {
             const int half = warp >> 2;                        // warps 0-3: low half of the columns, 4-7: high half
             tc_epilogue<BN>(ep, tmem_main, tmem_corr, nchunks > 0, m0, n0, M, m_end, N, split, NA == 1, tp.a_u8_div, -1,
-                            half * (BN / 2), half * (BN / 2) + BN / 2);
+                            half * (BN / 2), half * (BN / 2) + BN / 2, kCat ? tmem_main + 2 * BN : 0xffffffffu);
         }
         if (bias_cta && warp == 0) {
             // row `m_end` (= taps * Ca) of the result: lane 0 owns TMEM lane 0 of the bias accumulators

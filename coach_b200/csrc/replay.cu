@@ -23,6 +23,19 @@ namespace cb200 {
 // then replays the reference's comparisons out of registers with shuffles.  Same comparisons, same subtractions,
 // same order => same leaf, bit for bit.
 // =====================================================================================================================
+// 8 bytes -> 8 bf16 holding the integers exactly (0x4B0000vv is the float 2^23 + v; minus 2^23 leaves float(v), whose
+// upper half-word is its bf16)
+__device__ __forceinline__ uint4 u8x8_to_bf16_s2d(uint32_t w0, uint32_t w1) {
+    uint32_t f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f[j] = __float_as_uint(__uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7440 + j)) - 8388608.f);
+        f[4 + j] = __float_as_uint(__uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7440 + j)) - 8388608.f);
+    }
+    return make_uint4(__byte_perm(f[0], f[1], 0x7632), __byte_perm(f[2], f[3], 0x7632), __byte_perm(f[4], f[5], 0x7632),
+                      __byte_perm(f[6], f[7], 0x7632));
+}
+
 struct Descent {
     int64_t leaf;
     double priority;   // tree[leaf + size - 1]
@@ -207,6 +220,166 @@ __global__ void __launch_bounds__(1024) per_update_cta_kernel(UpdateParams up) {
         __syncthreads();
     }
     if (i == 0 && up.max_priority_out) *up.max_priority_out = __ldcg(up.max_tree);   // :201
+}
+
+// n <= 1024, one launch, no global round trip between levels.
+// The batch's leaves are sorted in shared memory (bitonic, key = leaf * 2048 + position), which (i) resolves duplicates
+// -- the last writer of a leaf is the last key of its run -- and (ii) makes paths that meet adjacent: the threads whose
+// paths pass through one node form a contiguous run [lo, hi], and a touched sibling is the run right next to it.  Each
+// thread then walks its path bottom-up holding its node's (sum, min, max) in registers: the sibling's values come from
+// the neighbouring run through shared memory when that sibling is itself being updated, otherwise from global memory,
+// where they cannot change during the kernel and are therefore fetched a few levels ahead.  One __syncthreads per
+// level on double-buffered shared arrays; every parent is op(left, right) of the final children, exactly what the
+// reference's sequential updates leave behind (SegmentTree.update :62-73 recomputes each ancestor from its children).
+constexpr int kUpdSortThreads = 1024;
+constexpr int kUpdAhead = 4;        // levels of untouched-sibling values in flight per thread
+
+__global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(UpdateParams up) {
+    __shared__ unsigned long long s_key[kUpdSortThreads];
+    __shared__ long long s_node[2][kUpdSortThreads];
+    __shared__ double s_sum[2][kUpdSortThreads], s_min[2][kUpdSortThreads], s_max[2][kUpdSortThreads];
+    __shared__ short s_lo[2][kUpdSortThreads], s_hi[2][kUpdSortThreads];
+    __shared__ int s_scan[kUpdSortThreads / 32];
+    __shared__ int s_m;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int P = 32;
+    while (P < up.n) P <<= 1;                               // sort width (power of two, <= 1024)
+    // ---- keys ------------------------------------------------------------------------------------------------------
+    unsigned long long key = ~0ull;                         // invalid / padding: sorts last
+    if (t < up.n) {
+        const int64_t leaf = upd_leaf(up, t);
+        if (leaf >= 0 && leaf < up.size) key = ((unsigned long long)leaf << 11) | (unsigned long long)t;
+    }
+    s_key[t] = key;
+    __syncthreads();
+    // ---- bitonic sort of s_key[0 .. P) -------------------------------------------------------------------------------
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (t < P) {
+                const int partner = t ^ j;
+                if (partner > t) {
+                    const unsigned long long a = s_key[t], b = s_key[partner];
+                    const bool up_dir = (t & k) == 0;
+                    if ((a > b) == up_dir) {
+                        s_key[t] = b;
+                        s_key[partner] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- last writer of every distinct leaf, compacted in leaf order ----------------------------------------------
+    bool winner = false;
+    if (t < P) {
+        const unsigned long long k0 = s_key[t];
+        winner = k0 != ~0ull && (t == P - 1 || (s_key[t + 1] >> 11) != (k0 >> 11));
+        key = k0;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, winner);
+    if (lane == 0) s_scan[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_scan[lane];
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        s_scan[lane] = incl - v;                            // exclusive prefix per warp
+        if (lane == 31) s_m = incl;
+    }
+    __syncthreads();
+    const int m = s_m;                                      // distinct leaves
+    if (winner) {
+        const int pos = s_scan[warp] + __popc(ballot & ((1u << lane) - 1u));
+        s_node[1][pos] = (long long)key;                    // parked in the second buffer until the loop starts
+    }
+    __syncthreads();
+    // ---- leaves -------------------------------------------------------------------------------------------------------
+    long long node = 0;                                     // 1-based heap index of this thread's current node
+    double v_sum = 0.0, v_min = 0.0, v_max = 0.0;
+    int lo = t, hi = t;
+    const bool act = t < m;
+    if (act) {
+        const unsigned long long k0 = (unsigned long long)s_node[1][t];
+        const int64_t leaf = (int64_t)(k0 >> 11);
+        const int src = (int)(k0 & 2047);
+        const double pa = up.idx ? up.p_alpha[src] : up.c_alpha;
+        const double pr = up.idx ? up.p_raw[src] : up.c_raw;
+        node = leaf + up.size;
+        __stcg(up.sum_tree + node - 1, pa);
+        __stcg(up.min_tree + node - 1, pa);
+        __stcg(up.max_tree + node - 1, pr);
+        v_sum = v_min = pa;
+        v_max = pr;
+    }
+    __syncthreads();                                        // s_node[1] is free again
+    // untouched-sibling values, kUpdAhead levels ahead
+    double p_sum[kUpdAhead], p_min[kUpdAhead], p_max[kUpdAhead];
+#pragma unroll
+    for (int w = 0; w < kUpdAhead; ++w) {
+        p_sum[w] = p_min[w] = p_max[w] = 0.0;
+        if (act && w < up.levels) {
+            const long long sib = ((node >> w) ^ 1) - 1;
+            p_sum[w] = __ldcg(up.sum_tree + sib);
+            p_min[w] = __ldcg(up.min_tree + sib);
+            p_max[w] = __ldcg(up.max_tree + sib);
+        }
+    }
+    const long long leaf_node = node;
+    for (int l0 = 0; l0 < up.levels; l0 += kUpdAhead) {
+#pragma unroll
+        for (int w = 0; w < kUpdAhead; ++w) {
+            const int l = l0 + w;
+            if (l >= up.levels) break;
+            const int buf = l & 1;
+            if (act) {
+                s_node[buf][t] = node;
+                s_sum[buf][t] = v_sum;
+                s_min[buf][t] = v_min;
+                s_max[buf][t] = v_max;
+                s_lo[buf][t] = (short)lo;
+                s_hi[buf][t] = (short)hi;
+            }
+            __syncthreads();
+            if (act) {
+                const bool is_left = (node & 1) == 0;       // children of p: 2p (left), 2p + 1 (right)
+                const int nb = is_left ? hi + 1 : lo - 1;
+                const bool touched = nb >= 0 && nb < m && s_node[buf][nb] == (is_left ? node + 1 : node - 1);
+                double o_sum = p_sum[w], o_min = p_min[w], o_max = p_max[w];
+                if (touched) {
+                    o_sum = s_sum[buf][nb];
+                    o_min = s_min[buf][nb];
+                    o_max = s_max[buf][nb];
+                    if (is_left) hi = s_hi[buf][nb];
+                    else lo = s_lo[buf][nb];
+                }
+                const double l_sum = is_left ? v_sum : o_sum, r_sum = is_left ? o_sum : v_sum;
+                const double l_min = is_left ? v_min : o_min, r_min = is_left ? o_min : v_min;
+                const double l_max = is_left ? v_max : o_max, r_max = is_left ? o_max : v_max;
+                v_sum = __dadd_rn(l_sum, r_sum);            // :72  tree[left] + tree[right]
+                v_min = py_min(l_min, r_min);
+                v_max = py_max(l_max, r_max);
+                node >>= 1;
+                if (t == lo) {                              // one writer per node
+                    __stcg(up.sum_tree + node - 1, v_sum);
+                    __stcg(up.min_tree + node - 1, v_min);
+                    __stcg(up.max_tree + node - 1, v_max);
+                }
+                // refill this slot with the sibling of level l + kUpdAhead
+                const int ln = l + kUpdAhead;
+                if (ln < up.levels) {
+                    const long long sib = ((leaf_node >> ln) ^ 1) - 1;
+                    p_sum[w] = __ldcg(up.sum_tree + sib);
+                    p_min[w] = __ldcg(up.min_tree + sib);
+                    p_max[w] = __ldcg(up.max_tree + sib);
+                }
+            }
+        }
+    }
+    if (t == 0 && up.max_priority_out) *up.max_priority_out = m > 0 ? v_max : __ldcg(up.max_tree);   // :201
 }
 
 // large n: separate launches
@@ -451,6 +624,134 @@ __global__ void __launch_bounds__(kGatherThreads) per_sample_gather_kernel(Sampl
     }
 }
 
+// =====================================================================================================================
+// Fused input path of the image agents: PER sample (or given indices) -> gather the uint8 frames of the drawn slots ->
+// bf16 plane of their space-to-depth(S) view, the operand format of the first convolution (nn.cu: u8_s2d_planes_kernel
+// documents the view: pixel (Y, X) = (y / S, x / S), channel ((y % S) * S + x % S) * C + c, plane row
+// (Y * (W / S) + X) * B + b, 8x8 core-tiled).  Replaces: staged uint8 copy written by the gather + two conversion
+// passes that re-read it.  HBM traffic: the frames are read once; the planes (2 bytes per pixel value) are written once.
+//
+// One CTA = 8 consecutive samples (one 8-row group of the plane matrix: every 128-byte core is written whole) x one
+// image column x one band of s2d rows.  Phase A: the CTA's 8 warps walk the sum tree for the 8 samples (3 dependent
+// round trips, warp_descent).  Phase B: lanes 0..7 of warp 0 stream the band in chunks of `rows_per_chunk` s2d rows --
+// one 1-D TMA bulk copy per sample and chunk (rows are contiguous in the ring), three chunks in flight on mbarriers --
+// while all 256 threads convert the chunk that has landed: thread = (pixel slot, y % S, b): `S * C` bytes from shared
+// memory (conflict-free: the per-sample stride is an odd multiple of 16 bytes) -> bf16 -> two 16-byte stores; the 8 b
+// lanes of a quarter-warp complete one 128-byte core.  The band's first CTA also publishes indices / importance
+// weights and copies the small columns.
+// =====================================================================================================================
+constexpr int kS2dThreads = 256;
+constexpr int kS2dStages = 3;
+
+struct S2dGatherParams {
+    const uint8_t* src[2];     // ring columns (uint8 [capacity, H * W * C])
+    uint16_t* plane[2];        // s2d planes [Hs * Ws * B, S * S * C] bf16, core-tiled
+    int n_img;
+    int64_t row_bytes;         // H * W * C
+    int H, W, C, S;
+    int B;                     // samples, multiple of 8
+    int parts;                 // bands of s2d rows per (group, column)
+    int rows_per_chunk;
+    int chunk_stride;          // bytes per sample inside a stage (chunk bytes + padding: odd multiple of 16)
+    const int64_t* idx_in;     // non-null: indices are given (uniform replay); null: sample the sum tree
+    SmallColumn small[CB200_MAX_COLUMNS];
+    int n_small;
+};
+
+__global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SampleParams sp, S2dGatherParams gp) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);                      // [kS2dStages]
+    int64_t* leaf_smem = reinterpret_cast<int64_t*>(smem + 64);                  // [8]
+    double* prio_smem = reinterpret_cast<double*>(smem + 128);                   // [8]
+    uint8_t* stage_mem = smem + 256;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int part = blockIdx.x % gp.parts;
+    const int col = (blockIdx.x / gp.parts) % gp.n_img;
+    const int group = blockIdx.x / (gp.parts * gp.n_img);
+    const int b0 = group * 8;
+    const int S = gp.S, C = gp.C, Hs = gp.H / S, Ws = gp.W / S, run = S * C, Cs = S * run;
+    const int s2d_row_bytes = S * gp.W * C;                                      // bytes of one s2d row of one sample
+    const int per = (Hs + gp.parts - 1) / gp.parts;
+    const int y_lo = part * per, y_hi = min(Hs, y_lo + per);
+    if (tid == 0) {
+        for (int s = 0; s < kS2dStages; ++s) mbar_init(full_bar + s, 1);
+        fence_mbar_init();
+    }
+    // ---- phase A: one warp per sample ----------------------------------------------------------------------------
+    {
+        const int64_t smp = b0 + warp;
+        if (gp.idx_in) {
+            if (lane == 0) leaf_smem[warp] = __ldg(gp.idx_in + smp);
+        } else {
+            const Descent d = per_sample_descend(sp, smp, reinterpret_cast<double*>(stage_mem) + warp * kScratchDoubles);
+            if (lane == 0) {
+                leaf_smem[warp] = d.leaf;
+                prio_smem[warp] = d.priority;
+            }
+        }
+    }
+    __syncthreads();
+    const int nchunks = y_hi > y_lo ? (y_hi - y_lo + gp.rows_per_chunk - 1) / gp.rows_per_chunk : 0;
+    auto issue = [&](int k) {        // executed by warp 0
+        const int st = k % kS2dStages;
+        const int ya = y_lo + k * gp.rows_per_chunk;
+        const int rc = min(gp.rows_per_chunk, y_hi - ya);
+        const uint32_t bytes = (uint32_t)(rc * s2d_row_bytes);
+        if (lane == 0) mbar_expect_tx(full_bar + st, 8u * bytes);
+        __syncwarp();
+        if (lane < 8)
+            bulk_g2s(stage_mem + (size_t)st * 8 * gp.chunk_stride + (size_t)lane * gp.chunk_stride,
+                     gp.src[col] + leaf_smem[lane] * gp.row_bytes + (size_t)ya * s2d_row_bytes, bytes, full_bar + st);
+    };
+    if (warp == 0) {
+        fence_proxy_async_smem();      // the stage memory served as descent scratch through the generic proxy
+        for (int k = 0; k < nchunks && k < kS2dStages; ++k) issue(k);
+    } else if (part == 0 && col == 0) {
+        // this (group)'s publisher: indices, importance weights, small columns -- off the copy's critical path
+        for (int w = warp - 1; w < 8; w += 7) {
+            const int64_t smp = b0 + w;
+            const int64_t leaf = leaf_smem[w];
+            if (lane == 0) {
+                if (gp.idx_in == nullptr) per_sample_publish(sp, smp, leaf, prio_smem[w]);
+            }
+            for (int c = 0; c < gp.n_small; ++c) {
+                const SmallColumn& sc = gp.small[c];
+                warp_copy_row(sc.dst + smp * sc.row_bytes, sc.src + leaf * sc.row_bytes, sc.row_bytes, lane);
+            }
+        }
+    }
+    // ---- phase B: convert the chunks as they land ----------------------------------------------------------------
+    const int per_pixel = 8 * S;                             // threads per s2d pixel: (y % S, b)
+    const int slots = kS2dThreads / per_pixel;               // pixels converted per pass
+    const int within = tid % per_pixel, slot = tid / per_pixel;
+    const int dy = within >> 3, b = within & 7;
+    uint16_t* plane = gp.plane[col];
+    for (int k = 0; k < nchunks; ++k) {
+        const int st = k % kS2dStages;
+        const int ya = y_lo + k * gp.rows_per_chunk;
+        const int rc = min(gp.rows_per_chunk, y_hi - ya);
+        mbar_wait(full_bar + st, (uint32_t)((k / kS2dStages) & 1));
+        const uint8_t* sbase = stage_mem + (size_t)st * 8 * gp.chunk_stride + (size_t)b * gp.chunk_stride;
+        if (slot < slots) {
+            for (int pi = slot; pi < rc * Ws; pi += slots) {
+                const int yl = pi / Ws, X = pi - yl * Ws;
+                const uint8_t* sp8 = sbase + ((size_t)(yl * S + dy) * gp.W + (size_t)X * S) * C;
+                const size_t prow = ((size_t)(ya + yl) * Ws + X) * gp.B + b0 + b;
+                for (int g = 0; g < run; g += 8) {
+                    const uint2 w = *reinterpret_cast<const uint2*>(sp8 + g);
+                    *reinterpret_cast<uint4*>(plane + ((prow >> 3) * (size_t)(Cs >> 3) + ((dy * run + g) >> 3)) * 64 +
+                                              (prow & 7) * 8) = u8x8_to_bf16_s2d(w.x, w.y);
+                }
+            }
+        }
+        __syncthreads();                                     // everyone is done reading this stage
+        if (warp == 0 && k + kS2dStages < nchunks) {
+            fence_proxy_async_smem();
+            issue(k + kS2dStages);
+        }
+    }
+}
+
 // generic row copy used by the ring append: dst row (cursor+i)%capacity <- src row i
 __global__ void __launch_bounds__(256) scatter_ring_kernel(uint8_t* ring, const uint8_t* staged, int64_t row_bytes,
                                                            int64_t cursor, int64_t capacity, int64_t n,
@@ -618,7 +919,9 @@ int cb200_per_init(double* sum_tree, double* min_tree, double* max_tree, int32_t
 static int run_update(UpdateParams& up, void* stream) {
     cudaStream_t st = as_stream(stream);
     if (up.n <= 0) return CB200_OK;
-    if (up.n <= 1024) {
+    if (up.n <= 1024 && up.levels <= 52 && tune_get("per_update_sorted", 1, 0, 1)) {
+        CB200_LAUNCH(per_update_sorted_kernel, 1, kUpdSortThreads, 0, st, up);
+    } else if (up.n <= 1024) {
         int threads = (int)((up.n + 31) / 32 * 32);
         CB200_LAUNCH(per_update_cta_kernel, 1, threads, 0, st, up);
     } else {
@@ -767,6 +1070,102 @@ int cb200_per_sample_gather(const double* sum_tree, const double* min_tree, int6
         configured = smem;
     }
     CB200_LAUNCH(per_sample_gather_kernel, grid, kGatherThreads, smem, st, sp, gp);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int64_t n, const cb200_column* img,
+                             int n_img, int h, int w, int c, int s, const cb200_column* small_cols, int n_small,
+                             cudaStream_t st) {
+    S2dGatherParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.n_img = n_img;
+    gp.row_bytes = (int64_t)h * w * c;
+    gp.H = h; gp.W = w; gp.C = c; gp.S = s;
+    gp.B = (int)n;
+    gp.idx_in = idx_in;
+    for (int k = 0; k < n_img; ++k) {
+        gp.src[k] = static_cast<const uint8_t*>(img[k].src);
+        gp.plane[k] = static_cast<uint16_t*>(img[k].dst);
+    }
+    gp.n_small = n_small;
+    for (int k = 0; k < n_small; ++k) {
+        gp.small[k].src = static_cast<const uint8_t*>(small_cols[k].src);
+        gp.small[k].dst = static_cast<uint8_t*>(small_cols[k].dst);
+        gp.small[k].row_bytes = small_cols[k].row_bytes;
+    }
+    const int hs = h / s;
+    const int s2d_row_bytes = s * w * c;
+    // chunks of about 4 KB per sample; the padded per-sample stride is an odd multiple of 16 bytes
+    int rc = 4096 / s2d_row_bytes;
+    if (rc < 1) rc = 1;
+    if (rc > hs) rc = hs;
+    gp.rows_per_chunk = rc;
+    int stride = rc * s2d_row_bytes;
+    if ((stride / 16) % 2 == 0) stride += 16;
+    gp.chunk_stride = stride;
+    // bands: enough CTAs for two per SM
+    const int groups = (int)(n / 8) * n_img;
+    int parts = (2 * sm_count() + groups - 1) / groups;
+    if (parts < 1) parts = 1;
+    if (parts > hs) parts = hs;
+    gp.parts = parts;
+    size_t smem = 256 + (size_t)kS2dStages * 8 * stride;
+    const size_t scratch = 256 + 8 * kScratchDoubles * sizeof(double);     // phase A: per-warp descent scratch
+    if (smem < scratch) smem = scratch;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(sample_gather_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return -1;
+        configured = smem;
+    }
+    CB200_LAUNCH(sample_gather_s2d_kernel, (unsigned)(groups * parts), kS2dThreads, smem, st, sp, gp);
+    return 0;
+}
+
+static int check_s2d_args(const cb200_column* img, int n_img, int64_t n, int h, int w, int c, int s,
+                          const cb200_column* small_cols, int n_small) {
+    if (!img || n_img < 1 || n_img > 2 || n <= 0 || n % 8 != 0) return -1;
+    if (s <= 0 || h % s || w % s || (s * c) % 8 != 0 || ((int64_t)s * w * c) % 16 != 0 || ((int64_t)h * w * c) % 16 != 0)
+        return -1;
+    if (n_small < 0 || n_small > CB200_MAX_COLUMNS || (n_small > 0 && !small_cols)) return -1;
+    for (int k = 0; k < n_img; ++k)
+        if (!img[k].src || !img[k].dst || img[k].row_bytes != (int64_t)h * w * c ||
+            ((reinterpret_cast<uintptr_t>(img[k].src) | reinterpret_cast<uintptr_t>(img[k].dst)) & 15))
+            return -1;
+    for (int k = 0; k < n_small; ++k)
+        if (!small_cols[k].src || !small_cols[k].dst || small_cols[k].row_bytes <= 0) return -1;
+    return 0;
+}
+
+int cb200_per_sample_gather_s2d(const double* sum_tree, const double* min_tree, int64_t size, const double* u, int64_t n,
+                                int64_t nt, double beta, int64_t* idx_out, double* w_out, float* w32_out,
+                                const cb200_column* image_columns, int n_image, int32_t h, int32_t w, int32_t c,
+                                int32_t s, const cb200_column* small_columns, int n_small, void* stream) {
+    SampleParams sp;
+    CB200_CHECK_ARG(fill_sample_params(sp, sum_tree, min_tree, size, u, n, nt, beta, idx_out, w_out, w32_out) == 0,
+                    "bad arguments (size must be a power of 2, n > 0, non-null trees / uniforms)");
+    CB200_CHECK_ARG(idx_out != nullptr, "idx_out is required");
+    CB200_CHECK_ARG(check_s2d_args(image_columns, n_image, n, h, w, c, s, small_columns, n_small) == 0,
+                    "bad image geometry / column table (n % 8 == 0, 1-2 uint8 image columns, 16-byte aligned rows)");
+    const int rc = launch_gather_s2d(sp, nullptr, n, image_columns, n_image, h, w, c, s, small_columns, n_small,
+                                     as_stream(stream));
+    CB200_CHECK_ARG(rc == 0, "could not configure the fused sample + gather + space-to-depth kernel");
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_gather_s2d(const int64_t* idx, int64_t n, const cb200_column* image_columns, int n_image, int32_t h, int32_t w,
+                     int32_t c, int32_t s, const cb200_column* small_columns, int n_small, void* stream) {
+    CB200_CHECK_ARG(idx != nullptr, "idx is required");
+    CB200_CHECK_ARG(check_s2d_args(image_columns, n_image, n, h, w, c, s, small_columns, n_small) == 0,
+                    "bad image geometry / column table (n % 8 == 0, 1-2 uint8 image columns, 16-byte aligned rows)");
+    SampleParams sp;
+    memset(&sp, 0, sizeof(sp));
+    const int rc = launch_gather_s2d(sp, idx, n, image_columns, n_image, h, w, c, s, small_columns, n_small,
+                                     as_stream(stream));
+    CB200_CHECK_ARG(rc == 0, "could not configure the fused gather + space-to-depth kernel");
     CB200_CHECK_LAUNCH();
     return CB200_OK;
 }

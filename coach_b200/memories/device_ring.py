@@ -22,6 +22,10 @@ import torch
 from coach_b200 import _lib
 
 
+def _ptr_of(p):
+    return p.data_ptr() if torch.is_tensor(p) else p.ptr
+
+
 class ColumnSpec(object):
     def __init__(self, name, shape, dtype):
         self.name = name
@@ -249,6 +253,42 @@ class DeviceTransitionRing(object):
                 self._table_cache.clear()
                 self._table_cache[key] = hit
         return hit
+
+    def s2d_tables(self, s2d, out, n):
+        """ctypes tables of the fused gather + space-to-depth launch (cb200_per_sample_gather_s2d / cb200_gather_s2d).
+        s2d: {"columns": {ring column name: plane tensor / PlaneBuf}, "geometry": (H, W, C, S)}; every other column
+        is copied into ``out``.  Returns (image table, n_image, small table, n_small, image names)."""
+        key = ("s2d", int(n)) + tuple(_ptr_of(p) for p in s2d["columns"].values()) + \
+            tuple(out[name].data_ptr() for name in self.specs if name not in s2d["columns"])
+        hit = self._table_cache.get(key)
+        if hit is None:
+            H, W, C, S = s2d["geometry"]
+            img, small = [], []
+            for name, sp in self.specs.items():
+                if name in s2d["columns"]:
+                    if sp.dtype != np.uint8 or sp.row_bytes != H * W * C:
+                        raise ValueError("column %r is %s%s, the fused image path needs uint8 [%d, %d, %d] frames"
+                                         % (name, sp.dtype, sp.shape, H, W, C))
+                    img.append((self.columns[name].data_ptr(), _ptr_of(s2d["columns"][name]), sp.row_bytes))
+                else:
+                    t = out[name]
+                    if t.dtype != sp.torch_dtype() or t.numel() * t.element_size() != n * sp.row_bytes or \
+                            not t.is_contiguous():
+                        raise ValueError("batch buffer %r does not match the replay's %s%s" % (name, sp.dtype, sp.shape))
+                    small.append((self.columns[name].data_ptr(), t.data_ptr(), sp.row_bytes))
+            ia, ni = _lib.make_columns(img)
+            sa, ns = _lib.make_columns(small)
+            hit = self._table_cache[key] = (ia, ni, sa, ns)
+        return hit
+
+    def gather_column(self, name, idx):
+        """one column of the given slots as a typed tensor (lazy materialisation of un-staged batch columns)"""
+        sp = self.specs[name]
+        n = idx.shape[0]
+        out = torch.empty((n,) + sp.shape, dtype=sp.torch_dtype(), device=self.device)
+        arr, cnt = _lib.make_columns([(self.columns[name].data_ptr(), out.data_ptr(), sp.row_bytes)])
+        _lib.check(self.lib.cb200_gather(arr, cnt, idx.data_ptr(), n, _lib.current_stream()))
+        return out
 
     def gather(self, idx, out=None):
         """out[c][i] = column c of slot idx[i]; idx int64 CUDA tensor."""

@@ -105,12 +105,22 @@ class ExperienceReplay(Memory):
         r = self.ring
         return (r.cursor - r.count + pos) % r.capacity
 
-    def sample_batch(self, size: int, out: dict = None) -> DeviceBatch:
-        """Fast path: one H2D copy of the drawn slots + one gather launch; returns device-resident columns."""
+    def sample_batch(self, size: int, out: dict = None, s2d: dict = None) -> DeviceBatch:
+        """Fast path: one H2D copy of the drawn slots + one gather launch; returns device-resident columns.
+        ``s2d``: image columns as space-to-depth operand planes (see PrioritizedExperienceReplay.sample_batch)."""
         pos = self._draw_positions(size)
         self._flush()
         slots = torch.from_numpy(self._positions_to_slots(pos).astype(np.int64))
         idx = slots.pin_memory().to(self.device, non_blocking=True) if self.device.type == "cuda" else slots
+        if s2d is not None:
+            from coach_b200.memories.prioritized_experience_replay import _LazyColumns
+            ia, ni, sa, ns = self.ring.s2d_tables(s2d, out, size)
+            H, W, C, S = s2d["geometry"]
+            _lib.check(self.lib.cb200_gather_s2d(idx.data_ptr(), size, ia, ni, H, W, C, S, sa, ns,
+                                                 _lib.current_stream()))
+            cols = {k: v for k, v in out.items() if k not in s2d["columns"]}
+            cols["idx"] = idx
+            return DeviceBatch(cols, size, lazy=_LazyColumns(self.ring, idx, tuple(s2d["columns"])))
         cols = self.ring.gather(idx, out)
         cols = dict(cols)
         cols["idx"] = idx

@@ -40,6 +40,18 @@ class PrioritizedExperienceReplayParameters(ExperienceReplayParameters):
         return 'coach_b200.memories.prioritized_experience_replay:PrioritizedExperienceReplay'
 
 
+class _LazyColumns(object):
+    """materialises an un-staged batch column from the drawn slots (DeviceBatch.column)"""
+
+    def __init__(self, ring, idx, names):
+        self.ring, self.idx, self.names = ring, idx, names
+
+    def __call__(self, name):
+        if name not in self.names:
+            raise KeyError(name)
+        return self.ring.gather_column(name, self.idx.clone())
+
+
 class PrioritizedExperienceReplay(ExperienceReplay):
     def __init__(self, max_size: Tuple[MemoryGranularity, int], alpha: float = 0.6,
                  beta: Schedule = ConstantSchedule(0.4), epsilon: float = 1e-6,
@@ -177,10 +189,13 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         return torch.from_numpy(a).to(self.device)
 
     # ---- sample --------------------------------------------------------------------------------------------------
-    def sample_batch(self, size: int, out: dict = None, uniforms=None) -> DeviceBatch:
+    def sample_batch(self, size: int, out: dict = None, uniforms=None, s2d: dict = None) -> DeviceBatch:
         """:219-262 as ONE fused kernel launch (tree descent + importance weights + column gather).  ``uniforms``
         (optional) are the raw ``random.random()`` draws; by default they are drawn here from Python's global
-        generator, one per sample, exactly the stream ``random.uniform`` consumes at :244."""
+        generator, one per sample, exactly the stream ``random.uniform`` consumes at :244.
+        ``s2d`` ({"columns": {ring column: bf16 plane}, "geometry": (H, W, C, S)}): the image columns leave the kernel
+        as the space-to-depth operand planes of the first convolution instead of a staged uint8 copy
+        (cb200_per_sample_gather_s2d); the batch materialises them on demand (``DeviceBatch.column``)."""
         if not self.num_transitions() >= size:
             raise ValueError("The replay buffer cannot be sampled since there are not enough transitions yet. "
                              "There are currently {} transitions".format(self.num_transitions()))
@@ -194,8 +209,23 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         for k, dt in (("idx", torch.int64), ("weight", torch.float64), ("weight32", torch.float32)):
             if k not in out:
                 out[k] = torch.empty(size, dtype=dt, device=self.device)
-        arr, cnt = self.ring.column_table(out, size)
         ke = getattr(self, "kernel_events", None)      # (start, end) CUDA events recorded right around the launch
+        if s2d is not None:
+            ia, ni, sa, ns = self.ring.s2d_tables(s2d, out, size)
+            H, W, C, S = s2d["geometry"]
+            if ke:
+                ke[0].record()
+            _lib.check(self.lib.cb200_per_sample_gather_s2d(
+                self.sum_tree.data_ptr(), self.min_tree.data_ptr(), self.power_of_2_size, u.data_ptr(), size,
+                self.num_transitions(), float(self.beta.current_value), out["idx"].data_ptr(),
+                out["weight"].data_ptr(), out["weight32"].data_ptr(), ia, ni, H, W, C, S, sa, ns,
+                _lib.current_stream()))
+            if ke:
+                ke[1].record()
+            self.beta.step()
+            cols = {k: v for k, v in out.items() if k not in s2d["columns"]}
+            return DeviceBatch(cols, size, lazy=_LazyColumns(self.ring, cols["idx"], tuple(s2d["columns"])))
+        arr, cnt = self.ring.column_table(out, size)
         if ke:
             ke[0].record()
         _lib.check(self.lib.cb200_per_sample_gather(

@@ -127,6 +127,24 @@ int cb200_per_sample_gather(const double* sum_tree, const double* min_tree, int6
                             int64_t nt, double beta, int64_t* idx_out, double* w_out, float* w32_out,
                             const cb200_column* h_columns, int n_columns, void* stream);
 
+/* Fused input path of the image agents (one launch): PER sample -> gather the uint8 frames of the drawn slots -> bf16
+ * plane of their space-to-depth(s) view, i.e. the operand of the first convolution (cb200_u8_s2d_planes documents the
+ * view and the plane format).  Replaces, for the image columns, the staged uint8 copy of cb200_per_sample_gather
+ * (memories/non_episodic/prioritized_experience_replay.py:219-262 + core_types.py:488-511) AND the conversion passes
+ * over it (embedders/embedder.py:103 input rescale is applied by the GEMM, see cb200_tgemm_desc.a_u8_div).
+ *   image_columns[k]: src = ring column (uint8 [capacity, h*w*c]), dst = plane (bf16 [(h/s)*(w/s)*n, s*s*c],
+ *                     core-tiled), row_bytes = h*w*c; 1 or 2 columns (state, next_state)
+ *   small_columns   : the remaining columns, copied row by row into their staged [n, row_bytes] buffers
+ * n must be a multiple of 8 (whole 8-row groups of the plane matrix).  idx_out / w_out / w32_out as cb200_per_sample. */
+int cb200_per_sample_gather_s2d(const double* sum_tree, const double* min_tree, int64_t size, const double* u, int64_t n,
+                                int64_t num_transitions, double beta, int64_t* idx_out, double* w_out, float* w32_out,
+                                const cb200_column* image_columns, int n_image, int32_t h, int32_t w, int32_t c,
+                                int32_t s, const cb200_column* small_columns, int n_small, void* stream);
+
+/* The same for given slot indices (uniform ExperienceReplay.sample, experience_replay.py:71-93). */
+int cb200_gather_s2d(const int64_t* idx, int64_t n, const cb200_column* image_columns, int n_image, int32_t h, int32_t w,
+                     int32_t c, int32_t s, const cb200_column* small_columns, int n_small, void* stream);
+
 /* Ring append: src[c][(cursor + i) % capacity, :] = staged[c][i, :] (experience_replay.py:131-150 store; the
  * `cb200_column.src` member is the ring (written), `.dst` the staged rows (read)). */
 int cb200_scatter_ring(const cb200_column* h_columns, int n_columns, int64_t cursor, int64_t capacity, int64_t n,
@@ -256,6 +274,10 @@ typedef struct cb200_tgemm_desc {
     float a_u8_div;             /*    accumulated sum is divided by a_u8_div (x / 255 input rescale, embedder.py:103)  */
     int64_t a_rows;             /* rows of the A plane matrix (a_pixels * B) and of the B operand's plane matrix      */
     int64_t b_rows;             /*   (mode 0: blocks * a_cols, mode 1: num_q * B): bounds of the TMA tensor maps      */
+    int32_t b_interleaved;      /* mode 0, n <= 64 (or n % 128 != 0): the B planes are "row-group interleaved" --        */
+                                /*   (row group | plane | column core | 64), written with plane_stride -1 by              */
+                                /*   cb200_split_planes (segment layout 1) / cb200_permute_f32 -- and the 3xBF16 product  */
+                                /*   set is issued as three wide tcgen05.mma on the [b1|b2|b3] operand                    */
     /* private: TMA tensor maps of the operands, built by the first call with this descriptor (keep the descriptor    */
     /* alive and unchanged between calls; zero-initialise)                                                            */
     uint64_t tmap_key;
@@ -271,7 +293,9 @@ int cb200_u8_s2d_planes(const void* x, int32_t batch, int32_t h, int32_t w, int3
                         void* stream);
 
 /* fp32 row-major matrices -> tiled planes, one launch for a list of matrices inside one fp32 buffer (the parameter
- * buffer, once per step): d_segments[k] = {src offset, rows, cols, plane offset} in elements (device memory). */
+ * buffer, once per step): d_segments[k] = {src offset, rows, cols, plane offset, layout} in elements (device memory);
+ * layout 0: three planes `plane_stride` apart; layout 1: row-group interleaved planes (cb200_tgemm_desc.b_interleaved),
+ * the segment occupies 3 * rows * cols elements from its plane offset. */
 int cb200_split_planes(const float* src, void* planes, int64_t plane_stride, const int64_t* d_segments,
                        int32_t num_segments, int64_t max_segment_elems, void* stream);
 
@@ -281,6 +305,7 @@ int cb200_colsum(const float* x, int64_t rows, int64_t cols, float* out, float* 
 
 /* dst[i] = src[table[i]], i < n  (fp32; static permutations of weight tensors for the data-gradient GEMMs, e.g. the
  * per-stride-class [taps*N, Cin] matrices of the transposed convolution) */
+/* (plane_stride -1: row-group interleaved planes, see cb200_tgemm_desc.b_interleaved) */
 int cb200_permute_f32(const float* src, const int32_t* table, int64_t n, float* dst, void* dst_planes,
                       int64_t plane_stride, int32_t plane_cols, void* stream);
                       /* dst_planes optional (NULL): also write dst, seen as [n / plane_cols, plane_cols], as planes */

@@ -65,7 +65,7 @@ def test_dense_forward_backward(B, K, N, act, planes):
     if planes:          # pre-split operands (tiled bf16 planes next to every fp32 buffer): cb200_gemm_tiled
         if B % 32 or K % 8 or N % 8:
             pytest.skip("shape has no plane form")
-        wp = tl.PlaneBuf(K, N, dev).load(lib, wd)
+        wp = tl.PlaneBuf(K, N, dev, interleaved=tl.b_interleaved(N)).load(lib, wd)
         ctx = tl.PlaneCtx(x=tl.PlaneBuf(B, K, dev).load(lib, xd), y=tl.PlaneBuf(B, N, dev),
                           dy=tl.PlaneBuf(B, N, dev).load(lib, dyd), dx=tl.PlaneBuf(B, K, dev), w_ptr=wp.ptr,
                           w_stride=wp.stride)
@@ -126,7 +126,7 @@ def test_conv_forward_backward(B, H, C, N, K, S, u8, planes):
     if planes:
         if B % 32 or C % 4 or N % 8:
             pytest.skip("shape has no plane form")
-        wp = tl.PlaneBuf(K * K * C, N, dev).load(lib, wd)
+        wp = tl.PlaneBuf(K * K * C, N, dev, interleaved=tl.b_interleaved(N)).load(lib, wd)
         xp = None if u8 else tl.PlaneBuf(H * H * B, C, dev, npix=H * H).load(lib, _pixel_major(xd, B, H * H, C))
         ctx = tl.PlaneCtx(x=xp, y=tl.PlaneBuf(OH * OH * B, N, dev, npix=OH * OH),
                           dy=tl.PlaneBuf(OH * OH * B, N, dev, npix=OH * OH).load(lib, _pixel_major(dyd, B, OH * OH, N)),
@@ -296,11 +296,15 @@ def test_dqn_learn_step_matches_oracle(cfg):
         random.seed(10 + step)
         np.random.seed(10 + step)
         batch = agent.sample_batch()
-        cols = {k: v.cpu().numpy() for k, v in batch.columns.items()}
         if step == 0:
             opt32 = on.AdamTF([torch.from_numpy(v) for v in online_named.values()], 2.5e-4, 0.9, 0.99, 1e-4)
         loss, losses, gnorm = agent.learn_from_batch(batch)
         torch.cuda.synchronize()
+        # (read after the step: on the fused input path the frames reach the network as operand planes and the uint8
+        # columns are gathered on demand from the drawn slots)
+        for k in ("state:observation", "next_state:observation"):
+            batch.column(k)
+        cols = {k: v.cpu().numpy() for k, v in batch.columns.items()}
         ob = dict(states=cols["state:observation"], next_states=cols["next_state:observation"],
                   actions=cols["action"], rewards=cols["reward"], game_overs=cols["game_over"].astype(bool),
                   weights=cols["weight32"] if cfg["per"] else None)
@@ -437,7 +441,7 @@ def test_persistent_schedule_is_bit_identical():
             dw, db = flat[:K * K * C * N].view(K, K, C, N), flat[K * K * C * N:]
             dx = torch.empty(B, H * H * C, device=dev)
             ws = Workspace(dev)
-            wp = tl.PlaneBuf(K * K * C, N, dev).load(lib, w)
+            wp = tl.PlaneBuf(K * K * C, N, dev, interleaved=tl.b_interleaved(N)).load(lib, w)
             ctx = tl.PlaneCtx(x=tl.PlaneBuf(H * H * B, C, dev, npix=H * H).load(lib, _pixel_major(x, B, H * H, C)),
                               y=tl.PlaneBuf(OH * OH * B, N, dev, npix=OH * OH),
                               dy=tl.PlaneBuf(OH * OH * B, N, dev, npix=OH * OH).load(lib, _pixel_major(dy, B, OH * OH, N)),

@@ -198,9 +198,22 @@ def test_theta_planes_cover_the_tensor_core_layers_of_the_atari_network():
     lib = _lib.load()
     net = QNetworkDef("cpu", (84, 84, 4), 6)
     tp = tl.ThetaPlanes(lib, net.store, net.store.theta)
-    segs = {int(o): (int(r), int(c)) for o, r, c, _ in tp.segs.tolist()}
+    segs = {int(o): (int(r), int(c)) for o, r, c, _, _ in tp.segs.tolist()}
     shapes = sorted(segs.values())
     assert shapes == sorted([(256, 32), (512, 64), (576, 64), (3136, 512)])
+    # narrow kernels (tile width <= 64) are row-group interleaved -- the second half of the plane buffer, 3 x their
+    # offset -- and wide ones planar at their own offset; the regions are disjoint
+    regions = []
+    for o, r, c, po, il in tp.segs.tolist():
+        assert bool(il) == tl.b_interleaved(int(c))
+        if il:
+            assert po == 3 * net.store.size + 3 * o
+            regions.append((po, po + 3 * r * c))
+        else:
+            assert po == o
+            regions += [(k * net.store.size + o, k * net.store.size + o + r * c) for k in range(3)]
+    regions.sort()
+    assert all(a[1] <= b[0] for a, b in zip(regions, regions[1:])) and regions[-1][1] <= tp.buf.numel()
     for name, (off, shape) in net.store.entries.items():
         assert off % 8 == 0, name
         if name.endswith("kernel"):
@@ -212,7 +225,7 @@ def test_theta_planes_cover_the_tensor_core_layers_of_the_atari_network():
 
 @pytest.mark.parametrize("tiles,total", [(324, 16), (196, 18), (16, 98), (4, 1296), (5, 784), (100, 16), (1600, 8)])
 def test_split_choice_respects_the_accumulation_cap(tiles, total):
-    """at most 32 reduction chunks (64 accumulating MMAs) per launch slice, whatever the tile count"""
+    """at most TILED_MAX_CHUNKS reduction chunks (40 accumulating MMAs) per launch slice, whatever the tile count"""
     s = tl.pick_splits_tiled(tiles, total)
     cps = -(-total // s)
-    assert 1 <= s <= max(1, total) and cps <= 32
+    assert 1 <= s <= max(1, total) and cps <= tl.TILED_MAX_CHUNKS
