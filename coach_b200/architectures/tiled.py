@@ -15,6 +15,7 @@ Dense layers are the one-pixel case; a dense layer on a flattened conv map has o
 Reference semantics: rl_coach/architectures/tensorflow_components/layers.py:108-183 (+ tf.gradients).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -175,7 +176,7 @@ class PlaneCtx(object):
         self.w_ptr, self.w_stride = w_ptr, w_stride
 
 
-TILED_MAX_CHUNKS = 20
+TILED_MAX_CHUNKS = int(os.environ.get("CB200_TILED_MAX_CHUNKS", "20"))
 
 
 def pick_splits_tiled(tiles, total_chunks, sm=148):

@@ -233,12 +233,18 @@ __global__ void __launch_bounds__(1024) per_update_cta_kernel(UpdateParams up) {
 // reference's sequential updates leave behind (SegmentTree.update :62-73 recomputes each ancestor from its children).
 constexpr int kUpdSortThreads = 1024;
 constexpr int kUpdAhead = 4;        // levels of untouched-sibling values in flight per thread
+constexpr int kUpdSortSmem = 80 * kUpdSortThreads;
 
 __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(UpdateParams up) {
-    __shared__ unsigned long long s_key[kUpdSortThreads];
-    __shared__ long long s_node[2][kUpdSortThreads];
-    __shared__ double s_sum[2][kUpdSortThreads], s_min[2][kUpdSortThreads], s_max[2][kUpdSortThreads];
-    __shared__ short s_lo[2][kUpdSortThreads], s_hi[2][kUpdSortThreads];
+    extern __shared__ __align__(16) uint8_t upd_smem[];      // kUpdSortSmem bytes (dynamic: above the 48 KB static limit)
+    constexpr int T = kUpdSortThreads;
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(upd_smem);
+    long long(*s_node)[T] = reinterpret_cast<long long(*)[T]>(upd_smem + 8 * T);
+    double(*s_sum)[T] = reinterpret_cast<double(*)[T]>(upd_smem + 24 * T);
+    double(*s_min)[T] = reinterpret_cast<double(*)[T]>(upd_smem + 40 * T);
+    double(*s_max)[T] = reinterpret_cast<double(*)[T]>(upd_smem + 56 * T);
+    short(*s_lo)[T] = reinterpret_cast<short(*)[T]>(upd_smem + 72 * T);
+    short(*s_hi)[T] = reinterpret_cast<short(*)[T]>(upd_smem + 76 * T);
     __shared__ int s_scan[kUpdSortThreads / 32];
     __shared__ int s_m;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -920,7 +926,13 @@ static int run_update(UpdateParams& up, void* stream) {
     cudaStream_t st = as_stream(stream);
     if (up.n <= 0) return CB200_OK;
     if (up.n <= 1024 && up.levels <= 52 && tune_get("per_update_sorted", 1, 0, 1)) {
-        CB200_LAUNCH(per_update_sorted_kernel, 1, kUpdSortThreads, 0, st, up);
+        static bool configured = false;
+        if (!configured) {
+            CB200_CUDA(cudaFuncSetAttribute(per_update_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kUpdSortSmem));
+            configured = true;
+        }
+        CB200_LAUNCH(per_update_sorted_kernel, 1, kUpdSortThreads, kUpdSortSmem, st, up);
     } else if (up.n <= 1024) {
         int threads = (int)((up.n + 31) / 32 * 32);
         CB200_LAUNCH(per_update_cta_kernel, 1, threads, 0, st, up);
@@ -1104,9 +1116,10 @@ static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int6
     int stride = rc * s2d_row_bytes;
     if ((stride / 16) % 2 == 0) stride += 16;
     gp.chunk_stride = stride;
-    // bands: enough CTAs for two per SM
+    // bands: as many CTAs as fit in ONE wave of two per SM (a CTA is a chain of dependent round trips -- tree descent,
+    // first chunk, conversion -- so a second, partial wave would double the kernel's duration)
     const int groups = (int)(n / 8) * n_img;
-    int parts = (2 * sm_count() + groups - 1) / groups;
+    int parts = (2 * sm_count()) / groups;
     if (parts < 1) parts = 1;
     if (parts > hs) parts = hs;
     gp.parts = parts;

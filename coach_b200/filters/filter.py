@@ -130,20 +130,27 @@ class DeviceRunningStats(object):
         return self._std
 
     def push(self, samples: torch.Tensor):
-        """samples: fp32 CUDA tensor [rows, *shape]"""
+        """samples: fp32 CUDA tensor [rows, *shape].  With several ranks the statistics are SHARED (the reference's
+        SharedRunningStats): every rank pushes its own rollout shard and the increments are merged by one all-reduce of
+        (sum, sum of squares, rows) before mean / std are refreshed, so all ranks normalise with the same numbers."""
+        from coach_b200 import parallel
         x = samples.reshape(samples.shape[0], -1).contiguous()
         st = _lib.current_stream()
-        _lib.check(self.lib.cb200_running_stats_push(x.data_ptr(), x.shape[0], x.shape[1], self._sum.data_ptr(),
-                                                     self._sum_squares.data_ptr(), st))
-        self._count += x.shape[0]
+        rows = x.shape[0]
+        if parallel.is_distributed():
+            d_sum, d_sq = torch.zeros_like(self._sum), torch.zeros_like(self._sum_squares)
+            _lib.check(self.lib.cb200_running_stats_push(x.data_ptr(), rows, x.shape[1], d_sum.data_ptr(),
+                                                         d_sq.data_ptr(), st))
+            rows = parallel.allreduce_running_stats(d_sum, d_sq, rows)
+            self._sum += d_sum
+            self._sum_squares += d_sq
+        else:
+            _lib.check(self.lib.cb200_running_stats_push(x.data_ptr(), rows, x.shape[1], self._sum.data_ptr(),
+                                                         self._sum_squares.data_ptr(), st))
+        self._count += rows
         _lib.check(self.lib.cb200_running_stats_finalize(self._sum.data_ptr(), self._sum_squares.data_ptr(),
                                                          float(self._count), float(self.epsilon), x.shape[1],
                                                          self._mean.data_ptr(), self._std.data_ptr(), st))
-
-    def allreduce(self, delta_sum, delta_sumsq, delta_count):
-        """multi-GPU: merge the increments of all ranks (one extra all-reduce of
-        (count, sum, sumsq)); see ObservationNormalizationFilter.filter_device."""
-        raise NotImplementedError
 
     def normalize(self, batch: torch.Tensor, out=None):
         x = batch.reshape(batch.shape[0], -1).contiguous()

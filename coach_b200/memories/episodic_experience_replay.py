@@ -44,6 +44,7 @@ class EpisodicExperienceReplay(ExperienceReplay):
         self.episode_lengths = []          # complete episodes, oldest first
         self._open_len = 0                 # transitions of the episode currently being filled
         self._returns = None               # fp64 [capacity] n-step discounted returns (valid for complete episodes)
+        self._bootstrap = None             # uint8 [capacity] info['should_bootstrap_next_state'] (n_step > 1 only)
 
     # ---- counters (episodic_experience_replay.py:75-100) -----------------------------------------------------------
     def length(self, lock: bool = False) -> int:
@@ -57,11 +58,38 @@ class EpisodicExperienceReplay(ExperienceReplay):
         return int(sum(self.episode_lengths))
 
     # ---- store -------------------------------------------------------------------------------------------------------
+    def num_transitions(self) -> int:
+        return self.num_transitions_in_complete_episodes() + self._open_len
+
+    def _evict(self):
+        """_enforce_max_length (:215-228, Transitions granularity): whole oldest episodes go while the buffer holds
+        more transitions than max_size -- checked at every store, like the reference, so the ring (capacity =
+        max_size slots) never overwrites a slot of an episode that is still listed"""
+        while self.episode_lengths and sum(self.episode_lengths) + self._open_len > self.ring.capacity:
+            self.episode_lengths.pop(0)
+        if self._open_len > self.ring.capacity:
+            raise ValueError("an episode longer than the replay (%d transitions) cannot be held" % self.ring.capacity)
+
     def store(self, transition: Transition, lock: bool = True) -> None:
         ExperienceReplay.store(self, transition)
         self._open_len += 1
+        self._evict()
         if transition.game_over:
             self._close_episode()
+
+    def store_episode(self, episode, lock: bool = True) -> None:
+        """episodic_experience_replay.py:294-318: a whole episode (any object with ``.transitions``) is appended and
+        closed -- whether or not its last transition carries game_over.  The reference lets this happen while another
+        episode is being filled (that one then stays in the buffer, never closed); the ring cannot interleave two
+        episodes, so that case raises."""
+        self.assert_not_frozen()
+        if self._open_len != 0:
+            raise NotImplementedError("store_episode while an episode is being filled transition by transition")
+        for t in episode.transitions:
+            ExperienceReplay.store(self, t)
+            self._open_len += 1
+            self._evict()
+        self._close_episode()
 
     def store_columns(self, columns: dict, episode_lengths: List[int] = None) -> None:
         """Batched ingest of whole episodes laid out back to back; ``episode_lengths`` defaults to the split implied
@@ -106,28 +134,56 @@ class EpisodicExperienceReplay(ExperienceReplay):
             idx = (torch.arange(L, device=self.device) + start) % r.capacity
             rew = r.columns["reward"].view(torch.float64).reshape(-1)[idx]
             self._returns[idx] = rl_math.nstep_returns(rew.contiguous(), [L], self.discount, self.n_step)
-        # drop whole episodes that the ring has overwritten
-        while sum(self.episode_lengths) + self._open_len > r.capacity:
-            self.episode_lengths.pop(0)
+        if self.n_step > 1:
+            self._relink(start, L)
+        self._evict()
+
+    def _relink(self, start, L):
+        """core_types.py:807-818 (n_step > 1): next_state of transition i becomes the state of transition i + n -- or,
+        past the end of the episode, the episode's last next_state -- and info['should_bootstrap_next_state'] says
+        which.  Row moves inside the HBM columns; the source rows are read before anything is written."""
+        r = self.ring
+        n = self.n_step if self.n_step < L else L
+        slots = (torch.arange(L, device=self.device) + start) % r.capacity
+        j = torch.arange(L, device=self.device) + n
+        inside = j < L
+        if self._bootstrap is None:
+            self._bootstrap = torch.zeros(r.capacity, dtype=torch.uint8, device=self.device)
+        self._bootstrap[slots] = inside.to(torch.uint8)
+        src = slots[torch.clamp(j, max=L - 1)]
+        for name in r.specs:
+            if not name.startswith("next_state:"):
+                continue
+            ns_col, s_col = r.columns[name], r.columns["state:" + name[len("next_state:"):]]
+            last = ns_col[slots[L - 1]].clone()
+            new = torch.where(inside[:, None], s_col[src], last[None, :])
+            ns_col[slots] = new
 
     def verify_last_episode_is_closed(self) -> None:
         pass
 
     # ---- read --------------------------------------------------------------------------------------------------------
-    def _slots_of_complete_episodes(self):
+    def _slots_of_complete_episodes(self, pos=None):
+        """ring slots of list positions ``pos`` (default: all) of the complete episodes, oldest first"""
         r = self.ring
         n = self.num_transitions_in_complete_episodes()
-        start = (r.cursor - self.ring._pending - self._open_len - n) % r.capacity
-        return (np.arange(n, dtype=np.int64) + start) % r.capacity
+        start = (r.cursor - self._open_len - n) % r.capacity
+        pos = np.arange(n, dtype=np.int64) if pos is None else np.asarray(pos, dtype=np.int64)
+        return (pos + start) % r.capacity
 
     def transitions_batch(self) -> DeviceBatch:
         """All transitions of the complete episodes, in order (``memory.transitions`` of the reference restricted to
         what ClippedPPO trains on: the agent only trains once the episode is complete, agent.py:681-699)."""
         self._flush()
+        if self.num_transitions_in_complete_episodes() < 1:
+            raise ValueError("The episodic replay buffer holds no complete episode yet. "
+                             "There is currently 1 episodes with {} transitions".format(self._open_len))
         slots = self._slots_of_complete_episodes()
         idx = torch.from_numpy(slots).to(self.device)
         cols = dict(self.ring.gather(idx))
         cols["n_step_discounted_rewards"] = self._returns[idx] if self._returns is not None else None
+        if self._bootstrap is not None and self.n_step > 1:
+            cols["should_bootstrap_next_state"] = self._bootstrap[idx]
         cols["idx"] = idx
         return DeviceBatch(cols, len(slots))
 
@@ -143,7 +199,7 @@ class EpisodicExperienceReplay(ExperienceReplay):
                              "There is currently 1 episodes with {} transitions".format(self._open_len))
         self._flush()
         pos = np.random.randint(n, size=size)                                   # :121
-        slots = self._slots_of_complete_episodes()[pos]
+        slots = self._slots_of_complete_episodes(pos)       # only the drawn positions: no O(buffer) host work per step
         idx = torch.from_numpy(slots).to(self.device)
         cols = dict(self.ring.gather(idx, out))
         cols["idx"] = idx

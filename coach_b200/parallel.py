@@ -61,3 +61,42 @@ def max_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def allreduce_running_stats(delta_sum: torch.Tensor, delta_sumsq: torch.Tensor, rows: int):
+    """Shared observation statistics across rollout shards (the reference's SharedRunningStats keeps ONE set of
+    (count, sum, sum of squares) that every worker pushes into, utilities/shared_running_stats.py:115-164): the ranks'
+    increments of one push are merged with ONE all-reduce of the packed vector [sum | sumsq | rows].  In place on the two
+    tensors; returns the total number of rows pushed by all ranks."""
+    _, ws = world()
+    if ws == 1:
+        return int(rows)
+    d = delta_sum.numel()
+    packed = torch.empty(2 * d + 1, dtype=torch.float64, device=delta_sum.device)
+    packed[:d] = delta_sum.reshape(-1)
+    packed[d:2 * d] = delta_sumsq.reshape(-1)
+    packed[2 * d] = float(rows)
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+    delta_sum.reshape(-1).copy_(packed[:d])
+    delta_sumsq.reshape(-1).copy_(packed[d:2 * d])
+    return int(round(float(packed[2 * d].item())))
+
+
+def global_standardize_(x: torch.Tensor, n_valid: int):
+    """(x - mean) / population std over the first n_valid entries of EVERY rank's vector (ClippedPPO advantage
+    standardisation, clipped_ppo_agent.py:201, taken over the whole distributed rollout): two small all-reduces
+    (count and sum, then the centred sum of squares -- two-pass, no cancellation).  In place; entries >= n_valid become
+    NaN like the single-GPU kernel leaves them.  Returns (mean, std) as Python floats."""
+    _, ws = world()
+    v = x[:n_valid].to(torch.float64)
+    a = torch.stack([torch.tensor(float(n_valid), dtype=torch.float64, device=x.device), v.sum()])
+    if ws > 1:
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+    n_all, mean = float(a[0].item()), float((a[1] / a[0]).item())
+    b = ((v - mean) ** 2).sum().reshape(1)
+    if ws > 1:
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    std = float(torch.sqrt(b[0] / n_all).item())
+    x[:n_valid] = (v - mean) / std
+    x[n_valid:] = float("nan")
+    return mean, std

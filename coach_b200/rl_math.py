@@ -36,8 +36,13 @@ def standardize_(x, n_valid=None):
 def fill_advantages(rewards, values, game_overs, discount, gae_lambda):
     """ClippedPPOAgent.fill_advantages for policy_gradient_rescaler == GAE: returns (standardised advantages,
     value targets, n_valid)."""
+    from coach_b200 import parallel
     adv, tgt, n_valid = gae(rewards, values, game_overs, discount, gae_lambda)
-    standardize_(adv, n_valid)
+    if parallel.is_distributed():
+        # one rollout shard per rank: the moments are those of the whole distributed rollout
+        parallel.global_standardize_(adv, int(n_valid.item()))
+    else:
+        standardize_(adv, n_valid)
     return adv, tgt, n_valid
 
 

@@ -337,9 +337,78 @@ def main():
     golden_ddpg_td3(out, rng)
     golden_sac(out, rng)
     golden_batch(out, rng)
+    golden_episodic(out, np.random.RandomState(77))
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "agent_prologues.npz"), **out)
     print("agent_prologues", len(out), "arrays")
+
+
+
+# ---- EpisodicExperienceReplay: store / store_episode / n-step relink / eviction / sample ----------------------------
+def golden_episodic(out, rng):
+    """rl_coach/memories/episodic/episodic_experience_replay.py:60-330 + Episode (core_types.py:771-820): scripted
+    sessions; every transition carries a unique observation id so that the n-step ``next_state`` relink, the
+    ``should_bootstrap_next_state`` flags and whole-episode eviction are visible in the recorded contents."""
+    from rl_coach.core_types import Episode, Transition
+    from rl_coach.memories.episodic.episodic_experience_replay import EpisodicExperienceReplay
+    from rl_coach.memories.memory import MemoryGranularity
+    for k, (n_step, cap) in enumerate([(3, 150), (-1, 150), (1, 10000)]):
+        mem = EpisodicExperienceReplay((MemoryGranularity.Transitions, cap), n_step=n_step)
+        uid = [0]
+        script = []        # (kind, length): kind 0 = store() transition by transition, 1 = store_episode()
+
+        def make(T, last_done=True):
+            ts = []
+            for i in range(T):
+                s, s2 = uid[0], uid[0] + 100000
+                uid[0] += 1
+                ts.append(Transition(state={'observation': np.array([s], dtype=np.float32)}, action=int(rng.randint(0, 3)),
+                                     reward=float(np.round(rng.randn(), 3)),
+                                     next_state={'observation': np.array([s2], dtype=np.float32)},
+                                     game_over=bool(last_done and i == T - 1)))
+            return ts
+        all_ts = []
+        for e in range(14):
+            T = int(rng.randint(1, 40))
+            kind = int(e in (4, 9))
+            ts = make(T)
+            all_ts.append(ts)
+            if kind == 0:
+                for t in ts:
+                    mem.store(t)
+            else:
+                ep = Episode(n_step=n_step)
+                for t in ts:
+                    ep.insert(t)
+                mem.store_episode(ep)
+            script.append((kind, T))
+        tail = make(int(rng.randint(1, 8)), last_done=False)      # an open episode at the end
+        all_ts.append(tail)
+        for t in tail:
+            mem.store(t)
+        script.append((0, len(tail)))
+        out["epi%d_script" % k] = np.array(script, dtype=np.int64)
+        out["epi%d_n_step" % k], out["epi%d_capacity" % k] = n_step, cap
+        flat = [t for ts in all_ts for t in ts]
+        out["epi%d_in_state" % k] = np.array([t.state['observation'][0] for t in flat], dtype=np.float32)
+        out["epi%d_in_reward" % k] = np.array([t.reward for t in flat], dtype=np.float64)
+        out["epi%d_in_action" % k] = np.array([t.action for t in flat], dtype=np.int64)
+        # contents after the session (complete episodes only = what the agents train on)
+        nc = mem.num_transitions_in_complete_episodes()
+        kept = mem.transitions[:nc]
+        out["epi%d_state" % k] = np.array([t.state['observation'][0] for t in kept], dtype=np.float32)
+        out["epi%d_next_state" % k] = np.array([t.next_state['observation'][0] for t in kept], dtype=np.float32)
+        out["epi%d_reward" % k] = np.array([t.reward for t in kept], dtype=np.float64)
+        out["epi%d_game_over" % k] = np.array([t.game_over for t in kept], dtype=np.uint8)
+        out["epi%d_nstep" % k] = np.array([t.n_step_discounted_rewards for t in kept], dtype=np.float64)
+        out["epi%d_bootstrap" % k] = np.array([int(t.info.get('should_bootstrap_next_state', -1)) for t in kept],
+                                              dtype=np.int64)
+        out["epi%d_counts" % k] = np.array([mem.num_transitions(), nc, mem.num_complete_episodes(), mem.length()],
+                                           dtype=np.int64)
+        np.random.seed(11 + k)
+        got = mem.sample(32)
+        out["epi%d_sample_state" % k] = np.array([t.state['observation'][0] for t in got], dtype=np.float32)
+    out["epi_cases"] = 3
 
 
 if __name__ == "__main__":

@@ -133,3 +133,51 @@ def test_device_batch_matches_reference_batch(fx):
     b.slice(3, 11)
     assert b.size == int(fx["batch_slice_size"])
     np.testing.assert_array_equal(b.rewards().cpu().numpy(), fx["batch_slice_rewards"])
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_episodic_replay_matches_reference_session(fx, case):
+    """EpisodicExperienceReplay on the HBM ring replays a session recorded from the reference
+    (episodic_experience_replay.py:60-330, Episode core_types.py:771-820): store / store_episode, whole-episode
+    eviction, n-step discounted returns, the n-step next_state relink + should_bootstrap_next_state, counters, and the
+    uniform sample stream"""
+    from types import SimpleNamespace
+    from coach_b200.core_types import Transition
+    from coach_b200.memories.episodic_experience_replay import EpisodicExperienceReplay
+    from coach_b200.memories.memory import MemoryGranularity
+    p = "epi%d_" % case
+    n_step, cap = int(fx[p + "n_step"]), int(fx[p + "capacity"])
+    mem = EpisodicExperienceReplay((MemoryGranularity.Transitions, cap), n_step=n_step, discount=0.99)
+    st, rw, ac = fx[p + "in_state"], fx[p + "in_reward"], fx[p + "in_action"]
+    script = fx[p + "script"]
+    k = 0
+    for e, (kind, T) in enumerate(script):
+        last = e == len(script) - 1                       # the final entry is an episode left open
+        ts = [Transition(state={"observation": np.array([st[k + i]], dtype=np.float32)}, action=int(ac[k + i]),
+                         reward=float(rw[k + i]),
+                         next_state={"observation": np.array([st[k + i] + 100000], dtype=np.float32)},
+                         game_over=bool(i == T - 1 and not last)) for i in range(T)]
+        k += T
+        if kind == 1:
+            mem.store_episode(SimpleNamespace(transitions=ts))
+        else:
+            for t in ts:
+                mem.store(t)
+    counts = fx[p + "counts"]
+    assert [mem.num_transitions(), mem.num_transitions_in_complete_episodes(), mem.num_complete_episodes(),
+            mem.length()] == list(counts)
+    b = mem.transitions_batch()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(b.states(["observation"])["observation"].cpu().numpy()[:, 0], fx[p + "state"])
+    np.testing.assert_array_equal(b.next_states(["observation"])["observation"].cpu().numpy()[:, 0],
+                                  fx[p + "next_state"])
+    np.testing.assert_array_equal(b.rewards().cpu().numpy(), fx[p + "reward"])
+    np.testing.assert_array_equal(b.game_overs().cpu().numpy(), fx[p + "game_over"])
+    np.testing.assert_array_equal(b.n_step_discounted_rewards().cpu().numpy(), fx[p + "nstep"])
+    if n_step > 1:
+        np.testing.assert_array_equal(b.info("should_bootstrap_next_state").cpu().numpy(), fx[p + "bootstrap"])
+    else:
+        assert "should_bootstrap_next_state" not in b.columns and np.all(fx[p + "bootstrap"] == -1)
+    np.random.seed(11 + case)
+    s = mem.sample_batch(32)
+    np.testing.assert_array_equal(s.states(["observation"])["observation"].cpu().numpy()[:, 0], fx[p + "sample_state"])

@@ -31,7 +31,16 @@ def _worker(rank, world, port, out_q):
     g2 = torch.full((10,), float(rank + 1))
     scaler2 = parallel.allreduce_gradients(g2, scale_down=False)
     t = parallel.max_over_ranks(10.0 * (rank + 1))
-    out_q.put((rank, float(g[0]), scaler, float(theta[0]), float(g2[0]), scaler2, t))
+    # shared observation statistics: increments of both shards merged (SharedRunningStats semantics)
+    rng = np.random.RandomState(rank)
+    x = rng.randn(50 + 10 * rank, 17)
+    d_sum, d_sq = torch.from_numpy(x.sum(0)), torch.from_numpy((x * x).sum(0))
+    rows = parallel.allreduce_running_stats(d_sum, d_sq, x.shape[0])
+    # advantage standardisation over the whole distributed rollout
+    adv = torch.from_numpy(np.concatenate([rng.randn(40 + rank), [7.0, 7.0]]))
+    mean, std = parallel.global_standardize_(adv, 40 + rank)
+    out_q.put((rank, float(g[0]), scaler, float(theta[0]), float(g2[0]), scaler2, t, rows, d_sum.numpy(), d_sq.numpy(),
+               adv.numpy(), mean, std))
     torch.distributed.destroy_process_group()
 
 
@@ -46,7 +55,20 @@ def test_allreduce_world2_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, gsum, scaler, theta0, g2, scaler2, t in res:
+    xs = [np.random.RandomState(r).randn(50 + 10 * r, 17) for r in range(world)]
+    advs = []
+    for r in range(world):
+        rng = np.random.RandomState(r)
+        rng.randn(50 + 10 * r, 17)
+        advs.append(rng.randn(40 + r))
+    all_adv = np.concatenate(advs)
+    for rank, gsum, scaler, theta0, g2, scaler2, t, rows, d_sum, d_sq, adv, mean, std in res:
+        assert rows == sum(x.shape[0] for x in xs)
+        np.testing.assert_allclose(d_sum, sum(x.sum(0) for x in xs), rtol=1e-13)
+        np.testing.assert_allclose(d_sq, sum((x * x).sum(0) for x in xs), rtol=1e-13)
+        np.testing.assert_allclose([mean, std], [all_adv.mean(), all_adv.std()], rtol=1e-13)
+        np.testing.assert_allclose(adv[:40 + rank], (advs[rank] - all_adv.mean()) / all_adv.std(), rtol=1e-12)
+        assert np.all(np.isnan(adv[40 + rank:]))
         assert gsum == 3.0 and scaler == 0.5            # sum over ranks, mean applied by the optimizer step
         assert np.isclose(theta0, -0.1 * 3.0 * 0.5)     # replicas stay identical
         assert g2 == 3.0 and scaler2 == 1.0             # DDPG/TD3 semantics: sum, no scale-down

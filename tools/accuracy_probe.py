@@ -1,0 +1,59 @@
+"""Relative errors of one B = 512 DQN + PER learn step against the fp64 evaluation of the same graph (and the fp32
+oracle's own distance to it), for a given accumulation cap:  CB200_TILED_MAX_CHUNKS=10 python tools/accuracy_probe.py"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from oracle import nets as on            # noqa: E402
+import test_learn_gpu as T               # noqa: E402
+
+
+def main():
+    B, A = 512, 6
+    agent = T._make_agent((84, 84, 4), A, B, False, False, True, None, True)
+    rng = np.random.RandomState(3)
+    n = 1024
+    agent.memory.store_columns({"state:observation": rng.randint(0, 256, (n, 84, 84, 4)).astype(np.uint8),
+                                "next_state:observation": rng.randint(0, 256, (n, 84, 84, 4)).astype(np.uint8),
+                                "action": rng.randint(0, A, n).astype(np.int64),
+                                "reward": rng.randint(-1, 2, n).astype(np.float64),
+                                "game_over": (rng.rand(n) < 0.1).astype(np.uint8)})
+    agent.memory.update_priorities(np.arange(n), np.abs(rng.randn(n)))
+    store, net = agent.net_def.store, agent.networks["main"]
+    net.theta_target.copy_(store.theta * 0.9 + 0.01)
+    online, target = store.export_named(), store.export_named(net.theta_target)
+    random.seed(10)
+    batch = agent.sample_batch()
+    loss, _, gnorm = agent.learn_from_batch(batch)
+    torch.cuda.synchronize()
+    for k in ("state:observation", "next_state:observation"):
+        batch.column(k)
+    cols = {k: v.cpu().numpy() for k, v in batch.columns.items()}
+    ob = dict(states=cols["state:observation"], next_states=cols["next_state:observation"], actions=cols["action"],
+              rewards=cols["reward"], game_overs=cols["game_over"].astype(bool), weights=cols["weight32"])
+    res = {}
+    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        o = on.QNetOracle((84, 84, 4), A, False, dt)
+        opt = on.AdamTF([torch.from_numpy(v).to(dt) for v in online.values()], 2.5e-4, 0.9, 0.99, 1e-4, dtype=dt)
+        res[name] = on.dqn_learn_step(o, o.cast(online), o.cast(target), opt, ob, 0.99, True, False, None)
+    r64, r32 = res["f64"], res["f32"]
+    print("cap %s: loss rel err ours %.2e (fp32 oracle %.2e); grad_norm rel err ours %.2e (fp32 oracle %.2e)"
+          % (os.environ.get("CB200_TILED_MAX_CHUNKS", "20"), abs(loss - r64["loss"]) / r64["loss"],
+             abs(r32["loss"] - r64["loss"]) / r64["loss"], abs(gnorm - r64["grad_norm"]) / r64["grad_norm"],
+             abs(r32["grad_norm"] - r64["grad_norm"]) / r64["grad_norm"]))
+    got = store.export_named(store.grad)
+    for name in r64["grads"]:
+        w = r64["grads"][name].numpy()
+        s = np.abs(w).max() + 1e-30
+        print("   %-45s ours %.2e  fp32 oracle %.2e   (max abs err / max |grad|)"
+              % (name.split("network_0/")[-1], np.abs(got[name] - w).max() / s,
+                 np.abs(r32["grads"][name].numpy() - w).max() / s))
+
+
+if __name__ == "__main__":
+    main()

@@ -10,7 +10,7 @@ def main(path):
     hdr = rows[hi]
     kn, mv, gs = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
     data = [r for r in rows[hi + 1:] if len(r) == len(hdr) and r[0].isdigit()]
-    idx = [i for i, r in enumerate(data) if "per_sample_gather" in r[kn]]
+    idx = [i for i, r in enumerate(data) if "sample_gather" in r[kn]]
     seg = data[idx[-2]:idx[-1]] if len(idx) >= 2 else data
     tot = 0.0
     for r in seg:
