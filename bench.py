@@ -42,6 +42,9 @@ ENV_STEPS_PER_TRAIN = 4
 # algorithmic bytes of ONE fused sample+gather launch (SURVEY.md section 8d / BASELINE.md contract figure, staged copy
 # written): read B*(2*28224+8+8+1) of transition columns + B*21*8 of tree, write the same columns + B*(8+8) idx/weight
 GATHER_BYTES = BATCH * (2 * ROW + 8 + 8 + 1) * 2 + BATCH * 21 * 8 + BATCH * 16
+# what the fused sample + gather + space-to-depth kernel moves: the uint8 frames are read once (28.9 MB), the bf16
+# operand planes of the first convolution are written (2 bytes per pixel value: 57.8 MB), plus tree / small columns
+GATHER_S2D_MOVED = BATCH * 2 * ROW * (1 + 2) + BATCH * (8 + 8 + 1) * 2 + BATCH * 21 * 8 + BATCH * 16
 # multiply-accumulates of one learn step per sample: target fwd + online fwd (9.346 M each) + backward
 # (weight grads 9.346 M + data grads 6.069 M: conv2, conv3, fc1, out); the online forward is computed once
 MACS_PER_SAMPLE = 2 * 9346048 + 9346048 + (9346048 - 3276800)
@@ -59,7 +62,7 @@ class ClockSampler(object):
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -69,7 +72,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -88,7 +91,7 @@ class ClockSampler(object):
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, busy, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -98,11 +101,16 @@ class ClockSampler(object):
                 mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                busy.append(float(f[9]) >= 50.0)
+            except (ValueError, IndexError):
+                busy.append(True)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        load = [c for c, b in zip(sm, busy) if b] or sm        # samples taken while the GPU was busy with the step
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(load)}
 
 
 # =====================================================================================================================
@@ -110,22 +118,33 @@ def synth_chunk(rng, n):
     return (rng.randint(0, 6, n).astype(np.int64), rng.randint(-1, 2, n).astype(np.float64))
 
 
-def build_device_agent(capacity, seed, device):
+def build_device_agent(capacity, seed, device, config="dqn"):
     import torch
-    from coach_b200.agents.dqn_agent import DQNAgent, DQNAgentParameters
+    from coach_b200.agents.dqn_agent import DDQNAgent, DDQNAgentParameters, DQNAgent, DQNAgentParameters
+    from coach_b200.base_parameters import MiddlewareScheme
     from coach_b200.base_parameters import TrainingSteps
     from coach_b200.memories.memory import MemoryGranularity
     from coach_b200.memories.prioritized_experience_replay import PrioritizedExperienceReplayParameters
     from coach_b200.schedules import LinearSchedule
-    ap = DQNAgentParameters()
+    dueling = config == "dueling"
+    ap = DDQNAgentParameters() if dueling else DQNAgentParameters()
     ap.memory = PrioritizedExperienceReplayParameters()
     ap.memory.max_size = (MemoryGranularity.Transitions, capacity)
     ap.memory.beta = LinearSchedule(0.4, 1, 12500000)
-    ap.algorithm.num_steps_between_copying_online_weights_to_target = TrainingSteps(2500)
+    ap.algorithm.num_steps_between_copying_online_weights_to_target = TrainingSteps(2500 if not dueling else 10000)
     ap.algorithm.num_consecutive_playing_steps.num_steps = ENV_STEPS_PER_TRAIN
     net = ap.network_wrappers["main"]
     net.batch_size = BATCH
-    agent = DQNAgent(ap, observation_shape=OBS, num_actions=N_ACTIONS, device=device, seed=seed)
+    net.replace_mse_with_huber_loss = True
+    if dueling:
+        # BASELINE config 5 = presets/Atari_Dueling_DDQN_with_PER_OpenAI.py:14-19: DDQN, dueling head directly on the
+        # conv map (MiddlewareScheme.Empty), lr 1e-4, global-norm clip 10, target copy every 40000 env steps
+        net.learning_rate = 0.0001
+        net.middleware_parameters.scheme = MiddlewareScheme.Empty
+        net.heads_parameters = ["DuelingQHead"]
+        net.clip_gradients = 10
+    agent = (DDQNAgent if dueling else DQNAgent)(ap, observation_shape=OBS, num_actions=N_ACTIONS, device=device,
+                                                 seed=seed)
     mem = agent.memory
     size = mem.power_of_2_size
     gen = torch.Generator(device=device).manual_seed(seed)
@@ -175,7 +194,7 @@ def run_device(args):
         os.environ["CB200_GEMM_TILED"] = "0"      # no pre-split planes / tiled tcgen05 GEMMs either
     random.seed(1000 + rank)
     np.random.seed(1000 + rank)
-    agent = build_device_agent(args.capacity, 100 + rank, device)
+    agent = build_device_agent(args.capacity, 100 + rank, device, args.config)
     mem = agent.memory
     if not args.no_l2_persist:
         lib.cb200_l2_persist(mem.sum_tree.data_ptr(), (1 << 17) * 8, _lib.current_stream())
@@ -191,14 +210,17 @@ def run_device(args):
         return agent.train(fetch=fetch)
 
     # ---- device-resident leg (value) ------------------------------------------------------------------------------
+    # clocks / throttle reasons: nvidia-smi samples every 20 ms from BEFORE the warm-up; the timed region of a short run
+    # (20 steps = 15 ms) is shorter than one sampling period, so the same step keeps running after it (untimed) until
+    # the sampler has seen the GPU under this load for >= 0.6 s
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(W):
         one_step(False)
     barrier()
     launches0 = lib.cb200_launch_count()
     graph_launches0 = agent.graph_kernel_launches     # kernels run through CUDA-graph replays of the learn step
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     # per-kernel-group device timing inside the timed region: events around the fused sample+gather launch
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -225,7 +247,14 @@ def run_device(args):
     mem.kernel_events = None
     ms_total = t0.elapsed_time(t1)
     launches = lib.cb200_launch_count() - launches0 + agent.graph_kernel_launches - graph_launches0
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.6:         # same step, same load, untimed: lets the 20 ms sampler see it
+        for _ in range(50):
+            one_step(False)
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + 0.6 s of the same steps (nvidia-smi -lms 20)"
     gather_us = float(np.mean([a.elapsed_time(b) for a, b, _ in ev])) * 1e3
     learn_us = float(np.mean([b.elapsed_time(c) for _, b, c in ev])) * 1e3
     ms_total = parallel.max_over_ranks(ms_total, device)
@@ -323,6 +352,7 @@ def run_device(args):
                                    o["launches_per_step"] for o in ops),
                      "bound": "tensor", "achieved": round(tiled_tflops, 1), "peak": pk["bf16_tflops_sustained"],
                      "unit": "TFLOP/s", "frac": round(tiled_tflops / pk["bf16_tflops_sustained"], 4),
+                     "frac_algorithmic": round(tl_useful / tl_us / 1e6 / pk["bf16_tflops_sustained"], 4) if tl_us else 0.0,
                      "peak_kind": pk_kind + " (sustained dense bf16, kernel timed inside the step)",
                      "us_per_step": round(tl_us, 1), "share_of_step": round(tl_us / (ms_total / K * 1e3), 3),
                      "algorithmic_flops_per_step": tl_issued, "fp32_equivalent_tflops": round(tl_useful / tl_us / 1e6, 1)
@@ -330,12 +360,24 @@ def run_device(args):
                      "what": "achieved = bf16 tensor-core FLOPs issued (3xBF16 split: 6 products per fp32 MAC, 3 for "
                              "the exact uint8 operand) / CUDA-event time of the launches (each prepared call timed over "
                              "10 back-to-back launches incl. its split-reduce pass, weighted by launches per step)",
-                     "traffic": TRAFFIC_NCU.get("gemm_tc_tiled"), "ops": ops},
-        "roofline_gather": {"kernel": "per_sample_gather_kernel (fused sum-tree descent + IS weights + TMA bulk-copy gather)",
+                     "traffic": TRAFFIC_NCU.get("gemm_tc_tiled"),
+                     "traffic_note": "dram bytes summed over the launches of one step, from the committed ncu --set full "
+                                     "capture under profiles/ (cold caches), not this run", "ops": ops},
+        "roofline_gather": {"kernel": ("sample_gather_s2d_kernel (fused sum-tree descent + IS weights + TMA bulk-copy gather + "
+                                       "uint8 -> bf16 space-to-depth operand plane of conv1: replaces the staged uint8 "
+                                       "copy and the two conversion passes over it)") if agent.s2d is not None else
+                            "per_sample_gather_kernel (fused sum-tree descent + IS weights + TMA bulk-copy gather)",
                      "bound": "hbm", "achieved": round(gather_gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": round(gather_gbs / pk["hbm_gbs"], 4), "peak_kind": pk_kind + " (burst copy)",
                      "us_per_launch": round(gather_us, 2), "algorithmic_bytes": GATHER_BYTES,
-                     "traffic": TRAFFIC_NCU.get("per_sample_gather"),
+                     "algorithmic_bytes_note": "the 57.9 MB contract figure of SURVEY 8d (columns read + staged copy "
+                                               "written)" + ("; this kernel reads 28.9 MB of frames and writes 57.8 MB "
+                                               "of bf16 planes: bytes_moved" if agent.s2d is not None else ""),
+                     "bytes_moved": GATHER_S2D_MOVED if agent.s2d is not None else GATHER_BYTES,
+                     "frac_bytes_moved": round((GATHER_S2D_MOVED if agent.s2d is not None else GATHER_BYTES)
+                                               / gather_us / 1e3 / pk["hbm_gbs"], 4),
+                     "traffic": TRAFFIC_NCU.get("sample_gather_s2d" if agent.s2d is not None else "per_sample_gather"),
+                     "traffic_note": "dram bytes from the committed ncu --set full capture under profiles/, not this run",
                      "frac_of_8TBps": round(gather_gbs / 8000.0, 4)},
         "roofline_learn": {"kernels": ("fp32 FFMA gather-GEMMs" if args.no_tc else
                                        "tcgen05 gather-GEMMs (3xBF16 split, 6 MMAs per product, fp32 TMEM accumulators)")
@@ -449,9 +491,10 @@ def run_reference(args):
         return
     K, W = args.steps, args.warmup
     K = min(K, 40)                      # bounded: the CPU step takes a sizeable fraction of a second
-    base = cpu_reference(steps=K, warmup=min(W, 2))
+    W = max(3, min(W, 10))              # same warm-up as the device arm (bounded: a CPU step is ~0.2 s)
+    base = cpu_reference(steps=K, warmup=W)
     line = {"impl": "reference", "metric": "learn_from_batch steps/sec (DQN PER batch 512)", "value": base["value"],
-            "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": min(W, 2),
+            "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(1e3 / base["value"], 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Atari-shaped DQN + PrioritizedExperienceReplay, 2^20-leaf trees, batch 512 "
@@ -471,6 +514,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the cpu_baseline leg")
     ap.add_argument("--no-l2-persist", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="fp32 FFMA GEMMs instead of the tcgen05 3xBF16 path")
+    ap.add_argument("--config", default="dqn", choices=["dqn", "dueling"],
+                    help="dqn: BASELINE config 2 (Atari DQN + PER, the headline metric, default); dueling: config 5 "
+                         "(dueling DDQN + PER, no middleware, clip-norm 10)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -50,6 +50,17 @@ class TGemmDesc(ctypes.Structure):
                 ("b_interleaved", ctypes.c_int32), ("tmap_key", ctypes.c_uint64), ("tmap_storage", ctypes.c_uint8 * (2 * 128 + 64))]
 
 
+class DqnHeadDesc(ctypes.Structure):
+    """struct cb200_dqn_head_desc"""
+    _fields_ = [("h_next", c_void_p), ("h_online", c_void_p), ("h_select", c_void_p), ("w_target", c_void_p),
+                ("b_target", c_void_p), ("w_online", c_void_p), ("b_online", c_void_p), ("actions", c_void_p),
+                ("rewards", c_void_p), ("game_overs", c_void_p), ("weights", c_void_p), ("discount", c_double),
+                ("huber", ctypes.c_int32), ("batch", c_i64), ("features", ctypes.c_int32),
+                ("n_actions", ctypes.c_int32), ("q_online", c_void_p), ("q_next", c_void_p), ("targets", c_void_p),
+                ("td_err", c_void_p), ("dq", c_void_p), ("loss", c_void_p), ("dh", c_void_p), ("dh_planes", c_void_p),
+                ("dh_plane_stride", c_i64), ("dw", c_void_p), ("db", c_void_p), ("workspace", c_void_p)]
+
+
 class Column(ctypes.Structure):
     """struct cb200_column"""
     _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_bytes", c_i64)]
@@ -65,7 +76,7 @@ PROTOTYPES = {
     "cb200_l2_persist": (c_int, [c_void_p, c_i64, c_void_p]),
     "cb200_per_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "cb200_per_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64,
-                                 c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p]),
     "cb200_per_priorities_device": (c_int, [c_void_p, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                             c_void_p]),
     "cb200_host_priorities": (c_int, [c_void_p, c_i64, c_double, c_double, c_void_p, c_void_p]),
@@ -95,6 +106,7 @@ PROTOTYPES = {
                                      c_i64, c_void_p, c_void_p, c_void_p]),
     "cb200_regression_head_loss_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int, c_float, c_void_p,
                                                 c_void_p, c_void_p]),
+    "cb200_dqn_head_fused": (c_int, [c_void_p, c_void_p]),
     "cb200_dueling_combine_fwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p]),
     "cb200_dueling_combine_bwd": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p]),
     "cb200_sumsq": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),

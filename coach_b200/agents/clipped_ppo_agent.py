@@ -41,9 +41,8 @@ class ClippedPPONetworkParameters(NetworkParameters):
         self.clip_gradients = None
         self.use_separate_networks_per_head = True
         self.create_target_network = True
-        self.learning_rate = 0.0003                     # presets/Mujoco_ClippedPPO.py:29-36
-        self.optimizer_epsilon = 1e-5
-        self.adam_optimizer_beta2 = 0.999
+        # (learning rate, Adam epsilon / beta2 keep the NetworkParameters defaults like the reference class does; the
+        # Mujoco preset sets 3e-4 / 1e-5 / 0.999: coach_b200/presets/Mujoco_ClippedPPO.py)
         self.hidden_units = 64
 
 

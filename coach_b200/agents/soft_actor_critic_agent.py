@@ -51,6 +51,8 @@ class SoftActorCriticAgentParameters(AgentParameters):
         super().__init__(algorithm=SoftActorCriticAlgorithmParameters(), memory=ExperienceReplayParameters(),
                          networks={"policy": SACNetworkParameters(), "q": SACNetworkParameters(),
                                    "v": SACNetworkParameters()})
+        # only the state-value network has a target copy (soft_actor_critic_agent.py:46)
+        self.network_wrappers["v"].create_target_network = True
 
     @property
     def path(self):

@@ -3,6 +3,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "nn_gemm_tc.cuh"
 
 namespace cb200 {
 
@@ -79,6 +80,208 @@ __global__ void __launch_bounds__(1024) regression_head_kernel(const float* __re
         __syncthreads();
     }
     if (threadIdx.x == 0 && loss_out) *loss_out = red[0] * inv_b;
+}
+
+// ---- fused DQN / DDQN Q-head step -----------------------------------------------------------------------------------
+// Everything between the feature layer and the loss in ONE launch (+ one small reduction launch):
+//   Q(s') of the target head, Q(s) of the online head [, Q(s') of the online head: DDQN action selection]
+//   (q_head.py:52-54: Dense(num_actions) on the middleware output)  ->  TD targets / errors (dqn_agent.py:92-103,
+//   fp64, bit-exact given the Q values)  ->  Huber / MSE head loss and dL/dQ (head.py:165-177)  ->  the head's own
+//   backward: dL/dW = h^T dQ, dL/db = sum_b dQ, and the gradient w.r.t. the feature layer's pre-activation
+//   dL/dz = (dQ W^T) * relu'(h), written as fp32 and as operand planes for the feature layer's tensor-core GEMMs.
+// Replaces 8-9 launches of latency-bound kernels (three 512x512x6 skinny GEMMs, TD targets, loss, two backward GEMMs, a
+// transpose) whose arithmetic is 12 MFLOP in total.
+// One warp = kHeadRows batch rows; lane l owns features [l K/32, (l+1) K/32): its slice of a row of h is contiguous, so
+// is its slice of W [K, A] (row-major), and the dL/dz planes get whole 16-byte core rows.  Dot products are reduced with
+// an xor butterfly (every lane ends with the same bits); batch-wise sums (dW, db, loss) go through per-warp partials in
+// global memory and a fixed-order second pass: run-to-run identical bits.
+constexpr int kHeadMaxA = 8;
+constexpr int kHeadRows = 2;
+constexpr int kHeadWarps = 8;
+
+struct HeadParams {
+    const float *h_next, *h_online, *h_select;
+    const float *w_target, *b_target, *w_online, *b_online;
+    const int64_t* actions;
+    const double* rewards;
+    const uint8_t* game_overs;
+    const float* weights;
+    double discount;
+    int huber, B, K, A;
+    float *q_online, *q_next, *targets;
+    double* td_err;
+    float *dq, *loss, *dh;
+    uint16_t* dh_planes;
+    int64_t dh_plane_stride;
+    float *dw, *db, *workspace;
+};
+
+template <int KPL>
+__device__ __forceinline__ void head_dot(const float* __restrict__ hrow, const float* __restrict__ w,
+                                         const float* __restrict__ bias, int A, int lane, float (&hv)[KPL],
+                                         float (&q)[kHeadMaxA]) {
+    const float4* hp = reinterpret_cast<const float4*>(hrow + lane * KPL);
+#pragma unroll
+    for (int j = 0; j < KPL / 4; ++j) {
+        const float4 v = __ldg(hp + j);
+        hv[4 * j] = v.x; hv[4 * j + 1] = v.y; hv[4 * j + 2] = v.z; hv[4 * j + 3] = v.w;
+    }
+#pragma unroll
+    for (int a = 0; a < kHeadMaxA; ++a) q[a] = 0.f;
+    const float* wl = w + (size_t)lane * KPL * A;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j)
+#pragma unroll
+        for (int a = 0; a < kHeadMaxA; ++a)
+            if (a < A) q[a] = fmaf(hv[j], __ldg(wl + j * A + a), q[a]);
+#pragma unroll
+    for (int a = 0; a < kHeadMaxA; ++a) {
+        if (a < A) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) q[a] += __shfl_xor_sync(0xffffffffu, q[a], o);
+            q[a] += __ldg(bias + a);
+        }
+    }
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(32 * kHeadWarps) dqn_head_fused_kernel(HeadParams p) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * kHeadWarps + (threadIdx.x >> 5);          // global warp
+    const int A = p.A, K = p.K;
+    float acc_w[KPL][kHeadMaxA];                                          // this lane's slice of dW, over the warp's rows
+    float acc_b[kHeadMaxA], acc_loss = 0.f;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j)
+#pragma unroll
+        for (int a = 0; a < kHeadMaxA; ++a) acc_w[j][a] = 0.f;
+#pragma unroll
+    for (int a = 0; a < kHeadMaxA; ++a) acc_b[a] = 0.f;
+    const float inv_b = 1.0f / (float)p.B;
+    for (int rr = 0; rr < kHeadRows; ++rr) {
+        const int r = gw * kHeadRows + rr;
+        if (r >= p.B) break;
+        float hv[KPL], qn[kHeadMaxA], qs[kHeadMaxA], qo[kHeadMaxA];
+        head_dot<KPL>(p.h_next + (size_t)r * K, p.w_target, p.b_target, A, lane, hv, qn);
+        if (p.h_select) head_dot<KPL>(p.h_select + (size_t)r * K, p.w_online, p.b_online, A, lane, hv, qs);
+        head_dot<KPL>(p.h_online + (size_t)r * K, p.w_online, p.b_online, A, lane, hv, qo);    // hv = h_online slice
+        // ---- TD target (every lane, identical values) -- dqn_agent.py:92-103 ------------------------------------------
+        int best = 0;
+        {
+            const float* sel = p.h_select ? qs : qn;                      // ddqn_agent.py:42-43 / dqn_agent.py:78-79
+            float bv = sel[0];
+#pragma unroll
+            for (int a = 1; a < kHeadMaxA; ++a)
+                if (a < A && sel[a] > bv) {
+                    bv = sel[a];
+                    best = a;
+                }
+        }
+        float q_best = qn[0];
+#pragma unroll
+        for (int a = 1; a < kHeadMaxA; ++a)
+            if (a == best) q_best = qn[a];
+        const int64_t act = p.actions[r];
+        const double not_done = __dsub_rn(1.0, p.game_overs[r] ? 1.0 : 0.0);
+        const double y = __dadd_rn(p.rewards[r], __dmul_rn(__dmul_rn(not_done, p.discount), (double)q_best));
+        float tgt[kHeadMaxA], dq[kHeadMaxA];
+        double td = 0.0;
+#pragma unroll
+        for (int a = 0; a < kHeadMaxA; ++a) {
+            tgt[a] = qo[a];
+            if (a < A && a == act) {
+                td = fabs(__dsub_rn(y, (double)qo[a]));
+                tgt[a] = (float)y;
+            }
+        }
+        // ---- head loss and dL/dQ (head.py:165-177; tf.losses.huber_loss delta = 1 / mean_squared_error) ---------------
+        const float w = p.weights ? p.weights[r] : 1.0f;
+        float row = 0.f;
+#pragma unroll
+        for (int a = 0; a < kHeadMaxA; ++a) {
+            dq[a] = 0.f;
+            if (a < A) {
+                const float e = qo[a] - tgt[a];
+                float l, g;
+                if (p.huber) {
+                    const float ae = fabsf(e);
+                    const float qq = fminf(ae, 1.0f);
+                    l = 0.5f * qq * qq + (ae - qq);
+                    g = (ae <= 1.0f) ? e : (e > 0.f ? 1.0f : -1.0f);
+                } else {
+                    l = e * e;
+                    g = 2.0f * e;
+                }
+                row += l;
+                dq[a] = w * inv_b * g;
+            }
+        }
+        acc_loss += w * row;
+        if (lane == 0) {
+            for (int a = 0; a < A; ++a) {
+                p.q_online[(size_t)r * A + a] = qo[a];
+                if (p.q_next) p.q_next[(size_t)r * A + a] = qn[a];
+                p.targets[(size_t)r * A + a] = tgt[a];
+                p.dq[(size_t)r * A + a] = dq[a];
+            }
+            p.td_err[r] = td;
+        }
+        // ---- backward of the head for this row ---------------------------------------------------------------------------
+        const float* wl = p.w_online + (size_t)lane * KPL * A;
+        float dz[KPL];
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int a = 0; a < kHeadMaxA; ++a)
+                if (a < A) {
+                    s = fmaf(dq[a], __ldg(wl + j * A + a), s);
+                    acc_w[j][a] = fmaf(hv[j], dq[a], acc_w[j][a]);
+                }
+            dz[j] = hv[j] > 0.f ? s : 0.f;                                // relu'(h) on the post-activation value
+        }
+#pragma unroll
+        for (int a = 0; a < kHeadMaxA; ++a) acc_b[a] += dq[a];
+        if (p.dh) {
+            float4* o = reinterpret_cast<float4*>(p.dh + (size_t)r * K + lane * KPL);
+#pragma unroll
+            for (int j = 0; j < KPL / 4; ++j) o[j] = make_float4(dz[4 * j], dz[4 * j + 1], dz[4 * j + 2], dz[4 * j + 3]);
+        }
+        if (p.dh_planes) {
+#pragma unroll
+            for (int c8 = 0; c8 < KPL / 8; ++c8) {
+                const gemm::Split8 sp = gemm::split8(make_float4(dz[8 * c8], dz[8 * c8 + 1], dz[8 * c8 + 2], dz[8 * c8 + 3]),
+                                                     make_float4(dz[8 * c8 + 4], dz[8 * c8 + 5], dz[8 * c8 + 6], dz[8 * c8 + 7]));
+                uint16_t* d = p.dh_planes + gemm::tiled_elem((size_t)r, lane * KPL + 8 * c8, K);
+                *reinterpret_cast<uint4*>(d) = sp.h;
+                *reinterpret_cast<uint4*>(d + p.dh_plane_stride) = sp.m;
+                *reinterpret_cast<uint4*>(d + 2 * p.dh_plane_stride) = sp.l;
+            }
+        }
+    }
+    // ---- per-warp partials: [dW (K * A) | db (A) | loss (1)] --------------------------------------------------------------
+    float* part = p.workspace + (size_t)gw * ((size_t)K * A + A + 1);
+#pragma unroll
+    for (int j = 0; j < KPL; ++j)
+#pragma unroll
+        for (int a = 0; a < kHeadMaxA; ++a)
+            if (a < A) part[((size_t)lane * KPL + j) * A + a] = acc_w[j][a];
+    if (lane == 0) {
+        for (int a = 0; a < A; ++a) part[(size_t)K * A + a] = acc_b[a];
+        part[(size_t)K * A + A] = acc_loss;
+    }
+}
+
+__global__ void __launch_bounds__(256) dqn_head_reduce_kernel(const float* __restrict__ ws, int nparts, int n_out,
+                                                              int KA, int A, float inv_b, float* __restrict__ dw,
+                                                              float* __restrict__ db, float* __restrict__ loss) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    float s = 0.f;
+    for (int q = 0; q < nparts; ++q) s += ws[(size_t)q * n_out + i];       // fixed order
+    if (i < KA) dw[i] = s;
+    else if (i < KA + A) db[i - KA] = s;
+    else if (loss) *loss = s * inv_b;
 }
 
 __global__ void dueling_fwd_kernel(const float* __restrict__ v, const float* __restrict__ adv, int64_t B, int64_t A,
@@ -217,6 +420,40 @@ int cb200_regression_head_loss_grad(const float* out, const float* target, const
     while (threads < batch && threads < 1024) threads *= 2;
     CB200_LAUNCH(regression_head_kernel, 1, threads, 0, as_stream(stream), out, target, weights, batch, width, huber,
                  loss_weight, d_out, loss_out);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_dqn_head_fused(const cb200_dqn_head_desc* d, void* stream) {
+    CB200_CHECK_ARG(d != nullptr, "null descriptor");
+    CB200_CHECK_ARG(d->h_next && d->h_online && d->w_target && d->b_target && d->w_online && d->b_online && d->actions &&
+                        d->rewards && d->game_overs && d->q_online && d->targets && d->td_err && d->dq && d->dw && d->db &&
+                        d->workspace,
+                    "null pointer");
+    CB200_CHECK_ARG(d->batch > 0 && d->n_actions > 0 && d->n_actions <= kHeadMaxA, "1 <= n_actions <= 8");
+    CB200_CHECK_ARG(d->features == 256 || d->features == 512, "features must be 256 or 512");
+    CB200_CHECK_ARG(!d->dh_planes || (d->dh_plane_stride % 8 == 0 && d->batch % 8 == 0), "planes: batch % 8, stride % 8");
+    HeadParams p;
+    p.h_next = d->h_next; p.h_online = d->h_online; p.h_select = d->h_select;
+    p.w_target = d->w_target; p.b_target = d->b_target; p.w_online = d->w_online; p.b_online = d->b_online;
+    p.actions = d->actions; p.rewards = d->rewards; p.game_overs = d->game_overs; p.weights = d->weights;
+    p.discount = d->discount; p.huber = d->huber; p.B = (int)d->batch; p.K = d->features; p.A = d->n_actions;
+    p.q_online = d->q_online; p.q_next = d->q_next; p.targets = d->targets; p.td_err = d->td_err;
+    p.dq = d->dq; p.loss = d->loss; p.dh = d->dh;
+    p.dh_planes = static_cast<uint16_t*>(d->dh_planes); p.dh_plane_stride = d->dh_plane_stride;
+    p.dw = d->dw; p.db = d->db; p.workspace = d->workspace;
+    const int warps = (p.B + kHeadRows - 1) / kHeadRows;
+    const unsigned grid = (unsigned)((warps + kHeadWarps - 1) / kHeadWarps);
+    const int nparts = (int)grid * kHeadWarps;                 // idle warps of the last block write zero partials
+    cudaStream_t st = as_stream(stream);
+    if (p.K == 512) {
+        CB200_LAUNCH(dqn_head_fused_kernel<16>, grid, 32 * kHeadWarps, 0, st, p);
+    } else {
+        CB200_LAUNCH(dqn_head_fused_kernel<8>, grid, 32 * kHeadWarps, 0, st, p);
+    }
+    const int n_out = p.K * p.A + p.A + 1;
+    CB200_LAUNCH(dqn_head_reduce_kernel, (unsigned)((n_out + 255) / 256), 256, 0, st, p.workspace, nparts, n_out,
+                 p.K * p.A, p.A, 1.0f / (float)p.B, p.dw, p.db, p.loss);
     CB200_CHECK_LAUNCH();
     return CB200_OK;
 }

@@ -157,10 +157,21 @@ struct UpdateParams {
     double c_alpha, c_raw;
     int64_t n;
     double* max_priority_out;
+    int32_t* error_flags;    // optional: bit 1 (value 2) is set when a leaf index is out of range
 };
 
+// leaf of batch entry i, or -1 when the entry must not be applied: out of range (flagged), or carrying the negative
+// priority marker cb200_per_priorities_device leaves for an invalid (negative / NaN) error
 __device__ __forceinline__ int64_t upd_leaf(const UpdateParams& up, int64_t i) {
-    if (up.idx) return up.idx[i];
+    if (up.idx) {
+        const int64_t leaf = up.idx[i];
+        if (leaf < 0 || leaf >= up.size) {
+            if (up.error_flags) atomicOr(up.error_flags, 2);
+            return -1;
+        }
+        if (up.p_alpha[i] < 0.0) return -1;
+        return leaf;
+    }
     return (up.cursor + i) & (up.size - 1);
 }
 __device__ __forceinline__ double py_min(double a, double b) { return (b < a) ? b : a; }   // builtin min(a, b)
@@ -441,7 +452,12 @@ __global__ void per_priorities_kernel(const double* err, int64_t n, double epsil
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double e = err[i];
-    if (e < 0 && neg_flag) *neg_flag = 1;      // :195
+    if (!(e >= 0)) {                           // :195 (negative; NaN too): flag it and mark the entry as "do not apply"
+        if (neg_flag) atomicOr(neg_flag, 1);
+        p_raw[i] = -1.0;
+        p_alpha[i] = -1.0;
+        return;
+    }
     const double p = __dadd_rn(e, epsilon);    // :197
     p_raw[i] = p;
     p_alpha[i] = pow(p, alpha);                // :198
@@ -647,7 +663,7 @@ __global__ void __launch_bounds__(kGatherThreads) per_sample_gather_kernel(Sampl
 // weights and copies the small columns.
 // =====================================================================================================================
 constexpr int kS2dThreads = 256;
-constexpr int kS2dStages = 3;
+constexpr int kS2dStages = 2;
 
 struct S2dGatherParams {
     const uint8_t* src[2];     // ring columns (uint8 [capacity, H * W * C])
@@ -736,7 +752,8 @@ __global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SamplePa
         const int st = k % kS2dStages;
         const int ya = y_lo + k * gp.rows_per_chunk;
         const int rc = min(gp.rows_per_chunk, y_hi - ya);
-        mbar_wait(full_bar + st, (uint32_t)((k / kS2dStages) & 1));
+        if (lane == 0) mbar_wait(full_bar + st, (uint32_t)((k / kS2dStages) & 1));   // one poller per warp
+        __syncwarp();
         const uint8_t* sbase = stage_mem + (size_t)st * 8 * gp.chunk_stride + (size_t)b * gp.chunk_stride;
         if (slot < slots) {
             for (int pi = slot; pi < rc * Ws; pi += slots) {
@@ -951,14 +968,14 @@ static int run_update(UpdateParams& up, void* stream) {
 
 int cb200_per_update(double* sum_tree, double* min_tree, double* max_tree, int32_t* winner, int64_t size,
                      const int64_t* idx, const double* p_alpha, const double* p_raw, int64_t n,
-                     double* max_priority_out, void* stream) {
+                     double* max_priority_out, int32_t* error_flags, void* stream) {
     CB200_CHECK_ARG(sum_tree && min_tree && max_tree && winner, "null tree pointer");
     CB200_CHECK_ARG(n >= 0, "negative n");
     CB200_CHECK_ARG(n == 0 || (idx && p_alpha && p_raw), "null batch pointer");
     const int levels = ilog2_exact(size);
     CB200_CHECK_ARG(levels >= 0, "size must be a positive power of 2");
     UpdateParams up{sum_tree, min_tree, max_tree, winner, size, levels, idx, p_alpha, p_raw, 0, 0.0, 0.0, n,
-                    max_priority_out};
+                    max_priority_out, error_flags};
     return run_update(up, stream);
 }
 
@@ -970,7 +987,7 @@ int cb200_per_store(double* sum_tree, double* min_tree, double* max_tree, int32_
     CB200_CHECK_ARG(cursor >= 0 && cursor < size && n >= 0, "bad cursor / n");
     CB200_CHECK_ARG(n <= size, "storing more than one full ring per call is not supported");
     UpdateParams up{sum_tree, min_tree, max_tree, winner, size, levels, nullptr, nullptr, nullptr, cursor, p_alpha,
-                    p_raw, n, nullptr};
+                    p_raw, n, nullptr, nullptr};
     return run_update(up, stream);
 }
 
@@ -1108,18 +1125,19 @@ static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int6
     }
     const int hs = h / s;
     const int s2d_row_bytes = s * w * c;
-    // chunks of about 4 KB per sample; the padded per-sample stride is an odd multiple of 16 bytes
-    int rc = 4096 / s2d_row_bytes;
+    // chunks of about 2.7 KB per sample (two stages of 8 samples = 43 KB of shared memory: four CTAs per SM, whose
+    // descents / copies / conversions overlap each other); the padded per-sample stride is an odd multiple of 16 bytes
+    int rc = 2816 / s2d_row_bytes;
     if (rc < 1) rc = 1;
     if (rc > hs) rc = hs;
     gp.rows_per_chunk = rc;
     int stride = rc * s2d_row_bytes;
     if ((stride / 16) % 2 == 0) stride += 16;
     gp.chunk_stride = stride;
-    // bands: as many CTAs as fit in ONE wave of two per SM (a CTA is a chain of dependent round trips -- tree descent,
+    // bands: as many CTAs as fit in ONE wave of four per SM (a CTA is a chain of dependent round trips -- tree descent,
     // first chunk, conversion -- so a second, partial wave would double the kernel's duration)
     const int groups = (int)(n / 8) * n_img;
-    int parts = (2 * sm_count()) / groups;
+    int parts = (4 * sm_count()) / groups;
     if (parts < 1) parts = 1;
     if (parts > hs) parts = hs;
     gp.parts = parts;

@@ -191,6 +191,30 @@ class EpisodicExperienceReplay(ExperienceReplay):
     def transitions(self):
         return self.transitions_batch().to_transitions()
 
+    def get_episode(self, episode_index: int, lock: bool = True):
+        """episodic_experience_replay.py:320-336: the episode at the given index (complete episodes, oldest first) as an
+        object with ``.transitions`` (host materialisation), or None"""
+        from types import SimpleNamespace
+        if episode_index < 0:
+            episode_index += len(self.episode_lengths)
+        if not 0 <= episode_index < len(self.episode_lengths):
+            return None
+        self._flush()
+        lo = int(sum(self.episode_lengths[:episode_index]))
+        pos = np.arange(lo, lo + self.episode_lengths[episode_index], dtype=np.int64)
+        idx = torch.from_numpy(self._slots_of_complete_episodes(pos)).to(self.device)
+        cols = dict(self.ring.gather(idx))
+        if self._returns is not None:
+            cols["n_step_discounted_rewards"] = self._returns[idx]
+        ts = DeviceBatch(cols, len(pos)).to_transitions()
+        if self._returns is not None:
+            for t, r in zip(ts, cols["n_step_discounted_rewards"].cpu().numpy()):
+                t.n_step_discounted_rewards = float(r)
+        return SimpleNamespace(transitions=ts, length=lambda: len(ts))
+
+    def get(self, episode_index: int, lock: bool = True):
+        return self.get_episode(episode_index, lock)
+
     def sample_batch(self, size: int, out: dict = None) -> DeviceBatch:
         """episodic_experience_replay.py:102-130: uniform over the transitions of complete episodes."""
         n = self.num_transitions_in_complete_episodes()

@@ -83,6 +83,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         self._maxp_stale = False
         self._list_len = 0                  # len(self.transitions) of the reference (doubled, capped)
         self._u_ring = {}                   # batch size -> rotating pinned / device buffers of the uniform draws
+        self._flag_host, self._flag_event = None, None
 
     def _init_trees(self):
         _lib.check(self.lib.cb200_per_init(self.sum_tree.data_ptr(), self.min_tree.data_ptr(),
@@ -175,8 +176,41 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         _lib.check(self.lib.cb200_per_update(self.sum_tree.data_ptr(), self.min_tree.data_ptr(),
                                              self.max_tree.data_ptr(), self._winner.data_ptr(), self.power_of_2_size,
                                              idx.data_ptr(), p_alpha.data_ptr(), p_raw.data_ptr(), idx.shape[0],
-                                             self._maxp_dev.data_ptr(), _lib.current_stream()))
+                                             self._maxp_dev.data_ptr(), self._neg_flag.data_ptr(),
+                                             _lib.current_stream()))
         self._maxp_stale = True
+        self._post_flag_check()
+
+    # ---- device-side error flags (priority_mode='device', CUDA-tensor indices) ---------------------------------------
+    # Invalid entries never reach the trees (the kernels skip them); the condition is reported like the reference
+    # reports it -- a ValueError -- at the next host-side call that can observe it, without ever blocking the stream:
+    # the flag word is copied to a pinned mirror behind every update and read once the copy's event has completed.
+    def _post_flag_check(self):
+        if self.device.type != "cuda":
+            return
+        if self._flag_host is None:
+            self._flag_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+        self._flag_host.copy_(self._neg_flag, non_blocking=True)
+        self._flag_event = torch.cuda.Event()
+        self._flag_event.record()
+
+    def check_device_errors(self, wait=False):
+        """raises the reference's ValueError if a device-side priority update met a negative error or an out-of-range
+        leaf since the last check (wait=True synchronises with the last update first)"""
+        if self._flag_event is None:
+            return
+        if wait:
+            self._flag_event.synchronize()
+        if not self._flag_event.query():
+            return
+        self._flag_event = None
+        flags = int(self._flag_host[0])
+        if flags:
+            self._neg_flag.zero_()
+            if flags & 1:
+                raise ValueError("The priorities must be non-negative values")                       # :195
+            raise ValueError("The given left index can not be found in the tree. The available leaves are: 0-{}"
+                             .format(self.power_of_2_size - 1))                                       # :124-126
 
     def _as_device(self, v, dtype, check_range=False):
         if torch.is_tensor(v):
@@ -200,6 +234,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
             raise ValueError("The replay buffer cannot be sampled since there are not enough transitions yet. "
                              "There are currently {} transitions".format(self.num_transitions()))
         self._flush()
+        self.check_device_errors()
         if uniforms is None:
             rnd = random.random
             uniforms = [rnd() for _ in range(size)]

@@ -65,16 +65,21 @@ int cb200_per_init(double* sum_tree, double* min_tree, double* max_tree, int32_t
  * tree p_raw[i]; duplicates resolve last-writer-wins in batch order (the reference applies them sequentially); every
  * ancestor is then recomputed as op(left, right) level by level, which is bit-identical to the sequential reference
  * because parents are recomputed, never incrementally adjusted.  `max_priority_out` (device double, may be NULL)
- * receives max_tree[0] (= self.maximal_priority, :201).  n <= 1024 runs as one CTA; larger n uses one launch per
- * tree level. */
+ * receives max_tree[0] (= self.maximal_priority, :201).  n <= 1024 runs as ONE launch of one CTA that sorts the batch's
+ * leaves in shared memory and walks all paths bottom-up without global round trips between levels; larger n uses one
+ * launch per tree level.  Entries that must not be applied are skipped: a leaf outside [0, size) (the reference raises
+ * ValueError :124-126; here bit 1 of *error_flags, device int32, may be NULL, is set) and entries whose p_alpha is
+ * negative (the marker cb200_per_priorities_device leaves for a negative / NaN error). */
 int cb200_per_update(double* sum_tree, double* min_tree, double* max_tree, int32_t* winner, int64_t size,
                      const int64_t* idx, const double* p_alpha, const double* p_raw, int64_t n,
-                     double* max_priority_out, void* stream);
+                     double* max_priority_out, int32_t* error_flags, void* stream);
 
 /* priority = error + epsilon; p_raw = priority; p_alpha = priority ** alpha  (:197-200) computed ON DEVICE with CUDA's
  * pow (<= 2 ulp; glibc's pow, which the reference uses, is not correctly rounded either, so device and reference
  * can differ in the last bit of ~0.1% of leaves -- see cb200_host_priorities for the libm-exact route).
- * *neg_flag (device int32, may be NULL) is set to 1 if any err[i] < 0 (reference raises ValueError :195). */
+ * Bit 0 of *neg_flag (device int32, may be NULL) is set if any err[i] is negative or NaN (the reference raises
+ * ValueError :195); such entries get p_alpha = p_raw = -1, which cb200_per_update skips, so an invalid error can never
+ * reach the trees. */
 int cb200_per_priorities_device(const double* err, int64_t n, double epsilon, double alpha, double* p_alpha,
                                 double* p_raw, int32_t* neg_flag, void* stream);
 
@@ -337,6 +342,44 @@ int cb200_dqn_td_targets(const float* q_next, const float* q_select, const float
 int cb200_regression_head_loss_grad(const float* out, const float* target, const float* weights, int64_t batch,
                                     int64_t width, int huber, float loss_weight, float* d_out, float* loss_out,
                                     void* stream);
+
+/* Fused DQN / DDQN Q-head step: Q(s') of the target head, Q(s) [and Q(s'), DDQN] of the online head (q_head.py:52-54),
+ * TD targets / errors (agents/dqn_agent.py:92-103, ddqn_agent.py:42-43; fp64, bit-exact given the Q values), Huber / MSE
+ * head loss and dL/dQ (heads/head.py:165-177), and the head's backward pass: dL/dW, dL/db and the gradient w.r.t. the
+ * feature layer's pre-activation (dQ W^T masked with relu'(h)), as fp32 and / or as operand planes.  Two launches
+ * instead of the eight or nine of cb200_gemm x 5 + cb200_dqn_td_targets + cb200_regression_head_loss_grad. */
+typedef struct cb200_dqn_head_desc {
+    const float* h_next;        /* [batch, features] post-ReLU features of s' from the TARGET network                      */
+    const float* h_online;      /* [batch, features] features of s from the online network                                */
+    const float* h_select;      /* DDQN: features of s' from the ONLINE network (action selection); NULL for DQN          */
+    const float* w_target;      /* target head kernel [features, n_actions] and bias                                      */
+    const float* b_target;
+    const float* w_online;
+    const float* b_online;
+    const int64_t* actions;     /* [batch]                                                                                 */
+    const double* rewards;
+    const uint8_t* game_overs;
+    const float* weights;       /* importance weights [batch] or NULL                                                     */
+    double discount;
+    int32_t huber;              /* 1: tf.losses.huber_loss(delta 1), 0: mean squared error                                */
+    int64_t batch;
+    int32_t features;           /* 256 or 512                                                                              */
+    int32_t n_actions;          /* <= 8                                                                                    */
+    float* q_online;            /* out [batch, n_actions]                                                                  */
+    float* q_next;              /* out, optional                                                                           */
+    float* targets;             /* out [batch, n_actions]: Q(s) with the taken action's entry replaced by the TD target    */
+    double* td_err;             /* out [batch]: |target - Q(s, a)| (the PER priorities' errors)                           */
+    float* dq;                  /* out [batch, n_actions]: dL/dQ                                                           */
+    float* loss;                /* out scalar, optional                                                                    */
+    float* dh;                  /* out, optional: [batch, features] dL/d(pre-activation of the feature layer)             */
+    void* dh_planes;            /* out, optional: the same as tiled bf16 hi / mid / lo planes                              */
+    int64_t dh_plane_stride;
+    float* dw;                  /* out [features, n_actions]: gradient of the online head kernel                          */
+    float* db;                  /* out [n_actions]                                                                         */
+    float* workspace;           /* ceil(batch / 16) * 8 * (features * n_actions + n_actions + 1) floats                    */
+} cb200_dqn_head_desc;
+
+int cb200_dqn_head_fused(const cb200_dqn_head_desc* h_desc, void* stream);
 
 /* DuelingQHead (heads/dueling_q_head.py:33-47): q = v + (adv - mean_a adv); backward: d_v = sum_a dq,
  * d_adv = dq - mean_a dq. */

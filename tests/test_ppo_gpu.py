@@ -17,6 +17,8 @@ def _agent(D=17, A=6, B=64, beta_entropy=0.0, seed=0, graph=True, truncate=True)
     from coach_b200.agents.clipped_ppo_agent import ClippedPPOAgent, ClippedPPOAgentParameters
     from coach_b200.memories.memory import MemoryGranularity
     ap = ClippedPPOAgentParameters()
+    net = ap.network_wrappers["main"]          # presets/Mujoco_ClippedPPO.py:29-36
+    net.learning_rate, net.optimizer_epsilon, net.adam_optimizer_beta2 = 0.0003, 1e-5, 0.999
     ap.memory.max_size = (MemoryGranularity.Transitions, 8192)
     ap.network_wrappers["main"].batch_size = B
     ap.algorithm.beta_entropy = beta_entropy

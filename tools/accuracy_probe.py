@@ -26,34 +26,38 @@ def main():
     agent.memory.update_priorities(np.arange(n), np.abs(rng.randn(n)))
     store, net = agent.net_def.store, agent.networks["main"]
     net.theta_target.copy_(store.theta * 0.9 + 0.01)
-    online, target = store.export_named(), store.export_named(net.theta_target)
-    random.seed(10)
-    batch = agent.sample_batch()
-    loss, _, gnorm = agent.learn_from_batch(batch)
-    torch.cuda.synchronize()
-    for k in ("state:observation", "next_state:observation"):
-        batch.column(k)
-    cols = {k: v.cpu().numpy() for k, v in batch.columns.items()}
-    ob = dict(states=cols["state:observation"], next_states=cols["next_state:observation"], actions=cols["action"],
-              rewards=cols["reward"], game_overs=cols["game_over"].astype(bool), weights=cols["weight32"])
-    res = {}
-    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
-        o = on.QNetOracle((84, 84, 4), A, False, dt)
-        opt = on.AdamTF([torch.from_numpy(v).to(dt) for v in online.values()], 2.5e-4, 0.9, 0.99, 1e-4, dtype=dt)
-        res[name] = on.dqn_learn_step(o, o.cast(online), o.cast(target), opt, ob, 0.99, True, False, None)
-    r64, r32 = res["f64"], res["f32"]
-    print("cap %s: loss rel err ours %.2e (fp32 oracle %.2e); grad_norm rel err ours %.2e (fp32 oracle %.2e)"
-          % (os.environ.get("CB200_TILED_MAX_CHUNKS", "20"), abs(loss - r64["loss"]) / r64["loss"],
-             abs(r32["loss"] - r64["loss"]) / r64["loss"], abs(gnorm - r64["grad_norm"]) / r64["grad_norm"],
-             abs(r32["grad_norm"] - r64["grad_norm"]) / r64["grad_norm"]))
-    got = store.export_named(store.grad)
-    for name in r64["grads"]:
-        w = r64["grads"][name].numpy()
-        s = np.abs(w).max() + 1e-30
-        print("   %-45s ours %.2e  fp32 oracle %.2e   (max abs err / max |grad|)"
-              % (name.split("network_0/")[-1], np.abs(got[name] - w).max() / s,
-                 np.abs(r32["grads"][name].numpy() - w).max() / s))
-
+    for step in range(int(os.environ.get("PROBE_STEPS", "2"))):
+        online, target = store.export_named(), store.export_named(net.theta_target)
+        random.seed(10 + step)
+        np.random.seed(10 + step)
+        batch = agent.sample_batch()
+        loss, _, gnorm = agent.learn_from_batch(batch)
+        torch.cuda.synchronize()
+        for k in ("state:observation", "next_state:observation"):
+            batch.column(k)
+        cols = {k: v.cpu().numpy() for k, v in batch.columns.items()}
+        ob = dict(states=cols["state:observation"], next_states=cols["next_state:observation"], actions=cols["action"],
+                  rewards=cols["reward"], game_overs=cols["game_over"].astype(bool), weights=cols["weight32"])
+        res = {}
+        for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            o = on.QNetOracle((84, 84, 4), A, False, dt)
+            opt = on.AdamTF([torch.from_numpy(v).to(dt) for v in online.values()], 2.5e-4, 0.9, 0.99, 1e-4, dtype=dt)
+            res[name] = on.dqn_learn_step(o, o.cast(online), o.cast(target), opt, ob, 0.99, True, False, None)
+        r64, r32 = res["f64"], res["f32"]
+        print("step %d cap %s: loss rel err ours %.2e (fp32 oracle %.2e); grad_norm rel err ours %.2e (fp32 oracle %.2e); "
+              "q_online max err %.2e" % (step, os.environ.get("CB200_TILED_MAX_CHUNKS", "20"),
+                                         abs(loss - r64["loss"]) / r64["loss"],
+                                         abs(r32["loss"] - r64["loss"]) / r64["loss"],
+                                         abs(gnorm - r64["grad_norm"]) / r64["grad_norm"],
+                                         abs(r32["grad_norm"] - r64["grad_norm"]) / r64["grad_norm"],
+                                         np.abs(net.online_s.q.cpu().numpy() - r64["q_online"]).max()))
+        got = store.export_named(store.grad)
+        for name in r64["grads"]:
+            w = r64["grads"][name].numpy()
+            s = np.abs(w).max() + 1e-30
+            print("   %-45s ours %.2e  fp32 oracle %.2e   (max abs err / max |grad|)"
+                  % (name.split("network_0/")[-1], np.abs(got[name] - w).max() / s,
+                     np.abs(r32["grads"][name].numpy() - w).max() / s))
 
 if __name__ == "__main__":
     main()
