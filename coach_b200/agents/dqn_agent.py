@@ -191,6 +191,13 @@ class DQNAgent(object):
                                                  input_planes=self.s2d["columns"] if self.s2d else None)}
         if self.networks["main"].has_target:
             self.networks["main"].sync()
+        # plain Q head: head forward passes, TD targets, loss and the head's backward pass are ONE fused launch
+        net = self.networks["main"]
+        self.head_desc = None
+        if (_lib.tune_default("fused_head", 1) and dev.type == "cuda" and net.has_target and
+                net.online_s.head_fusable() and net.target_s2.head_fusable() and
+                (net.online_s2 is None or net.online_s2.head_fusable())):
+            self._build_head_desc()
         self.targets = torch.zeros((B, A), dtype=torch.float32, device=dev)
         self.td_err = torch.zeros(B, dtype=torch.float64, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -208,6 +215,7 @@ class DQNAgent(object):
         self.use_graph = bool(_lib.tune_default("dqn_graph", 1)) and dev.type == "cuda" and B >= 128
         self.networks["main"].device_adam_state = self.use_graph
         self._graphs = None
+        self._head_weights, self._head_split = None, False
         self._grad_sync = None                    # exchange buffer of the overlapped gradient all-reduce
         self._eager_steps = 0
         self.graph_kernel_launches = 0            # kernels executed through graph replays (bench.py gpu_launches)
@@ -252,6 +260,31 @@ class DQNAgent(object):
             self.last_training_phase_step = self.total_steps_counter
         return should
 
+    def _build_head_desc(self):
+        net, B, A = self.networks["main"], self.batch_size, self.num_actions
+        store, on = net.store, net.online_s
+        wname, bname = self.net_def.trunk.names[-1]
+        K = on.trunk.layers[-1].K
+        d = _lib.DqnHeadDesc()
+        self._head_keep = [torch.zeros(((B + 15) // 16) * 8 * (K * A + A + 1), dtype=torch.float32, device=self.device)]
+        d.h_next, d.h_online = net.target_s2.trunk.acts[-2].data_ptr(), on.trunk.acts[-2].data_ptr()
+        d.h_select = net.online_s2.trunk.acts[-2].data_ptr() if net.online_s2 is not None else None
+        d.w_target, d.b_target = store.view(net.theta_target, wname).data_ptr(), store.view(net.theta_target, bname).data_ptr()
+        d.w_online, d.b_online = store.view(net.theta, wname).data_ptr(), store.view(net.theta, bname).data_ptr()
+        d.discount = float(self.ap.algorithm.discount)
+        d.huber = 1 if net.params.replace_mse_with_huber_loss else 0
+        d.batch, d.features, d.n_actions = B, K, A
+        d.q_online, d.dq = on.q.data_ptr(), on.dq.data_ptr()
+        d.q_next = net.target_s2.q.data_ptr()
+        dz = on.trunk.dzs[-2]
+        d.dh = dz.data_ptr() if dz is not None else None
+        pl = on.trunk.dz_planes[-2]
+        if pl is not None:
+            d.dh_planes, d.dh_plane_stride = pl.ptr, pl.stride
+        d.dw, d.db = store.view(store.grad, wname).data_ptr(), store.view(store.grad, bname).data_ptr()
+        d.workspace = self._head_keep[0].data_ptr()
+        self.head_desc = d
+
     # ---- the hot path ------------------------------------------------------------------------------------------------
     def sample_batch(self):
         """memory sample straight into the persistent minibatch buffers"""
@@ -263,6 +296,23 @@ class DQNAgent(object):
         """target / online forward passes, TD targets and errors (dqn_agent.py:87-103); kernels and one D2H copy"""
         lib, st = self.lib, _lib.current_stream()
         net = self.networks["main"]
+        if self.head_desc is not None and not self._head_split:
+            # feature layers of the three bindings, then the fused head launch: Q values, TD targets / errors, head loss,
+            # dL/dQ and the head's backward pass (cb200_dqn_head_fused)
+            import ctypes
+            d = self.head_desc
+            net.target_s2.forward_features()
+            net.online_s.forward_features()
+            if self.double_dqn:
+                net.online_s2.forward_features()
+            d.actions, d.rewards, d.game_overs = cols["action"].data_ptr(), cols["reward"].data_ptr(), \
+                cols["game_over"].data_ptr()
+            d.weights = self._head_weights.data_ptr() if self._head_weights is not None else None
+            d.targets, d.td_err, d.loss = self.targets.data_ptr(), self.td_err.data_ptr(), self.loss_dev.data_ptr()
+            _lib.check(lib.cb200_dqn_head_fused(ctypes.byref(d), st))
+            if per_libm:
+                self._td_host.copy_(self.td_err, non_blocking=True)
+            return
         q_next = net.target_s2.forward()                          # dqn_agent.py:87-90
         q_online = net.online_s.forward()
         q_select = net.online_s2.forward() if self.double_dqn else q_next      # ddqn_agent.py:42-43
@@ -279,6 +329,20 @@ class DQNAgent(object):
         layers) / "bottom" (conv layers + norm) when the all-reduce of the dense gradients overlaps the rest"""
         lib, st = self.lib, _lib.current_stream()
         net = self.networks["main"]
+        if self.head_desc is not None and not self._head_split:
+            # loss, dL/dQ and the head's gradients were produced by the fused head launch of the forward part
+            net.online_s.backward_features()
+            n = net.store.size
+            _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(), st))
+            clip = net.params.clip_gradients
+            if clip is not None and clip != 0:
+                if net.params.gradients_clipping_method != "ClipByGlobalNorm":
+                    raise NotImplementedError("only ClipByGlobalNorm is implemented on device")
+                _lib.check(lib.cb200_clip_by_global_norm(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), float(clip),
+                                                         st))
+            if with_optimizer:
+                net.apply_gradients(1.0)
+            return
         if part != "bottom":
             huber = 1 if net.params.replace_mse_with_huber_loss else 0
             _lib.check(lib.cb200_regression_head_loss_grad(net.online_s.q.data_ptr(), self.targets.data_ptr(),
@@ -364,6 +428,7 @@ class DQNAgent(object):
             weights = cols["weight32"] if "weight32" in cols else cols["weight"].to(torch.float32)
             own = own and weights.data_ptr() == self.batch_buffers["weight32"].data_ptr()
         per_libm = per and self.memory.priority_mode == "libm"
+        self._head_weights = weights
         single = not parallel.is_distributed()                    # no all-reduce between backward and optimizer
         # several ranks, no global-norm clipping (which needs the complete local gradient first), plain Q head: the
         # all-reduce of the dense layers' gradients can run under the conv backward pass (CB200_DQN_OVERLAP_ALLREDUCE=1).
@@ -372,6 +437,7 @@ class DQNAgent(object):
         clip = net.params.clip_gradients
         overlap = (not single) and not (clip is not None and clip != 0) and not self.net_def.dueling and \
             bool(_lib.tune_default("dqn_overlap_allreduce", 0))
+        self._head_split = overlap          # the overlapped all-reduce needs the head's backward as a separate part
         if overlap and self._grad_sync is None:
             self._grad_sync = torch.zeros_like(net.store.grad)
         graph = self.use_graph and own and self._eager_steps >= 2

@@ -204,8 +204,9 @@ class SequentialInstance(object):
         layer.prepare(lib, ws, B, dev, x, y, w, b, None, None, None, None, x_is_u8=x_is_u8, lut=lut, need_dx=False,
                       planes=ctx)
 
-    def forward(self):
-        for layer in self.layers:
+    def forward(self, upto=None):
+        """upto: run only the first ``upto`` layers (the caller computes the rest itself, e.g. a fused head kernel)"""
+        for layer in (self.layers if upto is None else self.layers[:upto]):
             layer.forward()
         return self.out
 

@@ -161,6 +161,26 @@ class QNetworkInstance(object):
                                                           _lib.current_stream()))
         return self.q
 
+    # ---- plain Q head computed by the agent's fused head kernel (cb200_dqn_head_fused) ------------------------------------
+    def head_fusable(self):
+        """plain Dense(num_actions) head on a 256- or 512-wide feature layer whose fp32 activations are kept"""
+        if self.net.dueling or len(self.trunk.layers) < 2:
+            return False
+        head = self.trunk.layers[-1]
+        return (type(head).__name__ == "Dense" and head.K in (256, 512) and head.N <= 8 and
+                self.trunk.acts[-2] is not None and self.trunk.layers[-2].act == 1)
+
+    def forward_features(self):
+        """everything below the head: the feature layer's post-ReLU output is ``features``"""
+        if self.theta_planes is not None:
+            self.theta_planes.refresh()
+        self.trunk.forward(upto=len(self.trunk.layers) - 1)
+        return self.trunk.acts[-2]
+
+    def backward_features(self):
+        """expects the gradient w.r.t. the feature layer's pre-activation in trunk.dzs[-2] (/ its planes)"""
+        self.trunk.backward(layers=(0, len(self.trunk.layers) - 1))
+
     def backward_top(self):
         """plain Q head only: the dense layers (middleware + head) of the trunk, which hold ~95 % of the parameters;
         their gradients are complete -- and can be all-reduced -- while ``backward_bottom`` still runs"""

@@ -3,7 +3,6 @@
 #include <math.h>
 
 #include "common.cuh"
-#include "nn_gemm_tc.cuh"
 
 namespace cb200 {
 
@@ -95,6 +94,33 @@ __global__ void __launch_bounds__(1024) regression_head_kernel(const float* __re
 // is its slice of W [K, A] (row-major), and the dL/dz planes get whole 16-byte core rows.  Dot products are reduced with
 // an xor butterfly (every lane ends with the same bits); batch-wise sums (dW, db, loss) go through per-warp partials in
 // global memory and a fixed-order second pass: run-to-run identical bits.
+// exact 3-way bf16 truncation split of 8 fp32 values into three 16-byte groups (same arithmetic as gemm::split8 of
+// nn_gemm_tc.cuh, restated here because that header defines kernels) and the core-tiled element index of nn_gemm.cuh
+struct HeadSplit8 {
+    uint4 h, m, l;
+};
+__device__ __forceinline__ HeadSplit8 head_split8(const float (&x)[8]) {
+    uint32_t hb[8], mb[8], lb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        hb[j] = __float_as_uint(x[j]) & 0xffff0000u;
+        const float r1 = x[j] - __uint_as_float(hb[j]);
+        mb[j] = __float_as_uint(r1) & 0xffff0000u;
+        lb[j] = __float_as_uint(r1 - __uint_as_float(mb[j]));
+    }
+    HeadSplit8 s;
+    s.h = make_uint4(__byte_perm(hb[0], hb[1], 0x7632), __byte_perm(hb[2], hb[3], 0x7632),
+                     __byte_perm(hb[4], hb[5], 0x7632), __byte_perm(hb[6], hb[7], 0x7632));
+    s.m = make_uint4(__byte_perm(mb[0], mb[1], 0x7632), __byte_perm(mb[2], mb[3], 0x7632),
+                     __byte_perm(mb[4], mb[5], 0x7632), __byte_perm(mb[6], mb[7], 0x7632));
+    s.l = make_uint4(__byte_perm(lb[0], lb[1], 0x7632), __byte_perm(lb[2], lb[3], 0x7632),
+                     __byte_perm(lb[4], lb[5], 0x7632), __byte_perm(lb[6], lb[7], 0x7632));
+    return s;
+}
+__device__ __forceinline__ size_t head_tiled_elem(size_t prow, int col, int pcols) {
+    return ((prow >> 3) * (size_t)(pcols >> 3) + (size_t)(col >> 3)) * 64 + (prow & 7) * 8 + (col & 7);
+}
+
 constexpr int kHeadMaxA = 8;
 constexpr int kHeadRows = 2;
 constexpr int kHeadWarps = 8;
@@ -250,9 +276,10 @@ __global__ void __launch_bounds__(32 * kHeadWarps) dqn_head_fused_kernel(HeadPar
         if (p.dh_planes) {
 #pragma unroll
             for (int c8 = 0; c8 < KPL / 8; ++c8) {
-                const gemm::Split8 sp = gemm::split8(make_float4(dz[8 * c8], dz[8 * c8 + 1], dz[8 * c8 + 2], dz[8 * c8 + 3]),
-                                                     make_float4(dz[8 * c8 + 4], dz[8 * c8 + 5], dz[8 * c8 + 6], dz[8 * c8 + 7]));
-                uint16_t* d = p.dh_planes + gemm::tiled_elem((size_t)r, lane * KPL + 8 * c8, K);
+                const float x8[8] = {dz[8 * c8], dz[8 * c8 + 1], dz[8 * c8 + 2], dz[8 * c8 + 3],
+                                     dz[8 * c8 + 4], dz[8 * c8 + 5], dz[8 * c8 + 6], dz[8 * c8 + 7]};
+                const HeadSplit8 sp = head_split8(x8);
+                uint16_t* d = p.dh_planes + head_tiled_elem((size_t)r, lane * KPL + 8 * c8, K);
                 *reinterpret_cast<uint4*>(d) = sp.h;
                 *reinterpret_cast<uint4*>(d + p.dh_plane_stride) = sp.m;
                 *reinterpret_cast<uint4*>(d + 2 * p.dh_plane_stride) = sp.l;
