@@ -25,6 +25,8 @@ def main():
                                 "game_over": (rng.rand(n) < 0.1).astype(np.uint8)})
     agent.memory.update_priorities(np.arange(n), np.abs(rng.randn(n)))
     store, net = agent.net_def.store, agent.networks["main"]
+    if "PROBE_LR" in os.environ:
+        net.params.learning_rate = float(os.environ["PROBE_LR"])
     net.theta_target.copy_(store.theta * 0.9 + 0.01)
     for step in range(int(os.environ.get("PROBE_STEPS", "2"))):
         online, target = store.export_named(), store.export_named(net.theta_target)
@@ -41,7 +43,7 @@ def main():
         res = {}
         for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
             o = on.QNetOracle((84, 84, 4), A, False, dt)
-            opt = on.AdamTF([torch.from_numpy(v).to(dt) for v in online.values()], 2.5e-4, 0.9, 0.99, 1e-4, dtype=dt)
+            opt = on.AdamTF([torch.from_numpy(v).to(dt) for v in online.values()], float(net.params.learning_rate), 0.9, 0.99, 1e-4, dtype=dt)
             res[name] = on.dqn_learn_step(o, o.cast(online), o.cast(target), opt, ob, 0.99, True, False, None)
         r64, r32 = res["f64"], res["f32"]
         print("step %d cap %s: loss rel err ours %.2e (fp32 oracle %.2e); grad_norm rel err ours %.2e (fp32 oracle %.2e); "

@@ -46,7 +46,7 @@ def main():
     pr = torch.from_numpy(np.abs(rng.randn(size)) + 1e-6).to(dev)
     idx_all = torch.arange(size, dtype=torch.int64, device=dev)
     _lib.check(lib.cb200_per_update(*[t.data_ptr() for t in trees], winner.data_ptr(), size, idx_all.data_ptr(),
-                                    (pr ** 0.6).data_ptr(), pr.data_ptr(), size, None, None))
+                                    (pr ** 0.6).data_ptr(), pr.data_ptr(), size, None, None, None))
     state = torch.randint(0, 256, (cap, row), dtype=torch.uint8, device=dev)
     nstate = torch.randint(0, 256, (cap, row), dtype=torch.uint8, device=dev)
     action = torch.randint(0, 6, (cap,), dtype=torch.int64, device=dev)
@@ -63,7 +63,7 @@ def main():
     # priorities only on the first `cap` leaves so that sampled leaves are valid ring rows
     _lib.check(lib.cb200_per_init(*[t.data_ptr() for t in trees], winner.data_ptr(), size, None))
     _lib.check(lib.cb200_per_update(*[t.data_ptr() for t in trees], winner.data_ptr(), size, idx_all.data_ptr(),
-                                    (pr ** 0.6).data_ptr(), pr.data_ptr(), cap, None, None))
+                                    (pr ** 0.6).data_ptr(), pr.data_ptr(), cap, None, None, None))
     u = torch.rand(B, dtype=torch.float64, device=dev)
     arr, cnt = _lib.make_columns([(state.data_ptr(), o_s.data_ptr(), row), (nstate.data_ptr(), o_n.data_ptr(), row),
                                   (action.data_ptr(), o_a.data_ptr(), 8), (reward.data_ptr(), o_r.data_ptr(), 8),
@@ -99,7 +99,7 @@ def main():
         _lib.check(lib.cb200_per_priorities_device(err.data_ptr(), B, 1e-6, 0.6, pa.data_ptr(), praw.data_ptr(), None,
                                                    None))
         _lib.check(lib.cb200_per_update(*[t.data_ptr() for t in trees], winner.data_ptr(), size, idx.data_ptr(),
-                                        pa.data_ptr(), praw.data_ptr(), B, maxp.data_ptr(), None))
+                                        pa.data_ptr(), praw.data_ptr(), B, maxp.data_ptr(), None, None))
 
     def torch_copy():
         o_s.copy_(state[:B])
