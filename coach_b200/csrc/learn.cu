@@ -142,39 +142,44 @@ struct HeadParams {
     float *dw, *db, *workspace;
 };
 
+// Lane l owns features k = l + 32 j (j < KPL): a row of h is read with coalesced 128-byte loads and the head kernels,
+// staged TRANSPOSED in shared memory (Wt[a][k]), are read conflict-free.  The row's dL/dz goes through a per-warp
+// shared-memory row so that it leaves as whole 16-byte core rows / float4s.
 template <int KPL>
-__device__ __forceinline__ void head_dot(const float* __restrict__ hrow, const float* __restrict__ w,
-                                         const float* __restrict__ bias, int A, int lane, float (&hv)[KPL],
+__device__ __forceinline__ void head_dot(const float* __restrict__ hrow, const float* __restrict__ wt /* smem [A][K] */,
+                                         const float* __restrict__ bias, int A, int K, int lane, float (&hv)[KPL],
                                          float (&q)[kHeadMaxA]) {
-    const float4* hp = reinterpret_cast<const float4*>(hrow + lane * KPL);
 #pragma unroll
-    for (int j = 0; j < KPL / 4; ++j) {
-        const float4 v = __ldg(hp + j);
-        hv[4 * j] = v.x; hv[4 * j + 1] = v.y; hv[4 * j + 2] = v.z; hv[4 * j + 3] = v.w;
-    }
-#pragma unroll
-    for (int a = 0; a < kHeadMaxA; ++a) q[a] = 0.f;
-    const float* wl = w + (size_t)lane * KPL * A;
-#pragma unroll
-    for (int j = 0; j < KPL; ++j)
-#pragma unroll
-        for (int a = 0; a < kHeadMaxA; ++a)
-            if (a < A) q[a] = fmaf(hv[j], __ldg(wl + j * A + a), q[a]);
+    for (int j = 0; j < KPL; ++j) hv[j] = __ldg(hrow + lane + 32 * j);
 #pragma unroll
     for (int a = 0; a < kHeadMaxA; ++a) {
+        q[a] = 0.f;
         if (a < A) {
+            float s = 0.f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) q[a] += __shfl_xor_sync(0xffffffffu, q[a], o);
-            q[a] += __ldg(bias + a);
+            for (int j = 0; j < KPL; ++j) s = fmaf(hv[j], wt[a * K + lane + 32 * j], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            q[a] = s + __ldg(bias + a);
         }
     }
 }
 
 template <int KPL>
 __global__ void __launch_bounds__(32 * kHeadWarps) dqn_head_fused_kernel(HeadParams p) {
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * kHeadWarps + (threadIdx.x >> 5);          // global warp
+    extern __shared__ __align__(16) float head_smem[];     // Wt_online [A][K] | Wt_target [A][K] | row buffers [warps][K]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * kHeadWarps + warp;                        // global warp
     const int A = p.A, K = p.K;
+    float* wt_on = head_smem;
+    float* wt_tg = head_smem + A * K;
+    float* rowbuf = head_smem + 2 * A * K + warp * K;
+    for (int i = threadIdx.x; i < A * K; i += blockDim.x) {               // W [K, A] row-major -> Wt [A][K]
+        const int k = i / A, a = i - k * A;
+        wt_on[a * K + k] = __ldg(p.w_online + i);
+        wt_tg[a * K + k] = __ldg(p.w_target + i);
+    }
+    __syncthreads();
     float acc_w[KPL][kHeadMaxA];                                          // this lane's slice of dW, over the warp's rows
     float acc_b[kHeadMaxA], acc_loss = 0.f;
 #pragma unroll
@@ -184,29 +189,28 @@ __global__ void __launch_bounds__(32 * kHeadWarps) dqn_head_fused_kernel(HeadPar
 #pragma unroll
     for (int a = 0; a < kHeadMaxA; ++a) acc_b[a] = 0.f;
     const float inv_b = 1.0f / (float)p.B;
+    const bool use_sel = p.h_select != nullptr;
     for (int rr = 0; rr < kHeadRows; ++rr) {
         const int r = gw * kHeadRows + rr;
         if (r >= p.B) break;
         float hv[KPL], qn[kHeadMaxA], qs[kHeadMaxA], qo[kHeadMaxA];
-        head_dot<KPL>(p.h_next + (size_t)r * K, p.w_target, p.b_target, A, lane, hv, qn);
-        if (p.h_select) head_dot<KPL>(p.h_select + (size_t)r * K, p.w_online, p.b_online, A, lane, hv, qs);
-        head_dot<KPL>(p.h_online + (size_t)r * K, p.w_online, p.b_online, A, lane, hv, qo);    // hv = h_online slice
+        head_dot<KPL>(p.h_next + (size_t)r * K, wt_tg, p.b_target, A, K, lane, hv, qn);
+        if (use_sel) head_dot<KPL>(p.h_select + (size_t)r * K, wt_on, p.b_online, A, K, lane, hv, qs);
+        head_dot<KPL>(p.h_online + (size_t)r * K, wt_on, p.b_online, A, K, lane, hv, qo);    // hv = h_online slice
         // ---- TD target (every lane, identical values) -- dqn_agent.py:92-103 ------------------------------------------
         int best = 0;
-        {
-            const float* sel = p.h_select ? qs : qn;                      // ddqn_agent.py:42-43 / dqn_agent.py:78-79
-            float bv = sel[0];
-#pragma unroll
-            for (int a = 1; a < kHeadMaxA; ++a)
-                if (a < A && sel[a] > bv) {
-                    bv = sel[a];
-                    best = a;
-                }
-        }
+        float bv = use_sel ? qs[0] : qn[0];                               // ddqn_agent.py:42-43 / dqn_agent.py:78-79
         float q_best = qn[0];
 #pragma unroll
-        for (int a = 1; a < kHeadMaxA; ++a)
-            if (a == best) q_best = qn[a];
+        for (int a = 1; a < kHeadMaxA; ++a) {
+            const float sv = use_sel ? qs[a] : qn[a];
+            if (a < A && sv > bv) {                                       // np.argmax: first maximum
+                bv = sv;
+                best = a;
+                q_best = qn[a];
+            }
+        }
+        (void)best;
         const int64_t act = p.actions[r];
         const double not_done = __dsub_rn(1.0, p.game_overs[r] ? 1.0 : 0.0);
         const double y = __dadd_rn(p.rewards[r], __dmul_rn(__dmul_rn(not_done, p.discount), (double)q_best));
@@ -244,30 +248,40 @@ __global__ void __launch_bounds__(32 * kHeadWarps) dqn_head_fused_kernel(HeadPar
         }
         acc_loss += w * row;
         if (lane == 0) {
-            for (int a = 0; a < A; ++a) {
-                p.q_online[(size_t)r * A + a] = qo[a];
-                if (p.q_next) p.q_next[(size_t)r * A + a] = qn[a];
-                p.targets[(size_t)r * A + a] = tgt[a];
-                p.dq[(size_t)r * A + a] = dq[a];
+#pragma unroll
+            for (int a = 0; a < kHeadMaxA; ++a) {
+                if (a < A) {
+                    p.q_online[(size_t)r * A + a] = qo[a];
+                    if (p.q_next) p.q_next[(size_t)r * A + a] = qn[a];
+                    p.targets[(size_t)r * A + a] = tgt[a];
+                    p.dq[(size_t)r * A + a] = dq[a];
+                }
             }
             p.td_err[r] = td;
         }
         // ---- backward of the head for this row ---------------------------------------------------------------------------
-        const float* wl = p.w_online + (size_t)lane * KPL * A;
-        float dz[KPL];
+        __syncwarp();                                                     // the previous row's readers are done
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
             float s = 0.f;
 #pragma unroll
             for (int a = 0; a < kHeadMaxA; ++a)
                 if (a < A) {
-                    s = fmaf(dq[a], __ldg(wl + j * A + a), s);
+                    s = fmaf(dq[a], wt_on[a * K + lane + 32 * j], s);
                     acc_w[j][a] = fmaf(hv[j], dq[a], acc_w[j][a]);
                 }
-            dz[j] = hv[j] > 0.f ? s : 0.f;                                // relu'(h) on the post-activation value
+            rowbuf[lane + 32 * j] = hv[j] > 0.f ? s : 0.f;                // relu'(h) on the post-activation value
         }
 #pragma unroll
         for (int a = 0; a < kHeadMaxA; ++a) acc_b[a] += dq[a];
+        __syncwarp();
+        // lane l now takes the KPL consecutive features [l KPL, (l + 1) KPL) of the row
+        float dz[KPL];
+#pragma unroll
+        for (int j = 0; j < KPL / 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(rowbuf + lane * KPL + 4 * j);
+            dz[4 * j] = v.x; dz[4 * j + 1] = v.y; dz[4 * j + 2] = v.z; dz[4 * j + 3] = v.w;
+        }
         if (p.dh) {
             float4* o = reinterpret_cast<float4*>(p.dh + (size_t)r * K + lane * KPL);
 #pragma unroll
@@ -292,23 +306,34 @@ __global__ void __launch_bounds__(32 * kHeadWarps) dqn_head_fused_kernel(HeadPar
     for (int j = 0; j < KPL; ++j)
 #pragma unroll
         for (int a = 0; a < kHeadMaxA; ++a)
-            if (a < A) part[((size_t)lane * KPL + j) * A + a] = acc_w[j][a];
+            if (a < A) part[((size_t)lane + 32 * j) * A + a] = acc_w[j][a];
     if (lane == 0) {
-        for (int a = 0; a < A; ++a) part[(size_t)K * A + a] = acc_b[a];
+#pragma unroll
+        for (int a = 0; a < kHeadMaxA; ++a)
+            if (a < A) part[(size_t)K * A + a] = acc_b[a];
         part[(size_t)K * A + A] = acc_loss;
     }
 }
 
+// [nparts][n_out] partials -> dW | db | loss: a block owns 32 consecutive outputs, its 8 warps walk the partials 8
+// apart (coalesced 128-byte reads) and the 8 sums are folded in a fixed order
 __global__ void __launch_bounds__(256) dqn_head_reduce_kernel(const float* __restrict__ ws, int nparts, int n_out,
                                                               int KA, int A, float inv_b, float* __restrict__ dw,
                                                               float* __restrict__ db, float* __restrict__ loss) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_out) return;
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
     float s = 0.f;
-    for (int q = 0; q < nparts; ++q) s += ws[(size_t)q * n_out + i];       // fixed order
-    if (i < KA) dw[i] = s;
-    else if (i < KA + A) db[i - KA] = s;
-    else if (loss) *loss = s * inv_b;
+    if (i < n_out)
+        for (int q = w; q < nparts; q += 8) s += ws[(size_t)q * n_out + i];
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < n_out) {
+        for (int k = 1; k < 8; ++k) s += red[k][lane];
+        if (i < KA) dw[i] = s;
+        else if (i < KA + A) db[i - KA] = s;
+        else if (loss) *loss = s * inv_b;
+    }
 }
 
 __global__ void dueling_fwd_kernel(const float* __restrict__ v, const float* __restrict__ adv, int64_t B, int64_t A,
@@ -473,13 +498,14 @@ int cb200_dqn_head_fused(const cb200_dqn_head_desc* d, void* stream) {
     const unsigned grid = (unsigned)((warps + kHeadWarps - 1) / kHeadWarps);
     const int nparts = (int)grid * kHeadWarps;                 // idle warps of the last block write zero partials
     cudaStream_t st = as_stream(stream);
+    const size_t smem = (size_t)(2 * p.A * p.K + kHeadWarps * p.K) * sizeof(float);      // <= 48 KB (A <= 8, K <= 512)
     if (p.K == 512) {
-        CB200_LAUNCH(dqn_head_fused_kernel<16>, grid, 32 * kHeadWarps, 0, st, p);
+        CB200_LAUNCH(dqn_head_fused_kernel<16>, grid, 32 * kHeadWarps, smem, st, p);
     } else {
-        CB200_LAUNCH(dqn_head_fused_kernel<8>, grid, 32 * kHeadWarps, 0, st, p);
+        CB200_LAUNCH(dqn_head_fused_kernel<8>, grid, 32 * kHeadWarps, smem, st, p);
     }
     const int n_out = p.K * p.A + p.A + 1;
-    CB200_LAUNCH(dqn_head_reduce_kernel, (unsigned)((n_out + 255) / 256), 256, 0, st, p.workspace, nparts, n_out,
+    CB200_LAUNCH(dqn_head_reduce_kernel, (unsigned)((n_out + 31) / 32), 256, 0, st, p.workspace, nparts, n_out,
                  p.K * p.A, p.A, 1.0f / (float)p.B, p.dw, p.db, p.loss);
     CB200_CHECK_LAUNCH();
     return CB200_OK;

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(1024) per_update_cta_kernel(UpdateParams up) {
 // level on double-buffered shared arrays; every parent is op(left, right) of the final children, exactly what the
 // reference's sequential updates leave behind (SegmentTree.update :62-73 recomputes each ancestor from its children).
 constexpr int kUpdSortThreads = 1024;
-constexpr int kUpdAhead = 4;        // levels of untouched-sibling values in flight per thread
+constexpr int kUpdAhead = 7;        // levels of untouched-sibling values in flight per thread (20 levels: 3 round trips)
 constexpr int kUpdSortSmem = 80 * kUpdSortThreads;
 
 __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(UpdateParams up) {
@@ -259,45 +259,40 @@ __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(Upda
     __shared__ int s_scan[kUpdSortThreads / 32];
     __shared__ int s_m;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    int P = 32;
-    while (P < up.n) P <<= 1;                               // sort width (power of two, <= 1024)
+    const int P = blockDim.x;                               // sort width = launch width (power of two >= n, >= 32)
     // ---- keys ------------------------------------------------------------------------------------------------------
     unsigned long long key = ~0ull;                         // invalid / padding: sorts last
     if (t < up.n) {
         const int64_t leaf = upd_leaf(up, t);
         if (leaf >= 0 && leaf < up.size) key = ((unsigned long long)leaf << 11) | (unsigned long long)t;
     }
-    s_key[t] = key;
-    __syncthreads();
-    // ---- bitonic sort of s_key[0 .. P) -------------------------------------------------------------------------------
+    // ---- bitonic sort of the P keys, one per thread: exchanges at distance < 32 are warp shuffles, larger ones go
+    // through shared memory (10 block-wide steps instead of 45 for P = 512) -----------------------------------------
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (t < P) {
-                const int partner = t ^ j;
-                if (partner > t) {
-                    const unsigned long long a = s_key[t], b = s_key[partner];
-                    const bool up_dir = (t & k) == 0;
-                    if ((a > b) == up_dir) {
-                        s_key[t] = b;
-                        s_key[partner] = a;
-                    }
-                }
+            unsigned long long other;
+            if (j >= 32) {
+                __syncthreads();                            // the previous step's readers are done
+                s_key[t] = key;
+                __syncthreads();
+                other = s_key[t ^ j];
+            } else {
+                other = __shfl_xor_sync(0xffffffffu, key, j);
             }
-            __syncthreads();
+            const bool keep_min = ((t & j) == 0) == ((t & k) == 0);
+            key = keep_min ? (other < key ? other : key) : (other > key ? other : key);
         }
     }
+    __syncthreads();
+    s_key[t] = key;
+    __syncthreads();
     // ---- last writer of every distinct leaf, compacted in leaf order ----------------------------------------------
-    bool winner = false;
-    if (t < P) {
-        const unsigned long long k0 = s_key[t];
-        winner = k0 != ~0ull && (t == P - 1 || (s_key[t + 1] >> 11) != (k0 >> 11));
-        key = k0;
-    }
+    const bool winner = key != ~0ull && (t == P - 1 || (s_key[t + 1] >> 11) != (key >> 11));
     const unsigned ballot = __ballot_sync(0xffffffffu, winner);
     if (lane == 0) s_scan[warp] = __popc(ballot);
     __syncthreads();
     if (warp == 0) {
-        int v = s_scan[lane];
+        int v = lane < (P >> 5) ? s_scan[lane] : 0;         // warps of this launch only
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -756,14 +751,35 @@ __global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SamplePa
         __syncwarp();
         const uint8_t* sbase = stage_mem + (size_t)st * 8 * gp.chunk_stride + (size_t)b * gp.chunk_stride;
         if (slot < slots) {
-            for (int pi = slot; pi < rc * Ws; pi += slots) {
-                const int yl = pi / Ws, X = pi - yl * Ws;
-                const uint8_t* sp8 = sbase + ((size_t)(yl * S + dy) * gp.W + (size_t)X * S) * C;
-                const size_t prow = ((size_t)(ya + yl) * Ws + X) * gp.B + b0 + b;
-                for (int g = 0; g < run; g += 8) {
-                    const uint2 w = *reinterpret_cast<const uint2*>(sp8 + g);
-                    *reinterpret_cast<uint4*>(plane + ((prow >> 3) * (size_t)(Cs >> 3) + ((dy * run + g) >> 3)) * 64 +
-                                              (prow & 7) * 8) = u8x8_to_bf16_s2d(w.x, w.y);
+            // pixel pi of the chunk: source = row (yl * S + dy) of the sample's band, S * C bytes at X; destination =
+            // row group (pix * B + b0) / 8 of the plane matrix, cores (dy * run) / 8 ..., row b of each core.  All
+            // strides are loop constants: the pixel index advances by `slots`, the addresses by fixed increments.
+            const int npx = rc * Ws;
+            const size_t core_stride = (size_t)(gp.B >> 3) * (size_t)(Cs >> 3) * 64;        // plane elements per pixel
+            uint16_t* out0 = plane + ((size_t)(b0 >> 3) * (size_t)(Cs >> 3) + (size_t)((dy * run) >> 3)) * 64 + b * 8 +
+                             (size_t)ya * Ws * core_stride;
+            const int src_row = gp.W * C;                                                  // bytes per image row
+            const uint8_t* src0 = sbase + (size_t)dy * src_row;
+            int yl = slot / Ws, X = slot - yl * Ws;
+            const int dyl = slots / Ws, dX = slots - dyl * Ws;
+            for (int pi = slot; pi < npx; pi += slots) {
+                const uint8_t* sp8 = src0 + (size_t)yl * S * src_row + X * run;
+                uint16_t* o = out0 + (size_t)(yl * Ws + X) * core_stride;
+                if (run == 16) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(sp8);
+                    *reinterpret_cast<uint4*>(o) = u8x8_to_bf16_s2d(w.x, w.y);
+                    *reinterpret_cast<uint4*>(o + 64) = u8x8_to_bf16_s2d(w.z, w.w);
+                } else {
+                    for (int g = 0; g < run; g += 8) {
+                        const uint2 w = *reinterpret_cast<const uint2*>(sp8 + g);
+                        *reinterpret_cast<uint4*>(o + (g >> 3) * 64) = u8x8_to_bf16_s2d(w.x, w.y);
+                    }
+                }
+                X += dX;
+                yl += dyl;
+                if (X >= Ws) {
+                    X -= Ws;
+                    ++yl;
                 }
             }
         }
@@ -949,7 +965,9 @@ static int run_update(UpdateParams& up, void* stream) {
                                             kUpdSortSmem));
             configured = true;
         }
-        CB200_LAUNCH(per_update_sorted_kernel, 1, kUpdSortThreads, kUpdSortSmem, st, up);
+        int threads = 32;
+        while (threads < up.n) threads <<= 1;
+        CB200_LAUNCH(per_update_sorted_kernel, 1, threads, kUpdSortSmem, st, up);
     } else if (up.n <= 1024) {
         int threads = (int)((up.n + 31) / 32 * 32);
         CB200_LAUNCH(per_update_cta_kernel, 1, threads, 0, st, up);

@@ -53,6 +53,25 @@ def main():
                                          abs(gnorm - r64["grad_norm"]) / r64["grad_norm"],
                                          abs(r32["grad_norm"] - r64["grad_norm"]) / r64["grad_norm"],
                                          np.abs(net.online_s.q.cpu().numpy() - r64["q_online"]).max()))
+        if os.environ.get("PROBE_DIAG"):
+            tr = net.online_s.trunk
+            fc1, conv3 = tr.layers[3], tr.layers[2]
+            W = store.view(store.theta, agent.net_def.trunk.names[3][0]).double()          # [3136, 512] AFTER Adam!
+            W_before = torch.from_numpy(online[agent.net_def.trunk.names[3][0]]).cuda().double()
+            npix, Ca, N = 49, 64, 512
+            for tag, Wm in (("theta before this step's Adam", W_before), ("theta after Adam", W)):
+                want_wT = Wm.reshape(npix, Ca, N).permute(0, 2, 1).reshape(npix * N, Ca)
+                got_wT = fc1.wT_planes.to_dense().double()
+                print("   [diag] fc1 wT planes vs %s: max abs diff %.3e" % (tag, (got_wT - want_wT).abs().max().item()))
+            dzf = tr.dz_planes[3].to_dense().double() if tr.dz_planes[3] is not None else tr.dzs[3].double()
+            act3 = tr.act_planes[2].to_dense().double()                                      # [49 * B, 64]
+            want = torch.zeros(npix * B, Ca, dtype=torch.float64, device="cuda")
+            for q in range(npix):
+                want[q * B:(q + 1) * B] = dzf @ W_before[q * Ca:(q + 1) * Ca].t()
+            want = want * (act3 > 0)
+            got_dz3 = tr.dz_planes[2].to_dense().double()
+            print("   [diag] dz3 (fc1.bwd_x output) vs recomputation with pre-Adam weights: max abs %.3e / scale %.3e"
+                  % ((got_dz3 - want).abs().max().item(), want.abs().max().item()))
         got = store.export_named(store.grad)
         for name in r64["grads"]:
             w = r64["grads"][name].numpy()
