@@ -50,29 +50,51 @@ class QNetOracle(object):
         self.dtype = dtype
         self.is_image = len(self.obs_shape) == 3
 
-    def forward(self, params, x):
-        """x: uint8 [B,H,W,C] (image) or float [B,K].  Returns Q [B,A]."""
+    def forward(self, params, x, kink=None):
+        """x: uint8 [B,H,W,C] (image) or float [B,K].  Returns Q [B,A].
+
+        kink (optional): {"masks": [bool tensor per ReLU, in the order the ReLUs are evaluated, this function's layout],
+        "tol": t}.  A ReLU is not differentiable at 0: where a pre-activation lies within rounding noise of zero
+        (|z| <= t * max|z|) both 0 and 1 are valid fp32 derivatives, and two correct implementations that sum in
+        different orders can land on different sides.  There -- and only there -- the given mask (the implementation
+        under test's) replaces this evaluation's own; "flipped" counts those elements, "hard" the disagreements
+        elsewhere (genuine errors, which the caller asserts to be zero)."""
         p = list(params.values())
         k = 0
         h = torch.as_tensor(x).to(self.dtype)
+        relu_i = [0]
+
+        def relu(z):
+            i = relu_i[0]
+            relu_i[0] += 1
+            if kink is None or i >= len(kink["masks"]) or kink["masks"][i] is None:
+                return F.relu(z)
+            own = z > 0
+            other = kink["masks"][i].to(torch.bool).reshape(z.shape)
+            near = z.detach().abs() <= kink["tol"] * z.detach().abs().max()
+            m = torch.where(near, other, own)
+            kink["flipped"] = kink.get("flipped", 0) + int((m != own).sum())
+            kink["hard"] = kink.get("hard", 0) + int(((other != own) & ~near).sum())
+            return z * m.to(z.dtype)
+
         if self.is_image:
             h = h / 255.0                                   # embedder.py:103 (true division)
             h = h.permute(0, 3, 1, 2)                       # NHWC -> NCHW for torch
             for stride in (4, 2, 1):
                 w, b = p[k], p[k + 1]
                 k += 2
-                h = F.relu(F.conv2d(h, w.permute(3, 2, 0, 1), b, stride=stride))     # HWIO -> OIHW, VALID
+                h = relu(F.conv2d(h, w.permute(3, 2, 0, 1), b, stride=stride))       # HWIO -> OIHW, VALID
             h = h.permute(0, 2, 3, 1).reshape(h.shape[0], -1)                         # flatten in NHWC order
         else:
-            h = F.relu(h @ p[k] + p[k + 1])
+            h = relu(h @ p[k] + p[k + 1])
             k += 2
         if self.middleware:
-            h = F.relu(h @ p[k] + p[k + 1])                 # middleware Dense(512)
+            h = relu(h @ p[k] + p[k + 1])                   # middleware Dense(512)
             k += 2
         if not self.dueling:
             return h @ p[k] + p[k + 1]
-        v = F.relu(h @ p[k] + p[k + 1]) @ p[k + 2] + p[k + 3]
-        a = F.relu(h @ p[k + 4] + p[k + 5]) @ p[k + 6] + p[k + 7]
+        v = relu(h @ p[k] + p[k + 1]) @ p[k + 2] + p[k + 3]
+        a = relu(h @ p[k + 4] + p[k + 5]) @ p[k + 6] + p[k + 7]
         return v + (a - a.mean(dim=1, keepdim=True))
 
     def cast(self, named):
@@ -128,9 +150,10 @@ class AdamTF(object):
 
 
 def dqn_learn_step(net, online, target, opt, batch, discount, huber_loss=True, double_dqn=False, clip=None,
-                   world_scale=1.0):
+                   world_scale=1.0, kink=None):
     """One learn_from_batch step.  batch: dict with states, next_states, actions, rewards, game_overs, weights (or None).
-    Returns dict(loss, grads (named), grad_norm, td_errors, targets, new_params (named), q_online)."""
+    Returns dict(loss, grads (named), grad_norm, td_errors, targets, new_params (named), q_online).
+    kink: ReLU masks of the implementation under test for the differentiated forward pass (QNetOracle.forward)."""
     names = list(online.keys())
     params = [online[n].clone().requires_grad_(True) for n in names]
     pd = OrderedDict(zip(names, params))
@@ -142,7 +165,7 @@ def dqn_learn_step(net, online, target, opt, batch, discount, huber_loss=True, d
                               batch["game_overs"], discount)
     w = batch.get("weights")
     wt = _t(np.asarray(w, dtype=np.float64), net.dtype) if w is not None else None
-    q = net.forward(pd, batch["states"])
+    q = net.forward(pd, batch["states"], kink=kink)
     loss = q_head_loss(q, _t(targets, net.dtype), wt, huber_loss)
     grads = torch.autograd.grad(loss, params, allow_unused=True)
     grads = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, params)]

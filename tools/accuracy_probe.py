@@ -72,6 +72,64 @@ def main():
             got_dz3 = tr.dz_planes[2].to_dense().double()
             print("   [diag] dz3 (fc1.bwd_x output) vs recomputation with pre-Adam weights: max abs %.3e / scale %.3e"
                   % ((got_dz3 - want).abs().max().item(), want.abs().max().item()))
+        if os.environ.get("PROBE_DIAG"):
+            tr = net.online_s.trunk
+            g3 = store.export_named(store.grad)
+            kname, bname = agent.net_def.trunk.names[2]
+            dz3 = tr.dz_planes[2].to_dense().double()                     # [49 * B, 64], rows q * B + b
+            act2 = tr.act_planes[1].to_dense().double()                   # [81 * B, 64]
+            want_b = dz3.sum(0).cpu().numpy()
+            print("   [diag] conv3 bias grad vs column sum of the device's dz3: max abs %.3e (scale %.3e); vs fp64 oracle %.3e"
+                  % (np.abs(g3[bname] - want_b).max(), np.abs(want_b).max(),
+                     np.abs(g3[bname] - r64["grads"][bname].numpy()).max()))
+            a2 = act2.reshape(9, 9, B, 64)
+            d3 = dz3.reshape(7, 7, B, 64)
+            want_w = torch.zeros(3, 3, 64, 64, dtype=torch.float64, device="cuda")
+            for ky in range(3):
+                for kx in range(3):
+                    xs = a2[ky:ky + 7, kx:kx + 7].reshape(-1, 64)
+                    want_w[ky, kx] = xs.t() @ d3.reshape(-1, 64)
+            want_w = want_w.cpu().numpy()
+            print("   [diag] conv3 kernel grad vs act2^T dz3 from the device's planes: max abs %.3e (scale %.3e); "
+                  "that recomputation vs fp64 oracle %.3e"
+                  % (np.abs(g3[kname] - want_w).max(), np.abs(want_w).max(),
+                     np.abs(want_w - r64["grads"][kname].numpy()).max()))
+            dzf = tr.dz_planes[3].to_dense().double()
+            print("   [diag] fc1 dz planes vs fp32 dz: max abs %.3e" % (dzf - tr.dzs[3].double()).abs().max().item())
+        if os.environ.get("PROBE_DIAG2"):
+            import torch.nn.functional as F
+            tr = net.online_s.trunk
+            P = [torch.from_numpy(v).double().requires_grad_(True) for v in online.values()]
+            x = torch.from_numpy(ob["states"]).double() / 255.0
+            hcur = x.permute(0, 3, 1, 2)
+            zs, k = [], 0
+            for stride in (4, 2, 1):
+                z = F.conv2d(hcur, P[k].permute(3, 2, 0, 1), P[k + 1], stride=stride)
+                z.retain_grad()
+                zs.append(z)
+                hcur = F.relu(z)
+                k += 2
+            flat = hcur.permute(0, 2, 3, 1).reshape(B, -1)
+            z4 = flat @ P[k] + P[k + 1]
+            z4.retain_grad()
+            zs.append(z4)
+            qq = F.relu(z4) @ P[k + 2] + P[k + 3]
+            loss64 = on.q_head_loss(qq, torch.from_numpy(r64["targets"]).double(),
+                                    torch.from_numpy(ob["weights"].astype(np.float64)), True)
+            loss64.backward()
+            for i, z in enumerate(zs[:3]):
+                npix = z.shape[2] * z.shape[3]
+                act_ref = F.relu(z).detach().permute(2, 3, 0, 1).reshape(npix * B, -1)      # rows pixel * B + b
+                dz_ref = z.grad.permute(2, 3, 0, 1).reshape(npix * B, -1)
+                act_dev = tr.act_planes[i].to_dense().double().cpu()
+                dz_dev = tr.dz_planes[i].to_dense().double().cpu()
+                print("   [diag2] conv%d: act max abs err %.2e (scale %.2e); dz max abs err %.2e (scale %.2e); "
+                      "mask mismatches %d" % (i + 1, (act_dev - act_ref).abs().max(), act_ref.abs().max(),
+                                               (dz_dev - dz_ref).abs().max(), dz_ref.abs().max(),
+                                               int(((act_dev > 0) != (act_ref > 0)).sum())))
+            dzf_dev = tr.dz_planes[3].to_dense().double().cpu()
+            print("   [diag2] fc1: dz max abs err %.2e (scale %.2e)" % ((dzf_dev - zs[3].grad).abs().max(),
+                                                                       zs[3].grad.abs().max()))
         got = store.export_named(store.grad)
         for name in r64["grads"]:
             w = r64["grads"][name].numpy()
