@@ -104,6 +104,32 @@ class QNetworkWrapper(object):
     def update_target_network(self, rate=1.0):
         _lib.check(self.lib.cb200_polyak(self.theta_target.data_ptr(), self.theta.data_ptr(), self.store.size,
                                          float(rate), _lib.current_stream()))
+        self.target_changed()
+
+    # ---- parameter planes (operands of the tensor-core GEMMs) are re-derived where the parameters are written, not in
+    # every forward pass: the target network's once per target update instead of once per learn step -----------------
+    def manage_planes(self):
+        self._managed = [i for i in (self.online_s, self.online_s2, self.target_s2) if i is not None and
+                         i.manage_planes()]
+        self.online_changed()
+        self.target_changed()
+
+    def _refresh(self, theta):
+        done = set()
+        for inst in getattr(self, "_managed", ()):
+            tp = inst.theta_planes
+            if tp.theta.data_ptr() == theta.data_ptr() and id(tp) not in done:
+                done.add(id(tp))
+                tp.refresh()
+
+    def online_changed(self):
+        """call after ANY write to ``theta`` other than apply_gradients (checkpoint load, manual edits)"""
+        self._refresh(self.theta)
+
+    def target_changed(self):
+        """call after ANY write to ``theta_target`` other than update_target_network"""
+        if self.theta_target is not None:
+            self._refresh(self.theta_target)
 
     def apply_gradients(self, scaler=1.0, grad=None):
         """clip is applied by the caller (accumulate_gradients side in the reference); here: optional rescale,
@@ -122,6 +148,7 @@ class QNetworkWrapper(object):
                                                   float(p.learning_rate), float(p.adam_optimizer_beta1),
                                                   float(p.adam_optimizer_beta2), float(p.optimizer_epsilon),
                                                   self.adam_state.data_ptr(), st))
+            self.online_changed()
             return
         _lib.check(self.lib.cb200_adam_tf(self.theta.data_ptr(), self.store.m.data_ptr(), self.store.v.data_ptr(),
                                           grad.data_ptr(), n, float(p.learning_rate),
@@ -130,6 +157,7 @@ class QNetworkWrapper(object):
                                           float(self.beta2_power), st))
         self.beta1_power = np.float32(self.beta1_power * np.float32(p.adam_optimizer_beta1))
         self.beta2_power = np.float32(self.beta2_power * np.float32(p.adam_optimizer_beta2))
+        self.online_changed()
 
 
 class DQNAgent(object):
@@ -191,6 +219,8 @@ class DQNAgent(object):
                                                  input_planes=self.s2d["columns"] if self.s2d else None)}
         if self.networks["main"].has_target:
             self.networks["main"].sync()
+        if _lib.tune_default("managed_planes", 1):
+            self.networks["main"].manage_planes()
         # plain Q head: head forward passes, TD targets, loss and the head's backward pass are ONE fused launch
         net = self.networks["main"]
         self.head_desc = None

@@ -238,6 +238,13 @@ class Dense(object):
     def forward(self):
         self.fwd.run()
 
+    def run_perms(self):
+        """weight-derived operands of this layer: the per-pixel transposed kernels of the data-gradient GEMM"""
+        if self.tiled_x and getattr(self, "perm", None) is not None:
+            _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), self.perm.data_ptr(), self.perm.numel(),
+                                                  self.wT.data_ptr(), self.wT_planes.ptr, self.wT_planes.stride,
+                                                  self.wT_planes.cols, _lib.current_stream()))
+
     def backward(self, weights=True):
         st = _lib.current_stream()
         if weights:
@@ -247,9 +254,8 @@ class Dense(object):
                 _lib.check(self.lib.cb200_colsum(dy.data_ptr(), B, N, db.data_ptr(), self.ws.ptr(), st))
         if self.bwd_x is not None:
             if self.tiled_x:
-                _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), self.perm.data_ptr(), self.perm.numel(),
-                                                      self.wT.data_ptr(), self.wT_planes.ptr, self.wT_planes.stride,
-                                                      self.wT_planes.cols, st))
+                if not getattr(self, "perms_managed", False):
+                    self.run_perms()
             else:
                 _lib.check(self.lib.cb200_transpose(self.w.data_ptr(), self.K, self.N, self.wT.data_ptr(), None, 0,
                                                     st))
@@ -455,10 +461,22 @@ class Conv2d(object):
             x, xp, B = self.s2d
             if x is not None:
                 _lib.check(self.lib.cb200_u8_s2d_planes(x.data_ptr(), B, self.H, self.W, self.C, self.S, xp.ptr, st))
+            if not getattr(self, "perms_managed", False):
+                self.run_perms()
+        self.fwd.run()
+
+    def run_perms(self):
+        """weight-derived operands of this layer: the space-to-depth kernel (forward) and the per-tap transposed
+        kernels of the data-gradient GEMM"""
+        st = _lib.current_stream()
+        if self.s2d is not None:
             _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), self.w_perm.data_ptr(), self.w_perm.numel(),
                                                   self.w_s2d.data_ptr(), self.w_s2d_planes.ptr,
                                                   self.w_s2d_planes.stride, self.w_s2d_planes.cols, st))
-        self.fwd.run()
+        if self.bwd_x is not None:
+            _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), self.perm.data_ptr(), self.perm.numel(),
+                                                  self.wT.data_ptr(), self.wT_planes.ptr, self.wT_planes.stride,
+                                                  self.wT_planes.cols, st))
 
     def backward(self, weights=True):
         st = _lib.current_stream()
@@ -472,7 +490,9 @@ class Conv2d(object):
                                                   None, 0, 0, st))
             op.run()
         if self.bwd_x is not None:
-            _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), self.perm.data_ptr(), self.perm.numel(),
-                                                  self.wT.data_ptr(), self.wT_planes.ptr, self.wT_planes.stride,
-                                                  self.wT_planes.cols, st))
+            if not getattr(self, "perms_managed", False):
+                st2 = _lib.current_stream()
+                _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), self.perm.data_ptr(), self.perm.numel(),
+                                                      self.wT.data_ptr(), self.wT_planes.ptr, self.wT_planes.stride,
+                                                      self.wT_planes.cols, st2))
             self.bwd_x.run()

@@ -140,18 +140,22 @@ class QNetworkInstance(object):
         op.tag = "DuelingTowers.bwd_x"
         self.towers_dx = (op, perm, wT, wT_planes, w_src, npix * H1)
 
-    def _run_towers_dx(self):
+    def _towers_perm(self):
         op, perm, wT, wT_planes, w_src, half = self.towers_dx
         st = _lib.current_stream()
         for t, w in enumerate(w_src):
             pv = wT_planes.view_rows(t * half, half)
             _lib.check(self.lib.cb200_permute_f32(w.data_ptr(), perm.data_ptr(), perm.numel(),
                                                   wT.data_ptr() + 4 * t * perm.numel(), pv.ptr, pv.stride, pv.cols, st))
-        op.run()
+
+    def _run_towers_dx(self):
+        if not getattr(self, "_towers_perm_managed", False):
+            self._towers_perm()
+        self.towers_dx[0].run()
 
     def forward(self):
         if self.theta_planes is not None:
-            self.theta_planes.refresh()
+            self.theta_planes.refresh_if_auto()
         self.trunk.forward()
         if self.net.dueling:
             self.v.forward()
@@ -173,13 +177,30 @@ class QNetworkInstance(object):
     def forward_features(self):
         """everything below the head: the feature layer's post-ReLU output is ``features``"""
         if self.theta_planes is not None:
-            self.theta_planes.refresh()
+            self.theta_planes.refresh_if_auto()
         self.trunk.forward(upto=len(self.trunk.layers) - 1)
         return self.trunk.acts[-2]
 
     def backward_features(self):
         """expects the gradient w.r.t. the feature layer's pre-activation in trunk.dzs[-2] (/ its planes)"""
         self.trunk.backward(layers=(0, len(self.trunk.layers) - 1))
+
+    def manage_planes(self):
+        """the owner takes over refreshing the parameter planes: the layers' weight permutes (per-tap transposed
+        kernels, space-to-depth kernel) move from every forward / backward pass into ThetaPlanes.refresh()"""
+        if self.theta_planes is None:
+            return False
+        self.theta_planes.auto = False
+        seqs = [self.trunk] + ([self.v, self.a] if self.net.dueling else [])
+        for sq in seqs:
+            for layer in sq.layers:
+                if hasattr(layer, "run_perms") and not getattr(layer, "perms_managed", False):
+                    layer.perms_managed = True
+                    self.theta_planes.derived.append(layer.run_perms)
+        if getattr(self, "towers_dx", None) is not None and not getattr(self, "_towers_perm_managed", False):
+            self._towers_perm_managed = True
+            self.theta_planes.derived.append(self._towers_perm)
+        return True
 
     def backward_top(self):
         """plain Q head only: the dense layers (middleware + head) of the trunk, which hold ~95 % of the parameters;

@@ -119,6 +119,12 @@ class ThetaPlanes(object):
 
     def __init__(self, lib, store, theta):
         self.lib, self.store, self.theta = lib, store, theta
+        # auto: every forward pass re-derives the planes (safe for any writer of theta).  An owner that knows every
+        # writer -- the DQN agent: Adam, target copies -- switches it off and calls refresh() right after each write;
+        # `derived` are further kernels over theta (transposed / permuted kernels of the data-gradient GEMMs, the
+        # space-to-depth kernel of the first convolution) that then run with the refresh instead of in every pass.
+        self.auto = True
+        self.derived = []
         # one buffer of 6 * size elements.  Planar kernels: plane p of the tensor at `off` sits at p * size + off
         # (first half).  Row-group interleaved kernels (narrow B operands, ``b_interleaved``): [3 off, 3 off + 3 rows
         # cols) of the second half.
@@ -160,7 +166,13 @@ class ThetaPlanes(object):
     def stride(self):
         return self.store.size
 
+    def refresh_if_auto(self):
+        if self.auto:
+            self.refresh()
+
     def refresh(self):
+        for fn in self.derived:
+            fn()
         if self.segs is not None:
             _lib.check(self.lib.cb200_split_planes(self.theta.data_ptr(), self.planes.data_ptr(), self.stride,
                                                    self.segs.data_ptr(), self.segs.shape[0], self.max_elems,
@@ -177,6 +189,7 @@ class PlaneCtx(object):
 
 
 TILED_MAX_CHUNKS = int(os.environ.get("CB200_TILED_MAX_CHUNKS", "20"))
+SPLIT_WAVES = int(os.environ.get("CB200_SPLIT_WAVES", "2"))     # CTAs per SM a split-reduction launch aims for
 
 
 def pick_splits_tiled(tiles, total_chunks, sm=148):
@@ -188,7 +201,7 @@ def pick_splits_tiled(tiles, total_chunks, sm=148):
     need = (total_chunks + TILED_MAX_CHUNKS - 1) // TILED_MAX_CHUNKS
     if tiles >= sm:
         return int(max(1, need))
-    s = max(1, (2 * sm + tiles - 1) // tiles)
+    s = max(1, (SPLIT_WAVES * sm + tiles - 1) // tiles)
     s = min(s, max(1, total_chunks // 4))
     return int(max(s, need))
 

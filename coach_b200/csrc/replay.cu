@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(1024) per_update_cta_kernel(UpdateParams up) {
     if (i == 0 && up.max_priority_out) *up.max_priority_out = __ldcg(up.max_tree);   // :201
 }
 
-// n <= 1024, one launch, no global round trip between levels.
+// n <= 512, one launch, no global round trip between levels.
 // The batch's leaves are sorted in shared memory (bitonic, key = leaf * 2048 + position), which (i) resolves duplicates
 // -- the last writer of a leaf is the last key of its run -- and (ii) makes paths that meet adjacent: the threads whose
 // paths pass through one node form a contiguous run [lo, hi], and a touched sibling is the run right next to it.  Each
@@ -242,9 +242,10 @@ __global__ void __launch_bounds__(1024) per_update_cta_kernel(UpdateParams up) {
 // where they cannot change during the kernel and are therefore fetched a few levels ahead.  One __syncthreads per
 // level on double-buffered shared arrays; every parent is op(left, right) of the final children, exactly what the
 // reference's sequential updates leave behind (SegmentTree.update :62-73 recomputes each ancestor from its children).
-constexpr int kUpdSortThreads = 1024;
-constexpr int kUpdAhead = 7;        // levels of untouched-sibling values in flight per thread (20 levels: 3 round trips)
-constexpr int kUpdSortSmem = 80 * kUpdSortThreads;
+constexpr int kUpdSortThreads = 512;     // 128 registers per thread: the bottom-level sibling values stay in registers
+constexpr int kUpdAhead = 10;       // bottom levels whose untouched-sibling values a thread fetches up front (registers)
+constexpr int kUpdTopLevels = 10;   // top levels of the three trees staged in shared memory (1023 nodes each)
+constexpr int kUpdSortSmem = 80 * kUpdSortThreads + 3 * 8 * (1 << kUpdTopLevels);
 
 __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(UpdateParams up) {
     extern __shared__ __align__(16) uint8_t upd_smem[];      // kUpdSortSmem bytes (dynamic: above the 48 KB static limit)
@@ -256,10 +257,22 @@ __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(Upda
     double(*s_max)[T] = reinterpret_cast<double(*)[T]>(upd_smem + 56 * T);
     short(*s_lo)[T] = reinterpret_cast<short(*)[T]>(upd_smem + 72 * T);
     short(*s_hi)[T] = reinterpret_cast<short(*)[T]>(upd_smem + 76 * T);
+    // untouched siblings in the top kUpdTopLevels levels come from a shared-memory copy of those levels (loaded once,
+    // coalesced, while the sort runs); only the bottom levels need per-thread global loads -- issued all at once, so
+    // the whole walk costs two dependent global round trips (indices -> leaves / siblings) instead of one per few levels
+    double* s_top = reinterpret_cast<double*>(upd_smem + 80 * T);          // [3][1 << kUpdTopLevels], 1-based heap index
     __shared__ int s_scan[kUpdSortThreads / 32];
     __shared__ int s_m;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int P = blockDim.x;                               // sort width = launch width (power of two >= n, >= 32)
+    {
+        const int top_nodes = (up.levels >= kUpdTopLevels ? (1 << kUpdTopLevels) : (1 << up.levels)) - 1;   // nodes 1 .. top_nodes
+        for (int j = t; j < top_nodes; j += P) {
+            s_top[j + 1] = __ldcg(up.sum_tree + j);
+            s_top[(1 << kUpdTopLevels) + j + 1] = __ldcg(up.min_tree + j);
+            s_top[2 * (1 << kUpdTopLevels) + j + 1] = __ldcg(up.max_tree + j);
+        }
+    }
     // ---- keys ------------------------------------------------------------------------------------------------------
     unsigned long long key = ~0ull;                         // invalid / padding: sorts last
     if (t < up.n) {
@@ -328,12 +341,13 @@ __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(Upda
         v_max = pr;
     }
     __syncthreads();                                        // s_node[1] is free again
-    // untouched-sibling values, kUpdAhead levels ahead
+    // untouched-sibling values of the bottom levels (node index >= 2^kUpdTopLevels): all loads in flight at once
+    const int n_bottom = up.levels > kUpdTopLevels ? up.levels - kUpdTopLevels : 0;       // levels 0 .. n_bottom - 1
     double p_sum[kUpdAhead], p_min[kUpdAhead], p_max[kUpdAhead];
 #pragma unroll
     for (int w = 0; w < kUpdAhead; ++w) {
         p_sum[w] = p_min[w] = p_max[w] = 0.0;
-        if (act && w < up.levels) {
+        if (act && w < n_bottom) {
             const long long sib = ((node >> w) ^ 1) - 1;
             p_sum[w] = __ldcg(up.sum_tree + sib);
             p_min[w] = __ldcg(up.min_tree + sib);
@@ -360,13 +374,22 @@ __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(Upda
                 const bool is_left = (node & 1) == 0;       // children of p: 2p (left), 2p + 1 (right)
                 const int nb = is_left ? hi + 1 : lo - 1;
                 const bool touched = nb >= 0 && nb < m && s_node[buf][nb] == (is_left ? node + 1 : node - 1);
-                double o_sum = p_sum[w], o_min = p_min[w], o_max = p_max[w];
+                double o_sum, o_min, o_max;
                 if (touched) {
                     o_sum = s_sum[buf][nb];
                     o_min = s_min[buf][nb];
                     o_max = s_max[buf][nb];
                     if (is_left) hi = s_hi[buf][nb];
                     else lo = s_lo[buf][nb];
+                } else if (l < n_bottom) {
+                    o_sum = p_sum[w];                       // (n_bottom <= kUpdAhead is checked by the launcher: l0 == 0 here)
+                    o_min = p_min[w];
+                    o_max = p_max[w];
+                } else {
+                    const int sib = (int)(node ^ 1);        // < 2^kUpdTopLevels: the staged copy of the top levels
+                    o_sum = s_top[sib];
+                    o_min = s_top[(1 << kUpdTopLevels) + sib];
+                    o_max = s_top[2 * (1 << kUpdTopLevels) + sib];
                 }
                 const double l_sum = is_left ? v_sum : o_sum, r_sum = is_left ? o_sum : v_sum;
                 const double l_min = is_left ? v_min : o_min, r_min = is_left ? o_min : v_min;
@@ -380,17 +403,10 @@ __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(Upda
                     __stcg(up.min_tree + node - 1, v_min);
                     __stcg(up.max_tree + node - 1, v_max);
                 }
-                // refill this slot with the sibling of level l + kUpdAhead
-                const int ln = l + kUpdAhead;
-                if (ln < up.levels) {
-                    const long long sib = ((leaf_node >> ln) ^ 1) - 1;
-                    p_sum[w] = __ldcg(up.sum_tree + sib);
-                    p_min[w] = __ldcg(up.min_tree + sib);
-                    p_max[w] = __ldcg(up.max_tree + sib);
-                }
             }
         }
     }
+    (void)leaf_node;
     if (t == 0 && up.max_priority_out) *up.max_priority_out = m > 0 ? v_max : __ldcg(up.max_tree);   // :201
 }
 
@@ -958,7 +974,7 @@ int cb200_per_init(double* sum_tree, double* min_tree, double* max_tree, int32_t
 static int run_update(UpdateParams& up, void* stream) {
     cudaStream_t st = as_stream(stream);
     if (up.n <= 0) return CB200_OK;
-    if (up.n <= 1024 && up.levels <= 52 && tune_get("per_update_sorted", 1, 0, 1)) {
+    if (up.n <= kUpdSortThreads && up.levels <= kUpdTopLevels + kUpdAhead && tune_get("per_update_sorted", 1, 0, 1)) {
         static bool configured = false;
         if (!configured) {
             CB200_CUDA(cudaFuncSetAttribute(per_update_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -313,6 +313,7 @@ def test_dqn_learn_step_matches_oracle(cfg):
     # make target != online so that the test can tell them apart
     net = agent.networks["main"]
     net.theta_target.copy_(store.theta * 0.9 + 0.01)
+    net.target_changed()                     # a direct write to the target parameters: re-derive their operand planes
     oracle32 = on.QNetOracle(cfg["obs"], A, cfg["dueling"], torch.float32, middleware=mw)
     oracle64 = on.QNetOracle(cfg["obs"], A, cfg["dueling"], torch.float64, middleware=mw)
     results = {}

@@ -28,6 +28,7 @@ def main():
     if "PROBE_LR" in os.environ:
         net.params.learning_rate = float(os.environ["PROBE_LR"])
     net.theta_target.copy_(store.theta * 0.9 + 0.01)
+    net.target_changed()                     # a direct write to the target parameters: re-derive their operand planes
     for step in range(int(os.environ.get("PROBE_STEPS", "2"))):
         online, target = store.export_named(), store.export_named(net.theta_target)
         random.seed(10 + step)
