@@ -243,8 +243,10 @@ __global__ void __launch_bounds__(1024) per_update_cta_kernel(UpdateParams up) {
 // level on double-buffered shared arrays; every parent is op(left, right) of the final children, exactly what the
 // reference's sequential updates leave behind (SegmentTree.update :62-73 recomputes each ancestor from its children).
 constexpr int kUpdSortThreads = 512;     // 128 registers per thread: the bottom-level sibling values stay in registers
-constexpr int kUpdAhead = 10;       // bottom levels whose untouched-sibling values a thread fetches up front (registers)
-constexpr int kUpdTopLevels = 10;   // top levels of the three trees staged in shared memory (1023 nodes each)
+constexpr int kUpdAhead = 11;       // bottom levels whose untouched-sibling values a thread fetches up front (registers)
+constexpr int kUpdTopLevels = 10;   // top levels of the three trees staged in shared memory (nodes 1 .. 1023, 1-based):
+                                    // a sibling is found there when the child being left has index < 2^kUpdTopLevels, i.e.
+                                    // from walk level l >= levels - (kUpdTopLevels - 1) on
 constexpr int kUpdSortSmem = 80 * kUpdSortThreads + 3 * 8 * (1 << kUpdTopLevels);
 
 __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(UpdateParams up) {
@@ -266,7 +268,9 @@ __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(Upda
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int P = blockDim.x;                               // sort width = launch width (power of two >= n, >= 32)
     {
-        const int top_nodes = (up.levels >= kUpdTopLevels ? (1 << kUpdTopLevels) : (1 << up.levels)) - 1;   // nodes 1 .. top_nodes
+        // nodes 1 .. top_nodes: the top kUpdTopLevels levels, or the whole (small) tree
+        const long long all_nodes = 2 * up.size - 1;
+        const int top_nodes = (int)(all_nodes < (1 << kUpdTopLevels) - 1 ? all_nodes : (1 << kUpdTopLevels) - 1);
         for (int j = t; j < top_nodes; j += P) {
             s_top[j + 1] = __ldcg(up.sum_tree + j);
             s_top[(1 << kUpdTopLevels) + j + 1] = __ldcg(up.min_tree + j);
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(kUpdSortThreads) per_update_sorted_kernel(Upda
     }
     __syncthreads();                                        // s_node[1] is free again
     // untouched-sibling values of the bottom levels (node index >= 2^kUpdTopLevels): all loads in flight at once
-    const int n_bottom = up.levels > kUpdTopLevels ? up.levels - kUpdTopLevels : 0;       // levels 0 .. n_bottom - 1
+    const int n_bottom = up.levels > kUpdTopLevels - 1 ? up.levels - (kUpdTopLevels - 1) : 0;   // levels 0 .. n_bottom - 1
     double p_sum[kUpdAhead], p_min[kUpdAhead], p_max[kUpdAhead];
 #pragma unroll
     for (int w = 0; w < kUpdAhead; ++w) {
@@ -974,7 +978,7 @@ int cb200_per_init(double* sum_tree, double* min_tree, double* max_tree, int32_t
 static int run_update(UpdateParams& up, void* stream) {
     cudaStream_t st = as_stream(stream);
     if (up.n <= 0) return CB200_OK;
-    if (up.n <= kUpdSortThreads && up.levels <= kUpdTopLevels + kUpdAhead && tune_get("per_update_sorted", 1, 0, 1)) {
+    if (up.n <= kUpdSortThreads && up.levels <= kUpdTopLevels - 1 + kUpdAhead && tune_get("per_update_sorted", 1, 0, 1)) {
         static bool configured = false;
         if (!configured) {
             CB200_CUDA(cudaFuncSetAttribute(per_update_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
