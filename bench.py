@@ -514,12 +514,19 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the cpu_baseline leg")
     ap.add_argument("--no-l2-persist", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="fp32 FFMA GEMMs instead of the tcgen05 3xBF16 path")
-    ap.add_argument("--config", default="dqn", choices=["dqn", "dueling"],
+    ap.add_argument("--config", default="dqn", choices=["dqn", "dueling", "cartpole", "ppo", "sac", "td3"],
                     help="dqn: BASELINE config 2 (Atari DQN + PER, the headline metric, default); dueling: config 5 "
-                         "(dueling DDQN + PER, no middleware, clip-norm 10)")
+                         "(dueling DDQN + PER, no middleware, clip-norm 10); cartpole / ppo / sac / td3: configs 1, 3, 4 "
+                         "(bench_configs.py)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config in ("cartpole", "ppo", "sac", "td3"):
+        import bench_configs
+        bench_configs.run(args, ClockSampler)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
     else:
         run_device(args)
         import torch.distributed as dist

@@ -27,6 +27,21 @@ class Filter(object):
     def __init__(self, name=None):
         self.name = name
 
+    def save_state_to_checkpoint(self, checkpoint_dir, checkpoint_prefix):
+        """filters/filter.py:452-465 of the reference: every filter with state saves it under its own prefix"""
+        for obs_name, flts in self._observation_filters.items():
+            for fname, f in flts.items():
+                st = getattr(f, "running_observation_stats", None)
+                if st is not None and getattr(st, "shape", None) is not None:
+                    st.save_state_to_checkpoint(checkpoint_dir, "%s.%s.%s" % (checkpoint_prefix, obs_name, fname))
+
+    def restore_state_from_checkpoint(self, checkpoint_dir, checkpoint_prefix):
+        for obs_name, flts in self._observation_filters.items():
+            for fname, f in flts.items():
+                st = getattr(f, "running_observation_stats", None)
+                if st is not None and getattr(st, "shape", None) is not None:
+                    st.restore_state_from_checkpoint(checkpoint_dir, "%s.%s.%s" % (checkpoint_prefix, obs_name, fname))
+
     def reset(self):
         pass
 
@@ -151,6 +166,17 @@ class DeviceRunningStats(object):
         _lib.check(self.lib.cb200_running_stats_finalize(self._sum.data_ptr(), self._sum_squares.data_ptr(),
                                                          float(self._count), float(self.epsilon), x.shape[1],
                                                          self._mean.data_ptr(), self._std.data_ptr(), st))
+
+    checkpoint_file_extension = 'srs'
+
+    def save_state_to_checkpoint(self, checkpoint_dir: str, checkpoint_prefix):
+        """utilities/shared_running_stats.py:170-179: the reference's pickle (same keys, same file name)"""
+        from coach_b200 import checkpoint
+        checkpoint.save_running_stats(self, checkpoint_dir, checkpoint_prefix, self.checkpoint_file_extension)
+
+    def restore_state_from_checkpoint(self, checkpoint_dir: str, checkpoint_prefix):
+        from coach_b200 import checkpoint
+        checkpoint.restore_running_stats(self, checkpoint_dir, checkpoint_prefix, self.checkpoint_file_extension)
 
     def normalize(self, batch: torch.Tensor, out=None):
         x = batch.reshape(batch.shape[0], -1).contiguous()
