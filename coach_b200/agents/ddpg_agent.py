@@ -99,6 +99,34 @@ class TD3AgentParameters(AgentParameters):
         return 'coach_b200.agents.ddpg_agent:TD3Agent'
 
 
+class GraphedKernels(object):
+    """A launch sequence with constant parameters and pointers, replayed as ONE CUDA graph from its third call on (the
+    first two run eagerly: lazy module loading, workspace sizing).  The actor-critic learn steps are 80-150 launches of
+    microsecond kernels; replayed as a graph they cost what the kernels cost, not what Python + ctypes cost per launch.
+    With several ranks the sequence contains NCCL all-reduces and stays eager unless CB200_GRAPH_COLLECTIVES=1."""
+
+    def __init__(self, fn, device):
+        self.fn = fn
+        self.enabled = bool(_lib.tune_default("ac_graph", 1)) and torch.device(device).type == "cuda" and \
+            (not parallel.is_distributed() or bool(_lib.tune_default("graph_collectives", 0)))
+        self.calls, self.graph, self.launches = 0, None, 0
+
+    def __call__(self):
+        if not self.enabled or self.calls < 2:
+            self.calls += 1
+            return self.fn()
+        if self.graph is None:
+            lib = _lib.load()
+            torch.cuda.synchronize()
+            c0 = lib.cb200_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.fn()
+            self.launches = int(lib.cb200_launch_count() - c0)
+            self.graph = g
+        self.graph.replay()
+
+
 class _Net(object):
     """one Coach "network wrapper": flat store + target buffer + device-state Adam"""
 
@@ -247,6 +275,7 @@ class DDPGAgent(object):
         self.total_steps_counter = 0
         self.last_training_phase_step = 0
         self.last_target_network_update_step = 0
+        self._graph_step, self._graph_actor = None, None
 
     @property
     def is_on_policy(self) -> bool:
@@ -305,11 +334,24 @@ class DDPGAgent(object):
         self._scaled_actions(self.actor_target_s2.forward(), self.critic_target.act)
 
     # ---- learn_from_batch ----------------------------------------------------------------------------------------------
-    def learn_from_batch(self, batch, fetch=True):
+    def _stage(self, batch):
+        """every column of a batch that does not already live in the agent's persistent buffers is copied there: the
+        kernels (and their CUDA graph) only ever read the persistent buffers"""
         cols = batch.columns
-        for k in ("state:observation", "next_state:observation"):
-            if cols[k].data_ptr() != self.batch_buffers[k].data_ptr():
-                self.batch_buffers[k].copy_(cols[k])
+        for k, buf in self.batch_buffers.items():
+            if k in cols and cols[k].data_ptr() != buf.data_ptr():
+                buf.copy_(cols[k].reshape(buf.shape))
+        return self.batch_buffers
+
+    def learn_from_batch(self, batch, fetch=True):
+        self._stage(batch)
+        if self._graph_step is None:
+            self._graph_step = GraphedKernels(self._ddpg_kernels, self.device)
+        self._graph_step()
+        return self._result(fetch)
+
+    def _ddpg_kernels(self):
+        cols = self.batch_buffers
         self._next_actions(cols)                                            # actor target on s'
         self.actor_online_s.forward()                                       # actions_mean = actor online on s
         q_next = self.critic_target.forward()[0]
@@ -331,7 +373,6 @@ class DDPGAgent(object):
                                           ai.d_out.data_ptr(), A, st))
         ai.backward()
         self.actor.apply(self.ws)
-        return self._result(fetch)
 
     def _result(self, fetch):
         loss = self.loss_dev[0] + self.loss_dev[1] if self.twin else self.loss_dev[0]
@@ -375,22 +416,27 @@ class TD3Agent(DDPGAgent):
         """``noise``: optional [B, A] array standing in for np.random.normal(0, policy_noise) (td3_agent.py:162);
         by default it is drawn here from numpy's global generator, like the reference."""
         alg = self.ap.algorithm
-        cols = batch.columns
-        for k in ("state:observation", "next_state:observation"):
-            if cols[k].data_ptr() != self.batch_buffers[k].data_ptr():
-                self.batch_buffers[k].copy_(cols[k])
-        lib, st, B, A = self.lib, _lib.current_stream(), self.B, self.A
-        self._next_actions(cols)
-        self.actor_online_s.forward()
+        self._stage(batch)
+        B, A = self.B, self.A
         if noise is None:
             noise = np.random.normal(0, alg.policy_noise, (B, A))
         self.noise.copy_(torch.as_tensor(np.asarray(noise, dtype=np.float64)))
+        if self._graph_step is None:
+            self._graph_step = GraphedKernels(self._td3_critic_kernels, self.device)
+            self._graph_actor = GraphedKernels(self._action_gradients_into_actor, self.device)
+        self._graph_step()
+        if self.training_iteration % alg.update_policy_every_x_episode_steps == 0:
+            self._graph_actor()                                             # with the UPDATED critic (:190-201)
+        return self._result(fetch)
+
+    def _td3_critic_kernels(self):
+        alg, cols = self.ap.algorithm, self.batch_buffers
+        lib, st, B, A = self.lib, _lib.current_stream(), self.B, self.A
+        self._next_actions(cols)
+        self.actor_online_s.forward()
         _lib.check(lib.cb200_td3_smooth_actions(self.critic_target.act.data_ptr(), self.noise.data_ptr(), B * A,
                                                 float(alg.noise_clipping), self.action_low, self.action_high, st))
         q1, q2 = self.critic_target.forward()
         _lib.check(lib.cb200_min2(q1.data_ptr(), q2.data_ptr(), B, self.q_min.data_ptr(), st))   # output #2
         self._td_targets(cols, self.q_min)
         self._train_critic(cols)
-        if self.training_iteration % alg.update_policy_every_x_episode_steps == 0:
-            self._action_gradients_into_actor()                             # with the UPDATED critic (:190-201)
-        return self._result(fetch)

@@ -245,6 +245,7 @@ class DQNAgent(object):
         self.use_graph = bool(_lib.tune_default("dqn_graph", 1)) and dev.type == "cuda" and B >= 128
         self.networks["main"].device_adam_state = self.use_graph
         self._graphs = None
+        self._graph_c = (None, 0)
         self._head_weights, self._head_split = None, False
         self._grad_sync = None                    # exchange buffer of the overlapped gradient all-reduce
         self._eager_steps = 0
@@ -415,6 +416,18 @@ class DQNAgent(object):
             with torch.cuda.graph(gb):
                 self._part_backward(weights, single)
         c2 = self.lib.cb200_launch_count()
+        gc = None
+        if not single and not overlap:
+            # several ranks: the eager NCCL all-reduce sits between the backward graph and a third graph holding the
+            # 1 / world rescale, the Adam step and the refresh of the parameter planes (one launch instead of ~8)
+            net = self.networks["main"]
+            ws = torch.distributed.get_world_size()
+            scaler = 1.0 / ws if net.params.scale_down_gradients_by_number_of_workers_for_sync_training else 1.0
+            gc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gc):
+                net.apply_gradients(scaler)
+        c3 = self.lib.cb200_launch_count()
+        self._graph_c = (gc, int(c3 - c2))
         self._graphs = (ga, gb, gb2, int(c1 - c0), int(c2 - c1))
 
     def _overlapped_allreduce_begin(self):
@@ -500,6 +513,10 @@ class DQNAgent(object):
             self._eager_steps += 1
         if pending is not None:
             self._overlapped_allreduce_end(*pending)
+        elif graph and not single and self._graph_c[0] is not None:
+            torch.distributed.all_reduce(net.store.grad, op=torch.distributed.ReduceOp.SUM)
+            self._graph_c[0].replay()
+            self.graph_kernel_launches += self._graph_c[1]
         elif not (graph and single):
             scaler = parallel.allreduce_gradients(
                 net.store.grad, net.params.scale_down_gradients_by_number_of_workers_for_sync_training)

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from coach_b200 import _lib, parallel
-from coach_b200.agents.ddpg_agent import _Net
+from coach_b200.agents.ddpg_agent import GraphedKernels, _Net
 from coach_b200.architectures.layers import Dense, Workspace
 from coach_b200.architectures.network import ParamStore, Sequential
 from coach_b200.base_parameters import AgentParameters, AlgorithmParameters, EnvironmentSteps, NetworkParameters
@@ -163,6 +163,7 @@ class SoftActorCriticAgent(object):
         self.training_iteration = 0
         self.total_steps_counter = 0
         self.last_target_network_update_step = 0
+        self._graph_step = None
 
     @property
     def is_on_policy(self) -> bool:
@@ -171,15 +172,27 @@ class SoftActorCriticAgent(object):
     def learn_from_batch(self, batch, fetch=True, noise=None):
         """``noise``: optional three [B, A] arrays standing in for the three independent samples TensorFlow draws in
         the three policy-network runs; by default drawn from numpy's global generator."""
-        lib, st, B, A = self.lib, _lib.current_stream(), self.B, self.A
+        B, A = self.B, self.A
         cols = batch.columns
-        for k in ("state:observation", "next_state:observation", "action"):
-            if cols[k].data_ptr() != self.batch_buffers[k].data_ptr():
-                self.batch_buffers[k].copy_(cols[k].reshape(self.batch_buffers[k].shape))
+        for k, buf in self.batch_buffers.items():          # the kernels (and their CUDA graph) read the agent's buffers
+            if k in cols and cols[k].data_ptr() != buf.data_ptr():
+                buf.copy_(cols[k].reshape(buf.shape))
         if noise is None:
             noise = [np.random.standard_normal((B, A)) for _ in range(3)]
         for e, n in zip(self.eps, noise):
             e.copy_(torch.as_tensor(np.asarray(n), dtype=torch.float32))
+        if self._graph_step is None:
+            self._graph_step = GraphedKernels(self._sac_kernels, self.device)
+        self._graph_step()
+        total = self.q_loss[0] + self.q_loss[1]
+        if fetch:
+            l = float(total.item())
+            return l, [l], float(torch.sqrt(self.q.sumsq).item())
+        return total, [total], self.q.sumsq
+
+    def _sac_kernels(self):
+        lib, st, B, A = self.lib, _lib.current_stream(), self.B, self.A
+        cols = self.batch_buffers
         # 1. policy forward + sample (eps1)
         z = self.policy_inst.forward()
         _lib.check(lib.cb200_sac_policy_sample(z.data_ptr(), self.eps[0].data_ptr(), B, A, None,
@@ -215,11 +228,6 @@ class SoftActorCriticAgent(object):
                                                            self.q_loss[k].data_ptr(), st))
             self.q_train[k].backward()
         self.q.apply(self.ws)
-        total = self.q_loss[0] + self.q_loss[1]
-        if fetch:
-            l = float(total.item())
-            return l, [l], float(torch.sqrt(self.q.sumsq).item())
-        return total, [total], self.q.sumsq
 
     def sample_batch(self):
         return self.memory.sample_batch(self.B, out=self.batch_buffers)

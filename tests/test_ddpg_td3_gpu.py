@@ -95,3 +95,47 @@ def test_train_driver_with_episodic_replay_and_polyak():
     assert not torch.equal(t0, ag.actor.target)
     diff = (ag.actor.target - ag.actor.store.theta).abs().max().item()
     assert diff > 0          # soft update, not a hard copy
+
+
+@pytest.mark.parametrize("kind", ["ddpg", "td3", "sac"])
+def test_graph_replay_of_the_actor_critic_steps_matches_eager(kind, monkeypatch):
+    """the CUDA-graph replay of the DDPG / TD3 / SAC learn step (agents/ddpg_agent.py: GraphedKernels) leaves exactly
+    the parameters the eager launch sequence leaves"""
+    from coach_b200.memories.memory import MemoryGranularity
+    res = []
+    for graph in (0, 1):
+        monkeypatch.setenv("CB200_AC_GRAPH", str(graph))
+        if kind == "sac":
+            from coach_b200.agents.soft_actor_critic_agent import SoftActorCriticAgent as cls, \
+                SoftActorCriticAgentParameters as P
+        elif kind == "td3":
+            from coach_b200.agents.ddpg_agent import TD3Agent as cls, TD3AgentParameters as P
+        else:
+            from coach_b200.agents.ddpg_agent import DDPGAgent as cls, DDPGAgentParameters as P
+        ap = P()
+        ap.memory.max_size = (MemoryGranularity.Transitions, 4096)
+        for nw in ap.network_wrappers.values():
+            nw.batch_size = 64
+        ag = cls(ap, observation_dim=17, action_dim=6, seed=3)
+        rng = np.random.RandomState(1)
+        n = 2000
+        cols = {"state:observation": rng.randn(n, 17).astype(np.float32),
+                "next_state:observation": rng.randn(n, 17).astype(np.float32),
+                "action": rng.uniform(-1, 1, (n, 6)).astype(np.float32), "reward": rng.randn(n)}
+        done = np.zeros(n, np.uint8)
+        done[99::100] = 1
+        cols["game_over"] = done
+        ag.memory.store_columns(cols)
+        np.random.seed(5)
+        losses = []
+        for step in range(7):                       # 2 eager steps, capture, replays (TD3: both graph variants)
+            ag.total_steps_counter += 1
+            losses.append(ag.train(fetch=True))
+        torch.cuda.synchronize()
+        stores = [getattr(ag, t).store.theta.clone() for t in ("actor", "critic", "policy", "q", "v") if hasattr(ag, t)]
+        res.append((losses, stores))
+        if graph:
+            assert ag._graph_step.graph is not None and ag._graph_step.launches > 20
+    assert res[0][0] == res[1][0]
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.equal(a, b)
