@@ -245,6 +245,7 @@ class DQNAgent(object):
         self.use_graph = bool(_lib.tune_default("dqn_graph", 1)) and dev.type == "cuda" and B >= 128
         self.networks["main"].device_adam_state = self.use_graph
         self._graphs = None
+        self._acting = {}                         # number of environments -> (input buffer, forward-only online network)
         self._graph_c = (None, 0)
         self._head_weights, self._head_split = None, False
         self._grad_sync = None                    # exchange buffer of the overlapped gradient all-reduce
@@ -315,6 +316,35 @@ class DQNAgent(object):
         d.dw, d.db = store.view(store.grad, wname).data_ptr(), store.view(store.grad, bname).data_ptr()
         d.workspace = self._head_keep[0].data_ptr()
         self.head_desc = d
+
+    # ---- acting path --------------------------------------------------------------------------------
+    def get_all_q_values_for_states(self, states):
+        """value_optimization_agent.py:68-72 for a batch of E rollout shards: ONE forward pass of the online network on
+        the device.  states: [E, *observation_shape] (uint8 frames / float vectors; host array or CUDA tensor).
+        Returns the Q-values as a CUDA tensor [E, num_actions] (persistent buffer, valid until the next call)."""
+        x = torch.as_tensor(states)
+        E = int(x.shape[0])
+        inst = self._acting.get(E)
+        if inst is None:
+            net = self.networks["main"]
+            buf = torch.zeros((E,) + self.observation_shape, dtype=self.batch_buffers["state:observation"].dtype,
+                              device=self.device)
+            on = self.net_def.instantiate(self.lib, net.ws, E, buf, net.theta)
+            if getattr(net, "_managed", None) is not None and on.manage_planes():
+                net._managed.append(on)
+                on.theta_planes.refresh()
+            inst = self._acting[E] = (buf, on)
+        buf, on = inst
+        buf.copy_(x.reshape(buf.shape), non_blocking=True)
+        return on.forward()
+
+    def choose_actions(self, states, exploration_policy):
+        """value_optimization_agent.py:90-128 for E environments stepped in lock-step: batched Q-values on the device,
+        then the reference's epsilon-greedy arithmetic on the [E, A] read-back
+        (exploration_policies/e_greedy.BatchedEGreedy).  Returns (actions int64 [E], action values [E, A] numpy)."""
+        q = self.get_all_q_values_for_states(states).cpu().numpy()
+        actions, _ = exploration_policy.get_actions(q)
+        return actions, q
 
     # ---- the hot path ------------------------------------------------------------------------------------------------
     def sample_batch(self):

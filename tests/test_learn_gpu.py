@@ -492,3 +492,31 @@ def test_persistent_schedule_is_bit_identical():
         lib.cb200_tune(b"gemm_persistent", 0)
     for a, c in zip(outs[0], outs[1]):
         assert torch.equal(a, c)
+
+
+@pytest.mark.parametrize("E", [16, 128])
+def test_acting_path_batched_q_values_and_e_greedy(E):
+    """DQNAgent.choose_actions: the batched online-network forward equals the oracle's Q-values and the actions are the
+    epsilon-greedy policy's on those values (the policy itself is pinned to the reference in tests/test_acting.py)"""
+    from coach_b200.exploration_policies.e_greedy import BatchedEGreedy
+    from coach_b200.schedules import ConstantSchedule
+    agent = _make_agent((84, 84, 4), 6, 128, False, False, True)
+    rng = np.random.RandomState(E)
+    states = rng.randint(0, 256, (E, 84, 84, 4)).astype(np.uint8)
+    np.random.seed(3)
+    pol = BatchedEGreedy(6, E, ConstantSchedule(0.25), 0.05)
+    actions, q = agent.choose_actions(states, pol)
+    oracle = on.QNetOracle((84, 84, 4), 6, False, torch.float64)
+    want = oracle.forward(oracle.cast(agent.net_def.store.export_named()), states).numpy()
+    close(q, want, name="acting Q-values")
+    np.random.seed(3)
+    pol2 = BatchedEGreedy(6, E, ConstantSchedule(0.25), 0.05)
+    want_actions, _ = pol2.get_actions(q)
+    np.testing.assert_array_equal(actions, want_actions)
+    greedy = ~(np.array([a != int(np.argmax(q[e])) for e, a in enumerate(actions)]))
+    assert greedy.mean() > 0.5                      # epsilon 0.25: most actions are the arg-max
+    # the weights change -> so do the acting Q-values (the acting network reads the live parameters)
+    agent.net_def.store.theta.mul_(1.01)
+    agent.networks["main"].online_changed()
+    q2 = agent.get_all_q_values_for_states(states).cpu().numpy()
+    assert np.abs(q2 - q).max() > 0
