@@ -329,7 +329,8 @@ class DQNAgent(object):
             net = self.networks["main"]
             buf = torch.zeros((E,) + self.observation_shape, dtype=self.batch_buffers["state:observation"].dtype,
                               device=self.device)
-            on = self.net_def.instantiate(self.lib, net.ws, E, buf, net.theta)
+            # (own workspace: growing the learn step's would invalidate the pointers baked into its CUDA graphs)
+            on = self.net_def.instantiate(self.lib, Workspace(self.device), E, buf, net.theta)
             if getattr(net, "_managed", None) is not None and on.manage_planes():
                 net._managed.append(on)
                 on.theta_planes.refresh()
