@@ -27,21 +27,6 @@ class Filter(object):
     def __init__(self, name=None):
         self.name = name
 
-    def save_state_to_checkpoint(self, checkpoint_dir, checkpoint_prefix):
-        """filters/filter.py:452-465 of the reference: every filter with state saves it under its own prefix"""
-        for obs_name, flts in self._observation_filters.items():
-            for fname, f in flts.items():
-                st = getattr(f, "running_observation_stats", None)
-                if st is not None and getattr(st, "shape", None) is not None:
-                    st.save_state_to_checkpoint(checkpoint_dir, "%s.%s.%s" % (checkpoint_prefix, obs_name, fname))
-
-    def restore_state_from_checkpoint(self, checkpoint_dir, checkpoint_prefix):
-        for obs_name, flts in self._observation_filters.items():
-            for fname, f in flts.items():
-                st = getattr(f, "running_observation_stats", None)
-                if st is not None and getattr(st, "shape", None) is not None:
-                    st.restore_state_from_checkpoint(checkpoint_dir, "%s.%s.%s" % (checkpoint_prefix, obs_name, fname))
-
     def reset(self):
         pass
 
@@ -292,6 +277,21 @@ class InputFilter(object):
         for f in self._reward_filters.values():
             f.set_device(device, memory_backend_params, mode)
 
+    def save_state_to_checkpoint(self, checkpoint_dir, checkpoint_prefix):
+        """filters/filter.py:452-465 of the reference: every filter with state saves it under its own prefix"""
+        for obs_name, flts in self._observation_filters.items():
+            for fname, f in flts.items():
+                st = getattr(f, "running_observation_stats", None)
+                if st is not None and getattr(st, "shape", None) is not None:
+                    st.save_state_to_checkpoint(checkpoint_dir, "%s.%s.%s" % (checkpoint_prefix, obs_name, fname))
+
+    def restore_state_from_checkpoint(self, checkpoint_dir, checkpoint_prefix):
+        for obs_name, flts in self._observation_filters.items():
+            for fname, f in flts.items():
+                st = getattr(f, "running_observation_stats", None)
+                if st is not None and getattr(st, "shape", None) is not None:
+                    st.restore_state_from_checkpoint(checkpoint_dir, "%s.%s.%s" % (checkpoint_prefix, obs_name, fname))
+
     def reset(self):
         for flt in self._observation_filters.values():
             for f in flt.values():
@@ -304,26 +304,33 @@ class InputFilter(object):
         if isinstance(unfiltered_data, DeviceBatch):
             return self._filter_device_batch(unfiltered_data, update_internal_state)
         is_list = isinstance(unfiltered_data, list)
-        data = unfiltered_data if is_list else [unfiltered_data]
-        data = copy.deepcopy(data) if deep_copy else [copy.copy(t) for t in data]
-        for obs_name, flt in self._observation_filters.items():
-            for f in flt.values():
-                if f.supports_batching:
-                    for attr in ("state", "next_state"):
-                        vals = [getattr(t, attr)[obs_name] for t in data]
+        data = copy.deepcopy(unfiltered_data) if deep_copy else [copy.copy(t) for t in unfiltered_data]
+        data = data if isinstance(data, list) else [data]
+        # Transitions: all states through all filters, then all next states; environment responses (no ``state``) have
+        # their next_state filtered -- the traversal order of filter.py:314-334, which stateful filters (frame
+        # stacking) observe
+        if hasattr(data[0], "state") and data[0].state is not None and hasattr(data[0], "next_state") and \
+                type(data[0]).__name__ != "EnvResponse":
+            state_lists = [[t.state for t in data], [t.next_state for t in data]]
+        else:
+            state_lists = [[t.next_state for t in data]]
+        for states in state_lists:
+            for obs_name, flt in self._observation_filters.items():
+                if obs_name not in states[0]:
+                    continue
+                for f in flt.values():
+                    vals = [st[obs_name] for st in states]
+                    if f.supports_batching:
                         out = f.filter(vals, update_internal_state=update_internal_state)
                         out = out.cpu().numpy() if torch.is_tensor(out) else out
-                        for t, v in zip(data, out):
-                            getattr(t, attr)[obs_name] = v
-                else:
-                    for t in data:
-                        for attr in ("state", "next_state"):
-                            getattr(t, attr)[obs_name] = f.filter(getattr(t, attr)[obs_name],
-                                                                  update_internal_state=update_internal_state)
+                    else:
+                        out = [f.filter(v, update_internal_state=update_internal_state) for v in vals]
+                    for st, v in zip(states, out):
+                        st[obs_name] = v
         for f in self._reward_filters.values():
             for t in data:
                 t.reward = f.filter(t.reward, update_internal_state=update_internal_state)
-        return data if is_list else data[0]
+        return data          # always a list, like the reference (force_list, filter.py:311)
 
     def _filter_device_batch(self, batch, update_internal_state):
         cols = dict(batch.columns)

@@ -338,6 +338,7 @@ def main():
     golden_sac(out, rng)
     golden_batch(out, rng)
     golden_episodic(out, np.random.RandomState(77))
+    golden_filters(out, np.random.RandomState(78))
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "agent_prologues.npz"), **out)
     print("agent_prologues", len(out), "arrays")
@@ -409,6 +410,56 @@ def golden_episodic(out, rng):
         got = mem.sample(32)
         out["epi%d_sample_state" % k] = np.array([t.state['observation'][0] for t in got], dtype=np.float32)
     out["epi_cases"] = 3
+
+
+# ---- InputFilter: observe-time chain (to-uint8 -> frame stacking, reward clipping / rescale) + Transition lists ---------
+def golden_filters(out, rng):
+    """rl_coach/filters/filter.py:295-350 driven like Agent.observe does (agents/agent.py:905-973): one EnvResponse per
+    environment step through the input filter, reset at episode ends; then a list of Transitions (the pre-network-filter
+    call of Agent.train, agent.py:735).  Filters: observation_to_uint8_filter.py, observation_stacking_filter.py (LazyStack,
+    first-frame replication), reward_clipping_filter.py (truthiness quirk Q13), reward_rescale_filter.py."""
+    from rl_coach.core_types import EnvResponse, Transition
+    from rl_coach.filters.filter import InputFilter
+    from rl_coach.filters.observation.observation_stacking_filter import ObservationStackingFilter
+    from rl_coach.filters.observation.observation_to_uint8_filter import ObservationToUInt8Filter
+    from rl_coach.filters.reward.reward_clipping_filter import RewardClippingFilter
+    from rl_coach.filters.reward.reward_rescale_filter import RewardRescaleFilter
+    f = InputFilter(is_a_reference_filter=False)
+    f.add_observation_filter('observation', 'to_uint8', ObservationToUInt8Filter(0, 1))
+    f.add_observation_filter('observation', 'stacking', ObservationStackingFilter(4))
+    f.add_reward_filter('rescale', RewardRescaleFilter(2.0))
+    f.add_reward_filter('clipping', RewardClippingFilter(-1.0, 1.0))
+    T = 23
+    frames = rng.rand(T, 6, 5)
+    rewards = rng.randn(T) * 2
+    ends = {8, 15}                                        # the filter is reset after these steps (episode ends)
+    stacked, filt_r = [], []
+    for t in range(T):
+        er = EnvResponse(next_state={'observation': frames[t]}, reward=float(rewards[t]), game_over=t in ends)
+        res = f.filter(er)[0]
+        stacked.append(np.array(res.next_state['observation']))
+        filt_r.append(res.reward)
+        if t in ends:
+            f.reset()
+    out["flt_frames"], out["flt_rewards"], out["flt_ends"] = frames, rewards, np.array(sorted(ends))
+    out["flt_stacked"], out["flt_filtered_rewards"] = np.array(stacked), np.array(filt_r, dtype=np.float64)
+    # peek without updating the stack (update_internal_state=False), then continue
+    peek = f.filter(EnvResponse(next_state={'observation': frames[0]}, reward=0.5, game_over=False),
+                    update_internal_state=False)[0]
+    out["flt_peek"] = np.array(peek.next_state['observation'])
+    # Transition list through a reward-only + to-uint8 filter (stateless): states first, then next states
+    g = InputFilter(is_a_reference_filter=False)
+    g.add_observation_filter('observation', 'to_uint8', ObservationToUInt8Filter(0, 2))
+    g.add_reward_filter('clipping', RewardClippingFilter(-1.0, 0))          # upper bound 0 is ignored (quirk Q13)
+    ts = [Transition(state={'observation': rng.rand(3) * 2}, action=0, reward=float(rng.randn() * 3),
+                     next_state={'observation': rng.rand(3) * 2}, game_over=False) for _ in range(7)]
+    out["flt_t_states"] = np.array([t.state['observation'] for t in ts])
+    out["flt_t_next"] = np.array([t.next_state['observation'] for t in ts])
+    out["flt_t_rewards"] = np.array([t.reward for t in ts])
+    res = g.filter(ts)
+    out["flt_t_states_out"] = np.array([t.state['observation'] for t in res])
+    out["flt_t_next_out"] = np.array([t.next_state['observation'] for t in res])
+    out["flt_t_rewards_out"] = np.array([t.reward for t in res])
 
 
 if __name__ == "__main__":

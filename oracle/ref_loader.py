@@ -21,7 +21,8 @@ def load():
     """Returns the imported ``rl_coach`` package (raises RuntimeError when the reference tree is absent)."""
     if not available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
-    for name in ("tensorflow", "tensorflow.contrib", "tensorflow.python", "redis", "pygame", "pygame.locals"):
+    for name in ("tensorflow", "tensorflow.contrib", "tensorflow.python", "redis", "pygame", "pygame.locals", "skimage",
+                 "skimage.transform"):
         if name not in sys.modules:
             sys.modules[name] = mock.MagicMock()
     if REFERENCE_ROOT not in sys.path:

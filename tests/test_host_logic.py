@@ -79,3 +79,47 @@ def test_plugin_path_strings_resolve():
               DDQNAgentParameters()):
         cls = short_dynamic_import(p.path)
         assert cls.__name__ in p.path
+
+
+def test_input_filter_chain_matches_reference_session():
+    """InputFilter driven like Agent.observe (one environment response per step, reset at episode ends) and like
+    Agent.train (a list of Transitions): replay of tests/golden/agent_prologues.npz, recorded from the reference's
+    filters/filter.py:295-350 + to-uint8 / stacking / reward clipping / rescale filters (oracle/make_golden_agents.py)"""
+    import os
+    from types import SimpleNamespace
+    from coach_b200.core_types import Transition
+    from coach_b200.filters.filter import (InputFilter, ObservationStackingFilter, ObservationToUInt8Filter,
+                                           RewardClippingFilter, RewardRescaleFilter)
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "agent_prologues.npz"))
+    f = InputFilter()
+    f.add_observation_filter('observation', 'to_uint8', ObservationToUInt8Filter(0, 1))
+    f.add_observation_filter('observation', 'stacking', ObservationStackingFilter(4))
+    f.add_reward_filter('rescale', RewardRescaleFilter(2.0))
+    f.add_reward_filter('clipping', RewardClippingFilter(-1.0, 1.0))
+    ends = set(int(e) for e in fx["flt_ends"])
+
+    class EnvResponse(SimpleNamespace):          # an environment response: next_state / reward / game_over, no state
+        pass
+    for t in range(len(fx["flt_frames"])):
+        er = EnvResponse(next_state={'observation': fx["flt_frames"][t]}, reward=float(fx["flt_rewards"][t]),
+                         game_over=t in ends)
+        res = f.filter(er)[0]
+        got = np.array(res.next_state['observation'])
+        assert got.dtype == fx["flt_stacked"].dtype and got.shape == fx["flt_stacked"][t].shape
+        np.testing.assert_array_equal(got, fx["flt_stacked"][t])
+        assert res.reward == fx["flt_filtered_rewards"][t]
+        assert np.array_equal(er.next_state['observation'], fx["flt_frames"][t])          # input untouched (deep copy)
+        if t in ends:
+            f.reset()
+    peek = f.filter(EnvResponse(next_state={'observation': fx["flt_frames"][0]}, reward=0.5, game_over=False),
+                    update_internal_state=False)[0]
+    np.testing.assert_array_equal(np.array(peek.next_state['observation']), fx["flt_peek"])
+    g = InputFilter()
+    g.add_observation_filter('observation', 'to_uint8', ObservationToUInt8Filter(0, 2))
+    g.add_reward_filter('clipping', RewardClippingFilter(-1.0, 0))
+    ts = [Transition(state={'observation': fx["flt_t_states"][i]}, action=0, reward=float(fx["flt_t_rewards"][i]),
+                     next_state={'observation': fx["flt_t_next"][i]}, game_over=False) for i in range(7)]
+    res = g.filter(ts)
+    np.testing.assert_array_equal(np.array([t.state['observation'] for t in res]), fx["flt_t_states_out"])
+    np.testing.assert_array_equal(np.array([t.next_state['observation'] for t in res]), fx["flt_t_next_out"])
+    np.testing.assert_array_equal(np.array([t.reward for t in res]), fx["flt_t_rewards_out"])
