@@ -504,6 +504,28 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _finish():
+    """Orderly end of a multi-rank run: CUDA graphs that captured NCCL kernels are destroyed BEFORE the communicator
+    (the other order can block in the communicator's teardown), and a teardown that still does not return within 20 s
+    ends the process instead of holding the launcher."""
+    import gc
+    import threading
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(20.0)
+    if t.is_alive():
+        sys.stderr.write("bench: process-group teardown did not return in 20 s, exiting\n")
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -524,14 +546,10 @@ def main():
     elif args.config in ("cartpole", "ppo", "sac", "td3"):
         import bench_configs
         bench_configs.run(args, ClockSampler)
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            dist.destroy_process_group()
+        _finish()
     else:
         run_device(args)
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            dist.destroy_process_group()
+        _finish()
 
 
 if __name__ == "__main__":

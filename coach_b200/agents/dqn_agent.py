@@ -247,6 +247,7 @@ class DQNAgent(object):
         self._graphs = None
         self._acting = {}                         # number of environments -> (input buffer, forward-only online network)
         self._graph_c = (None, 0)
+        self._collectives_in_graph = False
         self._head_weights, self._head_split = None, False
         self._grad_sync = None                    # exchange buffer of the overlapped gradient all-reduce
         self._eager_steps = 0
@@ -443,12 +444,23 @@ class DQNAgent(object):
                 self._part_backward(weights, False, "top")
             with torch.cuda.graph(gb2):
                 self._part_backward(weights, False, "bottom")
+        elif not single and bool(_lib.tune_default("graph_collectives", 0)):
+            # several ranks, NCCL all-reduce captured INSIDE the backward graph: backward -> all-reduce -> rescale + Adam
+            # + plane refresh replay as one graph launch (no eager launches between the graphs of a step)
+            net = self.networks["main"]
+            ws = torch.distributed.get_world_size()
+            scaler = 1.0 / ws if net.params.scale_down_gradients_by_number_of_workers_for_sync_training else 1.0
+            with torch.cuda.graph(gb):
+                self._part_backward(weights, False)
+                torch.distributed.all_reduce(net.store.grad, op=torch.distributed.ReduceOp.SUM)
+                net.apply_gradients(scaler)
+            self._collectives_in_graph = True
         else:
             with torch.cuda.graph(gb):
                 self._part_backward(weights, single)
         c2 = self.lib.cb200_launch_count()
         gc = None
-        if not single and not overlap:
+        if not single and not overlap and not self._collectives_in_graph:
             # several ranks: the eager NCCL all-reduce sits between the backward graph and a third graph holding the
             # 1 / world rescale, the Adam step and the refresh of the parameter planes (one launch instead of ~8)
             net = self.networks["main"]
@@ -544,6 +556,8 @@ class DQNAgent(object):
             self._eager_steps += 1
         if pending is not None:
             self._overlapped_allreduce_end(*pending)
+        elif graph and self._collectives_in_graph:
+            pass                                                  # all-reduce and optimizer ran inside the graph
         elif graph and not single and self._graph_c[0] is not None:
             torch.distributed.all_reduce(net.store.grad, op=torch.distributed.ReduceOp.SUM)
             self._graph_c[0].replay()
