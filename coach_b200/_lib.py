@@ -47,7 +47,9 @@ class TGemmDesc(ctypes.Structure):
                 ("mask_plane_stride", c_i64), ("bias_row", ctypes.c_int32),
                 ("a_num_planes", ctypes.c_int32),
                 ("a_u8_div", c_float), ("a_rows", c_i64), ("b_rows", c_i64),
-                ("b_interleaved", ctypes.c_int32), ("tmap_key", ctypes.c_uint64), ("tmap_storage", ctypes.c_uint8 * (2 * 128 + 64))]
+                ("b_interleaved", ctypes.c_int32), ("a_pix_host", c_void_p), ("tmap_key", ctypes.c_uint64),
+                ("a_tma", ctypes.c_int32), ("a_tile_class", ctypes.c_uint8 * 64),
+                ("tmap_storage", ctypes.c_uint8 * (4 * 128 + 64))]
 
 
 class DqnHeadDesc(ctypes.Structure):
@@ -136,6 +138,9 @@ PROTOTYPES = {
                                     ctypes.c_int32, c_double, c_double, c_void_p, c_void_p]),
     "cb200_min2": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "cb200_td3_smooth_actions": (c_int, [c_void_p, c_void_p, c_i64, c_double, c_double, c_double, c_void_p]),
+    "cb200_c51_head": (c_int, [c_void_p] * 8 + [c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                               ctypes.c_int32] + [c_void_p] * 8),
+    "cb200_c51_q_values": (c_int, [c_void_p, c_void_p, c_i64, ctypes.c_int32, c_void_p, c_void_p]),
     "cb200_gae_scan": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
     "cb200_standardize": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),

@@ -199,7 +199,8 @@ class DQNAgent(object):
         dueling = "DuelingQHead" in getattr(net_params, "heads_parameters", ["QHead"])
         gen = torch.Generator().manual_seed(int(seed)) if seed is not None else None
         scheme = getattr(getattr(net_params, "middleware_parameters", None), "scheme", MiddlewareScheme.Medium)
-        self.net_def = QNetworkDef(dev, self.observation_shape, A, dueling=dueling,
+        self.head_outputs = self._head_outputs()      # width of the head's output layer (C51: actions x atoms)
+        self.net_def = QNetworkDef(dev, self.observation_shape, self.head_outputs, dueling=dueling,
                                    middleware_units=MiddlewareScheme.units[getattr(scheme, "value", scheme)])
         self.net_def.store.init_glorot(gen)
         # Fused input path (image observations on the tensor-core path): the replay's sample kernel writes the
@@ -228,7 +229,7 @@ class DQNAgent(object):
                 net.online_s.head_fusable() and net.target_s2.head_fusable() and
                 (net.online_s2 is None or net.online_s2.head_fusable())):
             self._build_head_desc()
-        self.targets = torch.zeros((B, A), dtype=torch.float32, device=dev)
+        self.targets = torch.zeros((B, self.head_outputs), dtype=torch.float32, device=dev)
         self.td_err = torch.zeros(B, dtype=torch.float64, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         pin = dev.type == "cuda"
@@ -257,6 +258,9 @@ class DQNAgent(object):
         self.total_steps_counter = 0
         self.last_target_network_update_step = 0
         self.last_training_phase_step = 0
+
+    def _head_outputs(self):
+        return self.num_actions
 
     # ---- reference plumbing ------------------------------------------------------------------------------------------
     @property
@@ -379,13 +383,26 @@ class DQNAgent(object):
         q_next = net.target_s2.forward()                          # dqn_agent.py:87-90
         q_online = net.online_s.forward()
         q_select = net.online_s2.forward() if self.double_dqn else q_next      # ddqn_agent.py:42-43
-        _lib.check(lib.cb200_dqn_td_targets(q_next.data_ptr(), q_select.data_ptr(), q_online.data_ptr(),
-                                            cols["action"].data_ptr(), cols["reward"].data_ptr(),
-                                            cols["game_over"].data_ptr(), float(self.ap.algorithm.discount),
-                                            self.batch_size, self.num_actions, self.targets.data_ptr(),
-                                            self.td_err.data_ptr(), st))
+        self._head_targets(cols, q_next, q_select, q_online, st)
         if per_libm:
             self._td_host.copy_(self.td_err, non_blocking=True)
+
+    def _head_targets(self, cols, q_next, q_select, q_online, st):
+        """TD targets and the errors the memory is updated with (dqn_agent.py:87-103)"""
+        _lib.check(self.lib.cb200_dqn_td_targets(q_next.data_ptr(), q_select.data_ptr(), q_online.data_ptr(),
+                                                 cols["action"].data_ptr(), cols["reward"].data_ptr(),
+                                                 cols["game_over"].data_ptr(), float(self.ap.algorithm.discount),
+                                                 self.batch_size, self.num_actions, self.targets.data_ptr(),
+                                                 self.td_err.data_ptr(), st))
+
+    def _head_loss_grad(self, weights, st):
+        """head loss and dL/d(head output) of the training network (heads/q_head.py, head.py:152-181)"""
+        net = self.networks["main"]
+        huber = 1 if net.params.replace_mse_with_huber_loss else 0
+        _lib.check(self.lib.cb200_regression_head_loss_grad(net.online_s.q.data_ptr(), self.targets.data_ptr(),
+                                                            weights.data_ptr() if weights is not None else None,
+                                                            self.batch_size, self.num_actions, huber, 1.0,
+                                                            net.online_s.dq.data_ptr(), self.loss_dev.data_ptr(), st))
 
     def _part_backward(self, weights, with_optimizer, part="all"):
         """head loss, backward pass, global norm / clipping [, optimizer].  part: "all", or "top" (loss + dense
@@ -407,12 +424,7 @@ class DQNAgent(object):
                 net.apply_gradients(1.0)
             return
         if part != "bottom":
-            huber = 1 if net.params.replace_mse_with_huber_loss else 0
-            _lib.check(lib.cb200_regression_head_loss_grad(net.online_s.q.data_ptr(), self.targets.data_ptr(),
-                                                           weights.data_ptr() if weights is not None else None,
-                                                           self.batch_size, self.num_actions, huber, 1.0,
-                                                           net.online_s.dq.data_ptr(), self.loss_dev.data_ptr(),
-                                                           st))
+            self._head_loss_grad(weights, st)
         if part == "top":
             net.online_s.backward_top()
             return

@@ -306,7 +306,13 @@ def wgrad_op(lib, ws, B, device, x, Ca, g, N, a_pix, taps, num_q, dw, **extra):
     """mode 1: dw [taps * Ca, N] row-major fp32"""
     total = num_q * (B // 32)
     extra.setdefault("macs", taps * Ca * N * num_q * B)
-    return TGemmOp(lib, ws, mode=1, batch=B, a_planes=x, a_plane_stride=x.stride, a_cols=Ca, b_planes=g,
-                   b_plane_stride=g.stride, n=N, a_pix=_dev_i32(np.asarray(a_pix).reshape(-1), device), num_q=num_q,
-                   taps=taps, max_list_len=0, c=dw, ldc=N, act=0, a_rows=x.rows, b_rows=g.rows,
-                   splits=pick_splits_tiled(_tiles1(taps * Ca, N), total), a_num_planes=x.nplanes, **extra)
+    host = np.ascontiguousarray(np.asarray(a_pix).reshape(-1), dtype=np.int32)
+    op = TGemmOp(lib, ws, mode=1, batch=B, a_planes=x, a_plane_stride=x.stride, a_cols=Ca, b_planes=g,
+                 b_plane_stride=g.stride, n=N, a_pix=_dev_i32(host, device), num_q=num_q,
+                 taps=taps, max_list_len=0, c=dw, ldc=N, act=0, a_rows=x.rows, b_rows=g.rows,
+                 splits=pick_splits_tiled(_tiles1(taps * Ca, N), total), a_num_planes=x.nplanes, **extra)
+    if _lib.tune_default("wgrad_tma", 1):
+        # host copy of the tap table: lets the library fetch the A^T operand of a chunk with one TMA box
+        op.keep.append(host)
+        op.desc.a_pix_host = host.ctypes.data
+    return op

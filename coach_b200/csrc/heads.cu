@@ -220,6 +220,177 @@ __global__ void __launch_bounds__(256) td3_smooth_kernel(float* __restrict__ act
 }
 
 // =====================================================================================================================
+// CategoricalQHead + the distributional TD target of CategoricalDQNAgent / RainbowDQNAgent
+// (agents/categorical_dqn_agent.py:105-165, rainbow_dqn_agent.py:93-140, heads/categorical_q_head.py:41-57).
+// One warp per sample:
+//   p_next[a, :]  = softmax(next logits[a, :])  (fp32)      Q[a] = sum_j (double)p[a, j] * z[j]   (np.dot with fp64 z)
+//   a*            = argmax_a Q[a] of the target prediction  (of the `select` prediction for Rainbow's double-Q rule)
+//   m[:]          = the projection of  r + boot * gamma_n * z_j  onto the support, accumulated in fp64 in the
+//                   reference's order (j ascending; first the floor bin, then the ceil bin; an integral b_j adds
+//                   nothing to either bin -- the reference's arithmetic, kept)
+//   labels[a, :]  = online softmax for a != action (TD_targets starts as the online prediction), (float)m for the action
+//   loss[a]       = sum_j labels_j * (log sum_k exp(x_k - max) - (x_j - max))         (tf.nn.softmax_cross_entropy)
+//   dlogits[a, :] = softmax - labels for the taken action, exactly 0 elsewhere (labels ARE the softmax there)
+// next_is_prob: the "next" / "select" inputs already hold probabilities (parity tests pin the projection bit for bit).
+// =====================================================================================================================
+struct C51Params {
+    const float* next; const float* online; const float* select;
+    const int64_t* actions; const double* rewards; const uint8_t* game_overs; const double* bootstrap;
+    const double* z;
+    double gamma_n;
+    int B, A, N, next_is_prob;
+    float* labels; float* dlogits; float* loss_rows; double* td_err; double* q_online; int64_t* target_actions;
+};
+
+constexpr int kC51Warps = 4;
+
+__device__ __forceinline__ float warp_max(float v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// softmax of one row of N logits into dst (shared); returns (max, sum of exp) to every lane
+__device__ __forceinline__ void warp_softmax(const float* __restrict__ x, int N, int lane, float* dst, float& mx,
+                                             float& sum) {
+    float m = -INFINITY;
+    for (int j = lane; j < N; j += 32) m = fmaxf(m, x[j]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < N; j += 32) {
+        const float e = expf(x[j] - m);
+        dst[j] = e;
+        s += e;
+    }
+    s = warp_sum(s);
+    for (int j = lane; j < N; j += 32) dst[j] = dst[j] / s;
+    mx = m;
+    sum = s;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kC51Warps * 32) c51_head_kernel(C51Params p) {
+    extern __shared__ double c51_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kC51Warps + warp;
+    if (b >= p.B) return;
+    const int A = p.A, N = p.N;
+    double* s_m = c51_smem + (size_t)warp * N;                                         // [N] fp64 projection
+    float* s_p = reinterpret_cast<float*>(c51_smem + (size_t)kC51Warps * N) + (size_t)warp * 2 * N;   // [2][N]
+    float* s_sel = s_p + N;
+    const int64_t row = (int64_t)b * A * N;
+
+    // ---- target action ------------------------------------------------------------------------------------------
+    int best = 0;
+    double best_q = 0.0;
+    const float* sel_src = p.select ? p.select : p.next;
+    for (int a = 0; a < A; ++a) {
+        float mx, sum;
+        if (p.next_is_prob) {
+            for (int j = lane; j < N; j += 32) s_sel[j] = sel_src[row + (int64_t)a * N + j];
+            __syncwarp();
+        } else {
+            warp_softmax(sel_src + row + (int64_t)a * N, N, lane, s_sel, mx, sum);
+        }
+        double q = 0.0;
+        for (int j = lane; j < N; j += 32) q += (double)s_sel[j] * p.z[j];
+        q = warp_sum(q);
+        if (a == 0 || q > best_q) { best_q = q; best = a; }                            // np.argmax: first maximum
+        __syncwarp();
+    }
+    if (p.target_actions && lane == 0) p.target_actions[b] = best;
+    {   // distribution of the target network for the chosen action
+        float mx, sum;
+        if (p.next_is_prob) {
+            for (int j = lane; j < N; j += 32) s_p[j] = p.next[row + (int64_t)best * N + j];
+            __syncwarp();
+        } else {
+            warp_softmax(p.next + row + (int64_t)best * N, N, lane, s_p, mx, sum);
+        }
+    }
+    // ---- projection, sequential in j like the reference loop ---------------------------------------------------------
+    for (int j = lane; j < N; j += 32) s_m[j] = 0.0;
+    __syncwarp();
+    if (lane == 0) {
+        const double boot = p.bootstrap ? p.bootstrap[b] : __dsub_rn(1.0, p.game_overs[b] ? 1.0 : 0.0);
+        const double coef = __dmul_rn(boot, p.gamma_n);
+        const double r = p.rewards[b], z0 = p.z[0], zl = p.z[N - 1];
+        const double dz = __dsub_rn(p.z[1], z0);
+        for (int j = 0; j < N; ++j) {
+            const double tz = fmax(fmin(__dadd_rn(r, __dmul_rn(coef, p.z[j])), zl), z0);
+            const double bj = __ddiv_rn(__dsub_rn(tz, z0), dz);
+            const double u = ceil(bj), l = floor(bj);
+            const double pj = (double)s_p[j];
+            s_m[(int)l] = __dadd_rn(s_m[(int)l], __dmul_rn(pj, __dsub_rn(u, bj)));
+            s_m[(int)u] = __dadd_rn(s_m[(int)u], __dmul_rn(pj, __dsub_rn(bj, l)));
+        }
+    }
+    __syncwarp();
+    // ---- online head: labels, cross entropy, gradient ---------------------------------------------------------------
+    const int act = (int)p.actions[b];
+    for (int a = 0; a < A; ++a) {
+        const float* x = p.online + row + (int64_t)a * N;
+        float mx, sum;
+        warp_softmax(x, N, lane, s_sel, mx, sum);
+        const float lse = logf(sum);
+        float loss = 0.f;
+        double q = 0.0;
+        for (int j = lane; j < N; j += 32) {
+            const float sm = s_sel[j];
+            const float lab = (a == act) ? (float)s_m[j] : sm;
+            loss += lab * (lse - (x[j] - mx));
+            p.labels[row + (int64_t)a * N + j] = lab;
+            p.dlogits[row + (int64_t)a * N + j] = (a == act) ? (sm - lab) : 0.f;
+            q += (double)sm * p.z[j];
+        }
+        loss = warp_sum(loss);
+        q = warp_sum(q);
+        if (lane == 0) {
+            p.loss_rows[(int64_t)b * A + a] = loss;
+            if (p.q_online) p.q_online[(int64_t)b * A + a] = q;
+            if (a == act) p.td_err[b] = (double)loss;
+        }
+        __syncwarp();
+    }
+}
+
+// q_values of the CategoricalQHead (categorical_q_head.py:56): tensordot(cast(softmax, fp64), z), one warp per (b, a) row
+__global__ void __launch_bounds__(128) c51_q_values_kernel(const float* __restrict__ logits, const double* __restrict__ z,
+                                                           int64_t rows, int N, double* __restrict__ q) {
+    const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* x = logits + r * N;
+    float m = -INFINITY;
+    for (int j = lane; j < N; j += 32) m = fmaxf(m, x[j]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < N; j += 32) s += expf(x[j] - m);
+    s = warp_sum(s);
+    double acc = 0.0;
+    for (int j = lane; j < N; j += 32) acc += (double)(expf(x[j] - m) / s) * z[j];
+    acc = warp_sum(acc);
+    if (lane == 0) q[r] = acc;
+}
+
+// total loss = tf.reduce_sum over the [B, A] loss tensor (general_network.py:360), one block, fixed order
+__global__ void __launch_bounds__(256) c51_loss_sum_kernel(const float* __restrict__ loss_rows, int64_t n,
+                                                           float* __restrict__ total) {
+    __shared__ float red[256];
+    float v = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += 256) v += loss_rows[i];
+    const float t = block_sum(v, red);
+    if (threadIdx.x == 0) *total = t;
+}
+
+// =====================================================================================================================
 // SACPolicyHead (heads/sac_head.py:60-97): head output z = [mu | log_sigma_raw]  (2A columns),
 //   log_sigma = clip(log_sigma_raw, -20, 2);  u = mu + exp(log_sigma) * eps;  a = tanh(u);
 //   log pi(a|s) = sum_j [ -0.5 eps_j^2 - log_sigma_j - 0.5 log(2 pi) ] - sum_j log(1 - tanh(u_j)^2 + 1e-6)
@@ -392,6 +563,38 @@ int cb200_td3_smooth_actions(float* actions, const double* noise, int64_t n, dou
     return CB200_OK;
 }
 
+
+int cb200_c51_head(const float* next, const float* online, const float* select, const int64_t* actions,
+                   const double* rewards, const uint8_t* game_overs, const double* bootstrap, const double* z,
+                   double gamma_n, int32_t batch, int32_t n_actions, int32_t n_atoms, int32_t next_is_prob,
+                   float* labels, float* dlogits, float* loss_rows, float* total_loss, double* td_err,
+                   double* q_online, int64_t* target_actions, void* stream) {
+    CB200_CHECK_ARG(next && online && actions && rewards && (game_overs || bootstrap) && z, "bad arguments");
+    CB200_CHECK_ARG(labels && dlogits && loss_rows && total_loss && td_err, "bad output arguments");
+    CB200_CHECK_ARG(batch > 0 && n_actions > 0 && n_atoms >= 2 && n_atoms <= 1024, "bad shape");
+    C51Params p;
+    p.next = next; p.online = online; p.select = select; p.actions = actions; p.rewards = rewards;
+    p.game_overs = game_overs; p.bootstrap = bootstrap; p.z = z; p.gamma_n = gamma_n;
+    p.B = batch; p.A = n_actions; p.N = n_atoms; p.next_is_prob = next_is_prob;
+    p.labels = labels; p.dlogits = dlogits; p.loss_rows = loss_rows; p.td_err = td_err; p.q_online = q_online;
+    p.target_actions = target_actions;
+    const size_t smem = (size_t)kC51Warps * n_atoms * (sizeof(double) + 2 * sizeof(float));
+    CB200_LAUNCH(c51_head_kernel, (unsigned)((batch + kC51Warps - 1) / kC51Warps), kC51Warps * 32, smem,
+                 as_stream(stream), p);
+    CB200_CHECK_LAUNCH();
+    CB200_LAUNCH(c51_loss_sum_kernel, 1, 256, 0, as_stream(stream), loss_rows, (int64_t)batch * n_actions, total_loss);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+
+int cb200_c51_q_values(const float* logits, const double* z, int64_t rows, int32_t n_atoms, double* q_out, void* stream) {
+    CB200_CHECK_ARG(logits && z && q_out && rows > 0 && n_atoms >= 2, "bad arguments");
+    CB200_LAUNCH(c51_q_values_kernel, (unsigned)((rows + 3) / 4), 128, 0, as_stream(stream), logits, z, rows, n_atoms,
+                 q_out);
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
 
 int cb200_sac_policy_sample(const float* head_out, const float* eps, int64_t batch, int32_t action_dim, float* raw_out,
                             float* actions_out, float* logp_out, void* stream) {

@@ -142,8 +142,29 @@ static bool make_plane_map(CUtensorMap* map, const void* planes, int64_t plane_s
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// A^T operand of the weight-gradient GEMM (mode 1): planes of A [pixels * B, cols] as a 5-D tensor
+//   (64 | column cores | taps | row groups | planes)
+// whose "taps" dimension steps `tap_delta` PIXELS (tap_delta * B / 8 row groups) and has `tap_extent` valid entries; it
+// aliases the row-group dimension on purpose.  The box (64, box_cores, box_taps, 4, nplanes) lands as
+// [plane][k-group][tap][core] -- the MN-major A^T tile of nn_gemm_tiled.cuh; taps past tap_extent are zero-filled.
+static bool make_wgrad_map(CUtensorMap* map, const void* planes, int64_t plane_stride, int64_t rows, int cols, int batch,
+                           int64_t tap_delta, int tap_extent, int box_cores, int box_taps, int nplanes) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || tap_delta < 1) return false;
+    const cuuint64_t rg_stride = (cuuint64_t)(cols / 8) * 128;
+    cuuint64_t dims[5] = {64, (cuuint64_t)(cols / 8), (cuuint64_t)tap_extent, (cuuint64_t)(rows / 8), (cuuint64_t)nplanes};
+    cuuint64_t strides[4] = {128, (cuuint64_t)tap_delta * (cuuint64_t)(batch / 8) * rg_stride, rg_stride,
+                             (cuuint64_t)plane_stride * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)box_cores, (cuuint32_t)box_taps, 4, (cuuint32_t)nplanes};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (nplanes == 1) strides[3] = (cuuint64_t)(rows / 8) * rg_stride;      // any valid stride: the dimension has one entry
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(planes), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, bool kT, int NA, bool kCat = false>
-static int launch_tiled(const CUtensorMap& tmA, const CUtensorMap& tmB, const TiledParams& tp, const EpiParams& ep,
+static int launch_tiled(const CUtensorMap* maps, const TiledParams& tp, const EpiParams& ep,
                         int M, int gx, int splits, cudaStream_t st) {
     constexpr size_t smem = TiledCfg<BN, NA>::kSmemBytes;
     static bool configured = false;
@@ -154,7 +175,8 @@ static int launch_tiled(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ti
         configured = true;
     }
     dim3 grid(gx, (tp.n + BN - 1) / BN, splits);
-    gemm_tc_tiled_kernel<BN, kT, NA, kCat><<<grid, kTlThreads, smem, st>>>(tmA, tmB, tp, ep, M);
+    // maps: [0] A (mode 0) / A^T class 0 (mode 1), [1] B, [2], [3] A^T classes 1 and 2
+    gemm_tc_tiled_kernel<BN, kT, NA, kCat><<<grid, kTlThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], tp, ep, M);
     count_launch();
     if (splits > 1) {
         launch_split_reduce(ep, M, tp.n, st);
@@ -504,9 +526,60 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
             ok = ok && gemm::make_plane_map(maps + 0, d->a_planes, d->a_plane_stride, d->a_rows, d->a_cols, 4, 16, na);
         else
             maps[0] = maps[1];
+        maps[2] = maps[3] = maps[0];
+        md->a_tma = 0;
+        if (ok && d->mode == 1 && d->a_pix_host && tune_get("wgrad_tma", 1, 0, 1) != 0) {
+            // Tap-stride classes of the 128-row tiles: tile i covers taps t0 .. t0 + box_taps - 1 (a_cols < 128) or a
+            // 128-channel slice of one tap.  Usable when, inside every tile, consecutive taps sit the same positive
+            // number of pixels apart at every output pixel, with at most three distinct (stride, valid taps) pairs.
+            const int Ca = d->a_cols, cw = Ca < 128 ? Ca : 128, box_taps = 128 / cw;
+            const int tiles = (d->taps * Ca + 127) / 128;
+            struct Cls { int64_t delta; int extent; } cls[3];
+            int ncls = 0;
+            bool usable = tiles <= 64;
+            for (int i = 0; usable && i < tiles; ++i) {
+                const int t0 = Ca < 128 ? i * box_taps : (i * 128) / Ca;
+                const int valid = Ca < 128 ? (d->taps - t0 < box_taps ? d->taps - t0 : box_taps) : 1;
+                int64_t delta = 1;
+                if (valid > 1) {
+                    delta = (int64_t)d->a_pix_host[(size_t)(t0 + 1) * d->num_q] - d->a_pix_host[(size_t)t0 * d->num_q];
+                    for (int t = t0; usable && t + 1 < t0 + valid; ++t)
+                        for (int q = 0; q < d->num_q; ++q)
+                            if ((int64_t)d->a_pix_host[(size_t)(t + 1) * d->num_q + q] -
+                                    d->a_pix_host[(size_t)t * d->num_q + q] != delta) {
+                                usable = false;
+                                break;
+                            }
+                    if (delta < 1) usable = false;
+                }
+                int k = 0;
+                while (k < ncls && !(cls[k].delta == delta && cls[k].extent == valid)) ++k;
+                if (k == ncls) {
+                    if (ncls == 3) { usable = false; break; }
+                    cls[ncls].delta = delta;
+                    cls[ncls].extent = valid;
+                    ++ncls;
+                }
+                if (usable) md->a_tile_class[i] = (uint8_t)k;
+            }
+            if (usable) {
+                static const int slot[3] = {0, 2, 3};
+                for (int k = 0; usable && k < ncls; ++k)
+                    usable = gemm::make_wgrad_map(maps + slot[k], d->a_planes, d->a_plane_stride, d->a_rows, Ca, d->batch,
+                                                  cls[k].delta, cls[k].extent, cw / 8, box_taps, na);
+                for (int k = ncls; k < 3; ++k) maps[slot[k]] = maps[slot[0]];
+                if (usable) md->a_tma = ncls;
+                else maps[0] = maps[2] = maps[3] = maps[1];
+            }
+            if (getenv("CB200_DEBUG"))
+                fprintf(stderr, "cb200_gemm_tiled mode 1: taps %d a_cols %d num_q %d tiles %d -> A^T tensor maps: %d\n",
+                        d->taps, d->a_cols, d->num_q, tiles, md->a_tma);
+        }
         CB200_CHECK_ARG(ok, "cuTensorMapEncodeTiled failed (driver too old or bad plane geometry)");
         md->tmap_key = key;
     }
+    tp.a_tma = d->mode == 1 ? md->a_tma : 0;
+    for (int i = 0; i < 64; ++i) tp.tile_class[i] = md->a_tile_class[i];
     if (d->mode == 0) {
         CB200_CHECK_ARG(d->list_ptr && d->list && d->num_q > 0 && d->max_list_len > 0, "mode 0 needs the tap lists");
         M = d->num_q * d->batch;
@@ -535,13 +608,13 @@ int cb200_gemm_tiled(const cb200_tgemm_desc* d, void* stream) {
     cudaStream_t st = as_stream(stream);
     int rc;
 #define CB200_TL(BN_) \
-    (na == 1 ? (d->mode ? gemm::launch_tiled<BN_, true, 1>(maps[0], maps[1], tp, ep, M, gx, splits, st)   \
-                        : gemm::launch_tiled<BN_, false, 1>(maps[0], maps[1], tp, ep, M, gx, splits, st)) \
-             : (d->mode ? gemm::launch_tiled<BN_, true, 3>(maps[0], maps[1], tp, ep, M, gx, splits, st)   \
-                        : gemm::launch_tiled<BN_, false, 3>(maps[0], maps[1], tp, ep, M, gx, splits, st)))
+    (na == 1 ? (d->mode ? gemm::launch_tiled<BN_, true, 1>(maps, tp, ep, M, gx, splits, st)   \
+                        : gemm::launch_tiled<BN_, false, 1>(maps, tp, ep, M, gx, splits, st)) \
+             : (d->mode ? gemm::launch_tiled<BN_, true, 3>(maps, tp, ep, M, gx, splits, st)   \
+                        : gemm::launch_tiled<BN_, false, 3>(maps, tp, ep, M, gx, splits, st)))
 #define CB200_TLC(BN_) \
-    (na == 1 ? gemm::launch_tiled<BN_, false, 1, true>(maps[0], maps[1], tp, ep, M, gx, splits, st) \
-             : gemm::launch_tiled<BN_, false, 3, true>(maps[0], maps[1], tp, ep, M, gx, splits, st))
+    (na == 1 ? gemm::launch_tiled<BN_, false, 1, true>(maps, tp, ep, M, gx, splits, st) \
+             : gemm::launch_tiled<BN_, false, 3, true>(maps, tp, ep, M, gx, splits, st))
 #define CB200_TPC(BN_) \
     (na == 1 ? gemm::launch_tiled_persist<BN_, false, 1, true>(maps[0], maps[1], tp, ep, M, gx, splits, st) \
              : gemm::launch_tiled_persist<BN_, false, 3, true>(maps[0], maps[1], tp, ep, M, gx, splits, st))

@@ -70,6 +70,8 @@ struct TiledParams {
     int chunks_per_split;
     float a_u8_div;            // NA == 1: A holds raw uint8 values (exact in bf16); every sum is divided by this
     int bias_row;              // mode 1: also produce row M = sum over all rows of G (the bias gradient)
+    int a_tma;                 // mode 1: the A^T operand of a chunk is one 5-D TMA box (tensor map tile_class[tile])
+    uint8_t tile_class[64];
 };
 
 // NA = planes of the A operand: 3 (fp32 split) or 1 (uint8 values, exact: 3 products instead of 6)
@@ -83,6 +85,15 @@ struct TiledCfg {
     static constexpr int kStages = BN == 128 ? 4 : 3;
     static constexpr size_t kSmemBytes = (size_t)kStages * (NA * kTcBM * kTcBK * 2 + 3 * BN * kTcBK * 2) + 128 + 4096;
 };
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], "
+        "[%7];" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint64_t* bar) {
@@ -103,7 +114,9 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 // shared memory delivers -- the six narrow MMAs were bound by shared-memory reads, not by the tensor pipe.
 template <int BN, bool kTransA, int NA, bool kCat = false>
 __global__ void __launch_bounds__(kTlThreads) gemm_tc_tiled_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                            const __grid_constant__ CUtensorMap tmB, TiledParams tp,
+                                                            const __grid_constant__ CUtensorMap tmB,
+                                                            const __grid_constant__ CUtensorMap tmA1,
+                                                            const __grid_constant__ CUtensorMap tmA2, TiledParams tp,
                                                             EpiParams ep, int M) {
     constexpr int S = TiledCfg<BN, NA>::kStages;
     constexpr int A_SPLIT = kTcBM * kTcBK * 2;            // 8 KB per plane
@@ -190,11 +203,14 @@ __global__ void __launch_bounds__(kTlThreads) gemm_tc_tiled_kernel(const __grid_
         const int cw = kTransA ? min(Ca, kTcBM) : 0;                           // channels per tap inside the tile
         const int c0 = kTransA ? m0 % Ca : 0;
         // a tensor-map box always delivers (and counts) its full size, rows past the batch included
-        const uint32_t a_bytes = kTransA ? (uint32_t)(taps_in_tile * 4 * (cw / 8) * 128) : (uint32_t)A_SPLIT;
+        const bool a_tma = kTransA && tp.a_tma != 0;
+        const int a_cls = a_tma ? tp.tile_class[blockIdx.x & 63] : 0;
+        const CUtensorMap* a_map = a_cls == 0 ? &tmA : (a_cls == 1 ? &tmA1 : &tmA2);
+        const uint32_t a_bytes = (kTransA && !a_tma) ? (uint32_t)(taps_in_tile * 4 * (cw / 8) * 128) : (uint32_t)A_SPLIT;
         const uint32_t tx_bytes = (uint32_t)NA * a_bytes + 3u * (uint32_t)B_SPLIT;
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            if (!kTransA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            if (!kTransA || a_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(a_map) : "memory");
         }
         for (int j = 0; j < nchunks; ++j) {
             const int s = j % S, u = j / S;
@@ -218,6 +234,15 @@ __global__ void __launch_bounds__(kTlThreads) gemm_tc_tiled_kernel(const __grid_
             } else {
                 const int qq = cj / bc_per, bc = cj % bc_per;
                 if (lane == 0) tma_load_4d(sB, &tmB, 0, n0 >> 3, (int)(((size_t)qq * B + (size_t)bc * kTcBK) >> 3), 0, bar);
+                if (a_tma) {
+                    // A^T: the taps of the tile sit a constant number of pixels apart -- one 5-D box (64 | cores | taps
+                    // | 4 row groups | planes) lands as [plane][k-group][tap][core], the layout of the bulk path below
+                    if (lane == 0) {
+                        const int apix = __ldg(tp.a_pix + (size_t)t0 * tp.num_q + qq);
+                        tma_load_5d(sA, a_map, 0, c0 >> 3, 0, (int)(((size_t)apix * B + (size_t)bc * kTcBK) >> 3), 0, bar);
+                    }
+                    continue;
+                }
                 // A^T: per tap of the tile, 4 k-groups (8 batch rows each) x a run of cw / 8 cores.  A bulk copy costs
                 // ~60 cycles of issue in the issuing warp whatever its size, so the runs are dealt out over nine
                 // warps: this one and the eight epilogue warps, which are idle until the accumulators are complete.
@@ -306,7 +331,7 @@ __global__ void __launch_bounds__(kTlThreads) gemm_tc_tiled_kernel(const __grid_
             const int t0 = m0 / Ca, cw = min(Ca, kTcBM), c0 = m0 % Ca;
             for (int j = 0; j < nchunks; ++j) {
                 const int s = j % S, u = j / S;
-                if ((warp + 1) * 32 >= NA * 4 * taps_in_tile) break;           // nothing dealt to this warp
+                if (tp.a_tma != 0 || (warp + 1) * 32 >= NA * 4 * taps_in_tile) break;   // nothing dealt to this warp
                 if (u > 0) mbar_wait(empty_bar + s, (uint32_t)((u - 1) & 1));
                 uint8_t* sA = smem + s * STAGE;
                 uint64_t* bar = full_bar + s;

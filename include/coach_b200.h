@@ -283,10 +283,17 @@ typedef struct cb200_tgemm_desc {
                                 /*   (row group | plane | column core | 64), written with plane_stride -1 by              */
                                 /*   cb200_split_planes (segment layout 1) / cb200_permute_f32 -- and the 3xBF16 product  */
                                 /*   set is issued as three wide tcgen05.mma on the [b1|b2|b3] operand                    */
+    const int32_t* a_pix_host;  /* mode 1, optional: HOST copy of a_pix.  When the taps that share a 128-row tile of the   */
+                                /*   result sit a constant number of pixels apart (at most three distinct strides over   */
+                                /*   the tiles: every convolution of the path), the A^T operand of a reduction chunk is  */
+                                /*   ONE 5-D TMA box (64 | cores | taps | row groups | planes) instead of one 1-D bulk   */
+                                /*   copy per (plane, tap, row group); NULL: bulk copies                                 */
     /* private: TMA tensor maps of the operands, built by the first call with this descriptor (keep the descriptor    */
     /* alive and unchanged between calls; zero-initialise)                                                            */
     uint64_t tmap_key;
-    uint8_t tmap_storage[2 * 128 + 64];
+    int32_t a_tma;              /* private: number of A^T tensor maps in use (0: bulk copies)                           */
+    uint8_t a_tile_class[64];   /* private: tensor map of each 128-row tile                                             */
+    uint8_t tmap_storage[4 * 128 + 64];
 } cb200_tgemm_desc;
 
 int cb200_gemm_tiled(const cb200_tgemm_desc* h_desc, void* stream);
@@ -463,6 +470,27 @@ int cb200_min2(const float* a, const float* b, int64_t n, float* out, void* stre
  * to fp32 once (bit-exact with the reference, tests/golden/agent_prologues.npz) */
 int cb200_td3_smooth_actions(float* actions, const double* noise, int64_t n, double noise_clip, double lo, double hi,
                              void* stream);
+
+/* CategoricalQHead + distributional TD targets (agents/categorical_dqn_agent.py:105-165, rainbow_dqn_agent.py:93-140,
+ * architectures/tensorflow_components/heads/categorical_q_head.py:41-57).  Inputs are the [batch, n_actions, n_atoms]
+ * head logits of target(s'), online(s) and -- for the double-Q rule of Rainbow, else NULL -- online(s').  z = the fp64
+ * support (np.linspace); gamma_n = discount (** n_step); bootstrap (fp64 per sample, NULL -> 1 - game_over) is
+ * info['should_bootstrap_next_state'].  Writes: labels = TD_targets fed to the train op (online softmax, projected
+ * distribution m on the taken action's row; projection accumulated in fp64 in the reference's loop order, bit-exact
+ * given equal probabilities), dlogits = d(total loss)/d(online logits) (softmax - labels on the taken row, 0 elsewhere),
+ * loss_rows [batch, n_actions] = tf.nn.softmax_cross_entropy_with_logits, total_loss = their sum
+ * (general_network.py:360), td_err = loss_rows[b, action[b]] (what update_priorities is handed, :160-163), optional
+ * q_online [batch, n_actions] fp64 (distribution_prediction_to_q_values) and target_actions.  next_is_prob != 0: `next`
+ * / `select` already hold probabilities (parity tests feed the fixture's network outputs). */
+int cb200_c51_head(const float* next, const float* online, const float* select, const int64_t* actions,
+                   const double* rewards, const uint8_t* game_overs, const double* bootstrap, const double* z,
+                   double gamma_n, int32_t batch, int32_t n_actions, int32_t n_atoms, int32_t next_is_prob,
+                   float* labels, float* dlogits, float* loss_rows, float* total_loss, double* td_err,
+                   double* q_online, int64_t* target_actions, void* stream);
+
+/* q_values output of the CategoricalQHead (categorical_q_head.py:56): q[r] = sum_j (double)softmax(logits[r, :])_j * z[j]
+ * for rows = batch * n_actions rows of n_atoms logits; z = the fp32-rounded support cast back to fp64 (:36-37) */
+int cb200_c51_q_values(const float* logits, const double* z, int64_t rows, int32_t n_atoms, double* q_out, void* stream);
 
 /* SACPolicyHead (heads/sac_head.py:60-97).  head_out [batch, 2*action_dim] = [mu | raw log-sigma]; log-sigma is clipped
  * to [-20, 2]; u = mu + exp(log_sigma) * eps; a = tanh(u); logp = MVN-diag log-prob of u minus the tanh squash

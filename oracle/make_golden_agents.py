@@ -110,6 +110,63 @@ def golden_dqn(out, rng, B=64, A=6):
         assert rec["targets"].dtype == np.float32
 
 
+# ---- Categorical DQN / Rainbow targets -------------------------------------------------------------------------------
+def golden_c51(out, rng, B=64, A=6, N=51):
+    """categorical_dqn_agent.py:105-165 and rainbow_dqn_agent.py:93-140 with stand-in networks: the distributions the
+    networks return are given, the TD_targets handed to the train op and the errors handed to the memory are recorded"""
+    from rl_coach.agents.categorical_dqn_agent import CategoricalDQNAgent
+    from rl_coach.agents.rainbow_dqn_agent import RainbowDQNAgent
+    from rl_coach.core_types import Batch
+    from rl_coach.memories.non_episodic.prioritized_experience_replay import PrioritizedExperienceReplay
+    from rl_coach.memories.memory import MemoryGranularity
+
+    def softmax(x):
+        e = np.exp(x - x.max(axis=-1, keepdims=True))
+        return (e / e.sum(axis=-1, keepdims=True)).astype(np.float32)
+
+    for tag, cls in (("c51", CategoricalDQNAgent), ("rainbow", RainbowDQNAgent)):
+        ts = _transitions(rng, B, (4,), A)
+        for i, t in enumerate(ts):
+            t.reward = float(rng.choice([-1.0, 0.0, 1.0, 0.37, -12.5, 11.0]))    # integral b_j, clipped ends, generic
+            t.n_step_discounted_rewards = float(rng.randn() * 2)
+            t.info['should_bootstrap_next_state'] = bool(rng.rand() < 0.8)
+        batch = Batch(ts)
+        z = np.linspace(-10.0, 10.0, N)
+        d_next = softmax(rng.randn(B, A, N) * 2)
+        d_online = softmax(rng.randn(B, A, N))
+        d_select = softmax(rng.randn(B, A, N) * 2)
+        loss_rows = rng.rand(B, A).astype(np.float32)
+        rec = {}
+        nw, alg = _ap(discount=0.99, n_step=3)
+        mem = PrioritizedExperienceReplay((MemoryGranularity.Transitions, 1024))
+        net = SimpleNamespace(
+            target_network="T", online_network=SimpleNamespace(predict=lambda states: d_select.copy()),
+            parallel_prediction=lambda pairs: (d_next.copy(), d_online.copy()),
+            train_and_sync_networks=lambda states, targets, importance_weights=None: (
+                rec.update(targets=np.array(targets), w=None if importance_weights is None
+                           else np.array(importance_weights)) or (0.0, [loss_rows], 0.0)))
+        calls = []
+        fake = SimpleNamespace(ap=SimpleNamespace(network_wrappers={'main': nw}, algorithm=alg),
+                               networks={'main': net}, q_values=_Sig(), memory=mem, z_values=z,
+                               call_memory=lambda f, args: calls.append((f, args)))
+        fake.distribution_prediction_to_q_values = lambda pred: cls.distribution_prediction_to_q_values(fake, pred)
+        cls.learn_from_batch(fake, batch)
+        assert calls[0][0] == 'update_priorities'
+        out[tag + "_z"] = z
+        out[tag + "_dist_next"], out[tag + "_dist_online"], out[tag + "_dist_select"] = d_next, d_online, d_select
+        out[tag + "_actions"] = batch.actions().astype(np.int64)
+        out[tag + "_rewards"] = (batch.n_step_discounted_rewards() if tag == "rainbow" else batch.rewards()) \
+            .astype(np.float64)
+        out[tag + "_game_overs"] = batch.game_overs().astype(np.uint8)
+        out[tag + "_bootstrap"] = np.asarray(batch.info('should_bootstrap_next_state'), dtype=np.float64) \
+            if tag == "rainbow" else (1.0 - batch.game_overs()).astype(np.float64)
+        out[tag + "_gamma_n"] = np.float64(alg.discount ** alg.n_step if tag == "rainbow" else alg.discount)
+        out[tag + "_targets"] = rec["targets"]                       # float32 [B, A, N], fed to the train op
+        out[tag + "_loss_rows"] = loss_rows
+        out[tag + "_prio_errors"] = np.array(calls[0][1][1], dtype=np.float64)
+        assert rec["targets"].dtype == np.float32 and rec["targets"].shape == (B, A, N)
+
+
 # ---- ClippedPPO fill_advantages --------------------------------------------------------------------------------------
 def golden_ppo(out, rng):
     from rl_coach.agents.actor_critic_agent import ActorCriticAgent
@@ -339,6 +396,7 @@ def main():
     golden_batch(out, rng)
     golden_episodic(out, np.random.RandomState(77))
     golden_filters(out, np.random.RandomState(78))
+    golden_c51(out, np.random.RandomState(79))
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "agent_prologues.npz"), **out)
     print("agent_prologues", len(out), "arrays")

@@ -181,3 +181,55 @@ def test_episodic_replay_matches_reference_session(fx, case):
     np.random.seed(11 + case)
     s = mem.sample_batch(32)
     np.testing.assert_array_equal(s.states(["observation"])["observation"].cpu().numpy()[:, 0], fx[p + "sample_state"])
+
+
+@pytest.mark.parametrize("tag", ["c51", "rainbow"])
+def test_distributional_targets_match_reference_agents(fx, tag):
+    """cb200_c51_head fed the fixture's network outputs (probabilities): TD_targets bit-exact with what the reference
+    agents hand to the train op; target actions = the reference's argmax; loss / gradient against a torch evaluation"""
+    L, lib = _lib()
+    g = lambda k: fx[tag + "_" + k]                                                              # noqa: E731
+    B, A, N = g("dist_next").shape
+    d_online = g("dist_online")
+    logits_online = np.log(d_online).astype(np.float32)
+    nxt, onl = _dev(g("dist_next")), _dev(logits_online)
+    sel = _dev(g("dist_select")) if tag == "rainbow" else None
+    act, rew, done, boot, z = _dev(g("actions")), _dev(g("rewards")), _dev(g("game_overs")), _dev(g("bootstrap")), \
+        _dev(g("z"))
+    labels = torch.empty(B, A, N, device="cuda")
+    dlog = torch.empty(B, A, N, device="cuda")
+    rows = torch.empty(B, A, device="cuda")
+    total = torch.empty(1, device="cuda")
+    td = torch.empty(B, dtype=torch.float64, device="cuda")
+    q = torch.empty(B, A, dtype=torch.float64, device="cuda")
+    ta = torch.empty(B, dtype=torch.int64, device="cuda")
+    L.check(lib.cb200_c51_head(nxt.data_ptr(), onl.data_ptr(), sel.data_ptr() if sel is not None else None,
+                               act.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                               boot.data_ptr() if tag == "rainbow" else None, z.data_ptr(), float(g("gamma_n")),
+                               B, A, N, 1, labels.data_ptr(), dlog.data_ptr(), rows.data_ptr(), total.data_ptr(),
+                               td.data_ptr(), q.data_ptr(), ta.data_ptr(), None))
+    torch.cuda.synchronize()
+    want = g("targets")
+    got = labels.cpu().numpy()
+    actions = g("actions")
+    ar = np.arange(B)
+    # the taken action's row is the projected distribution: bit-exact
+    np.testing.assert_array_equal(got[ar, actions], want[ar, actions])
+    src = g("dist_select") if tag == "rainbow" else g("dist_next")
+    np.testing.assert_array_equal(ta.cpu().numpy(), np.argmax(np.dot(src, g("z")), axis=1))
+    # other rows: the online softmax (the fixture's was produced by numpy, the kernel's by expf: 1e-6)
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-8)
+    # loss rows / gradient vs torch on the kernel's own labels
+    lg = torch.from_numpy(logits_online).double()
+    lab = torch.from_numpy(got).double()
+    ref_rows = -(lab * torch.log_softmax(lg, dim=-1)).sum(-1)
+    np.testing.assert_allclose(rows.cpu().numpy(), ref_rows.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(float(total.cpu()), float(ref_rows.sum()), rtol=1e-5)
+    np.testing.assert_array_equal(td.cpu().numpy(), rows.cpu().numpy()[ar, actions].astype(np.float64))
+    ref_g = torch.softmax(lg, dim=-1) - lab
+    gk = dlog.cpu().numpy()
+    np.testing.assert_allclose(gk[ar, actions], ref_g.numpy()[ar, actions], atol=2e-7)
+    mask = np.ones((B, A), dtype=bool)
+    mask[ar, actions] = False
+    assert (gk[mask] == 0).all()
+    np.testing.assert_allclose(q.cpu().numpy(), np.dot(torch.softmax(lg, -1).numpy(), g("z")), rtol=1e-6, atol=1e-6)

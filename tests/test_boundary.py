@@ -91,6 +91,8 @@ def test_parameter_defaults_match_the_reference():
     from rl_coach.agents.ddpg_agent import DDPGAgentParameters as RDDPG
     from rl_coach.agents.td3_agent import TD3AgentParameters as RTD3
     from rl_coach.agents.soft_actor_critic_agent import SoftActorCriticAgentParameters as RSAC
+    from rl_coach.agents.categorical_dqn_agent import CategoricalDQNAgentParameters as RC51
+    from coach_b200.agents.categorical_dqn_agent import CategoricalDQNAgentParameters
     from coach_b200.agents.dqn_agent import DQNAgentParameters, DDQNAgentParameters
     from coach_b200.agents.clipped_ppo_agent import ClippedPPOAgentParameters
     from coach_b200.agents.ddpg_agent import DDPGAgentParameters, TD3AgentParameters
@@ -110,7 +112,8 @@ def test_parameter_defaults_match_the_reference():
     own_only = {"hidden_units", "truncate_dataset_to_playing_steps", "middleware_parameters", "heads_parameters"}
     for mine, ref in ((DQNAgentParameters(), RDQN()), (DDQNAgentParameters(), RDDQN()),
                       (ClippedPPOAgentParameters(), RPPO()), (DDPGAgentParameters(), RDDPG()),
-                      (TD3AgentParameters(), RTD3()), (SoftActorCriticAgentParameters(), RSAC())):
+                      (TD3AgentParameters(), RTD3()), (SoftActorCriticAgentParameters(), RSAC()),
+                      (CategoricalDQNAgentParameters(), RC51())):
         for k, v in vars(mine.algorithm).items():
             if k in own_only or not hasattr(ref.algorithm, k):
                 continue
@@ -128,7 +131,7 @@ def test_presets_define_the_five_baseline_configurations():
     """coach_b200/presets/*: agent parameters whose path strings resolve to the device classes"""
     from coach_b200.utils import short_dynamic_import
     for name in ("CartPole_DQN", "Atari_DQN_with_PER", "Atari_Dueling_DDQN_with_PER_OpenAI", "Mujoco_ClippedPPO",
-                 "Mujoco_SAC", "Mujoco_TD3"):
+                 "Mujoco_SAC", "Mujoco_TD3", "Atari_C51"):
         mod = importlib.import_module("coach_b200.presets." + name)
         ap = mod.agent_params
         assert short_dynamic_import(ap.path).__module__.startswith("coach_b200.agents")

@@ -217,3 +217,22 @@ def test_batch_matches_reference_batch(golden_dir):
     assert b.size == int(fx["batch_slice_size"])
     np.testing.assert_array_equal(b.rewards(), fx["batch_slice_rewards"])
     np.testing.assert_array_equal(b.states(["observation"])["observation"], fx["batch_slice_states"])
+
+
+@pytest.mark.parametrize("tag", ["c51", "rainbow"])
+def test_distributional_targets_match_reference_agents(golden_dir, tag):
+    """oracle/c51.py c51_targets == what CategoricalDQNAgent / RainbowDQNAgent.learn_from_batch hand to the train op
+    (categorical_dqn_agent.py:120-152, rainbow_dqn_agent.py:107-131), bit for bit, and the PER errors (:160-163)"""
+    from oracle import c51
+    fx = np.load(os.path.join(golden_dir, "agent_prologues.npz"))
+    g = lambda k: fx[tag + "_" + k]                                                              # noqa: E731
+    sel = g("dist_select") if tag == "rainbow" else None
+    targets, _, m = c51.c51_targets(g("dist_next"), g("dist_online"), sel, g("actions"), g("rewards"), g("bootstrap"),
+                                    float(g("gamma_n")), g("z"))
+    np.testing.assert_array_equal(targets, g("targets"))
+    assert targets.dtype == np.float32
+    # integral b_j loses its mass in the reference's arithmetic: at least one row of m does not sum to 1
+    assert (np.abs(m.sum(axis=1) - 1.0) > 1e-3).any()
+    B = targets.shape[0]
+    np.testing.assert_array_equal(g("loss_rows")[np.arange(B), g("actions")].astype(np.float64), g("prio_errors"))
+    np.testing.assert_array_equal(c51.z_values(-10.0, 10.0, 51), g("z"))
