@@ -118,7 +118,38 @@ def synth_chunk(rng, n):
     return (rng.randint(0, 6, n).astype(np.int64), rng.randint(-1, 2, n).astype(np.float64))
 
 
-def build_device_agent(capacity, seed, device, config="dqn"):
+def fill_frame_stream(mem, size, device, gen, rng, episode=1000):
+    """Synthetic Atari-like frame stream for the frame-deduplicated replay: episodes of `episode` transitions, every
+    transition adds ONE new frame (the first of an episode two), states are the sliding 4-frame windows with the
+    episode's first frame replicated at its start (observation_stacking_filter.py:89-101).  Appended in chunks of 16
+    episodes: the distinct frames once + int32 [n, 4] indices into them (DeviceTransitionRing._append_frames)."""
+    import torch
+    done_total = 0
+    while done_total < size:
+        n_ep = min(16, (size - done_total + episode - 1) // episode)
+        lens = [min(episode, size - done_total - e * episode) for e in range(n_ep)]
+        lens = [l for l in lens if l > 0]
+        n = int(sum(lens))
+        nf = n + len(lens)
+        frames = torch.randint(0, 256, (nf, 84 * 84), dtype=torch.uint8, device=device, generator=gen)
+        si, s2i, done = np.zeros((n, 4), np.int32), np.zeros((n, 4), np.int32), np.zeros(n, np.uint8)
+        t = f0 = 0
+        for L in lens:
+            j = np.arange(L)
+            for c in range(4):
+                si[t:t + L, c] = f0 + np.maximum(j - 3 + c, 0)
+                s2i[t:t + L, c] = f0 + np.maximum(j - 2 + c, 0)
+            done[t + L - 1] = 1 if L == episode else 0
+            t += L
+            f0 += L + 1
+        a, r = synth_chunk(rng, n)
+        mem.store_columns({"frames": frames, "state:observation": torch.from_numpy(si),
+                           "next_state:observation": torch.from_numpy(s2i), "action": a, "reward": r,
+                           "game_over": done})
+        done_total += n
+
+
+def build_device_agent(capacity, seed, device, config="dqn", frame_dedup=False):
     import torch
     from coach_b200.agents.dqn_agent import DDQNAgent, DDQNAgentParameters, DQNAgent, DQNAgentParameters
     from coach_b200.base_parameters import MiddlewareScheme
@@ -130,6 +161,7 @@ def build_device_agent(capacity, seed, device, config="dqn"):
     ap = DDQNAgentParameters() if dueling else DQNAgentParameters()
     ap.memory = PrioritizedExperienceReplayParameters()
     ap.memory.max_size = (MemoryGranularity.Transitions, capacity)
+    ap.memory.frame_dedup = bool(frame_dedup)
     ap.memory.beta = LinearSchedule(0.4, 1, 12500000)
     ap.algorithm.num_steps_between_copying_online_weights_to_target = TrainingSteps(2500 if not dueling else 10000)
     ap.algorithm.num_consecutive_playing_steps.num_steps = ENV_STEPS_PER_TRAIN
@@ -150,7 +182,9 @@ def build_device_agent(capacity, seed, device, config="dqn"):
     gen = torch.Generator(device=device).manual_seed(seed)
     rng = np.random.RandomState(seed)
     chunk = 1 << 14
-    for lo in range(0, size, chunk):
+    if frame_dedup:
+        fill_frame_stream(mem, size, device, gen, rng)
+    for lo in range(0, size if not frame_dedup else 0, chunk):
         n = min(chunk, size - lo)
         s = torch.randint(0, 256, (n, ROW), dtype=torch.uint8, device=device, generator=gen)
         s2 = torch.randint(0, 256, (n, ROW), dtype=torch.uint8, device=device, generator=gen)
@@ -169,10 +203,22 @@ def build_device_agent(capacity, seed, device, config="dqn"):
     return agent
 
 
-def host_transitions(rng, n):
-    """n new host-side transitions (what Agent.observe would hand to memory.store)"""
+def host_transitions(rng, n, stacked_by_filter=False):
+    """n new host-side transitions (what Agent.observe would hand to memory.store).  stacked_by_filter: the states are
+    the LazyStacks an ObservationStackingFilter(4) hands out along one episode (one new 84x84 frame per transition,
+    the other three shared with its neighbours), as in the reference's Atari presets."""
     from coach_b200.core_types import Transition
     out = []
+    if stacked_by_filter:
+        from coach_b200.filters.filter import ObservationStackingFilter
+        flt = ObservationStackingFilter(4)
+        s = flt.filter(rng.randint(0, 256, OBS[:2]).astype(np.uint8))
+        for _ in range(n):
+            s2 = flt.filter(rng.randint(0, 256, OBS[:2]).astype(np.uint8))
+            out.append(Transition(state={"observation": s}, action=int(rng.randint(0, N_ACTIONS)),
+                                  reward=float(rng.randint(-1, 2)), next_state={"observation": s2}, game_over=False))
+            s = s2
+        return out
     for _ in range(n):
         out.append(Transition(state={"observation": rng.randint(0, 256, OBS).astype(np.uint8)},
                               action=int(rng.randint(0, N_ACTIONS)), reward=float(rng.randint(-1, 2)),
@@ -194,7 +240,7 @@ def run_device(args):
         os.environ["CB200_GEMM_TILED"] = "0"      # no pre-split planes / tiled tcgen05 GEMMs either
     random.seed(1000 + rank)
     np.random.seed(1000 + rank)
-    agent = build_device_agent(args.capacity, 100 + rank, device, args.config)
+    agent = build_device_agent(args.capacity, 100 + rank, device, args.config, frame_dedup=args.frame_dedup)
     mem = agent.memory
     if not args.no_l2_persist:
         lib.cb200_l2_persist(mem.sum_tree.data_ptr(), (1 << 17) * 8, _lib.current_stream())
@@ -291,10 +337,17 @@ def run_device(args):
 
     # ---- end-to-end leg through the public API with host buffers ---------------------------------------------------
     rng = np.random.RandomState(7 + rank)
-    pool = host_transitions(rng, 64)
     Ke = max(5, K // 2)
+    dedup = bool(mem.ring.stack_cols)
+    # frame-deduplicated replay: the states are LazyStacks of one continuing episode (a fresh frame per transition)
+    pool = host_transitions(rng, ENV_STEPS_PER_TRAIN * (Ke + 3) if dedup else 64, stacked_by_filter=dedup)
+    if dedup:
+        pool_iter = iter(pool)
+        pool_at = lambda i: [next(pool_iter) for _ in range(ENV_STEPS_PER_TRAIN)]                  # noqa: E731
+    else:
+        pool_at = lambda i: pool[(4 * i) % 60:(4 * i) % 60 + ENV_STEPS_PER_TRAIN]                  # noqa: E731
     for i in range(3):
-        for t in pool[(4 * i) % 60:(4 * i) % 60 + ENV_STEPS_PER_TRAIN]:
+        for t in pool_at(i):
             mem.store(t)
         one_step(True)
     barrier()
@@ -302,13 +355,15 @@ def run_device(args):
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(Ke):
-        for t in pool[(4 * i) % 60:(4 * i) % 60 + ENV_STEPS_PER_TRAIN]:
+        for t in pool_at(i):
             mem.store(t)                              # host transition -> pinned staging -> H2D -> ring + tree
         loss = one_step(True)                         # reads the loss back (D2H) every step
     e1.record()
     barrier()
     e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), device)
-    h2d = ENV_STEPS_PER_TRAIN * (2 * ROW + 8 + 8 + 1) + BATCH * 8 + 2 * BATCH * 8
+    # per stored transition: both stacked states (verbatim ring) or ONE new 84x84 frame + two int32[4] slot rows
+    per_t = (ROW // 4 + 2 * 16 + 8 + 8 + 1) if dedup else (2 * ROW + 8 + 8 + 1)
+    h2d = ENV_STEPS_PER_TRAIN * per_t + BATCH * 8 + 2 * BATCH * 8
     d2h = BATCH * 8 + 4 + 4
 
     if rank != 0:
@@ -340,6 +395,7 @@ def run_device(args):
                                   int(np.log2(mem.power_of_2_size))),
                    "parallelism": "dp%d (one replay shard per GPU, flat fp32 gradient all-reduce over NCCL)" % world,
                    "l2": "inputs (ring) >> L2, no flush needed", "priority_mode": mem.priority_mode,
+                   "frame_dedup": bool(mem.ring.stack_cols),
                    "cuda_graph": bool(agent.use_graph),
                    "l2_persist_tree_top": not args.no_l2_persist},
         "clocks": clocks,
@@ -535,6 +591,8 @@ def main():
     ap.add_argument("--capacity", type=int, default=1000000, help="replay capacity in transitions (rounded up to 2^k)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the cpu_baseline leg")
     ap.add_argument("--no-l2-persist", action="store_true")
+    ap.add_argument("--frame-dedup", type=int, default=0, choices=[0, 1],
+                    help="1: frame-deduplicated replay (every 84x84 frame stored once, stacks assembled by the gather)")
     ap.add_argument("--no-tc", action="store_true", help="fp32 FFMA GEMMs instead of the tcgen05 3xBF16 path")
     ap.add_argument("--config", default="dqn", choices=["dqn", "dueling", "cartpole", "ppo", "sac", "td3"],
                     help="dqn: BASELINE config 2 (Atari DQN + PER, the headline metric, default); dueling: config 5 "

@@ -193,9 +193,10 @@ class DQNAgent(object):
         # the ring's column layout = the agent's batch buffers, fixed before the first store: store(Transition) then
         # casts what the environment hands out (gym: float64) instead of the gather overrunning float32 buffers
         if hasattr(self.memory, "declare_schema") and self.memory.ring.specs is None:
+            img = ("state:observation", "next_state:observation") if len(self.observation_shape) == 3 else ()
             self.memory.declare_schema({k: self.batch_buffers[k] for k in
                                         ("state:observation", "next_state:observation", "action", "reward",
-                                         "game_over")})
+                                         "game_over")}, image_columns=img)
         dueling = "DuelingQHead" in getattr(net_params, "heads_parameters", ["QHead"])
         gen = torch.Generator().manual_seed(int(seed)) if seed is not None else None
         scheme = getattr(getattr(net_params, "middleware_parameters", None), "scheme", MiddlewareScheme.Medium)

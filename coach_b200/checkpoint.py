@@ -96,6 +96,11 @@ def save_memory(mem, prefix):
         meta["rows"] = rows
         for k, (name, _) in enumerate(r.specs.items()):
             _save_tensor("%s.ring%d.npy" % (prefix, k), r.columns[name], rows)
+        if r.frames is not None:          # frame-deduplicated ring: the frame store and its cursor
+            meta["frame_stack"] = {name: list(shape) for name, shape in r.stack_cols.items()}
+            meta["frame_slack"], meta["frame_counter"] = r.frame_slack, int(r._fc)
+            _save_tensor(prefix + ".frames.npy", r.frames, min(int(r._fc), r.frame_capacity))
+            np.save(prefix + ".frame_min.npy", r._min_fc)
     if hasattr(mem, "sum_tree"):
         for tag in ("sum_tree", "min_tree", "max_tree"):
             _save_tensor("%s.%s.npy" % (prefix, tag), getattr(mem, tag))
@@ -124,12 +129,23 @@ def restore_memory(mem, prefix):
     if meta["specs"] is not None:
         specs = OrderedDict((name, ColumnSpec(name, tuple(shape), np.dtype(dt))) for name, shape, dt in meta["specs"])
         if r.specs is None:
+            if meta.get("frame_stack"):
+                r.frame_slack = float(meta["frame_slack"])
+                for name, shape in meta["frame_stack"].items():
+                    r.stack_cols[name] = tuple(shape)
             r.set_schema(specs)
         elif [(n, s.shape, s.dtype) for n, s in r.specs.items()] != [(n, s.shape, s.dtype) for n, s in specs.items()]:
             raise ValueError("checkpoint column layout differs from this replay's")
         for k, name in enumerate(r.specs):
             _load_into("%s.ring%d.npy" % (prefix, k), r.columns[name], meta["rows"])
     r.cursor, r.count = int(meta["cursor"]), int(meta["count"])
+    if meta.get("frame_stack"):
+        if {k: tuple(v) for k, v in meta["frame_stack"].items()} != dict(r.stack_cols):
+            raise ValueError("checkpoint holds a frame-deduplicated replay, this memory is laid out differently")
+        r._fc, r._pending_frames = int(meta["frame_counter"]), 0
+        r._recent.clear()                 # frame identities do not survive a restart: the next frames are stored anew
+        _load_into(prefix + ".frames.npy", r.frames, min(r._fc, r.frame_capacity))
+        r._min_fc[:] = np.load(prefix + ".frame_min.npy")
     if hasattr(mem, "sum_tree"):
         for tag in ("sum_tree", "min_tree", "max_tree"):
             _load_into("%s.%s.npy" % (prefix, tag), getattr(mem, tag))

@@ -693,6 +693,10 @@ struct S2dGatherParams {
     const int64_t* idx_in;     // non-null: indices are given (uniform replay); null: sample the sum tree
     SmallColumn small[CB200_MAX_COLUMNS];
     int n_small;
+    // frame-deduplicated ring (non-null `frames`): every H x W frame is stored ONCE in `frames` [frame slots, H * W];
+    // src[k] is then the int32 [capacity, C] table of the frame slots that make up the stack of column k
+    const uint8_t* frames;
+    int frame_sub;             // bytes between the frames of one sample inside a stage (rows_per_chunk * S * W)
 };
 
 __global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SampleParams sp, S2dGatherParams gp) {
@@ -736,9 +740,21 @@ __global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SamplePa
         const uint32_t bytes = (uint32_t)(rc * s2d_row_bytes);
         if (lane == 0) mbar_expect_tx(full_bar + st, 8u * bytes);
         __syncwarp();
-        if (lane < 8)
+        if (gp.frames) {
+            // one bulk copy per (sample, frame of its stack): rc * S image rows of W bytes, contiguous in the frame
+            const int32_t* fidx = reinterpret_cast<const int32_t*>(gp.src[col]);
+            const uint32_t fbytes = (uint32_t)(rc * S * gp.W);
+            for (int l = lane; l < 8 * C; l += 32) {
+                const int smp = l / C, c = l - smp * C;
+                const int64_t fslot = __ldg(fidx + leaf_smem[smp] * C + c);
+                bulk_g2s(stage_mem + (size_t)st * 8 * gp.chunk_stride + (size_t)smp * gp.chunk_stride +
+                             (size_t)c * gp.frame_sub,
+                         gp.frames + fslot * ((int64_t)gp.H * gp.W) + (size_t)ya * S * gp.W, fbytes, full_bar + st);
+            }
+        } else if (lane < 8) {
             bulk_g2s(stage_mem + (size_t)st * 8 * gp.chunk_stride + (size_t)lane * gp.chunk_stride,
                      gp.src[col] + leaf_smem[lane] * gp.row_bytes + (size_t)ya * s2d_row_bytes, bytes, full_bar + st);
+        }
     };
     if (warp == 0) {
         fence_proxy_async_smem();      // the stage memory served as descent scratch through the generic proxy
@@ -785,7 +801,21 @@ __global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SamplePa
             for (int pi = slot; pi < npx; pi += slots) {
                 const uint8_t* sp8 = src0 + (size_t)yl * S * src_row + X * run;
                 uint16_t* o = out0 + (size_t)(yl * Ws + X) * core_stride;
-                if (run == 16) {
+                if (gp.frames) {
+                    // planar frames (S == C == 4): 4 pixels of image row yl * S + dy from each of the 4 frames, byte-
+                    // transposed into the stack's channel-last order (dx, c)
+                    const uint8_t* f = sbase + (size_t)((yl * S + dy) * gp.W + X * S);
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(f);
+                    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(f + gp.frame_sub);
+                    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(f + 2 * gp.frame_sub);
+                    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(f + 3 * gp.frame_sub);
+                    const uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+                    const uint32_t t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+                    *reinterpret_cast<uint4*>(o) =
+                        u8x8_to_bf16_s2d(__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632));
+                    *reinterpret_cast<uint4*>(o + 64) =
+                        u8x8_to_bf16_s2d(__byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632));
+                } else if (run == 16) {
                     const uint4 w = *reinterpret_cast<const uint4*>(sp8);
                     *reinterpret_cast<uint4*>(o) = u8x8_to_bf16_s2d(w.x, w.y);
                     *reinterpret_cast<uint4*>(o + 64) = u8x8_to_bf16_s2d(w.z, w.w);
@@ -808,6 +838,21 @@ __global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SamplePa
             fence_proxy_async_smem();
             issue(k + kS2dStages);
         }
+    }
+}
+
+// Frame-deduplicated ring, un-fused readers: out[i, pix, c] = frames[fidx[idx[i], c], pix] -- the stacked observation
+// the reference materialises with np.stack(frames, axis=-1) (observation_stacking_filter.py:37-41).
+__global__ void __launch_bounds__(256) gather_stack_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes,
+                                                           const int32_t* __restrict__ fidx, int K,
+                                                           const int64_t* __restrict__ idx, int64_t n,
+                                                           uint8_t* __restrict__ out) {
+    const int64_t total = n * frame_bytes;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / frame_bytes, pix = t - i * frame_bytes;
+        const int32_t* fi = fidx + idx[i] * K;
+        uint8_t* o = out + t * K;
+        for (int c = 0; c < K; ++c) o[c] = frames[(int64_t)__ldg(fi + c) * frame_bytes + pix];
     }
 }
 
@@ -1143,7 +1188,7 @@ int cb200_per_sample_gather(const double* sum_tree, const double* min_tree, int6
 
 static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int64_t n, const cb200_column* img,
                              int n_img, int h, int w, int c, int s, const cb200_column* small_cols, int n_small,
-                             cudaStream_t st) {
+                             const void* frames, cudaStream_t st) {
     S2dGatherParams gp;
     memset(&gp, 0, sizeof(gp));
     gp.n_img = n_img;
@@ -1169,6 +1214,8 @@ static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int6
     if (rc < 1) rc = 1;
     if (rc > hs) rc = hs;
     gp.rows_per_chunk = rc;
+    gp.frames = static_cast<const uint8_t*>(frames);
+    gp.frame_sub = rc * s * w;
     int stride = rc * s2d_row_bytes;
     if ((stride / 16) % 2 == 0) stride += 16;
     gp.chunk_stride = stride;
@@ -1194,13 +1241,18 @@ static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int6
 }
 
 static int check_s2d_args(const cb200_column* img, int n_img, int64_t n, int h, int w, int c, int s,
-                          const cb200_column* small_cols, int n_small) {
+                          const cb200_column* small_cols, int n_small, const void* frames) {
     if (!img || n_img < 1 || n_img > 2 || n <= 0 || n % 8 != 0) return -1;
     if (s <= 0 || h % s || w % s || (s * c) % 8 != 0 || ((int64_t)s * w * c) % 16 != 0 || ((int64_t)h * w * c) % 16 != 0)
         return -1;
     if (n_small < 0 || n_small > CB200_MAX_COLUMNS || (n_small > 0 && !small_cols)) return -1;
+    // frame-deduplicated ring: 4 x 4 space-to-depth blocks of 4-frame stacks; frames and their row bands 16-byte aligned
+    if (frames && (s != 4 || c != 4 || ((int64_t)h * w) % 16 != 0 || ((int64_t)s * w) % 16 != 0 ||
+                   (reinterpret_cast<uintptr_t>(frames) & 15)))
+        return -1;
     for (int k = 0; k < n_img; ++k)
-        if (!img[k].src || !img[k].dst || img[k].row_bytes != (int64_t)h * w * c ||
+        if (!img[k].src || !img[k].dst ||
+            img[k].row_bytes != (frames ? (int64_t)c * (int64_t)sizeof(int32_t) : (int64_t)h * w * c) ||
             ((reinterpret_cast<uintptr_t>(img[k].src) | reinterpret_cast<uintptr_t>(img[k].dst)) & 15))
             return -1;
     for (int k = 0; k < n_small; ++k)
@@ -1211,30 +1263,45 @@ static int check_s2d_args(const cb200_column* img, int n_img, int64_t n, int h, 
 int cb200_per_sample_gather_s2d(const double* sum_tree, const double* min_tree, int64_t size, const double* u, int64_t n,
                                 int64_t nt, double beta, int64_t* idx_out, double* w_out, float* w32_out,
                                 const cb200_column* image_columns, int n_image, int32_t h, int32_t w, int32_t c,
-                                int32_t s, const cb200_column* small_columns, int n_small, void* stream) {
+                                int32_t s, const cb200_column* small_columns, int n_small, const void* frames,
+                                void* stream) {
     SampleParams sp;
     CB200_CHECK_ARG(fill_sample_params(sp, sum_tree, min_tree, size, u, n, nt, beta, idx_out, w_out, w32_out) == 0,
                     "bad arguments (size must be a power of 2, n > 0, non-null trees / uniforms)");
     CB200_CHECK_ARG(idx_out != nullptr, "idx_out is required");
-    CB200_CHECK_ARG(check_s2d_args(image_columns, n_image, n, h, w, c, s, small_columns, n_small) == 0,
+    CB200_CHECK_ARG(check_s2d_args(image_columns, n_image, n, h, w, c, s, small_columns, n_small, frames) == 0,
                     "bad image geometry / column table (n % 8 == 0, 1-2 uint8 image columns, 16-byte aligned rows)");
     const int rc = launch_gather_s2d(sp, nullptr, n, image_columns, n_image, h, w, c, s, small_columns, n_small,
-                                     as_stream(stream));
+                                     frames, as_stream(stream));
     CB200_CHECK_ARG(rc == 0, "could not configure the fused sample + gather + space-to-depth kernel");
     CB200_CHECK_LAUNCH();
     return CB200_OK;
 }
 
 int cb200_gather_s2d(const int64_t* idx, int64_t n, const cb200_column* image_columns, int n_image, int32_t h, int32_t w,
-                     int32_t c, int32_t s, const cb200_column* small_columns, int n_small, void* stream) {
+                     int32_t c, int32_t s, const cb200_column* small_columns, int n_small, const void* frames,
+                     void* stream) {
     CB200_CHECK_ARG(idx != nullptr, "idx is required");
-    CB200_CHECK_ARG(check_s2d_args(image_columns, n_image, n, h, w, c, s, small_columns, n_small) == 0,
+    CB200_CHECK_ARG(check_s2d_args(image_columns, n_image, n, h, w, c, s, small_columns, n_small, frames) == 0,
                     "bad image geometry / column table (n % 8 == 0, 1-2 uint8 image columns, 16-byte aligned rows)");
     SampleParams sp;
     memset(&sp, 0, sizeof(sp));
-    const int rc = launch_gather_s2d(sp, idx, n, image_columns, n_image, h, w, c, s, small_columns, n_small,
+    const int rc = launch_gather_s2d(sp, idx, n, image_columns, n_image, h, w, c, s, small_columns, n_small, frames,
                                      as_stream(stream));
     CB200_CHECK_ARG(rc == 0, "could not configure the fused gather + space-to-depth kernel");
+    CB200_CHECK_LAUNCH();
+    return CB200_OK;
+}
+
+int cb200_gather_stack(const void* frames, int64_t frame_bytes, const int32_t* frame_index, int32_t stack, const int64_t* idx,
+                       int64_t n, void* out, void* stream) {
+    CB200_CHECK_ARG(frames && frame_index && idx && out && frame_bytes > 0 && stack > 0 && n > 0, "bad arguments");
+    const int64_t total = n * frame_bytes;
+    unsigned grid = (unsigned)((total + 255) / 256);
+    const unsigned cap = (unsigned)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    CB200_LAUNCH(gather_stack_kernel, grid, 256, 0, as_stream(stream), static_cast<const uint8_t*>(frames), frame_bytes,
+                 frame_index, (int)stack, idx, n, static_cast<uint8_t*>(out));
     CB200_CHECK_LAUNCH();
     return CB200_OK;
 }

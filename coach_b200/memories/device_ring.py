@@ -8,6 +8,14 @@ and converts AoS -> SoA on every sample (core_types.py:488-623).  Here every tra
 Layout for the Atari configuration (2^20 slots): state 28,224 B + next_state 28,224 B + action 8 B + reward 8 B +
 game_over 1 B per slot = 59.2 GB, sized for the 180 GB of a B200.
 
+Frame-deduplicated mode (``declare_schema(..., frame_stack=[...])``): a stacked image observation
+[H, W, K] is K frames of which K-1 also belong to the neighbouring transitions -- the reference shares them by
+reference through ``LazyStack`` (filters/observation/observation_stacking_filter.py:27-41).  Here every distinct frame
+is stored ONCE in a frame store ``[frame_capacity, H * W]`` and the stacked columns hold int32 ``[capacity, K]`` frame
+slots; the gather kernels assemble the last-axis stack (cb200_per_sample_gather_s2d / cb200_gather_stack).  Atari:
+59.2 GB -> 9.3 GB for 2^20 transitions (frame_capacity = 1.25 x capacity), 5 frames read per sampled transition
+instead of 8, one 7 KB frame per ``store`` over PCIe instead of 56 KB.
+
 Columns
   ``state:<key>`` / ``next_state:<key>``  one per entry of the transition's state dict, dtype/shape as stored
   ``action``     int64 scalar (discrete) or float vector (continuous), as given
@@ -78,6 +86,15 @@ class DeviceTransitionRing(object):
         self._flush_event = None     # H2D of the pinned stage still in flight?
         self.cursor = 0              # next slot to write
         self.count = 0               # valid slots (<= capacity)
+        # frame-deduplicated mode
+        self.stack_cols = OrderedDict()      # column name -> (H, W, K)
+        self.frame_slack = 0.25
+        self.frames = None                   # uint8 [frame_capacity, H * W]
+        self.frame_capacity = 0
+        self._fc = 0                         # frames allocated so far (frame f lives in slot f % frame_capacity)
+        self._pending_frames = 0
+        self._recent = OrderedDict()         # id(frame array) -> (frame array, frame counter): identity cache
+        self._min_fc = None                  # per transition slot: oldest frame counter it references
 
     # -- schema ----------------------------------------------------------------------------------------------------
     def set_schema(self, specs):
@@ -90,25 +107,45 @@ class DeviceTransitionRing(object):
         # staging area: ONE pinned record per staged transition (columns at 16-byte aligned offsets inside it), so a
         # flush is one H2D copy of the used prefix plus one scatter launch for all columns
         self._rec_off, off = {}, 0
+        self._phys = {name: (4 * self.stack_cols[name][2] if name in self.stack_cols else sp.row_bytes)
+                      for name, sp in specs.items()}      # bytes per ring row (stacked columns: K int32 frame slots)
         for name, sp in specs.items():
             self._rec_off[name] = off
-            off = (off + sp.row_bytes + 15) // 16 * 16
+            off = (off + self._phys[name] + 15) // 16 * 16
         self._rec_bytes = off
         self._stage_host_all = torch.zeros((self.stage_rows, self._rec_bytes), dtype=torch.uint8, pin_memory=pin)
         self._stage_dev_all = torch.empty((self.stage_rows, self._rec_bytes), dtype=torch.uint8, device=self.device)
         host_np = self._stage_host_all.numpy()
         for name, sp in specs.items():
-            self.columns[name] = torch.empty((self.capacity, sp.row_bytes), dtype=torch.uint8, device=self.device)
+            self.columns[name] = torch.empty((self.capacity, self._phys[name]), dtype=torch.uint8, device=self.device)
             o = self._rec_off[name]
-            self._stage_np[name] = host_np[:, o:o + sp.row_bytes]      # same memory, no per-store tensor objects
+            self._stage_np[name] = host_np[:, o:o + self._phys[name]]  # same memory, no per-store tensor objects
         self._flush_table = None
+        if self.stack_cols:
+            geo = set(self.stack_cols.values())
+            if len(geo) != 1:
+                raise ValueError("frame-deduplicated columns must share one [H, W, K] geometry: %s" % self.stack_cols)
+            H, W, K = next(iter(geo))
+            self.frame_bytes, self.stack_depth = H * W, K
+            self.frame_capacity = int(self.capacity * (1.0 + self.frame_slack)) + 2 * K + 8
+            self.frames = torch.empty((self.frame_capacity, self.frame_bytes), dtype=torch.uint8, device=self.device)
+            self._frame_stage_rows = self.stage_rows + 2 * K * len(self.stack_cols)
+            self._frame_stage_host = torch.zeros((self._frame_stage_rows, self.frame_bytes), dtype=torch.uint8,
+                                                 pin_memory=pin)
+            self._frame_stage_dev = torch.empty((self._frame_stage_rows, self.frame_bytes), dtype=torch.uint8,
+                                                device=self.device)
+            self._frame_stage_np = self._frame_stage_host.numpy()
+            self._min_fc = np.zeros(self.capacity, dtype=np.int64)
 
-    def declare_schema(self, columns):
+    def declare_schema(self, columns, frame_stack=None, frame_slack=None):
         """Fix the column layout before the first store: {name: (shape, numpy dtype)} or {name: batch tensor [n, ...]}.
         ``store(Transition)`` then converts every field to the declared dtype (gym hands out float64 observations and
-        actions where the networks -- and the agents' persistent batch buffers -- are float32)."""
+        actions where the networks -- and the agents' persistent batch buffers -- are float32).
+        ``frame_stack``: names of uint8 [H, W, K] columns (stacked frames, last-axis) to keep frame-deduplicated."""
         if self.specs is not None:
             raise RuntimeError("the replay already holds transitions; the schema is fixed")
+        if frame_slack is not None:
+            self.frame_slack = float(frame_slack)
         specs = OrderedDict()
         for name, v in columns.items():
             if torch.is_tensor(v):
@@ -119,10 +156,70 @@ class DeviceTransitionRing(object):
         for need in ("action", "reward", "game_over"):
             if need not in specs:
                 raise ValueError("schema lacks the %r column" % need)
+        for name in (frame_stack or ()):
+            sp = specs[name]
+            if sp.dtype != np.uint8 or len(sp.shape) != 3:
+                raise ValueError("frame-deduplicated column %r must be uint8 [H, W, K], got %s%s" % (name, sp.dtype, sp.shape))
+            self.stack_cols[name] = sp.shape
         self.set_schema(specs)
 
     def hbm_bytes(self):
-        return 0 if self.columns is None else sum(c.numel() for c in self.columns.values())
+        n = 0 if self.columns is None else sum(c.numel() for c in self.columns.values())
+        return n + (self.frames.numel() if self.frames is not None else 0)
+
+    def frames_ptr(self):
+        """device pointer of the frame store (None: the ring stores stacked observations verbatim)"""
+        return self.frames.data_ptr() if self.frames is not None else None
+
+    # -- frame store ---------------------------------------------------------------------------------------------------
+    def _frame_slots(self, v, K, slot_row):
+        """Resolves the K frames of one stacked observation to frame-store slots, staging the ones not seen before.
+        ``v``: a LazyStack (reference or coach_b200: ``history`` list + ``axis``) whose frame OBJECTS are shared between
+        neighbouring observations -- matched by identity -- or a plain [H, W, K] array, whose frames are matched by
+        content against the most recent frames.  Returns the oldest frame counter referenced."""
+        hist = getattr(v, "history", None)
+        if hist is not None and hasattr(v, "axis"):
+            if len(hist) != K or v.axis not in (-1, 2):
+                raise ValueError("stacked observation must hold %d frames on the last axis" % K)
+            frames, by_identity = hist, True
+        else:
+            a = np.asarray(v)
+            if a.shape[-1] != K:
+                raise ValueError("stacked observation has shape %s, expected %d frames on the last axis" % (a.shape, K))
+            frames, by_identity = [a[..., c] for c in range(K)], False
+        oldest = None
+        for c, f in enumerate(frames):
+            hit = self._recent.get(id(f))
+            if hit is not None and hit[0] is not f:
+                hit = None
+            if hit is None and not by_identity:
+                for r in reversed(self._recent.values()):
+                    if r[0].shape == f.shape and np.array_equal(r[0], f):
+                        hit = r
+                        break
+            if hit is None:
+                fc = self._fc
+                if self.count + self._pending > 0:
+                    live = min(self.count + self._pending, self.capacity - 1)
+                    oldest_slot = (self.cursor + self._pending - live) % self.capacity
+                    if live > 0 and fc - self.frame_capacity >= self._min_fc[oldest_slot]:
+                        raise RuntimeError(
+                            "frame store exhausted: %d frame slots for %d transitions (episodes shorter than %.0f "
+                            "steps on average?); raise frame_slack" % (self.frame_capacity, self.capacity,
+                                                                       1.0 / max(self.frame_slack, 1e-9)))
+                fa = np.asarray(f, dtype=np.uint8)
+                if fa.size != self.frame_bytes:
+                    raise ValueError("frame of %d bytes, the replay stores %d-byte frames" % (fa.size, self.frame_bytes))
+                self._frame_stage_np[self._pending_frames] = fa.reshape(-1)
+                self._pending_frames += 1
+                self._fc += 1
+                hit = (f if by_identity else np.array(fa), fc)
+                self._recent[id(hit[0]) if not by_identity else id(f)] = hit
+                while len(self._recent) > 4 * K + 8:
+                    self._recent.popitem(last=False)
+            slot_row[c] = hit[1] % self.frame_capacity
+            oldest = hit[1] if oldest is None else min(oldest, hit[1])
+        return oldest
 
     # -- append ----------------------------------------------------------------------------------------------------
     def stage_transition(self, t):
@@ -133,7 +230,13 @@ class DeviceTransitionRing(object):
         if r == 0 and self._flush_event is not None:
             self._flush_event.synchronize()      # the previous flush's H2D must have drained the pinned rows
             self._flush_event = None
+        oldest = None
         for name, sp in self.specs.items():
+            if name in self.stack_cols:
+                v = t.state[name[6:]] if name.startswith("state:") else t.next_state[name[11:]]
+                o = self._frame_slots(v, sp.shape[2], self._stage_np[name][r].view(np.int32))
+                oldest = o if oldest is None else min(oldest, o)
+                continue
             if name.startswith("state:"):
                 v = t.state[name[6:]]
             elif name.startswith("next_state:"):
@@ -149,7 +252,11 @@ class DeviceTransitionRing(object):
                 raise ValueError("transition field %s has shape %s, the replay was created with %s"
                                  % (name, a.shape, sp.shape))
             self._stage_np[name][r] = a.reshape(-1).view(np.uint8)
+        if oldest is not None:
+            self._min_fc[(self.cursor + r) % self.capacity] = oldest
         self._pending += 1
+        if self.stack_cols and self._pending_frames + 2 * self.stack_depth * len(self.stack_cols) > self._frame_stage_rows:
+            return True
         return self._pending >= min(self.stage_rows, self.capacity)
 
     def flush(self):
@@ -158,10 +265,18 @@ class DeviceTransitionRing(object):
         if n == 0:
             return self.cursor, 0
         first = self.cursor
+        nf = self._pending_frames
+        if nf:
+            # new frames: one H2D copy + one scatter into the frame store at the frame cursor (it wraps like the ring)
+            self._frame_stage_dev[:nf].copy_(self._frame_stage_host[:nf], non_blocking=True)
+            arr, cnt = _lib.make_columns([(self.frames.data_ptr(), self._frame_stage_dev.data_ptr(), self.frame_bytes)])
+            _lib.check(self.lib.cb200_scatter_ring(arr, cnt, (self._fc - nf) % self.frame_capacity, self.frame_capacity,
+                                                   nf, _lib.current_stream()))
+            self._pending_frames = 0
         self._stage_dev_all[:n].copy_(self._stage_host_all[:n], non_blocking=True)
         if self._flush_table is None:
             base = self._stage_dev_all.data_ptr()
-            pairs = [(self.columns[name].data_ptr(), base + self._rec_off[name], sp.row_bytes)
+            pairs = [(self.columns[name].data_ptr(), base + self._rec_off[name], self._phys[name])
                      for name, sp in self.specs.items()]
             self._flush_table = [_lib.make_columns(pairs[k:k + _lib.CB200_MAX_COLUMNS])
                                  for k in range(0, len(pairs), _lib.CB200_MAX_COLUMNS)]
@@ -194,13 +309,20 @@ class DeviceTransitionRing(object):
                 dt = np.dtype(str(tt.dtype).replace("torch.", "")) if tt.dtype != torch.bool else np.dtype(np.uint8)
                 specs[name] = ColumnSpec(name, tuple(tt.shape[1:]), dt)
             self.set_schema(specs)
-        if set(staged) != set(self.specs):
+        if set(staged) - {"frames"} != set(self.specs):
             raise ValueError("append_columns needs exactly the columns %s" % list(self.specs))
         if n > self.capacity:
             raise ValueError("cannot append more rows than the ring holds in one call")
         first = self.cursor
         pairs, keep = [], []
+        if self.stack_cols:
+            staged = self._append_frames(staged, n)
         for name, sp in self.specs.items():
+            if name in self.stack_cols:
+                tt = staged[name]                                  # int32 [n, K] frame slots (device)
+                keep.append(tt)
+                pairs.append((self.columns[name].data_ptr(), tt.data_ptr(), self._phys[name]))
+                continue
             tt = staged[name].to(self.device, non_blocking=True).contiguous()
             tt = tt.view(torch.uint8).reshape(n, -1) if tt.dtype != torch.bool else tt.to(torch.uint8).reshape(n, -1)
             if tt.shape[1] != sp.row_bytes:
@@ -209,6 +331,49 @@ class DeviceTransitionRing(object):
             pairs.append((self.columns[name].data_ptr(), tt.data_ptr(), sp.row_bytes))
         self._scatter(pairs, n)
         return first, n
+
+    def _append_frames(self, staged, n):
+        """Bulk append in frame-deduplicated mode.  Either the stacked columns come as full [n, H, W, K] arrays -- every
+        frame is then stored as a new one (no sharing can be inferred; tests and small fills) -- or the caller passes the
+        distinct frames once, ``"frames"``: uint8 [nf, H, W], and int32 [n, K] indices into them for every stacked
+        column (a recorded frame stream: bench.py's synthetic fill)."""
+        K, dev = self.stack_depth, self.device
+        staged = dict(staged)
+        if "frames" in staged:
+            frames = staged.pop("frames").to(dev).reshape(-1, self.frame_bytes).contiguous()
+            rel = {name: staged[name].to(dev).to(torch.int64).reshape(n, K) for name in self.stack_cols}
+        else:
+            parts, rel, base = [], {}, 0
+            for name in self.stack_cols:
+                x = staged[name].to(dev)
+                if tuple(x.shape[1:]) != self.stack_cols[name]:
+                    raise ValueError("column %s: shape %s, expected [n, %s]" % (name, tuple(x.shape), self.stack_cols[name]))
+                parts.append(x.permute(0, 3, 1, 2).reshape(n * K, self.frame_bytes))
+                rel[name] = base + torch.arange(n * K, device=dev, dtype=torch.int64).reshape(n, K)
+                base += n * K
+            frames = torch.cat(parts).contiguous()
+        nf = int(frames.shape[0])
+        if nf > self.frame_capacity:
+            raise ValueError("%d frames in one append, the frame store holds %d" % (nf, self.frame_capacity))
+        if self.count > 0:
+            live = min(self.count, self.capacity - 1)
+            if self._fc + nf - self.frame_capacity > self._min_fc[(self.cursor - live) % self.capacity] and \
+                    n < self.capacity:
+                raise RuntimeError("frame store exhausted by a bulk append: raise frame_slack")
+        arr, cnt = _lib.make_columns([(self.frames.data_ptr(), frames.data_ptr(), self.frame_bytes)])
+        _lib.check(self.lib.cb200_scatter_ring(arr, cnt, self._fc % self.frame_capacity, self.frame_capacity, nf,
+                                               _lib.current_stream()))
+        lo = None
+        for name in self.stack_cols:
+            cnt_abs = rel[name] + self._fc
+            staged[name] = (cnt_abs % self.frame_capacity).to(torch.int32).contiguous()
+            m = cnt_abs.min(dim=1).values
+            lo = m if lo is None else torch.minimum(lo, m)
+        slots = (self.cursor + np.arange(n)) % self.capacity
+        self._min_fc[slots] = lo.cpu().numpy()
+        self._fc += nf
+        self._keep_frames = frames                 # alive until the scatter has run
+        return staged
 
     def _scatter(self, pairs, n):
         for k in range(0, len(pairs), _lib.CB200_MAX_COLUMNS):
@@ -221,6 +386,9 @@ class DeviceTransitionRing(object):
         self.cursor = 0
         self.count = 0
         self._pending = 0
+        self._fc = 0
+        self._pending_frames = 0
+        self._recent.clear()
 
     # -- gather ----------------------------------------------------------------------------------------------------
     def alloc_batch(self, n):
@@ -246,8 +414,9 @@ class DeviceTransitionRing(object):
                         "batch buffer %r is %s%s but the replay stores %s%s per transition (%d rows): declare the "
                         "schema up front (memory.declare_schema) or store transitions in the agent's dtypes"
                         % (name, t.dtype, tuple(t.shape), sp.dtype, sp.shape, n))
+            # (frame-deduplicated columns are assembled from the frame store: assemble_stacks)
             pairs = [(self.columns[name].data_ptr(), out[name].data_ptr(), sp.row_bytes)
-                     for name, sp in self.specs.items()]
+                     for name, sp in self.specs.items() if name not in self.stack_cols]
             hit = self._table_cache[key] = _lib.make_columns(pairs)
             if len(self._table_cache) > 64:
                 self._table_cache.clear()
@@ -269,7 +438,9 @@ class DeviceTransitionRing(object):
                     if sp.dtype != np.uint8 or sp.row_bytes != H * W * C:
                         raise ValueError("column %r is %s%s, the fused image path needs uint8 [%d, %d, %d] frames"
                                          % (name, sp.dtype, sp.shape, H, W, C))
-                    img.append((self.columns[name].data_ptr(), _ptr_of(s2d["columns"][name]), sp.row_bytes))
+                    if bool(self.stack_cols) != (name in self.stack_cols):
+                        raise ValueError("either all image columns of the fused path are frame-deduplicated or none")
+                    img.append((self.columns[name].data_ptr(), _ptr_of(s2d["columns"][name]), self._phys[name]))
                 else:
                     t = out[name]
                     if t.dtype != sp.torch_dtype() or t.numel() * t.element_size() != n * sp.row_bytes or \
@@ -286,6 +457,9 @@ class DeviceTransitionRing(object):
         sp = self.specs[name]
         n = idx.shape[0]
         out = torch.empty((n,) + sp.shape, dtype=sp.torch_dtype(), device=self.device)
+        if name in self.stack_cols:
+            self.assemble_stacks({name: out}, idx, n, names=(name,))
+            return out
         arr, cnt = _lib.make_columns([(self.columns[name].data_ptr(), out.data_ptr(), sp.row_bytes)])
         _lib.check(self.lib.cb200_gather(arr, cnt, idx.data_ptr(), n, _lib.current_stream()))
         return out
@@ -297,4 +471,17 @@ class DeviceTransitionRing(object):
             out = self.alloc_batch(n)
         arr, cnt = self.column_table(out, n)
         _lib.check(self.lib.cb200_gather(arr, cnt, idx.data_ptr(), n, _lib.current_stream()))
+        self.assemble_stacks(out, idx, n)
         return out
+
+    def assemble_stacks(self, out, idx, n, names=None):
+        """frame-deduplicated columns of the slots ``idx``: out[name][i] = np.stack(frames of slot idx[i], axis=-1)
+        (observation_stacking_filter.py:37-41) through cb200_gather_stack; no-op for a verbatim ring"""
+        for name in (names if names is not None else self.stack_cols):
+            t = out[name]
+            H, W, K = self.stack_cols[name]
+            if t.dtype != torch.uint8 or t.numel() != n * H * W * K or not t.is_contiguous():
+                raise ValueError("batch buffer %r must be a contiguous uint8 [%d, %d, %d, %d] tensor" % (name, n, H, W, K))
+            _lib.check(self.lib.cb200_gather_stack(self.frames.data_ptr(), self.frame_bytes,
+                                                   self.columns[name].data_ptr(), K, idx.data_ptr(), n, t.data_ptr(),
+                                                   _lib.current_stream()))

@@ -25,6 +25,10 @@ class ExperienceReplayParameters(MemoryParameters):
         super().__init__()
         self.max_size = (MemoryGranularity.Transitions, 1000000)
         self.allow_duplicates_in_batch_sampling = True
+        # coach_b200 only: store every frame of stacked image observations once (device_ring); the
+        # frame store holds (1 + frame_slack) x max_size frames
+        self.frame_dedup = False
+        self.frame_slack = 0.25
 
     @property
     def path(self):
@@ -35,8 +39,9 @@ class ExperienceReplay(Memory):
     """A regular replay buffer which stores transitions without any additional structure (HBM resident)."""
 
     def __init__(self, max_size: Tuple[MemoryGranularity, int], allow_duplicates_in_batch_sampling: bool = True,
-                 device=None):
+                 device=None, frame_dedup: bool = False, frame_slack: float = 0.25):
         super().__init__(max_size)
+        self.frame_dedup, self.frame_slack = bool(frame_dedup), float(frame_slack)
         if max_size[0] != MemoryGranularity.Transitions:
             raise ValueError("Experience replay size can only be configured in terms of transitions")
         self.allow_duplicates_in_batch_sampling = allow_duplicates_in_batch_sampling
@@ -76,10 +81,14 @@ class ExperienceReplay(Memory):
         if self.ring.count + self.ring._pending > self.ring.capacity:
             self._flush()
 
-    def declare_schema(self, columns: dict) -> None:
+    def declare_schema(self, columns: dict, image_columns=()) -> None:
         """Column layout of the ring ({name: (shape, dtype)} or the agent's batch buffers), fixed before the first store
-        so that ``store(Transition)`` casts to it (device_ring.DeviceTransitionRing.declare_schema)."""
-        self.ring.declare_schema(columns)
+        so that ``store(Transition)`` casts to it (device_ring.DeviceTransitionRing.declare_schema).  ``image_columns``:
+        the stacked-frame columns, kept frame-deduplicated when the memory was created with ``frame_dedup``."""
+        if self.frame_dedup and image_columns:
+            self.ring.declare_schema(columns, frame_stack=tuple(image_columns), frame_slack=self.frame_slack)
+        else:
+            self.ring.declare_schema(columns)
 
     def store_columns(self, columns: dict) -> None:
         """Batched ingest: {column name: array/tensor [n, ...]} with the ring's column names (see device_ring)."""
@@ -117,7 +126,7 @@ class ExperienceReplay(Memory):
             ia, ni, sa, ns = self.ring.s2d_tables(s2d, out, size)
             H, W, C, S = s2d["geometry"]
             _lib.check(self.lib.cb200_gather_s2d(idx.data_ptr(), size, ia, ni, H, W, C, S, sa, ns,
-                                                 _lib.current_stream()))
+                                                 self.ring.frames_ptr(), _lib.current_stream()))
             cols = {k: v for k, v in out.items() if k not in s2d["columns"]}
             cols["idx"] = idx
             return DeviceBatch(cols, size, lazy=_LazyColumns(self.ring, idx, tuple(s2d["columns"])))

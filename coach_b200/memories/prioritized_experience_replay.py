@@ -55,7 +55,8 @@ class _LazyColumns(object):
 class PrioritizedExperienceReplay(ExperienceReplay):
     def __init__(self, max_size: Tuple[MemoryGranularity, int], alpha: float = 0.6,
                  beta: Schedule = ConstantSchedule(0.4), epsilon: float = 1e-6,
-                 allow_duplicates_in_batch_sampling: bool = True, device=None, priority_mode: str = "libm"):
+                 allow_duplicates_in_batch_sampling: bool = True, device=None, priority_mode: str = "libm",
+                 frame_dedup: bool = False, frame_slack: float = 0.25):
         if max_size[0] != MemoryGranularity.Transitions:
             raise ValueError("Prioritized Experience Replay currently only support setting the memory size in "
                              "transitions granularity.")
@@ -65,7 +66,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         while self.power_of_2_size < max_size[1]:
             self.power_of_2_size *= 2                                                   # :176-178
         super().__init__((MemoryGranularity.Transitions, self.power_of_2_size), allow_duplicates_in_batch_sampling,
-                         device=device)
+                         device=device, frame_dedup=frame_dedup, frame_slack=frame_slack)
         self.alpha = alpha
         self.beta = beta
         self.epsilon = epsilon
@@ -254,7 +255,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
                 self.sum_tree.data_ptr(), self.min_tree.data_ptr(), self.power_of_2_size, u.data_ptr(), size,
                 self.num_transitions(), float(self.beta.current_value), out["idx"].data_ptr(),
                 out["weight"].data_ptr(), out["weight32"].data_ptr(), ia, ni, H, W, C, S, sa, ns,
-                _lib.current_stream()))
+                self.ring.frames_ptr(), _lib.current_stream()))
             if ke:
                 ke[1].record()
             self.beta.step()
@@ -267,6 +268,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
             self.sum_tree.data_ptr(), self.min_tree.data_ptr(), self.power_of_2_size, u.data_ptr(), size,
             self.num_transitions(), float(self.beta.current_value), out["idx"].data_ptr(), out["weight"].data_ptr(),
             out["weight32"].data_ptr(), arr, cnt, _lib.current_stream()))
+        self.ring.assemble_stacks(out, out["idx"], size)       # frame-deduplicated ring: stacks built from the frame store
         if ke:
             ke[1].record()
         self.beta.step()                                                                 # :255

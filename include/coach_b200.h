@@ -140,15 +140,28 @@ int cb200_per_sample_gather(const double* sum_tree, const double* min_tree, int6
  *   image_columns[k]: src = ring column (uint8 [capacity, h*w*c]), dst = plane (bf16 [(h/s)*(w/s)*n, s*s*c],
  *                     core-tiled), row_bytes = h*w*c; 1 or 2 columns (state, next_state)
  *   small_columns   : the remaining columns, copied row by row into their staged [n, row_bytes] buffers
- * n must be a multiple of 8 (whole 8-row groups of the plane matrix).  idx_out / w_out / w32_out as cb200_per_sample. */
+ * n must be a multiple of 8 (whole 8-row groups of the plane matrix).  idx_out / w_out / w32_out as cb200_per_sample.
+ * Frame-deduplicated ring (`frames` != NULL, s == c == 4): the ring stores every h x w frame ONCE in `frames`
+ * (uint8 [frame slots, h*w]) -- the reference shares them between s, s' and neighbouring transitions through LazyStack
+ * (filters/observation/observation_stacking_filter.py:27-41, agents/agent.py:905-973); image_columns[k].src is then the
+ * int32 [capacity, c] table of the frame slots of each transition's stack (row_bytes = 4*c) and the kernel assembles
+ * the last-axis stack while converting. */
 int cb200_per_sample_gather_s2d(const double* sum_tree, const double* min_tree, int64_t size, const double* u, int64_t n,
                                 int64_t num_transitions, double beta, int64_t* idx_out, double* w_out, float* w32_out,
                                 const cb200_column* image_columns, int n_image, int32_t h, int32_t w, int32_t c,
-                                int32_t s, const cb200_column* small_columns, int n_small, void* stream);
+                                int32_t s, const cb200_column* small_columns, int n_small, const void* frames,
+                                void* stream);
 
 /* The same for given slot indices (uniform ExperienceReplay.sample, experience_replay.py:71-93). */
 int cb200_gather_s2d(const int64_t* idx, int64_t n, const cb200_column* image_columns, int n_image, int32_t h, int32_t w,
-                     int32_t c, int32_t s, const cb200_column* small_columns, int n_small, void* stream);
+                     int32_t c, int32_t s, const cb200_column* small_columns, int n_small, const void* frames,
+                     void* stream);
+
+/* Frame-deduplicated ring, un-fused readers (Batch.states() of the slots idx, core_types.py:488-511):
+ * out[i, pix, c] = frames[frame_index[idx[i], c], pix], i.e. np.stack(frames, axis=-1) of observation_stacking_filter.py:
+ * 37-41 as a uint8 [n, frame_bytes, stack] array. */
+int cb200_gather_stack(const void* frames, int64_t frame_bytes, const int32_t* frame_index, int32_t stack, const int64_t* idx,
+                       int64_t n, void* out, void* stream);
 
 /* Ring append: src[c][(cursor + i) % capacity, :] = staged[c][i, :] (experience_replay.py:131-150 store; the
  * `cb200_column.src` member is the ring (written), `.dst` the staged rows (read)). */

@@ -397,6 +397,7 @@ def main():
     golden_episodic(out, np.random.RandomState(77))
     golden_filters(out, np.random.RandomState(78))
     golden_c51(out, np.random.RandomState(79))
+    golden_frame_stream(out, np.random.RandomState(80))
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "agent_prologues.npz"), **out)
     print("agent_prologues", len(out), "arrays")
@@ -471,6 +472,41 @@ def golden_episodic(out, rng):
 
 
 # ---- InputFilter: observe-time chain (to-uint8 -> frame stacking, reward clipping / rescale) + Transition lists ---------
+
+def golden_frame_stream(out, rng, H=16, W=16, K=4):
+    """An episode stream through the reference's ObservationStackingFilter (observation_stacking_filter.py:27-115): raw
+    frames in, the stacked state / next_state every transition carries (LazyStack materialised with np.array, i.e.
+    np.stack(..., axis=-1)) out -- what a frame-deduplicated ring must reproduce byte for byte when it gathers."""
+    from rl_coach.filters.observation.observation_stacking_filter import ObservationStackingFilter
+    flt = ObservationStackingFilter(K)
+    lengths = [5, 1, 9, 2, 14, 3, 11]
+    frames, starts, states, next_states, actions, rewards, dones = [], [], [], [], [], [], []
+    for L in lengths:
+        flt.reset()
+        f0 = rng.randint(0, 256, (H, W)).astype(np.uint8)
+        frames.append(f0)
+        starts.append(len(frames) - 1)
+        s = flt.filter(f0)
+        for t in range(L):
+            f = rng.randint(0, 256, (H, W)).astype(np.uint8)
+            frames.append(f)
+            s2 = flt.filter(f)
+            states.append(np.array(s))
+            next_states.append(np.array(s2))
+            actions.append(int(rng.randint(0, 4)))
+            rewards.append(float(rng.randn()))
+            dones.append(t == L - 1)
+            s = s2
+    out["fs_frames"] = np.stack(frames)
+    out["fs_episode_lengths"] = np.array(lengths, dtype=np.int64)
+    out["fs_states"] = np.stack(states)
+    out["fs_next_states"] = np.stack(next_states)
+    out["fs_actions"] = np.array(actions, dtype=np.int64)
+    out["fs_rewards"] = np.array(rewards, dtype=np.float64)
+    out["fs_game_overs"] = np.array(dones, dtype=np.uint8)
+    assert out["fs_states"].shape == (sum(lengths), H, W, K) and out["fs_states"].dtype == np.uint8
+
+
 def golden_filters(out, rng):
     """rl_coach/filters/filter.py:295-350 driven like Agent.observe does (agents/agent.py:905-973): one EnvResponse per
     environment step through the input filter, reset at episode ends; then a list of Transitions (the pre-network-filter

@@ -10,8 +10,8 @@ Two execution modes for the tree arithmetic:
   * ``backend='python'`` -- per-sample Python loops, the way the reference itself runs (one interpreter thread).
     This is what ``bench.py`` times as the ``"port"`` CPU baseline.
   * ``backend='c'``      -- the same arithmetic in plain C (oracle/segment_tree.c), used by the tests so that
-    2^20-leaf cases finish in seconds.  Both are checked against the imported reference in
-    tests/test_oracle_pinned.py and against each other.
+    2^20-leaf cases finish in seconds.  Both are checked against fixtures written by the imported reference
+    (tests/golden/, oracle/make_golden.py) in tests/test_oracle_golden.py, and against each other.
 """
 import ctypes
 import os
