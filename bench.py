@@ -45,6 +45,10 @@ GATHER_BYTES = BATCH * (2 * ROW + 8 + 8 + 1) * 2 + BATCH * 21 * 8 + BATCH * 16
 # what the fused sample + gather + space-to-depth kernel moves: the uint8 frames are read once (28.9 MB), the bf16
 # operand planes of the first convolution are written (2 bytes per pixel value: 57.8 MB), plus tree / small columns
 GATHER_S2D_MOVED = BATCH * 2 * ROW * (1 + 2) + BATCH * (8 + 8 + 1) * 2 + BATCH * 21 * 8 + BATCH * 16
+# frame-deduplicated replay: s and s' of a transition share 3 of their 8 frames -- 5 distinct 7,056-byte frames are read
+# per sample (18.1 MB per batch; the 3 repeats hit L2), plus two int32[4] slot rows; the planes are written as before
+GATHER_DEDUP_MOVED = BATCH * (5 * (ROW // 4) + 2 * 16) + BATCH * 2 * ROW * 2 + BATCH * (8 + 8 + 1) * 2 + BATCH * 21 * 8 + \
+    BATCH * 16
 # multiply-accumulates of one learn step per sample: target fwd + online fwd (9.346 M each) + backward
 # (weight grads 9.346 M + data grads 6.069 M: conv2, conv3, fc1, out); the online forward is computed once
 MACS_PER_SAMPLE = 2 * 9346048 + 9346048 + (9346048 - 3276800)
@@ -371,6 +375,7 @@ def run_device(args):
     pk, pk_kind = peaks()
     steps_per_s = world * K / (ms_total * 1e-3)
     gather_gbs = GATHER_BYTES / gather_us / 1e3
+    moved = GATHER_BYTES if agent.s2d is None else (GATHER_DEDUP_MOVED if mem.ring.stack_cols else GATHER_S2D_MOVED)
     gemm_tflops = 2.0 * MACS_PER_SAMPLE * BATCH / (learn_us * 1e-6) / 1e12
     # dominant kernel family: every launch of gemm_tc_tiled_kernel in one step.  "achieved" counts the bf16
     # tensor-core FLOPs actually ISSUED (6 products per fp32 multiply-accumulate, 3 for the exact uint8 operand): that
@@ -428,10 +433,11 @@ def run_device(args):
                      "us_per_launch": round(gather_us, 2), "algorithmic_bytes": GATHER_BYTES,
                      "algorithmic_bytes_note": "the 57.9 MB contract figure of SURVEY 8d (columns read + staged copy "
                                                "written)" + ("; this kernel reads 28.9 MB of frames and writes 57.8 MB "
-                                               "of bf16 planes: bytes_moved" if agent.s2d is not None else ""),
-                     "bytes_moved": GATHER_S2D_MOVED if agent.s2d is not None else GATHER_BYTES,
-                     "frac_bytes_moved": round((GATHER_S2D_MOVED if agent.s2d is not None else GATHER_BYTES)
-                                               / gather_us / 1e3 / pk["hbm_gbs"], 4),
+                                               "of bf16 planes: bytes_moved" if agent.s2d is not None else "") +
+                                              ("; frame-deduplicated replay: 18.1 MB of distinct frames read"
+                                               if mem.ring.stack_cols else ""),
+                     "bytes_moved": moved,
+                     "frac_bytes_moved": round(moved / gather_us / 1e3 / pk["hbm_gbs"], 4),
                      "traffic": TRAFFIC_NCU.get("sample_gather_s2d" if agent.s2d is not None else "per_sample_gather"),
                      "traffic_note": "dram bytes from the committed ncu --set full capture under profiles/, not this run",
                      "frac_of_8TBps": round(gather_gbs / 8000.0, 4)},
@@ -591,8 +597,9 @@ def main():
     ap.add_argument("--capacity", type=int, default=1000000, help="replay capacity in transitions (rounded up to 2^k)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the cpu_baseline leg")
     ap.add_argument("--no-l2-persist", action="store_true")
-    ap.add_argument("--frame-dedup", type=int, default=0, choices=[0, 1],
-                    help="1: frame-deduplicated replay (every 84x84 frame stored once, stacks assembled by the gather)")
+    ap.add_argument("--frame-dedup", type=int, default=1, choices=[0, 1],
+                    help="1 (default): frame-deduplicated replay -- every 84x84 frame stored once (9.3 GB instead of "
+                         "59.2 GB for 2^20 transitions), stacks assembled by the gather; 0: stacked states verbatim")
     ap.add_argument("--no-tc", action="store_true", help="fp32 FFMA GEMMs instead of the tcgen05 3xBF16 path")
     ap.add_argument("--config", default="dqn", choices=["dqn", "dueling", "cartpole", "ppo", "sac", "td3"],
                     help="dqn: BASELINE config 2 (Atari DQN + PER, the headline metric, default); dueling: config 5 "

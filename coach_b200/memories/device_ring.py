@@ -299,10 +299,12 @@ class DeviceTransitionRing(object):
         staged = {}
         for name, v in cols.items():
             tt = torch.as_tensor(v)
+            staged[name] = tt
+            if name == "frames":                    # frame-deduplicated bulk append: the distinct frames, any count
+                continue
             n = tt.shape[0] if n is None else n
             if tt.shape[0] != n:
                 raise ValueError("all columns must have the same number of rows")
-            staged[name] = tt
         if self.specs is None:
             specs = OrderedDict()
             for name, tt in staged.items():
