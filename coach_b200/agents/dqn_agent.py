@@ -20,7 +20,7 @@ import torch
 
 from coach_b200 import _lib
 from coach_b200.architectures import tiled as tl
-from coach_b200.architectures.layers import Workspace
+from coach_b200.architectures.layers import NO_SIDE, SideStream, Workspace
 from coach_b200.architectures.q_network import QNetworkDef
 from coach_b200.base_parameters import (AgentParameters, AlgorithmParameters, EnvironmentSteps, MiddlewareScheme,
                                         NetworkParameters, TrainingSteps)
@@ -77,13 +77,14 @@ class QNetworkWrapper(object):
         self.lib, self.net, self.params, self.B = lib, net_def, params, batch_size
         self.store = net_def.store
         self.ws = Workspace(device)
+        self.ws_target = Workspace(device)        # the target network's passes may run on a side stream
         self.theta = self.store.theta
         self.theta_target = self.store.new_buffer() if params.create_target_network else None
         s, s2 = batch_buffers["state:observation"], batch_buffers["next_state:observation"]
         if input_planes is not None:         # fused input path: the replay hands over the s2d operand planes directly
             s, s2 = input_planes["state:observation"], input_planes["next_state:observation"]
         self.online_s = net_def.instantiate(lib, self.ws, batch_size, s, self.theta, self.store.grad, train=True)
-        self.target_s2 = net_def.instantiate(lib, self.ws, batch_size, s2, self.theta_target) \
+        self.target_s2 = net_def.instantiate(lib, self.ws_target, batch_size, s2, self.theta_target) \
             if self.theta_target is not None else None
         self.online_s2 = net_def.instantiate(lib, self.ws, batch_size, s2, self.theta) if double_dqn else None
         # Adam state: fp32 running powers exactly like TF's non-slot beta1_power / beta2_power variables
@@ -246,6 +247,11 @@ class DQNAgent(object):
         # the TMA tensor maps, size the workspace and configure shared memory).
         self.use_graph = bool(_lib.tune_default("dqn_graph", 1)) and dev.type == "cuda" and B >= 128
         self.networks["main"].device_adam_state = self.use_graph
+        # two more CUDA streams per learn step: the target network's forward pass runs beside the online network's, the
+        # weight-gradient GEMMs beside the data-gradient chain (layers.SideStream; parallel branches of the CUDA graphs)
+        streams = bool(_lib.tune_default("dqn_streams", 1)) and dev.type == "cuda"
+        self._side_fwd = SideStream(dev) if streams else NO_SIDE
+        self._side_w = SideStream(dev) if streams else NO_SIDE
         self._graphs = None
         self._acting = {}                         # number of environments -> (input buffer, forward-only online network)
         self._graph_c = (None, 0)
@@ -369,10 +375,12 @@ class DQNAgent(object):
             # dL/dQ and the head's backward pass (cb200_dqn_head_fused)
             import ctypes
             d = self.head_desc
-            net.target_s2.forward_features()
+            with self._side_fwd:
+                net.target_s2.forward_features()
             net.online_s.forward_features()
             if self.double_dqn:
                 net.online_s2.forward_features()
+            self._side_fwd.join()
             d.actions, d.rewards, d.game_overs = cols["action"].data_ptr(), cols["reward"].data_ptr(), \
                 cols["game_over"].data_ptr()
             d.weights = self._head_weights.data_ptr() if self._head_weights is not None else None
@@ -381,9 +389,11 @@ class DQNAgent(object):
             if per_libm:
                 self._td_host.copy_(self.td_err, non_blocking=True)
             return
-        q_next = net.target_s2.forward()                          # dqn_agent.py:87-90
+        with self._side_fwd:
+            q_next = net.target_s2.forward()                      # dqn_agent.py:87-90
         q_online = net.online_s.forward()
         q_select = net.online_s2.forward() if self.double_dqn else q_next      # ddqn_agent.py:42-43
+        self._side_fwd.join()
         self._head_targets(cols, q_next, q_select, q_online, st)
         if per_libm:
             self._td_host.copy_(self.td_err, non_blocking=True)
@@ -412,7 +422,8 @@ class DQNAgent(object):
         net = self.networks["main"]
         if self.head_desc is not None and not self._head_split:
             # loss, dL/dQ and the head's gradients were produced by the fused head launch of the forward part
-            net.online_s.backward_features()
+            net.online_s.backward_features(side=self._side_w)
+            self._side_w.join()
             n = net.store.size
             _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(), st))
             clip = net.params.clip_gradients
@@ -432,7 +443,8 @@ class DQNAgent(object):
         if part == "bottom":
             net.online_s.backward_bottom()
         else:
-            net.online_s.backward()
+            net.online_s.backward(side=self._side_w)
+            self._side_w.join()
         n = net.store.size
         _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(), st))
         clip = net.params.clip_gradients

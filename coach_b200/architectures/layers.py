@@ -38,6 +38,14 @@ class Workspace(object):
     def __init__(self, device):
         self.device = device
         self.buf = torch.empty(1 << 20, dtype=torch.float32, device=device)
+        self._side = None
+
+    def side(self):
+        """a second scratch buffer for the ops that may run on a side stream concurrently with the others of the
+        network (the weight-gradient GEMMs and bias column sums, see SideStream)"""
+        if self._side is None:
+            self._side = Workspace(self.device)
+        return self._side
 
     def require(self, nfloats):
         if self.buf.numel() < nfloats:
@@ -45,6 +53,52 @@ class Workspace(object):
 
     def ptr(self):
         return self.buf.data_ptr()
+
+
+class SideStream(object):
+    """Fork / join of a second CUDA stream around a group of launches that only READ what the main stream has produced
+    so far and whose results are needed later: the launches inside ``with side:`` go to the side stream (ordered after
+    everything queued on the main stream at that point), ``side.join()`` makes the main stream wait for them.  Works
+    eagerly and under CUDA-graph capture (the captured graph gets parallel branches).  The tiled GEMMs of one network
+    leave SMs idle at their wave tails and during prologue / epilogue; two independent chains fill them."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self._ctx, self._dirty = None, False
+
+    def __enter__(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        self._ctx = torch.cuda.stream(self.stream)
+        self._ctx.__enter__()
+        self._dirty = True
+        return self
+
+    def __exit__(self, *exc):
+        self._ctx.__exit__(*exc)
+        self._ctx = None
+
+    def join(self):
+        if self._dirty:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self._dirty = False
+
+
+class _NoSide(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def join(self):
+        pass
+
+
+NO_SIDE = _NoSide()
 
 
 def _u8_div(lut, x_is_u8):
@@ -174,7 +228,7 @@ class Dense(object):
         self.bwd_w = None
         if dw is not None and dy is not None:
             ones = int(bool(vec) and _bias_rides_along(dw, db, K, N, skinny=not x_is_u8))
-            self.bwd_w = GemmOp(lib, ws, a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
+            self.bwd_w = GemmOp(lib, ws.side(), a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
                                 splits=pick_splits(_tiles(K + ones, N, vec), B), **common)
             if not ones:
                 self.db_args = (dy, B, N, db)
@@ -203,7 +257,7 @@ class Dense(object):
         if dw is not None and dy is not None:
             if pl.dy is not None:
                 fused = _bias_behind(dw, db, K, N)        # bias gradient as one more row of the same GEMM
-                self.bwd_w = tl.wgrad_op(lib, ws, B, device, xp, Ca, pl.dy, N, np.arange(npix), npix, 1, dw,
+                self.bwd_w = tl.wgrad_op(lib, ws.side(), B, device, xp, Ca, pl.dy, N, np.arange(npix), npix, 1, dw,
                                          bias_row=int(fused))
                 if not fused:
                     self.db_args = (dy, B, N, db)
@@ -211,7 +265,7 @@ class Dense(object):
             else:       # the gradient of this layer's output has no planes (written by a head kernel)
                 vec = int(K % 4 == 0)
                 ones = int(bool(vec) and _bias_rides_along(dw, db, K, N))
-                self.bwd_w = GemmOp(lib, ws, a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
+                self.bwd_w = GemmOp(lib, ws.side(), a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
                                     splits=pick_splits(_tiles(K + ones, N, vec), B),
                                     a_rowoff=_dev_i32(np.arange(B) * K, device), a_coloff=_dev_i32(np.arange(K), device),
                                     a_rows=B, a_cols=K, a_vec4=vec, a_src=x)
@@ -245,13 +299,15 @@ class Dense(object):
                                                   self.wT.data_ptr(), self.wT_planes.ptr, self.wT_planes.stride,
                                                   self.wT_planes.cols, _lib.current_stream()))
 
-    def backward(self, weights=True):
-        st = _lib.current_stream()
+    def backward(self, weights=True, side=NO_SIDE):
         if weights:
-            self.bwd_w.run()
-            if self.db_args is not None:
-                dy, B, N, db = self.db_args
-                _lib.check(self.lib.cb200_colsum(dy.data_ptr(), B, N, db.data_ptr(), self.ws.ptr(), st))
+            with side:        # weight / bias gradients only read dy and x: off the data-gradient chain
+                self.bwd_w.run()
+                if self.db_args is not None:
+                    dy, B, N, db = self.db_args
+                    _lib.check(self.lib.cb200_colsum(dy.data_ptr(), B, N, db.data_ptr(), self.ws.side().ptr(),
+                                                     _lib.current_stream()))
+        st = _lib.current_stream()
         if self.bwd_x is not None:
             if self.tiled_x:
                 if not getattr(self, "perms_managed", False):
@@ -331,7 +387,7 @@ class Conv2d(object):
         self.bwd_w = None
         if dw is not None and dy is not None:
             ones = int(bool(vec) and _bias_rides_along(dw, db, K, N))
-            self.bwd_w = GemmOp(lib, ws, a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
+            self.bwd_w = GemmOp(lib, ws.side(), a_transposed=1, b=dy, ldb=N, n=N, c=dw, ldc=N, a_ones_col=ones,
                                 splits=pick_splits(_tiles(K + ones, N, vec), M, min_chunk=512), **common, **gp)
             if not ones:
                 self.db_args = (dy, M, N, db)
@@ -402,7 +458,7 @@ class Conv2d(object):
         if dw is not None and dy is not None:
             assert pl.dy is not None, "s2d conv weight gradient needs the planes of dY"
             fused = _bias_behind(dw, db, T * Cs, N)
-            self.bwd_w = tl.wgrad_op(lib, ws, B, device, xp, Cs, pl.dy, N, pix_in, T, nq, dw, a_u8_div=div,
+            self.bwd_w = tl.wgrad_op(lib, ws.side(), B, device, xp, Cs, pl.dy, N, pix_in, T, nq, dw, a_u8_div=div,
                                      c_rowmap=_dev_i32(np.concatenate([orig_row, [T * Cs]]), device),
                                      bias_row=int(fused))
             if not fused:
@@ -427,7 +483,7 @@ class Conv2d(object):
         if dw is not None and dy is not None:
             assert pl.dy is not None, "tiled conv weight gradient needs the planes of dY"
             fused = _bias_behind(dw, db, T * C, N)
-            self.bwd_w = tl.wgrad_op(lib, ws, B, device, pl.x, C, pl.dy, N, pix_in, T, nq, dw, bias_row=int(fused))
+            self.bwd_w = tl.wgrad_op(lib, ws.side(), B, device, pl.x, C, pl.dy, N, pix_in, T, nq, dw, bias_row=int(fused))
             if not fused:
                 self.db_args = (dy, B * nq, N, db)
                 ws.require(1024 * N)
@@ -478,13 +534,15 @@ class Conv2d(object):
                                                   self.wT.data_ptr(), self.wT_planes.ptr, self.wT_planes.stride,
                                                   self.wT_planes.cols, st))
 
-    def backward(self, weights=True):
-        st = _lib.current_stream()
+    def backward(self, weights=True, side=NO_SIDE):
         if weights:
-            self.bwd_w.run()
-            if self.db_args is not None:
-                dy, M, N, db = self.db_args
-                _lib.check(self.lib.cb200_colsum(dy.data_ptr(), M, N, db.data_ptr(), self.ws.ptr(), st))
+            with side:        # weight / bias gradients only read dy and x: off the data-gradient chain
+                self.bwd_w.run()
+                if self.db_args is not None:
+                    dy, M, N, db = self.db_args
+                    _lib.check(self.lib.cb200_colsum(dy.data_ptr(), M, N, db.data_ptr(), self.ws.side().ptr(),
+                                                     _lib.current_stream()))
+        st = _lib.current_stream()
         for op, wt, perm in self.classes:
             _lib.check(self.lib.cb200_permute_f32(self.w.data_ptr(), perm.data_ptr(), perm.numel(), wt.data_ptr(),
                                                   None, 0, 0, st))

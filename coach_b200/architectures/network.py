@@ -210,12 +210,15 @@ class SequentialInstance(object):
             layer.forward()
         return self.out
 
-    def backward(self, weights=True, layers=None):
+    def backward(self, weights=True, layers=None, side=None):
         """weights=False: data gradients only (d(out)/d(input), e.g. dQ/da through the critic).  layers=(lo, hi): only
         layers lo <= i < hi, last first (lets a caller start the all-reduce of the top layers' gradients early)."""
         lo, hi = (0, len(self.layers)) if layers is None else layers
         for i in reversed(range(lo, hi)):
-            self.layers[i].backward(weights)
+            if side is not None:
+                self.layers[i].backward(weights, side=side)
+            else:
+                self.layers[i].backward(weights)
 
 
 def make_u8_lut(device, rescale=255.0, offset=0.0):

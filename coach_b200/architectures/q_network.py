@@ -181,9 +181,10 @@ class QNetworkInstance(object):
         self.trunk.forward(upto=len(self.trunk.layers) - 1)
         return self.trunk.acts[-2]
 
-    def backward_features(self):
-        """expects the gradient w.r.t. the feature layer's pre-activation in trunk.dzs[-2] (/ its planes)"""
-        self.trunk.backward(layers=(0, len(self.trunk.layers) - 1))
+    def backward_features(self, side=None):
+        """expects the gradient w.r.t. the feature layer's pre-activation in trunk.dzs[-2] (/ its planes).
+        side: a layers.SideStream for the weight-gradient launches (they leave the data-gradient chain)"""
+        self.trunk.backward(layers=(0, len(self.trunk.layers) - 1), side=side)
 
     def manage_planes(self):
         """the owner takes over refreshing the parameter planes: the layers' weight permutes (per-tap transposed
@@ -216,14 +217,14 @@ class QNetworkInstance(object):
         """element offset in the flat gradient buffer where the top (dense) layers' gradients start"""
         return self.net.store.entries[self.net.trunk.names[self.net.n_embedder][0]][0]
 
-    def backward(self):
+    def backward(self, side=None):
         """expects d(loss)/dq in self.dq; leaves all parameter gradients in the grad buffer"""
         if self.net.dueling:
             _lib.check(self.lib.cb200_dueling_combine_bwd(self.dq.data_ptr(), self.B, self.net.num_actions,
                                                           self.v.d_out.data_ptr(), self.a.d_out.data_ptr(),
                                                           _lib.current_stream()))
-            self.v.backward()      # writes d(middleware pre-activation)
-            self.a.backward()      # accumulates into it
+            self.v.backward(side=side)      # writes d(middleware pre-activation)
+            self.a.backward(side=side)      # accumulates into it
             if self.towers_dx is not None:
                 self._run_towers_dx()      # both towers' data gradients into the conv map, one GEMM
-        self.trunk.backward()
+        self.trunk.backward(side=side)

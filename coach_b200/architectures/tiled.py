@@ -171,12 +171,25 @@ class ThetaPlanes(object):
             self.refresh()
 
     def refresh(self):
-        for fn in self.derived:
-            fn()
+        if len(self.derived) > 1 and self.theta.is_cuda and _lib.tune_default("refresh_streams", 1):
+            # the derived kernels (weight permutes) and the plane split are independent readers of theta: two side
+            # streams next to the caller's (parallel branches when the caller is being captured into a CUDA graph)
+            from coach_b200.architectures.layers import SideStream
+            if getattr(self, "_sides", None) is None:
+                self._sides = (SideStream(self.theta.device), SideStream(self.theta.device))
+            for k, side in enumerate(self._sides):
+                with side:
+                    for fn in self.derived[k::2]:
+                        fn()
+        else:
+            for fn in self.derived:
+                fn()
         if self.segs is not None:
             _lib.check(self.lib.cb200_split_planes(self.theta.data_ptr(), self.planes.data_ptr(), self.stride,
                                                    self.segs.data_ptr(), self.segs.shape[0], self.max_elems,
                                                    _lib.current_stream()))
+        for side in (getattr(self, "_sides", None) or ()):
+            side.join()
 
 
 class PlaneCtx(object):
