@@ -252,6 +252,11 @@ class DQNAgent(object):
         streams = bool(_lib.tune_default("dqn_streams", 1)) and dev.type == "cuda"
         self._side_fwd = SideStream(dev) if streams else NO_SIDE
         self._side_w = SideStream(dev) if streams else NO_SIDE
+        # the tree update of a step only needs the TD errors of its forward part: it runs beside the backward pass and
+        # the optimizer; the next sample waits for it (sample_batch)
+        self._side_upd = SideStream(dev) if streams else NO_SIDE
+        if streams and isinstance(self.memory, PrioritizedExperienceReplay):
+            self.memory._update_side = self._side_upd          # every other tree access of the memory joins it first
         self._graphs = None
         self._acting = {}                         # number of environments -> (input buffer, forward-only online network)
         self._graph_c = (None, 0)
@@ -362,6 +367,7 @@ class DQNAgent(object):
     # ---- the hot path ------------------------------------------------------------------------------------------------
     def sample_batch(self):
         """memory sample straight into the persistent minibatch buffers"""
+        self._side_upd.join()                     # the previous step's priority update (side stream) comes first
         if self.s2d is not None:
             return self.memory.sample_batch(self.batch_size, out=self.batch_buffers, s2d=self.s2d)
         return self.memory.sample_batch(self.batch_size, out=self.batch_buffers)
@@ -425,8 +431,16 @@ class DQNAgent(object):
             net.online_s.backward_features(side=self._side_w)
             self._side_w.join()
             n = net.store.size
-            _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(), st))
             clip = net.params.clip_gradients
+            if with_optimizer and not (clip is not None and clip != 0) and self._side_w is not NO_SIDE:
+                # no clipping: the gradient norm is only reported -- it is reduced beside the optimizer step
+                with self._side_w:
+                    _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(),
+                                               _lib.current_stream()))
+                net.apply_gradients(1.0)
+                self._side_w.join()
+                return
+            _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(), st))
             if clip is not None and clip != 0:
                 if net.params.gradients_clipping_method != "ClipByGlobalNorm":
                     raise NotImplementedError("only ClipByGlobalNorm is implemented on device")
@@ -597,9 +611,11 @@ class DQNAgent(object):
                 pa, pr = self.memory.host_priorities(self._td_host.numpy())
                 self._pa_host.numpy()[:] = pa
                 self._pr_host.numpy()[:] = pr
-                self._pa_dev.copy_(self._pa_host, non_blocking=True)
-                self._pr_dev.copy_(self._pr_host, non_blocking=True)
-                self.memory.update_priorities_device(cols["idx"], self._pa_dev, self._pr_dev)
+                side = self._side_upd.after(ev) if self._side_upd is not NO_SIDE else NO_SIDE
+                with side:
+                    self._pa_dev.copy_(self._pa_host, non_blocking=True)
+                    self._pr_dev.copy_(self._pr_host, non_blocking=True)
+                    self.memory.update_priorities_device(cols["idx"], self._pa_dev, self._pr_dev)
             else:
                 self.memory.update_priorities(cols["idx"], self.td_err)
         if fetch:

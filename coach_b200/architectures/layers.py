@@ -66,9 +66,17 @@ class SideStream(object):
         self.stream = torch.cuda.Stream(device=device)
         self._ctx, self._dirty = None, False
 
+    def after(self, event):
+        """the next ``with`` block is ordered after ``event`` instead of after everything queued on the current stream"""
+        self._after = event
+        return self
+
     def __enter__(self):
-        ev = torch.cuda.Event()
-        ev.record()
+        ev = getattr(self, "_after", None)
+        self._after = None
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record()
         self.stream.wait_event(ev)
         self._ctx = torch.cuda.stream(self.stream)
         self._ctx.__enter__()

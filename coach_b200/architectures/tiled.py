@@ -171,9 +171,11 @@ class ThetaPlanes(object):
             self.refresh()
 
     def refresh(self):
-        if len(self.derived) > 1 and self.theta.is_cuda and _lib.tune_default("refresh_streams", 1):
+        if len(self.derived) > 1 and self.theta.is_cuda and _lib.tune_default("refresh_streams", 0):
             # the derived kernels (weight permutes) and the plane split are independent readers of theta: two side
-            # streams next to the caller's (parallel branches when the caller is being captured into a CUDA graph)
+            # streams next to the caller's (parallel branches when the caller is being captured into a CUDA graph).
+            # Measured (profiles/README.md, r2h): 0.621 ms per DQN step against 0.608 ms without -- the fork / join
+            # costs more than the five small kernels gain from running side by side -- hence opt-in.
             from coach_b200.architectures.layers import SideStream
             if getattr(self, "_sides", None) is None:
                 self._sides = (SideStream(self.theta.device), SideStream(self.theta.device))

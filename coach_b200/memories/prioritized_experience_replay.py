@@ -85,6 +85,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         self._list_len = 0                  # len(self.transitions) of the reference (doubled, capped)
         self._u_ring = {}                   # batch size -> rotating pinned / device buffers of the uniform draws
         self._flag_host, self._flag_event = None, None
+        self._update_side = None            # layers.SideStream an owner runs update_priorities_device on (DQNAgent)
 
     def _init_trees(self):
         _lib.check(self.lib.cb200_per_init(self.sum_tree.data_ptr(), self.min_tree.data_ptr(),
@@ -92,9 +93,15 @@ class PrioritizedExperienceReplay(ExperienceReplay):
                                            _lib.current_stream()))
 
     # ---- reference-visible state ---------------------------------------------------------------------------------
+    def _join_update(self):
+        """a tree update an owner queued on its side stream is ordered before whatever the current stream does next"""
+        if self._update_side is not None:
+            self._update_side.join()
+
     @property
     def maximal_priority(self) -> float:
         if self._maxp_stale:
+            self._join_update()
             self._maximal_priority = float(self._maxp_dev.item())      # 8-byte D2H, only when a store needs it
             self._maxp_stale = False
         return self._maximal_priority
@@ -116,6 +123,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
             self._flush()
 
     def _flush(self):
+        self._join_update()
         first, n = self.ring.flush()
         self._tree_store(first, n)
         return first, n
@@ -321,6 +329,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
     # ---- misc ----------------------------------------------------------------------------------------------------
     def clean(self, lock=True) -> None:
         self.assert_not_frozen()
+        self._join_update()
         self.ring.clear()
         self._list_len = 0
         self._init_trees()                                                               # :294-296
