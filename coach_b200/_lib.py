@@ -92,9 +92,10 @@ PROTOTYPES = {
     "cb200_per_sample_gather_s2d": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_double, c_void_p,
                                             c_void_p, c_void_p, ctypes.POINTER(Column), c_int, ctypes.c_int32,
                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(Column),
-                                            c_int, c_void_p, c_void_p]),
+                                            c_int, c_void_p, c_i64, c_void_p]),
     "cb200_gather_s2d": (c_int, [c_void_p, c_i64, ctypes.POINTER(Column), c_int, ctypes.c_int32, ctypes.c_int32,
-                                 ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(Column), c_int, c_void_p, c_void_p]),
+                                 ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(Column), c_int, c_void_p, c_i64,
+                                 c_void_p]),
     "cb200_gather_stack": (c_int, [c_void_p, c_i64, c_void_p, ctypes.c_int32, c_void_p, c_i64, c_void_p, c_void_p]),
     "cb200_scatter_ring": (c_int, [ctypes.POINTER(Column), c_int, c_i64, c_i64, c_i64, c_void_p]),
     "cb200_scatter_ring_packed": (c_int, [ctypes.POINTER(Column), c_int, c_i64, c_i64, c_i64, c_i64, c_void_p]),

@@ -12,6 +12,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace cb200 {
@@ -697,9 +699,20 @@ struct S2dGatherParams {
     // src[k] is then the int32 [capacity, C] table of the frame slots that make up the stack of column k
     const uint8_t* frames;
     int frame_sub;             // bytes between the frames of one sample inside a stage (rows_per_chunk * S * W)
+    int frame_tma;             // a stack whose 4 frames sit in consecutive slots is fetched by ONE 2-D TMA box (tmF)
 };
 
-__global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SampleParams sp, S2dGatherParams gp) {
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// tmF (frame-deduplicated ring): the frame store as a 2-D uint32 tensor (H * W / 4 words | frame slots) with box
+// (rows_per_chunk * S * W / 4, 4): the bands of four consecutive frames in one operation, landing as [frame][band]
+__global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SampleParams sp, S2dGatherParams gp,
+                                                                        const __grid_constant__ CUtensorMap tmF) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);                      // [kS2dStages]
     int64_t* leaf_smem = reinterpret_cast<int64_t*>(smem + 64);                  // [8]
@@ -741,14 +754,22 @@ __global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SamplePa
         if (lane == 0) mbar_expect_tx(full_bar + st, 8u * bytes);
         __syncwarp();
         if (gp.frames) {
-            // one bulk copy per (sample, frame of its stack): rc * S image rows of W bytes, contiguous in the frame
-            const int32_t* fidx = reinterpret_cast<const int32_t*>(gp.src[col]);
+            // lane = (sample, frame of its stack).  The four frames of a stack normally sit in consecutive slots (one
+            // new frame per transition): their bands -- rc * S image rows of W bytes each -- then come with ONE 2-D
+            // TMA box issued by the sample's first lane; otherwise (episode start: replicated first frame, wrap of the
+            // frame store, a partial last chunk) one 1-D bulk copy per frame.
+            const int4* fidx = reinterpret_cast<const int4*>(gp.src[col]);
             const uint32_t fbytes = (uint32_t)(rc * S * gp.W);
-            for (int l = lane; l < 8 * C; l += 32) {
-                const int smp = l / C, c = l - smp * C;
-                const int64_t fslot = __ldg(fidx + leaf_smem[smp] * C + c);
-                bulk_g2s(stage_mem + (size_t)st * 8 * gp.chunk_stride + (size_t)smp * gp.chunk_stride +
-                             (size_t)c * gp.frame_sub,
+            const int smp = lane >> 2, c = lane & 3;
+            const int4 f = __ldg(fidx + leaf_smem[smp]);
+            uint8_t* dst = stage_mem + (size_t)st * 8 * gp.chunk_stride + (size_t)smp * gp.chunk_stride;
+            const bool one_box = gp.frame_tma && rc == gp.rows_per_chunk && f.y == f.x + 1 && f.z == f.x + 2 &&
+                                 f.w == f.x + 3;
+            if (one_box) {
+                if (c == 0) tma_load_2d(dst, &tmF, (ya * S * gp.W) >> 2, f.x, full_bar + st);
+            } else {
+                const int64_t fslot = c == 0 ? f.x : (c == 1 ? f.y : (c == 2 ? f.z : f.w));
+                bulk_g2s(dst + (size_t)c * gp.frame_sub,
                          gp.frames + fslot * ((int64_t)gp.H * gp.W) + (size_t)ya * S * gp.W, fbytes, full_bar + st);
             }
         } else if (lane < 8) {
@@ -804,11 +825,19 @@ __global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SamplePa
                 if (gp.frames) {
                     // planar frames (S == C == 4): 4 pixels of image row yl * S + dy from each of the 4 frames, byte-
                     // transposed into the stack's channel-last order (dx, c)
+                    // (the 8 b-lanes of a quarter-warp sit a multiple of 128 bytes apart -- the TMA box needs that
+                    // alignment -- i.e. in the same bank: each lane starts with another frame, 2-way conflicts remain)
                     const uint8_t* f = sbase + (size_t)((yl * S + dy) * gp.W + X * S);
-                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(f);
-                    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(f + gp.frame_sub);
-                    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(f + 2 * gp.frame_sub);
-                    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(f + 3 * gp.frame_sub);
+                    const int r0 = b & 3;
+                    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(f + r0 * gp.frame_sub);
+                    const uint32_t a1 = *reinterpret_cast<const uint32_t*>(f + ((r0 + 1) & 3) * gp.frame_sub);
+                    const uint32_t a2 = *reinterpret_cast<const uint32_t*>(f + ((r0 + 2) & 3) * gp.frame_sub);
+                    const uint32_t a3 = *reinterpret_cast<const uint32_t*>(f + ((r0 + 3) & 3) * gp.frame_sub);
+                    // a_k holds frame (r0 + k) & 3
+                    const uint32_t w0 = r0 == 0 ? a0 : (r0 == 1 ? a3 : (r0 == 2 ? a2 : a1));
+                    const uint32_t w1 = r0 == 0 ? a1 : (r0 == 1 ? a0 : (r0 == 2 ? a3 : a2));
+                    const uint32_t w2 = r0 == 0 ? a2 : (r0 == 1 ? a1 : (r0 == 2 ? a0 : a3));
+                    const uint32_t w3 = r0 == 0 ? a3 : (r0 == 1 ? a2 : (r0 == 2 ? a1 : a0));
                     const uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
                     const uint32_t t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
                     *reinterpret_cast<uint4*>(o) =
@@ -1186,9 +1215,46 @@ int cb200_per_sample_gather(const double* sum_tree, const double* min_tree, int6
     return CB200_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// frame store [slots, frame_bytes] as a 2-D uint32 tensor with box (band_bytes / 4, 4 slots); cached per geometry
+static bool frame_store_map(CUtensorMap* out, const void* frames, int64_t frame_bytes, int64_t slots, int band_bytes) {
+    static CUtensorMap cached;
+    static const void* c_frames = nullptr;
+    static int64_t c_bytes = 0, c_slots = 0;
+    static int c_band = 0;
+    if (c_frames == frames && c_bytes == frame_bytes && c_slots == slots && c_band == band_bytes) {
+        *out = cached;
+        return true;
+    }
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return false;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    if (frame_bytes % 16 || band_bytes % 16 || band_bytes / 4 > 256 || slots < 4) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)(frame_bytes / 4), (cuuint64_t)slots};
+    const cuuint64_t strides[1] = {(cuuint64_t)frame_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)(band_bytes / 4), 4};
+    const cuuint32_t estr[2] = {1, 1};
+    if (fn(&cached, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(frames), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    c_frames = frames; c_bytes = frame_bytes; c_slots = slots; c_band = band_bytes;
+    *out = cached;
+    return true;
+}
+
 static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int64_t n, const cb200_column* img,
                              int n_img, int h, int w, int c, int s, const cb200_column* small_cols, int n_small,
-                             const void* frames, cudaStream_t st) {
+                             const void* frames, int64_t frame_slots, cudaStream_t st) {
     S2dGatherParams gp;
     memset(&gp, 0, sizeof(gp));
     gp.n_img = n_img;
@@ -1210,15 +1276,6 @@ static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int6
     const int s2d_row_bytes = s * w * c;
     // chunks of about 2.7 KB per sample (two stages of 8 samples = 43 KB of shared memory: four CTAs per SM, whose
     // descents / copies / conversions overlap each other); the padded per-sample stride is an odd multiple of 16 bytes
-    int rc = 2816 / s2d_row_bytes;
-    if (rc < 1) rc = 1;
-    if (rc > hs) rc = hs;
-    gp.rows_per_chunk = rc;
-    gp.frames = static_cast<const uint8_t*>(frames);
-    gp.frame_sub = rc * s * w;
-    int stride = rc * s2d_row_bytes;
-    if ((stride / 16) % 2 == 0) stride += 16;
-    gp.chunk_stride = stride;
     // bands: as many CTAs as fit in ONE wave of four per SM (a CTA is a chain of dependent round trips -- tree descent,
     // first chunk, conversion -- so a second, partial wave would double the kernel's duration)
     const int groups = (int)(n / 8) * n_img;
@@ -1226,6 +1283,22 @@ static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int6
     if (parts < 1) parts = 1;
     if (parts > hs) parts = hs;
     gp.parts = parts;
+    const int per_band = (hs + parts - 1) / parts;
+    int rc = 2816 / s2d_row_bytes;
+    if (rc < 1) rc = 1;
+    if (rc > per_band) rc = per_band;
+    gp.rows_per_chunk = rc;
+    gp.frames = static_cast<const uint8_t*>(frames);
+    gp.frame_sub = rc * s * w;
+    int stride = rc * s2d_row_bytes;
+    CUtensorMap tmF;
+    memset(&tmF, 0, sizeof(tmF));
+    // frame store: per-sample stage regions 128 bytes apart in alignment (TMA box destination) when the tensor map can
+    // be built; otherwise (and for the verbatim ring) the padded odd-multiple-of-16 stride of the bulk-copy path
+    gp.frame_tma = frames && frame_slots >= 4 && stride % 128 == 0 && tune_get("frame_tma", 1, 0, 1) != 0 &&
+                   frame_store_map(&tmF, frames, (int64_t)h * w, frame_slots, rc * s * w);
+    if (!gp.frame_tma && (stride / 16) % 2 == 0) stride += 16;
+    gp.chunk_stride = stride;
     size_t smem = 256 + (size_t)kS2dStages * 8 * stride;
     const size_t scratch = 256 + 8 * kScratchDoubles * sizeof(double);     // phase A: per-warp descent scratch
     if (smem < scratch) smem = scratch;
@@ -1236,7 +1309,7 @@ static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int6
             return -1;
         configured = smem;
     }
-    CB200_LAUNCH(sample_gather_s2d_kernel, (unsigned)(groups * parts), kS2dThreads, smem, st, sp, gp);
+    CB200_LAUNCH(sample_gather_s2d_kernel, (unsigned)(groups * parts), kS2dThreads, smem, st, sp, gp, tmF);
     return 0;
 }
 
@@ -1264,7 +1337,7 @@ int cb200_per_sample_gather_s2d(const double* sum_tree, const double* min_tree, 
                                 int64_t nt, double beta, int64_t* idx_out, double* w_out, float* w32_out,
                                 const cb200_column* image_columns, int n_image, int32_t h, int32_t w, int32_t c,
                                 int32_t s, const cb200_column* small_columns, int n_small, const void* frames,
-                                void* stream) {
+                                int64_t frame_slots, void* stream) {
     SampleParams sp;
     CB200_CHECK_ARG(fill_sample_params(sp, sum_tree, min_tree, size, u, n, nt, beta, idx_out, w_out, w32_out) == 0,
                     "bad arguments (size must be a power of 2, n > 0, non-null trees / uniforms)");
@@ -1272,7 +1345,7 @@ int cb200_per_sample_gather_s2d(const double* sum_tree, const double* min_tree, 
     CB200_CHECK_ARG(check_s2d_args(image_columns, n_image, n, h, w, c, s, small_columns, n_small, frames) == 0,
                     "bad image geometry / column table (n % 8 == 0, 1-2 uint8 image columns, 16-byte aligned rows)");
     const int rc = launch_gather_s2d(sp, nullptr, n, image_columns, n_image, h, w, c, s, small_columns, n_small,
-                                     frames, as_stream(stream));
+                                     frames, frame_slots, as_stream(stream));
     CB200_CHECK_ARG(rc == 0, "could not configure the fused sample + gather + space-to-depth kernel");
     CB200_CHECK_LAUNCH();
     return CB200_OK;
@@ -1280,14 +1353,14 @@ int cb200_per_sample_gather_s2d(const double* sum_tree, const double* min_tree, 
 
 int cb200_gather_s2d(const int64_t* idx, int64_t n, const cb200_column* image_columns, int n_image, int32_t h, int32_t w,
                      int32_t c, int32_t s, const cb200_column* small_columns, int n_small, const void* frames,
-                     void* stream) {
+                     int64_t frame_slots, void* stream) {
     CB200_CHECK_ARG(idx != nullptr, "idx is required");
     CB200_CHECK_ARG(check_s2d_args(image_columns, n_image, n, h, w, c, s, small_columns, n_small, frames) == 0,
                     "bad image geometry / column table (n % 8 == 0, 1-2 uint8 image columns, 16-byte aligned rows)");
     SampleParams sp;
     memset(&sp, 0, sizeof(sp));
     const int rc = launch_gather_s2d(sp, idx, n, image_columns, n_image, h, w, c, s, small_columns, n_small, frames,
-                                     as_stream(stream));
+                                     frame_slots, as_stream(stream));
     CB200_CHECK_ARG(rc == 0, "could not configure the fused gather + space-to-depth kernel");
     CB200_CHECK_LAUNCH();
     return CB200_OK;

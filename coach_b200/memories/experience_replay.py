@@ -126,7 +126,7 @@ class ExperienceReplay(Memory):
             ia, ni, sa, ns = self.ring.s2d_tables(s2d, out, size)
             H, W, C, S = s2d["geometry"]
             _lib.check(self.lib.cb200_gather_s2d(idx.data_ptr(), size, ia, ni, H, W, C, S, sa, ns,
-                                                 self.ring.frames_ptr(), _lib.current_stream()))
+                                                 self.ring.frames_ptr(), self.ring.frame_capacity, _lib.current_stream()))
             cols = {k: v for k, v in out.items() if k not in s2d["columns"]}
             cols["idx"] = idx
             return DeviceBatch(cols, size, lazy=_LazyColumns(self.ring, idx, tuple(s2d["columns"])))

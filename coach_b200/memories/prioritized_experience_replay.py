@@ -263,7 +263,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
                 self.sum_tree.data_ptr(), self.min_tree.data_ptr(), self.power_of_2_size, u.data_ptr(), size,
                 self.num_transitions(), float(self.beta.current_value), out["idx"].data_ptr(),
                 out["weight"].data_ptr(), out["weight32"].data_ptr(), ia, ni, H, W, C, S, sa, ns,
-                self.ring.frames_ptr(), _lib.current_stream()))
+                self.ring.frames_ptr(), self.ring.frame_capacity, _lib.current_stream()))
             if ke:
                 ke[1].record()
             self.beta.step()

@@ -145,17 +145,18 @@ int cb200_per_sample_gather(const double* sum_tree, const double* min_tree, int6
  * (uint8 [frame slots, h*w]) -- the reference shares them between s, s' and neighbouring transitions through LazyStack
  * (filters/observation/observation_stacking_filter.py:27-41, agents/agent.py:905-973); image_columns[k].src is then the
  * int32 [capacity, c] table of the frame slots of each transition's stack (row_bytes = 4*c) and the kernel assembles
- * the last-axis stack while converting. */
+ * the last-axis stack while converting; frame_slots = rows of `frames` (a stack in four consecutive slots is fetched
+ * by one 2-D TMA box per chunk). */
 int cb200_per_sample_gather_s2d(const double* sum_tree, const double* min_tree, int64_t size, const double* u, int64_t n,
                                 int64_t num_transitions, double beta, int64_t* idx_out, double* w_out, float* w32_out,
                                 const cb200_column* image_columns, int n_image, int32_t h, int32_t w, int32_t c,
                                 int32_t s, const cb200_column* small_columns, int n_small, const void* frames,
-                                void* stream);
+                                int64_t frame_slots, void* stream);
 
 /* The same for given slot indices (uniform ExperienceReplay.sample, experience_replay.py:71-93). */
 int cb200_gather_s2d(const int64_t* idx, int64_t n, const cb200_column* image_columns, int n_image, int32_t h, int32_t w,
                      int32_t c, int32_t s, const cb200_column* small_columns, int n_small, const void* frames,
-                     void* stream);
+                     int64_t frame_slots, void* stream);
 
 /* Frame-deduplicated ring, un-fused readers (Batch.states() of the slots idx, core_types.py:488-511):
  * out[i, pix, c] = frames[frame_index[idx[i], c], pix], i.e. np.stack(frames, axis=-1) of observation_stacking_filter.py:
