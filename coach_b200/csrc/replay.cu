@@ -1283,28 +1283,10 @@ static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int6
     if (parts < 1) parts = 1;
     if (parts > hs) parts = hs;
     gp.parts = parts;
-    int per_band = (hs + parts - 1) / parts;
+    const int per_band = (hs + parts - 1) / parts;
     int rc = 2816 / s2d_row_bytes;
     if (rc < 1) rc = 1;
     if (rc > per_band) rc = per_band;
-    int nstages = kS2dStages;
-    if (frames) {
-        // Frame store: a chunk is one request PER FRAME (4 x 8 per CTA), and the copy engine of an SM works requests
-        // off one after the other -- small chunks made the kernel request-bound (measured: 50 us against 33 us for the
-        // verbatim ring).  So: the whole band of a CTA in ONE chunk (no second stage), bands as tall as three CTAs
-        // per SM allow, provided all CTAs still fit in one wave.
-        const int rc_cap = (int)((75000 - 256) / (8 * (int64_t)s2d_row_bytes));
-        if (rc_cap >= 1) {
-            const int parts_f = (hs + rc_cap - 1) / rc_cap;
-            if ((int64_t)groups * parts_f <= 3 * (int64_t)sm_count() || parts_f <= parts) {
-                parts = parts_f;
-                per_band = (hs + parts - 1) / parts;
-                rc = per_band;
-                nstages = 1;
-                gp.parts = parts;
-            }
-        }
-    }
     gp.rows_per_chunk = rc;
     gp.frames = static_cast<const uint8_t*>(frames);
     gp.frame_sub = rc * s * w;
@@ -1317,7 +1299,7 @@ static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int6
                    frame_store_map(&tmF, frames, (int64_t)h * w, frame_slots, rc * s * w);
     if (!gp.frame_tma && (stride / 16) % 2 == 0) stride += 16;
     gp.chunk_stride = stride;
-    size_t smem = 256 + (size_t)nstages * 8 * stride;
+    size_t smem = 256 + (size_t)kS2dStages * 8 * stride;
     const size_t scratch = 256 + 8 * kScratchDoubles * sizeof(double);     // phase A: per-warp descent scratch
     if (smem < scratch) smem = scratch;
     static size_t configured = 0;
