@@ -597,9 +597,11 @@ def main():
     ap.add_argument("--capacity", type=int, default=1000000, help="replay capacity in transitions (rounded up to 2^k)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the cpu_baseline leg")
     ap.add_argument("--no-l2-persist", action="store_true")
-    ap.add_argument("--frame-dedup", type=int, default=1, choices=[0, 1],
-                    help="1 (default): frame-deduplicated replay -- every 84x84 frame stored once (9.3 GB instead of "
-                         "59.2 GB for 2^20 transitions), stacks assembled by the gather; 0: stacked states verbatim")
+    ap.add_argument("--frame-dedup", type=int, default=0, choices=[0, 1],
+                    help="1: frame-deduplicated replay -- every 84x84 frame stored once (9.3 GB instead of 59.2 GB for "
+                         "2^20 transitions, 41 KB instead of 238 KB over PCIe per step), stacks assembled by the "
+                         "gather (measured 3 %% slower per step: profiles/README.md); 0 (default): stacked states "
+                         "verbatim")
     ap.add_argument("--no-tc", action="store_true", help="fp32 FFMA GEMMs instead of the tcgen05 3xBF16 path")
     ap.add_argument("--config", default="dqn", choices=["dqn", "dueling", "cartpole", "ppo", "sac", "td3"],
                     help="dqn: BASELINE config 2 (Atari DQN + PER, the headline metric, default); dueling: config 5 "

@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(kS2dThreads) sample_gather_s2d_kernel(SamplePa
                     // (the 8 b-lanes of a quarter-warp sit a multiple of 128 bytes apart -- the TMA box needs that
                     // alignment -- i.e. in the same bank: each lane starts with another frame, 2-way conflicts remain)
                     const uint8_t* f = sbase + (size_t)((yl * S + dy) * gp.W + X * S);
-                    const int r0 = b & 3;
+                    const int r0 = gp.frame_tma ? (b & 3) : 0;      // (bulk path: odd 16-byte stride, no conflicts)
                     const uint32_t a0 = *reinterpret_cast<const uint32_t*>(f + r0 * gp.frame_sub);
                     const uint32_t a1 = *reinterpret_cast<const uint32_t*>(f + ((r0 + 1) & 3) * gp.frame_sub);
                     const uint32_t a2 = *reinterpret_cast<const uint32_t*>(f + ((r0 + 2) & 3) * gp.frame_sub);
@@ -1293,9 +1293,11 @@ static int launch_gather_s2d(const SampleParams& sp, const int64_t* idx_in, int6
     int stride = rc * s2d_row_bytes;
     CUtensorMap tmF;
     memset(&tmF, 0, sizeof(tmF));
-    // frame store: per-sample stage regions 128 bytes apart in alignment (TMA box destination) when the tensor map can
-    // be built; otherwise (and for the verbatim ring) the padded odd-multiple-of-16 stride of the bulk-copy path
-    gp.frame_tma = frames && frame_slots >= 4 && stride % 128 == 0 && tune_get("frame_tma", 1, 0, 1) != 0 &&
+    // frame store, opt-in (cb200_tune("frame_tma", 1)): per-sample stage regions 128 bytes apart in alignment (TMA box
+    // destination) when the tensor map can be built; otherwise (and for the verbatim ring) the padded odd-multiple-of-
+    // 16 stride of the bulk-copy path.  Measured (profiles/README.md r2i): 49.5 us with the boxes, 50.7 us with four
+    // bulk copies per stack -- the kernel is not bound by the number of copy requests -- so the simpler path is default.
+    gp.frame_tma = frames && frame_slots >= 4 && stride % 128 == 0 && tune_get("frame_tma", 0, 0, 1) != 0 &&
                    frame_store_map(&tmF, frames, (int64_t)h * w, frame_slots, rc * s * w);
     if (!gp.frame_tma && (stride / 16) % 2 == 0) stride += 16;
     gp.chunk_stride = stride;
