@@ -83,12 +83,15 @@ def test_gathered_stacks_equal_the_reference_filter_stream(fx, per, lazy):
     np.testing.assert_array_equal(b.columns["state:observation"].cpu().numpy(), fx["fs_states"][k])
 
 
+@pytest.mark.parametrize("tma", [0, 1], ids=["bulk_copies", "tma_boxes"])
 @pytest.mark.parametrize("per", [True, False])
-def test_fused_s2d_planes_from_the_frame_store(fx, per):
-    """cb200_per_sample_gather_s2d / cb200_gather_s2d on the frame store == cb200_u8_s2d_planes of the reference stacks"""
+def test_fused_s2d_planes_from_the_frame_store(fx, per, tma):
+    """cb200_per_sample_gather_s2d / cb200_gather_s2d on the frame store == cb200_u8_s2d_planes of the reference stacks
+    (both copy paths: one bulk copy per frame, or one 2-D TMA box per stack in consecutive slots)"""
     from coach_b200 import _lib as L
     from coach_b200.architectures import tiled as tl
     lib = L.load()
+    lib.cb200_tune(b"frame_tma", tma)
     dev = torch.device("cuda")
     ts = _stream_transitions(fx, True)
     mem = _memory(per, 64)
@@ -113,6 +116,7 @@ def test_fused_s2d_planes_from_the_frame_store(fx, per):
             torch.cuda.synchronize()
             assert torch.equal(planes[name].t, want.t), name
             assert torch.equal(got.column(name), x)                    # lazily materialised uint8 column
+    lib.cb200_tune(b"frame_tma", 0)
 
 
 def test_ring_and_frame_store_wrap_around(fx):
