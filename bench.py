@@ -291,6 +291,8 @@ def run_device(args):
         step_i[0] = i
         one_step(False)
         ev[i][2].record()
+    if hasattr(agent, "_join_optimizer"):
+        agent._join_optimizer()            # the last step's optimizer part (own stream) belongs to the timed region
     t1.record()
     barrier()
     agent.sample_batch = orig_sample

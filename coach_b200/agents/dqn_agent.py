@@ -255,12 +255,16 @@ class DQNAgent(object):
         # the tree update of a step only needs the TD errors of its forward part: it runs beside the backward pass and
         # the optimizer; the next sample waits for it (sample_batch)
         self._side_upd = SideStream(dev) if streams else NO_SIDE
+        # ... and the optimizer part of a step ([all-reduce,] Adam, plane refresh) runs on a fourth stream: the next
+        # step's sample + gather does not depend on it and starts as soon as the backward pass is done
+        self._side_opt = SideStream(dev) if streams and _lib.tune_default("dqn_opt_stream", 1) else NO_SIDE
         if streams and isinstance(self.memory, PrioritizedExperienceReplay):
             self.memory._update_side = self._side_upd          # every other tree access of the memory joins it first
         self._graphs = None
         self._acting = {}                         # number of environments -> (input buffer, forward-only online network)
         self._graph_c = (None, 0)
         self._collectives_in_graph = False
+        self._opt_on_stream = False
         self._head_weights, self._head_split = None, False
         self._grad_sync = None                    # exchange buffer of the overlapped gradient all-reduce
         self._eager_steps = 0
@@ -339,6 +343,7 @@ class DQNAgent(object):
         """value_optimization_agent.py:68-72 for a batch of E rollout shards: ONE forward pass of the online network on
         the device.  states: [E, *observation_shape] (uint8 frames / float vectors; host array or CUDA tensor).
         Returns the Q-values as a CUDA tensor [E, num_actions] (persistent buffer, valid until the next call)."""
+        self._join_optimizer()
         x = torch.as_tensor(states)
         E = int(x.shape[0])
         inst = self._acting.get(E)
@@ -421,7 +426,21 @@ class DQNAgent(object):
                                                             self.batch_size, self.num_actions, huber, 1.0,
                                                             net.online_s.dq.data_ptr(), self.loss_dev.data_ptr(), st))
 
-    def _part_backward(self, weights, with_optimizer, part="all"):
+    def _part_optimizer(self, scaler, with_norm):
+        """[gradient norm beside] rescale + Adam + refresh of the parameter planes"""
+        net = self.networks["main"]
+        if with_norm:
+            with self._side_w:
+                _lib.check(self.lib.cb200_sumsq(net.store.grad.data_ptr(), net.store.size, net.sumsq.data_ptr(),
+                                                net.ws.ptr(), _lib.current_stream()))
+        net.apply_gradients(scaler)
+        self._side_w.join()
+
+    def _join_optimizer(self):
+        """the optimizer part of the previous step (own stream) is ordered before whatever the current stream does next"""
+        self._side_opt.join()
+
+    def _part_backward(self, weights, with_optimizer, part="all", with_norm=True):
         """head loss, backward pass, global norm / clipping [, optimizer].  part: "all", or "top" (loss + dense
         layers) / "bottom" (conv layers + norm) when the all-reduce of the dense gradients overlaps the rest"""
         lib, st = self.lib, _lib.current_stream()
@@ -432,13 +451,11 @@ class DQNAgent(object):
             self._side_w.join()
             n = net.store.size
             clip = net.params.clip_gradients
+            if not with_norm:
+                return                                            # the norm is reduced beside the optimizer step
             if with_optimizer and not (clip is not None and clip != 0) and self._side_w is not NO_SIDE:
                 # no clipping: the gradient norm is only reported -- it is reduced beside the optimizer step
-                with self._side_w:
-                    _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(),
-                                               _lib.current_stream()))
-                net.apply_gradients(1.0)
-                self._side_w.join()
+                self._part_optimizer(1.0, True)
                 return
             _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(), st))
             if clip is not None and clip != 0:
@@ -460,6 +477,8 @@ class DQNAgent(object):
             net.online_s.backward(side=self._side_w)
             self._side_w.join()
         n = net.store.size
+        if not with_norm:
+            return
         _lib.check(lib.cb200_sumsq(net.store.grad.data_ptr(), n, net.sumsq.data_ptr(), net.ws.ptr(), st))
         clip = net.params.clip_gradients
         if clip is not None and clip != 0:
@@ -494,6 +513,27 @@ class DQNAgent(object):
                 torch.distributed.all_reduce(net.store.grad, op=torch.distributed.ReduceOp.SUM)
                 net.apply_gradients(scaler)
             self._collectives_in_graph = True
+        elif self._side_opt is not NO_SIDE:
+            # backward | optimizer as separate graphs: the optimizer graph is replayed on its own stream (after the
+            # all-reduce when there are several ranks) while the main stream already runs the next sample + gather
+            net = self.networks["main"]
+            clip = net.params.clip_gradients
+            self._norm_in_opt = single and not (clip is not None and clip != 0)
+            scaler = 1.0
+            if not single:
+                ws = torch.distributed.get_world_size()
+                scaler = 1.0 / ws if net.params.scale_down_gradients_by_number_of_workers_for_sync_training else 1.0
+            with torch.cuda.graph(gb):
+                self._part_backward(weights, False, with_norm=not self._norm_in_opt)
+            c2 = self.lib.cb200_launch_count()
+            gc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gc):
+                self._part_optimizer(scaler, self._norm_in_opt)
+            c3 = self.lib.cb200_launch_count()
+            self._graph_c = (gc, int(c3 - c2))
+            self._graphs = (ga, gb, gb2, int(c1 - c0), int(c2 - c1))
+            self._opt_on_stream = True
+            return
         else:
             with torch.cuda.graph(gb):
                 self._part_backward(weights, single)
@@ -566,6 +606,7 @@ class DQNAgent(object):
         if overlap and self._grad_sync is None:
             self._grad_sync = torch.zeros_like(net.store.grad)
         graph = self.use_graph and own and self._eager_steps >= 2
+        self._join_optimizer()             # the previous step's Adam / plane refresh (own stream) comes first
         if graph and self._graphs is None:
             self._capture(cols, weights, per_libm, single, overlap)
         ev = None
@@ -595,6 +636,12 @@ class DQNAgent(object):
             self._eager_steps += 1
         if pending is not None:
             self._overlapped_allreduce_end(*pending)
+        elif graph and self._opt_on_stream:
+            with self._side_opt:                                  # ordered after the backward graph; joined lazily
+                if not single:
+                    torch.distributed.all_reduce(net.store.grad, op=torch.distributed.ReduceOp.SUM)
+                self._graph_c[0].replay()
+            self.graph_kernel_launches += self._graph_c[1]
         elif graph and self._collectives_in_graph:
             pass                                                  # all-reduce and optimizer ran inside the graph
         elif graph and not single and self._graph_c[0] is not None:
@@ -620,6 +667,8 @@ class DQNAgent(object):
                 self.memory.update_priorities(cols["idx"], self.td_err)
         if fetch:
             # one synchronisation for both scalars (loss, squared gradient norm) through a pinned pair
+            if self._opt_on_stream and getattr(self, "_norm_in_opt", False):
+                self._join_optimizer()                            # the norm is reduced on the optimizer's stream
             self._fetch_host[0:1].copy_(self.loss_dev, non_blocking=True)
             self._fetch_host[1:2].copy_(net.sumsq, non_blocking=True)
             torch.cuda.current_stream().synchronize() if self.device.type == "cuda" else None
@@ -639,6 +688,7 @@ class DQNAgent(object):
             loss = loss + total_loss if fetch else total_loss
             net = self.networks["main"]
             if net.has_target and self._should_update_online_weights_to_target():
+                self._join_optimizer()
                 net.update_target_network(self.ap.algorithm.rate_for_copying_weights_to_target)
         return loss
 

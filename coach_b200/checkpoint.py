@@ -189,6 +189,8 @@ def save_checkpoint(agent, checkpoint_dir: str, checkpoint_id: int = 0, env_step
     """Writes one checkpoint of the agent (networks + optimizer + replay + filters + counters) and, last, the state
     file.  Returns the checkpoint name."""
     os.makedirs(checkpoint_dir, exist_ok=True)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()          # side streams of the learn step (optimizer, priority update) included
     env_steps = int(getattr(agent, "total_steps_counter", 0) if env_steps is None else env_steps)
     name = checkpoint_name(checkpoint_id, env_steps)
     prefix = os.path.join(checkpoint_dir, name)
@@ -224,6 +226,8 @@ def restore_checkpoint(agent, checkpoint_dir: str, name: str = None) -> str:
     if name is None:
         raise FileNotFoundError("no complete checkpoint in %s (%s missing or malformed)" % (checkpoint_dir, STATE_FILE))
     prefix = os.path.join(checkpoint_dir, name)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()          # nothing of a running learn step may still write what is restored here
     with open(prefix + ".agent.json") as f:
         meta = json.load(f)
     if meta["agent"] != type(agent).__name__:
