@@ -418,7 +418,12 @@ def run_device(args):
                      "frac_algorithmic": round(tl_useful / tl_us / 1e6 / pk["bf16_tflops_sustained"], 4) if tl_us else 0.0,
                      "peak_kind": pk_kind + " (sustained dense bf16, kernel timed inside the step)",
                      "us_per_step": round(tl_us, 1), "share_of_step": round(tl_us / (ms_total / K * 1e3), 3),
-                     "algorithmic_flops_per_step": tl_issued, "fp32_equivalent_tflops": round(tl_useful / tl_us / 1e6, 1)
+                     "share_of_step_note": "sum of the launches' stand-alone durations / step time; inside the step "
+                                           "the target forward, the weight gradients and the optimizer run on side "
+                                           "streams beside the main chain, so the launches overlap",
+                     "frac_over_whole_step": round(tl_issued / (ms_total / K * 1e-3) / 1e12
+                                                   / pk["bf16_tflops_sustained"], 4),
+                     "issued_flops_per_step": tl_issued, "algorithmic_flops_per_step": tl_useful, "fp32_equivalent_tflops": round(tl_useful / tl_us / 1e6, 1)
                      if tl_us else 0.0,
                      "what": "achieved = bf16 tensor-core FLOPs issued (3xBF16 split: 6 products per fp32 MAC, 3 for "
                              "the exact uint8 operand) / CUDA-event time of the launches (each prepared call timed over "
@@ -463,7 +468,10 @@ def run_device(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)
 # (gemm_tc_tiled: sum over the 15 launches of one step, profiles/ncu_tiled_gemm_r1p_summary.txt -- cold caches under ncu)
-TRAFFIC_NCU = {"per_sample_gather": 30270000, "gemm_tc_tiled": 500000000}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (per step for the GEMM family: 16 launches), cold caches:
+# profiles/ncu_step_r2f_summary.txt (sample_gather_s2d: 30.4 MB read + 4.9 MB written -- the bf16 planes stay in L2),
+# profiles/ncu_tiled_r2f_summary.txt, profiles/ncu_per_sample_gather_r1b_summary.txt
+TRAFFIC_NCU = {"per_sample_gather": 30270000, "sample_gather_s2d": 35286016, "gemm_tc_tiled": 473743616}
 
 
 # =====================================================================================================================
