@@ -309,6 +309,11 @@ class ClippedPPOAgent(object):
             n_rows = batch.size
             if alg.truncate_dataset_to_playing_steps:
                 n_rows = min(n_rows, alg.num_consecutive_playing_steps.num_steps)
+            if n_rows < self.B:
+                raise ValueError("the rollout holds %d transitions, fewer than one minibatch of %d: nothing to train on "
+                                 "(the reference would train on one partial minibatch)" % (n_rows, self.B))
+            # whole minibatches only: the reference also trains on the partial tail batch (clipped_ppo_agent.py:225,
+            # ceil(size / batch_size)); with the presets' 2048-step rollouts and batch 64 there is none
             n_rows = (n_rows // self.B) * self.B
             _, _, p_old = self._full_instances(batch.size)
             old_mu = p_old.forward()                                   # frozen target network, whole rollout at once
