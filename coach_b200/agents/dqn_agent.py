@@ -669,8 +669,8 @@ class DQNAgent(object):
                 self.memory.update_priorities(cols["idx"], self.td_err)
         if fetch:
             # one synchronisation for both scalars (loss, squared gradient norm) through a pinned pair
-            if self._opt_on_stream and getattr(self, "_norm_in_opt", False):
-                self._join_optimizer()                            # the norm is reduced on the optimizer's stream
+            self._join_optimizer()      # the optimizer's stream (where the norm is reduced when nothing clips) too:
+                                        # a fetched step is complete, parameters included, when this call returns
             self._fetch_host[0:1].copy_(self.loss_dev, non_blocking=True)
             self._fetch_host[1:2].copy_(net.sumsq, non_blocking=True)
             torch.cuda.current_stream().synchronize() if self.device.type == "cuda" else None
