@@ -241,6 +241,7 @@ class DQNAgent(object):
         self._pa_dev = torch.zeros(B, dtype=torch.float64, device=dev)
         self._pr_dev = torch.zeros(B, dtype=torch.float64, device=dev)
         self._fetch_host = torch.zeros(2, dtype=torch.float32, pin_memory=pin)
+        self._loss_host = torch.zeros(1, dtype=torch.float32, pin_memory=pin)    # loss of the forward part (fused head)
         # CUDA graphs of the learn step (own minibatch buffers only): forward + TD targets | loss + backward + clip
         # [+ Adam when there is no all-reduce in between].  Every launch parameter of those kernels is constant from
         # step to step, so two graph launches replace ~45 kernel launches; the first steps run eagerly (they build
@@ -265,6 +266,7 @@ class DQNAgent(object):
         self._graph_c = (None, 0)
         self._collectives_in_graph = False
         self._opt_on_stream = False
+        self._early_loss = bool(_lib.tune_default("dqn_early_loss", 1))
         self._head_weights, self._head_split = None, False
         self._grad_sync = None                    # exchange buffer of the overlapped gradient all-reduce
         self._eager_steps = 0
@@ -399,6 +401,7 @@ class DQNAgent(object):
             _lib.check(lib.cb200_dqn_head_fused(ctypes.byref(d), st))
             if per_libm:
                 self._td_host.copy_(self.td_err, non_blocking=True)
+            self._loss_host.copy_(self.loss_dev, non_blocking=True)   # the loss is final here: train() reads it early
             return
         with self._side_fwd:
             q_next = net.target_s2.forward()                      # dqn_agent.py:87-90
@@ -667,6 +670,16 @@ class DQNAgent(object):
                     self.memory.update_priorities_device(cols["idx"], self._pa_dev, self._pr_dev)
             else:
                 self.memory.update_priorities(cols["idx"], self.td_err)
+        if fetch == "loss" and self.head_desc is not None and not self._head_split and self.device.type == "cuda":
+            # train(): only the loss goes back to the caller.  With the fused head it is final when the forward part is
+            # (its D2H copy sits right behind the head launch), so the host returns while the backward pass, the tree
+            # update and the optimizer are still running -- the next step's store() / sample preparation overlaps them.
+            if ev is None:
+                ev = torch.cuda.Event()
+                ev.record()             # (no libm priorities: nothing waited for the forward part yet; conservative)
+            ev.synchronize()
+            loss = float(self._loss_host[0])
+            return loss, [loss], None
         if fetch:
             # one synchronisation for both scalars (loss, squared gradient norm) through a pinned pair
             self._join_optimizer()      # the optimizer's stream (where the norm is reduced when nothing clips) too:
@@ -686,7 +699,8 @@ class DQNAgent(object):
         for _ in range(self.ap.algorithm.num_consecutive_training_steps):
             self.training_iteration += 1
             batch = self.sample_batch()
-            total_loss, losses, unclipped_grads = self.learn_from_batch(batch, fetch=fetch)
+            total_loss, losses, unclipped_grads = self.learn_from_batch(
+                batch, fetch=("loss" if self._early_loss else True) if fetch else False)
             loss = loss + total_loss if fetch else total_loss
             net = self.networks["main"]
             if net.has_target and self._should_update_online_weights_to_target():

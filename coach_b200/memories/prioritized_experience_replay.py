@@ -82,6 +82,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         self._init_trees()
         self._maximal_priority = 1.0
         self._maxp_stale = False
+        self._maxp_host, self._maxp_event = None, None   # pinned mirror of the max-tree root behind every update
         self._list_len = 0                  # len(self.transitions) of the reference (doubled, capped)
         self._u_ring = {}                   # batch size -> rotating pinned / device buffers of the uniform draws
         self._flag_host, self._flag_event = None, None
@@ -101,8 +102,13 @@ class PrioritizedExperienceReplay(ExperienceReplay):
     @property
     def maximal_priority(self) -> float:
         if self._maxp_stale:
-            self._join_update()
-            self._maximal_priority = float(self._maxp_dev.item())      # 8-byte D2H, only when a store needs it
+            if self._maxp_event is not None:
+                # mirrored behind the update kernel on ITS stream: wait for that copy only, not for the learn step
+                self._maxp_event.synchronize()
+                self._maximal_priority = float(self._maxp_host[0])
+            else:
+                self._join_update()
+                self._maximal_priority = float(self._maxp_dev.item())  # 8-byte D2H, only when a store needs it
             self._maxp_stale = False
         return self._maximal_priority
 
@@ -187,6 +193,12 @@ class PrioritizedExperienceReplay(ExperienceReplay):
                                              idx.data_ptr(), p_alpha.data_ptr(), p_raw.data_ptr(), idx.shape[0],
                                              self._maxp_dev.data_ptr(), self._neg_flag.data_ptr(),
                                              _lib.current_stream()))
+        if self.device.type == "cuda":
+            if self._maxp_host is None:
+                self._maxp_host = torch.zeros(1, dtype=torch.float64, pin_memory=True)
+            self._maxp_host.copy_(self._maxp_dev, non_blocking=True)
+            self._maxp_event = torch.cuda.Event()
+            self._maxp_event.record()
         self._maxp_stale = True
         self._post_flag_check()
 
