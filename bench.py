@@ -420,7 +420,10 @@ def run_device(args):
                      "us_per_step": round(tl_us, 1), "share_of_step": round(tl_us / (ms_total / K * 1e3), 3),
                      "share_of_step_note": "sum of the launches' stand-alone durations / step time; inside the step "
                                            "the target forward, the weight gradients and the optimizer run on side "
-                                           "streams beside the main chain, so the launches overlap",
+                                           "streams beside the main chain, so the launches overlap.  Serialised "
+                                           "(profiles/launches_r2k_one_step.txt, ncu, one launch at a time, cold "
+                                           "caches): the same launches incl. their split-reduce passes are 545 of "
+                                           "680 us = 0.80 of the step",
                      "frac_over_whole_step": round(tl_issued / (ms_total / K * 1e-3) / 1e12
                                                    / pk["bf16_tflops_sustained"], 4),
                      "issued_flops_per_step": tl_issued, "algorithmic_flops_per_step": tl_useful, "fp32_equivalent_tflops": round(tl_useful / tl_us / 1e6, 1)
