@@ -89,6 +89,7 @@ class DeviceTransitionRing(object):
         # frame-deduplicated mode
         self.stack_cols = OrderedDict()      # column name -> (H, W, K)
         self.frame_slack = 0.25
+        self.frame_streams = 1               # interleaved episode streams (rollout shards) feeding store(): sizes the identity cache
         self.frames = None                   # uint8 [frame_capacity, H * W]
         self.frame_capacity = 0
         self._fc = 0                         # frames allocated so far (frame f lives in slot f % frame_capacity)
@@ -137,15 +138,19 @@ class DeviceTransitionRing(object):
             self._frame_stage_np = self._frame_stage_host.numpy()
             self._min_fc = np.zeros(self.capacity, dtype=np.int64)
 
-    def declare_schema(self, columns, frame_stack=None, frame_slack=None):
+    def declare_schema(self, columns, frame_stack=None, frame_slack=None, frame_streams=None):
         """Fix the column layout before the first store: {name: (shape, numpy dtype)} or {name: batch tensor [n, ...]}.
         ``store(Transition)`` then converts every field to the declared dtype (gym hands out float64 observations and
         actions where the networks -- and the agents' persistent batch buffers -- are float32).
-        ``frame_stack``: names of uint8 [H, W, K] columns (stacked frames, last-axis) to keep frame-deduplicated."""
+        ``frame_stack``: names of uint8 [H, W, K] columns (stacked frames, last-axis) to keep frame-deduplicated;
+        ``frame_streams``: how many episode streams (vectorised environments / rollout shards) call ``store`` in turn --
+        the cache of recently seen frames is sized for that many (a frame that fell out of it is simply stored again)."""
         if self.specs is not None:
             raise RuntimeError("the replay already holds transitions; the schema is fixed")
         if frame_slack is not None:
             self.frame_slack = float(frame_slack)
+        if frame_streams is not None:
+            self.frame_streams = max(1, int(frame_streams))
         specs = OrderedDict()
         for name, v in columns.items():
             if torch.is_tensor(v):
@@ -215,7 +220,7 @@ class DeviceTransitionRing(object):
                 self._fc += 1
                 hit = (f if by_identity else np.array(fa), fc)
                 self._recent[id(hit[0]) if not by_identity else id(f)] = hit
-                while len(self._recent) > 4 * K + 8:
+                while len(self._recent) > (4 * K + 8) * self.frame_streams:
                     self._recent.popitem(last=False)
             slot_row[c] = hit[1] % self.frame_capacity
             oldest = hit[1] if oldest is None else min(oldest, hit[1])

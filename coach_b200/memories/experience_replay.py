@@ -29,6 +29,7 @@ class ExperienceReplayParameters(MemoryParameters):
         # frame store holds (1 + frame_slack) x max_size frames
         self.frame_dedup = False
         self.frame_slack = 0.25
+        self.frame_streams = 1          # environments whose transitions are store()d in turn (sizes the frame cache)
 
     @property
     def path(self):
@@ -39,9 +40,9 @@ class ExperienceReplay(Memory):
     """A regular replay buffer which stores transitions without any additional structure (HBM resident)."""
 
     def __init__(self, max_size: Tuple[MemoryGranularity, int], allow_duplicates_in_batch_sampling: bool = True,
-                 device=None, frame_dedup: bool = False, frame_slack: float = 0.25):
+                 device=None, frame_dedup: bool = False, frame_slack: float = 0.25, frame_streams: int = 1):
         super().__init__(max_size)
-        self.frame_dedup, self.frame_slack = bool(frame_dedup), float(frame_slack)
+        self.frame_dedup, self.frame_slack, self.frame_streams = bool(frame_dedup), float(frame_slack), int(frame_streams)
         if max_size[0] != MemoryGranularity.Transitions:
             raise ValueError("Experience replay size can only be configured in terms of transitions")
         self.allow_duplicates_in_batch_sampling = allow_duplicates_in_batch_sampling
@@ -86,7 +87,8 @@ class ExperienceReplay(Memory):
         so that ``store(Transition)`` casts to it (device_ring.DeviceTransitionRing.declare_schema).  ``image_columns``:
         the stacked-frame columns, kept frame-deduplicated when the memory was created with ``frame_dedup``."""
         if self.frame_dedup and image_columns:
-            self.ring.declare_schema(columns, frame_stack=tuple(image_columns), frame_slack=self.frame_slack)
+            self.ring.declare_schema(columns, frame_stack=tuple(image_columns), frame_slack=self.frame_slack,
+                                     frame_streams=self.frame_streams)
         else:
             self.ring.declare_schema(columns)
 

@@ -56,7 +56,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
     def __init__(self, max_size: Tuple[MemoryGranularity, int], alpha: float = 0.6,
                  beta: Schedule = ConstantSchedule(0.4), epsilon: float = 1e-6,
                  allow_duplicates_in_batch_sampling: bool = True, device=None, priority_mode: str = "libm",
-                 frame_dedup: bool = False, frame_slack: float = 0.25):
+                 frame_dedup: bool = False, frame_slack: float = 0.25, frame_streams: int = 1):
         if max_size[0] != MemoryGranularity.Transitions:
             raise ValueError("Prioritized Experience Replay currently only support setting the memory size in "
                              "transitions granularity.")
@@ -66,7 +66,7 @@ class PrioritizedExperienceReplay(ExperienceReplay):
         while self.power_of_2_size < max_size[1]:
             self.power_of_2_size *= 2                                                   # :176-178
         super().__init__((MemoryGranularity.Transitions, self.power_of_2_size), allow_duplicates_in_batch_sampling,
-                         device=device, frame_dedup=frame_dedup, frame_slack=frame_slack)
+                         device=device, frame_dedup=frame_dedup, frame_slack=frame_slack, frame_streams=frame_streams)
         self.alpha = alpha
         self.beta = beta
         self.epsilon = epsilon

@@ -15,6 +15,7 @@ def _bare_ring(capacity, frame_capacity, frame_bytes, stage_rows=512):
     r = DeviceTransitionRing.__new__(DeviceTransitionRing)
     r.capacity, r.count, r._pending, r.cursor = capacity, 0, 0, 0
     r.frame_capacity, r._fc, r._pending_frames, r.frame_bytes, r.frame_slack = frame_capacity, 0, 0, frame_bytes, 0.25
+    r.frame_streams = 1
     r._recent = OrderedDict()
     r._min_fc = np.zeros(capacity, dtype=np.int64)
     r._frame_stage_np = np.zeros((stage_rows, frame_bytes), dtype=np.uint8)
@@ -90,3 +91,33 @@ def test_frame_store_guard_and_argument_checks():
     with pytest.raises(ValueError, match="-byte frames"):
         ring3 = _bare_ring(4, 64, 16)
         ring3._frame_slots(np.zeros((5, 5, 4), np.uint8), 4, row)
+
+
+def test_interleaved_environment_streams_share_frames_within_each_stream():
+    """E environments store() in turn: with the identity cache sized for E streams every frame is still staged once"""
+    E, T = 6, 20
+    rng = np.random.RandomState(1)
+    for streams, exact in ((E, True), (1, False)):
+        ring = _bare_ring(4096, 8192, 16, stage_rows=2048)
+        ring.frame_streams = streams
+        flts = [ObservationStackingFilter(4) for _ in range(E)]
+        cur = [f.filter(rng.randint(0, 256, (4, 4)).astype(np.uint8)) for f in flts]
+        row = np.zeros(4, np.int32)
+        stacks = []
+        for t in range(T):
+            for e in range(E):
+                nxt = flts[e].filter(rng.randint(0, 256, (4, 4)).astype(np.uint8))
+                a, b = np.zeros(4, np.int32), np.zeros(4, np.int32)
+                ring._frame_slots(cur[e], 4, a)
+                ring._frame_slots(nxt, 4, b)
+                stacks.append((np.array(cur[e]), a, np.array(nxt), b))
+                ring._pending += 1
+                cur[e] = nxt
+        store = ring._frame_stage_np[:ring._fc].reshape(-1, 4, 4)
+        for s, a, s2, b in stacks:               # correct either way ...
+            np.testing.assert_array_equal(np.stack([store[i] for i in a], axis=-1), s)
+            np.testing.assert_array_equal(np.stack([store[i] for i in b], axis=-1), s2)
+        if exact:                                # ... and without a single duplicate when the cache covers the streams
+            assert ring._fc == E * (T + 1)
+        else:
+            assert ring._fc > E * (T + 1)
