@@ -136,3 +136,41 @@ def test_c51_acting_q_values():
     p = (e / e.sum(-1, keepdims=True)).astype(np.float32).astype(np.float64)
     want = p @ agent.z_values.astype(np.float32).astype(np.float64)
     np.testing.assert_allclose(q, want, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["c51", "dueling_nomw"])
+def test_graph_replay_matches_eager_on_the_general_head_path(monkeypatch, kind):
+    """the CUDA-graph / multi-stream schedule of the learn step is bit-identical to the eager launch sequence also where
+    the head is not the fused DQN head: Categorical DQN (loss in the forward part) and the dueling network of BASELINE
+    config 5 (global-norm clipping: the norm stays in the backward graph)"""
+    results = []
+    for graph in (0, 1):
+        monkeypatch.setenv("CB200_DQN_GRAPH", str(graph))
+        torch.manual_seed(0)
+        if kind == "c51":
+            agent = _agent((84, 84, 4), 6, 128, True)
+        else:
+            from test_learn_gpu import _make_agent
+            agent = _make_agent((84, 84, 4), 6, 128, True, True, True, 10.0, True, seed=5, middleware=False)
+        assert agent.use_graph == bool(graph)
+        rng = np.random.RandomState(3)
+        n = 512
+        agent.memory.store_columns({
+            "state:observation": rng.randint(0, 256, (n, 84, 84, 4)).astype(np.uint8),
+            "next_state:observation": rng.randint(0, 256, (n, 84, 84, 4)).astype(np.uint8),
+            "action": rng.randint(0, 6, n).astype(np.int64), "reward": rng.randint(-1, 2, n).astype(np.float64),
+            "game_over": (rng.rand(n) < 0.1).astype(np.uint8)})
+        agent.memory.update_priorities(np.arange(n), np.abs(rng.randn(n)))
+        losses = []
+        for step in range(6):                       # 2 eager steps, capture, 3 replays
+            random.seed(20 + step)
+            np.random.seed(20 + step)
+            agent.total_steps_counter += 4
+            losses.append(agent.train() if step % 2 else agent.learn_from_batch(agent.sample_batch())[0])
+        torch.cuda.synchronize()
+        if graph:
+            assert agent._graphs is not None and agent.graph_kernel_launches > 0
+        results.append((losses, agent.net_def.store.theta.clone(), agent.memory.sum_tree.clone()))
+    assert results[0][0] == results[1][0]
+    assert torch.equal(results[0][1], results[1][1])
+    assert torch.equal(results[0][2], results[1][2])
