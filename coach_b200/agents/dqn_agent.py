@@ -683,7 +683,7 @@ class DQNAgent(object):
         if fetch:
             # one synchronisation for both scalars (loss, squared gradient norm) through a pinned pair
             self._join_optimizer()      # the optimizer's stream (where the norm is reduced when nothing clips) too:
-                                        # a fetched step is complete, parameters included, when this call returns
+            self._side_upd.join()       # a fetched step is complete -- parameters and trees -- when this call returns
             self._fetch_host[0:1].copy_(self.loss_dev, non_blocking=True)
             self._fetch_host[1:2].copy_(net.sumsq, non_blocking=True)
             torch.cuda.current_stream().synchronize() if self.device.type == "cuda" else None
