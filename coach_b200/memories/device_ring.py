@@ -349,6 +349,11 @@ class DeviceTransitionRing(object):
         if "frames" in staged:
             frames = staged.pop("frames").to(dev).reshape(-1, self.frame_bytes).contiguous()
             rel = {name: staged[name].to(dev).to(torch.int64).reshape(n, K) for name in self.stack_cols}
+            for name, r in rel.items():
+                lo_i, hi_i = int(r.min()), int(r.max())
+                if lo_i < 0 or hi_i >= frames.shape[0]:
+                    raise ValueError("column %s: frame indices %d..%d outside the %d frames of this append"
+                                     % (name, lo_i, hi_i, frames.shape[0]))
         else:
             parts, rel, base = [], {}, 0
             for name in self.stack_cols:
