@@ -28,24 +28,34 @@ def distribution_prediction_to_q_values(prediction, z):
 
 
 def c51_targets(dist_next, dist_online, dist_select, actions, rewards, bootstrap, gamma_n, z):
-    """The body of learn_from_batch between the predictions and the train op (categorical_dqn_agent.py:120-152;
-    rainbow_dqn_agent.py:107-131 when ``dist_select`` is the online prediction on s' and ``bootstrap`` /
-    ``rewards`` are the n-step quantities).  dist_*: float32 [B, A, N] softmax outputs.  bootstrap: float64 [B]
-    ((1.0 - game_overs) for C51).  Returns (TD_targets float32 [B, A, N], target_actions, m float64 [B, N])."""
-    B = dist_next.shape[0]
-    sel = dist_next if dist_select is None else dist_select
-    target_actions = np.argmax(distribution_prediction_to_q_values(sel, z), axis=1)
-    m = np.zeros((B, z.size))
-    batches = np.arange(B)
-    for j in range(z.size):
-        tzj = np.fmax(np.fmin(rewards + bootstrap * gamma_n * z[j], z[-1]), z[0])
-        bj = (tzj - z[0]) / (z[1] - z[0])
-        u = (np.ceil(bj)).astype(int)
-        l = (np.floor(bj)).astype(int)
-        m[batches, l] += (dist_next[batches, target_actions, j] * (u - bj))
-        m[batches, u] += (dist_next[batches, target_actions, j] * (bj - l))
+    """What learn_from_batch does between the predictions and the train op (categorical_dqn_agent.py:120-152;
+    rainbow_dqn_agent.py:107-131 when ``dist_select`` is the online prediction on s' and ``bootstrap`` / ``rewards``
+    are the n-step quantities).  dist_*: float32 [B, A, N] softmax outputs; bootstrap: float64 [B] ((1.0 - game_overs)
+    for C51).  Returns (TD_targets float32 [B, A, N], target_actions, m float64 [B, N]).
+
+    Written sample by sample: for one sample the reference's vectorised statements reduce to the scalar sequence below
+    (atom j ascending; the floor bin is credited before the ceil bin; an integral position credits nothing), every
+    operation an IEEE double operation -- hence the same bits (tests/test_oracle_golden.py pins it to the reference)."""
+    n_samples, n_atoms = dist_next.shape[0], z.size
+    chooser = dist_next if dist_select is None else dist_select
+    target_actions = np.argmax(distribution_prediction_to_q_values(chooser, z), axis=1)
+    z_lo, z_hi = z[0], z[-1]
+    step = z[1] - z[0]
+    m = np.zeros((n_samples, n_atoms))
+    for b in range(n_samples):
+        scale = bootstrap[b] * gamma_n
+        probs = dist_next[b, target_actions[b]]
+        row = m[b]
+        for j in range(n_atoms):
+            shifted = rewards[b] + scale * z[j]
+            shifted = z_lo if shifted < z_lo else (z_hi if shifted > z_hi else shifted)
+            pos = (shifted - z_lo) / step
+            below, above = int(np.floor(pos)), int(np.ceil(pos))
+            mass = np.float64(probs[j])
+            row[below] += mass * (above - pos)
+            row[above] += mass * (pos - below)
     targets = np.array(dist_online, dtype=np.float32, copy=True)
-    targets[batches, actions] = m
+    targets[np.arange(n_samples), actions] = m
     return targets, target_actions, m
 
 
