@@ -143,3 +143,32 @@ def test_presets_define_the_five_baseline_configurations():
     qn = QNetworkDef("cpu", p5.observation_shape, p5.num_actions, dueling="DuelingQHead" in net.heads_parameters,
                      middleware_units=MiddlewareScheme.units[net.middleware_parameters.scheme])
     assert qn.store.num_params() - 1 == 3293863          # SURVEY section 8d, config 5 (+1: the rescaler scalar)
+
+
+@needs_ref
+def test_checkpoint_names_and_state_file_interoperate_with_the_reference(tmp_path):
+    """coach_b200/checkpoint.py follows the reference's on-disk conventions (checkpoint.py:115-155, :247-273,
+    graph_manager.py:630): the reference's CheckpointStateFile / CheckpointFilenameParser read what we write -- number
+    and name -- and we read what the reference writes; a half-written or foreign state file is ignored by both."""
+    ref_loader.load()
+    from rl_coach.checkpoint import (CheckpointFilenameParser, CheckpointStateFile, CheckpointStateReader,
+                                     SingleCheckpoint)
+    from coach_b200 import checkpoint as ck
+    d = str(tmp_path)
+    name = ck.checkpoint_name(7, 123456)
+    assert name == "7_Step-123456.ckpt"                                   # '{}_Step-{}.ckpt' of graph_manager.py:630
+    parsed = CheckpointFilenameParser().parse(name)
+    assert parsed is not None and parsed.num == 7 and parsed.name == name
+    ck._write_state_file(d, name)
+    assert CheckpointStateFile.checkpoint_state_filename == ck.STATE_FILE
+    got = CheckpointStateFile(d).read()
+    assert got == SingleCheckpoint(7, name)
+    assert CheckpointStateReader(d, checkpoint_state_optional=False).get_latest() == SingleCheckpoint(7, name)
+    # the other direction
+    CheckpointStateFile(d).write(SingleCheckpoint(12, ck.checkpoint_name(12, 99)))
+    assert ck.read_state_file(d) == "12_Step-99.ckpt"
+    # garbage in the state file: no checkpoint for either reader
+    with open(str(tmp_path / ck.STATE_FILE), "w") as f:
+        f.write("not a checkpoint")
+    assert ck.read_state_file(d) is None
+    assert CheckpointStateFile(d).read() is None
